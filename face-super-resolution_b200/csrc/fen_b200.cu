@@ -1,0 +1,653 @@
+// C-ABI implementation (include/fen_b200.h) of the B200-native FaceEnhanceNet forward path.
+// Host orchestration + the small CUDA-core kernels; the tensor-core convolution lives in
+// conv3x3_umma.cuh.  Build: see face-super-resolution_b200/build.py (nvcc, sm_100a only).
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fen_b200.h"
+#include "conv3x3_umma.cuh"
+
+namespace fen {
+
+// ===================================================================== error plumbing
+static thread_local std::string g_err;
+static thread_local int g_launches = 0;
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define FEN_CUDA(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t e_ = (expr);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return fail(FEN_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));          \
+  } while (0)
+
+static int check_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(FEN_ENODEV, "no CUDA device (the FaceEnhanceNet kernels need an sm_100 GPU; there is no CPU fallback)");
+  }
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess || major != 10) {
+    cudaGetLastError();
+    return fail(FEN_ENODEV, "device is not sm_100 (Blackwell B200); kernels are built for sm_100a only");
+  }
+  return FEN_OK;
+}
+
+// ===================================================================== tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult q;
+    void* p = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// NHWC bf16 activation [B][H][W][64]: box = 64 ch x 66 px x 4 rows, 128B swizzle, OOB -> zeros.
+static int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(FEN_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[4] = {cuuint64_t(kC), cuuint64_t(W), cuuint64_t(H), cuuint64_t(B)};
+  cuuint64_t strides[3] = {cuuint64_t(kC) * 2, cuuint64_t(W) * kC * 2, cuuint64_t(H) * W * kC * 2};
+  cuuint32_t box[4] = {cuuint32_t(kC), cuuint32_t(kPitch), cuuint32_t(kBoxRows), 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FEN_ECUDA, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string(int(r)));
+  return FEN_OK;
+}
+// packed weights [rows][64] bf16, box = 64 x N rows.
+static int make_w_map(CUtensorMap* m, const void* ptr, int rows, int n) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(FEN_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {cuuint64_t(kC), cuuint64_t(rows)};
+  cuuint64_t strides[1] = {cuuint64_t(kC) * 2};
+  cuuint32_t box[2] = {cuuint32_t(kC), cuuint32_t(n)};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FEN_ECUDA, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string(int(r)));
+  return FEN_OK;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ===================================================================== conv launcher
+struct ConvArgs {
+  const void* x;        // NHWC bf16 [B][H][W][64]
+  const void* w;        // packed bf16 [groups*9*N][64]
+  int n;                // 64 or 16
+  int groups;           // gridDim.y (4 for the PixelShuffle convs)
+  ConvParams p;
+};
+
+template <int N>
+static int launch_conv_n(const ConvArgs& a, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    FEN_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  ConvSmem<N>::kDynBytes));
+    attr_set = true;
+  }
+  CUtensorMap tm_in, tm_w;
+  int rc = make_act_map(&tm_in, a.x, a.p.B, a.p.H, a.p.W);
+  if (rc) return rc;
+  rc = make_w_map(&tm_w, a.w, a.groups * 9 * N, N);
+  if (rc) return rc;
+  ConvParams p = a.p;
+  p.strips = p.W / kStripW;
+  p.tiles_per_seg = (p.H * kPitch + kTileM - 1) / kTileM;
+  p.total_tiles = p.B * p.strips * p.tiles_per_seg;
+  const int ctas_y = a.groups;
+  int ctas_x = num_sms() / ctas_y;
+  if (ctas_x < 1) ctas_x = 1;
+  p.tiles_per_cta = (p.total_tiles + ctas_x - 1) / ctas_x;
+  ctas_x = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  dim3 grid(ctas_x, ctas_y);
+  conv3x3_umma_kernel<N><<<grid, kConvThreads, ConvSmem<N>::kDynBytes, st>>>(tm_in, tm_w, p);
+  FEN_CUDA(cudaGetLastError());
+  ++g_launches;
+  return FEN_OK;
+}
+
+static int launch_conv(const ConvArgs& a, cudaStream_t st) {
+  if (a.p.W % kStripW || a.p.H <= 0 || a.p.B <= 0) return fail(FEN_EINVAL, "conv: W must be a positive multiple of 64");
+  if (a.n == 64) return launch_conv_n<64>(a, st);
+  if (a.n == 16) return launch_conv_n<16>(a, st);
+  return fail(FEN_EINVAL, "conv: unsupported N");
+}
+
+// ===================================================================== small kernels
+// fp32 OIHW [cout][64][3][3] -> bf16 [grp][tap][n_grp][64].  perm = 0: one group of cout_pad rows
+// (row r <- cout r, zero if r >= cout).  perm = 1: PixelShuffle grouping, 4 groups of 64 rows,
+// group `sub` row c <- cout 4c + sub  (out[c, 2h+i, 2w+j] = in[4c + 2i + j, h, w], blocks.py:215).
+__global__ void pack_conv_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int cout, int n_grp,
+                                 int groups, int perm) {
+  const int total = groups * 9 * n_grp * kC;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ci = i % kC;
+    const int r = (i / kC) % n_grp;
+    const int tap = (i / (kC * n_grp)) % 9;
+    const int grp = i / (kC * n_grp * 9);
+    const int co = perm ? 4 * r + grp : r;
+    float v = 0.f;
+    if (co < cout) v = w[(size_t(co) * kC + ci) * 9 + tap];
+    dst[i] = __float2bfloat16(v);
+  }
+}
+// dst[g*n + r] = src[perm ? 4r + g : r] (0 when out of range)
+__global__ void pack_vec_kernel(const float* __restrict__ src, float* __restrict__ dst, int count, int n_grp,
+                                int groups, int perm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= groups * n_grp) return;
+  const int r = i % n_grp, g = i / n_grp;
+  const int s = perm ? 4 * r + g : r;
+  dst[i] = s < count ? src[s] : 0.f;
+}
+// conv_first weights OIHW [64][3][3][3] -> [27][64] (k = ci*9 + tap major, cout minor)
+__global__ void pack_first_kernel(const float* __restrict__ w, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 27 * kC) return;
+  const int co = i % kC, k = i / kC;
+  dst[i] = w[co * 27 + k];
+}
+
+// conv_first (custom.py:91-94,164): 3 -> 64 channels, fp32 math on CUDA cores (K = 27 is a poor MMA
+// shape and 0.03 % of the FLOPs).  x fp32 NCHW -> out bf16 NHWC.  One block = one image row.
+__global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ wk,
+                                                         const float* __restrict__ bias, bf16* __restrict__ out,
+                                                         int H, int W) {
+  __shared__ float sw[27 * kC];
+  __shared__ float sb[kC];
+  for (int i = threadIdx.x; i < 27 * kC; i += blockDim.x) sw[i] = wk[i];
+  if (threadIdx.x < kC) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int n = blockIdx.y, y = blockIdx.x;
+  const int q = threadIdx.x >> 6;  // 16-channel quarter, warp-uniform
+  for (int x0 = 0; x0 < W; x0 += 64) {
+    const int xx = x0 + (threadIdx.x & 63);
+    float in[27];
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int yy = y + ky - 1, xc = xx + kx - 1;
+          in[ci * 9 + ky * 3 + kx] =
+              (yy >= 0 && yy < H && xc >= 0 && xc < W) ? __ldg(x + ((size_t(n) * 3 + ci) * H + yy) * W + xc) : 0.f;
+        }
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = sb[q * 16 + c];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      const float4* wp = reinterpret_cast<const float4*>(sw + k * kC + q * 16);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w4 = wp[j];
+        acc[4 * j + 0] = fmaf(in[k], w4.x, acc[4 * j + 0]);
+        acc[4 * j + 1] = fmaf(in[k], w4.y, acc[4 * j + 1]);
+        acc[4 * j + 2] = fmaf(in[k], w4.z, acc[4 * j + 2]);
+        acc[4 * j + 3] = fmaf(in[k], w4.w, acc[4 * j + 3]);
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + ((size_t(n) * H + y) * W + xx) * kC + q * 16);
+    uint4 o0, o1;
+    o0.x = pack_bf16(acc[0], acc[1]);   o0.y = pack_bf16(acc[2], acc[3]);
+    o0.z = pack_bf16(acc[4], acc[5]);   o0.w = pack_bf16(acc[6], acc[7]);
+    o1.x = pack_bf16(acc[8], acc[9]);   o1.y = pack_bf16(acc[10], acc[11]);
+    o1.z = pack_bf16(acc[12], acc[13]); o1.w = pack_bf16(acc[14], acc[15]);
+    dst[0] = o0;
+    dst[1] = o1;
+  }
+}
+
+// Squeeze-and-excitation + residual (blocks.py:86-92,153):
+//   s = sigmoid(W2 relu(W0 mean_hw(o)));  x' = o * s * res_scale + x
+// `sums` holds the per-image channel sums produced by the conv2 epilogue.  grid (chunks, B).
+__global__ void __launch_bounds__(256) se_residual_kernel(const bf16* __restrict__ x, const bf16* __restrict__ o,
+                                                          const float* __restrict__ sums,
+                                                          const float* __restrict__ fc0, const float* __restrict__ fc2,
+                                                          int R, float inv_hw, float res_scale, bf16* __restrict__ xout,
+                                                          float* __restrict__ se_out, int se_stride, int hw) {
+  __shared__ float s_mean[kC], s_hid[kC], s_scale[kC];
+  const int n = blockIdx.y, tid = threadIdx.x;
+  if (tid < kC) s_mean[tid] = sums[n * kC + tid] * inv_hw;
+  __syncthreads();
+  if (tid < R) {
+    float a = 0.f;
+    for (int c = 0; c < kC; ++c) a = fmaf(fc0[tid * kC + c], s_mean[c], a);
+    s_hid[tid] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  if (tid < kC) {
+    float a = 0.f;
+    for (int j = 0; j < R; ++j) a = fmaf(fc2[tid * R + j], s_hid[j], a);
+    const float s = 1.f / (1.f + expf(-a));
+    s_scale[tid] = s * res_scale;
+    if (se_out && blockIdx.x == 0) se_out[size_t(n) * se_stride + tid] = s;
+  }
+  __syncthreads();
+  const size_t base = size_t(n) * hw * (kC / 8);
+  const int total = hw * (kC / 8);
+  const uint4* xv = reinterpret_cast<const uint4*>(x) + base;
+  const uint4* ov = reinterpret_cast<const uint4*>(o) + base;
+  uint4* dv = reinterpret_cast<uint4*>(xout) + base;
+  for (int i = blockIdx.x * blockDim.x + tid; i < total; i += gridDim.x * blockDim.x) {
+    const int c0 = (i & 7) * 8;
+    const uint4 a = __ldg(xv + i), b = __ldg(ov + i);
+    uint4 r;
+    r.x = pack_bf16(fmaf(bf16lo(b.x), s_scale[c0 + 0], bf16lo(a.x)), fmaf(bf16hi(b.x), s_scale[c0 + 1], bf16hi(a.x)));
+    r.y = pack_bf16(fmaf(bf16lo(b.y), s_scale[c0 + 2], bf16lo(a.y)), fmaf(bf16hi(b.y), s_scale[c0 + 3], bf16hi(a.y)));
+    r.z = pack_bf16(fmaf(bf16lo(b.z), s_scale[c0 + 4], bf16lo(a.z)), fmaf(bf16hi(b.z), s_scale[c0 + 5], bf16hi(a.z)));
+    r.w = pack_bf16(fmaf(bf16lo(b.w), s_scale[c0 + 6], bf16lo(a.w)), fmaf(bf16hi(b.w), s_scale[c0 + 7], bf16hi(a.w)));
+    dv[i] = r;
+  }
+}
+
+// Bicubic /4 LR generator, integer and bit-exact against cv2.resize(INTER_CUBIC) on uint8
+// (dataset.py:296, prepare_data.py:38): u = sum a_i a_j hr[4y+i][4x+j][c], a = [-3,19,19,-3],
+// lr = clamp(round_half_even(u / 1024), 0, 255).  One thread per output pixel (all C channels).
+template <int C>
+__global__ void __launch_bounds__(256) lr_from_hr_kernel(const uint8_t* __restrict__ hr, uint8_t* __restrict__ lr_u8,
+                                                         float* __restrict__ lr_f32, int B, int H, int W) {
+  const int w = W >> 2, h = H >> 2;
+  const size_t total = size_t(B) * h * w;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int x = int(i % w);
+    const int y = int((i / w) % h);
+    const int n = int(i / (size_t(w) * h));
+    const uint8_t* src = hr + ((size_t(n) * H + 4 * y) * W + 4 * x) * C;
+    int u[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) u[c] = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int ar = (r == 0 || r == 3) ? -3 : 19;
+      uint8_t px[4 * C];
+      if constexpr ((4 * C) % 4 == 0) {
+        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src + size_t(r) * W * C);  // 4*C*x is 4-aligned
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+          const uint32_t v = __ldg(s32 + k);
+          px[4 * k + 0] = v & 0xff; px[4 * k + 1] = (v >> 8) & 0xff;
+          px[4 * k + 2] = (v >> 16) & 0xff; px[4 * k + 3] = v >> 24;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int rowv = -3 * int(px[c]) + 19 * int(px[C + c]) + 19 * int(px[2 * C + c]) - 3 * int(px[3 * C + c]);
+        u[c] += ar * rowv;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      int qv = (u[c] + 511 + ((u[c] >> 10) & 1)) >> 10;
+      qv = min(max(qv, 0), 255);
+      if (lr_u8) lr_u8[i * C + c] = uint8_t(qv);
+      if (lr_f32) lr_f32[((size_t(n) * C + c) * h + y) * w + x] = float(qv) / 255.0f;
+    }
+  }
+}
+
+// ===================================================================== parameter / blob layout
+struct Layout {
+  int C, G, Bk, R, n_rcab;
+  // flat fp32 parameter offsets (elements)
+  int64_t p_first_w, p_first_b, p_rcab0, p_rcab_stride, p_group_stride, p_gconv_w_in_group, p_after_w, p_after_b,
+      p_up[2], p_last_w, p_last_b, p_total;
+  // packed blob offsets (bytes)
+  int64_t k_first_w, k_first_b, k_rcab0, k_rcab_stride, k_gconv0, k_gconv_stride, k_after, k_up[2], k_last, k_total;
+};
+// per-RCAB flat params: conv1.w conv1.b prelu conv2.w conv2.b fc0 fc2
+static constexpr int64_t kConvW = 64 * 64 * 9;
+static constexpr int64_t kConvWBytes = 9 * 64 * 64 * 2;
+static int64_t align256(int64_t v) { return (v + 255) & ~int64_t(255); }
+
+// packed RCAB record: [w1 bf16][w2 bf16][b1 64f][slope 64f][b2 64f][fc0 R*64 f][fc2 64*R f]
+struct RcabRec { int64_t w1, w2, b1, slope, b2, fc0, fc2, size; };
+static RcabRec rcab_rec(int R) {
+  RcabRec r;
+  r.w1 = 0; r.w2 = kConvWBytes; r.b1 = 2 * kConvWBytes; r.slope = r.b1 + 256; r.b2 = r.slope + 256;
+  r.fc0 = r.b2 + 256; r.fc2 = r.fc0 + int64_t(R) * 64 * 4; r.size = align256(r.fc2 + int64_t(R) * 64 * 4);
+  return r;
+}
+// packed plain conv record: [w bf16][b 64f]
+static constexpr int64_t kPlainRec = kConvWBytes + 256;
+// packed upsample record: [w bf16 4 groups][b 256f permuted][slope 64f]
+static constexpr int64_t kUpRec = 4 * kConvWBytes + 1024 + 256;
+// packed conv_last record: [w bf16 9*16*64][b 16f]
+static constexpr int64_t kLastRec = 9 * 16 * 64 * 2 + 256;
+
+static int make_layout(const fen_config* cfg, Layout* L) {
+  if (!cfg) return fail(FEN_EINVAL, "null config");
+  if (cfg->num_channels != 64) return fail(FEN_EINVAL, "unsupported config: num_channels must be 64 (no fallback path)");
+  if (cfg->scale_factor != 4) return fail(FEN_EINVAL, "unsupported config: scale_factor must be 4");
+  if (cfg->num_groups < 1 || cfg->blocks_per_group < 1) return fail(FEN_EINVAL, "num_groups and blocks_per_group must be >= 1");
+  if (cfg->reduction_ratio < 1) return fail(FEN_EINVAL, "reduction_ratio must be >= 1");
+  L->C = 64; L->G = cfg->num_groups; L->Bk = cfg->blocks_per_group;
+  L->R = 64 / cfg->reduction_ratio; if (L->R < 8) L->R = 8;
+  if (L->R > 64) return fail(FEN_EINVAL, "SE hidden width > 64 unsupported");
+  L->n_rcab = L->G * L->Bk;
+  const int64_t rcab_p = 2 * (kConvW + 64) + 64 + 2 * int64_t(L->R) * 64;
+  int64_t o = 0;
+  L->p_first_w = o; o += 64 * 27; L->p_first_b = o; o += 64;
+  L->p_rcab0 = o; L->p_rcab_stride = rcab_p;
+  L->p_gconv_w_in_group = L->Bk * rcab_p;
+  L->p_group_stride = L->Bk * rcab_p + kConvW + 64;
+  o += L->G * L->p_group_stride;
+  L->p_after_w = o; o += kConvW; L->p_after_b = o; o += 64;
+  for (int s = 0; s < 2; ++s) { L->p_up[s] = o; o += 4 * kConvW + 256 + 64; }
+  L->p_last_w = o; o += 3 * 64 * 9; L->p_last_b = o; o += 3;
+  L->p_total = o;
+  const RcabRec rr = rcab_rec(L->R);
+  int64_t k = 0;
+  L->k_first_w = k; k += align256(27 * 64 * 4); L->k_first_b = k; k += 256;
+  L->k_rcab0 = k; L->k_rcab_stride = rr.size; k += int64_t(L->n_rcab) * rr.size;
+  L->k_gconv0 = k; L->k_gconv_stride = kPlainRec; k += int64_t(L->G) * kPlainRec;
+  L->k_after = k; k += kPlainRec;
+  for (int s = 0; s < 2; ++s) { L->k_up[s] = k; k += kUpRec; }
+  L->k_last = k; k += kLastRec;
+  L->k_total = align256(k);
+  return FEN_OK;
+}
+
+static int pack_conv(const float* w, int cout, int n_grp, int groups, int perm, void* dst, cudaStream_t st) {
+  const int total = groups * 9 * n_grp * kC;
+  pack_conv_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, reinterpret_cast<bf16*>(dst), cout, n_grp, groups, perm);
+  FEN_CUDA(cudaGetLastError());
+  return FEN_OK;
+}
+static int pack_vec(const float* src, int count, int n_grp, int groups, int perm, void* dst, cudaStream_t st) {
+  pack_vec_kernel<<<(groups * n_grp + 255) / 256, 256, 0, st>>>(src, reinterpret_cast<float*>(dst), count, n_grp, groups, perm);
+  FEN_CUDA(cudaGetLastError());
+  return FEN_OK;
+}
+
+// ===================================================================== workspace
+struct Workspace {
+  int64_t f0, x[2], h, o, grp0, grp_stride, u0, u1, sums, total;
+};
+static void make_workspace(const Layout& L, int B, int H, int W, Workspace* ws) {
+  const int64_t act = align256(int64_t(B) * H * W * 64 * 2);
+  int64_t o = 0;
+  ws->f0 = o; o += act;
+  ws->x[0] = o; o += act; ws->x[1] = o; o += act;
+  ws->h = o; o += act; ws->o = o; o += act;
+  ws->grp0 = o; ws->grp_stride = act; o += act * L.G;
+  ws->u0 = o; o += 4 * act;
+  ws->u1 = o; o += 16 * act;
+  ws->sums = o; o += align256(int64_t(L.n_rcab) * B * 64 * 4);
+  ws->total = o;
+}
+
+}  // namespace fen
+
+using namespace fen;
+
+// ===================================================================== C ABI
+extern "C" {
+
+int fen_abi_version(void) { return FEN_ABI_VERSION; }
+const char* fen_last_error(void) { return g_err.c_str(); }
+int fen_last_launch_count(void) { return g_launches; }
+
+int64_t fen_param_count(const fen_config* cfg) {
+  Layout L;
+  if (make_layout(cfg, &L)) return FEN_EINVAL;
+  return L.p_total;
+}
+int64_t fen_packed_bytes(const fen_config* cfg) {
+  Layout L;
+  if (make_layout(cfg, &L)) return FEN_EINVAL;
+  return L.k_total;
+}
+
+int fen_pack_conv3x3(const float* w_oihw, int cout, int cout_pad, void* w_packed, void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  if (!w_oihw || !w_packed || cout < 1 || cout_pad < cout) return fail(FEN_EINVAL, "fen_pack_conv3x3: bad arguments");
+  return pack_conv(w_oihw, cout, cout_pad, 1, 0, w_packed, static_cast<cudaStream_t>(stream));
+}
+
+int fen_pack_weights(const fen_config* cfg, const float* params, void* packed, void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  Layout L;
+  if ((rc = make_layout(cfg, &L))) return rc;
+  if (!params || !packed) return fail(FEN_EINVAL, "fen_pack_weights: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* k = static_cast<uint8_t*>(packed);
+  const RcabRec rr = rcab_rec(L.R);
+  pack_first_kernel<<<(27 * 64 + 255) / 256, 256, 0, st>>>(params + L.p_first_w, reinterpret_cast<float*>(k + L.k_first_w));
+  FEN_CUDA(cudaGetLastError());
+  if ((rc = pack_vec(params + L.p_first_b, 64, 64, 1, 0, k + L.k_first_b, st))) return rc;
+  for (int g = 0; g < L.G; ++g) {
+    const float* pg = params + L.p_rcab0 + g * L.p_group_stride;
+    for (int b = 0; b < L.Bk; ++b) {
+      const float* pr = pg + b * L.p_rcab_stride;
+      uint8_t* kr = k + L.k_rcab0 + int64_t(g * L.Bk + b) * L.k_rcab_stride;
+      const float* c1w = pr; const float* c1b = c1w + kConvW; const float* sl = c1b + 64;
+      const float* c2w = sl + 64; const float* c2b = c2w + kConvW; const float* fc0 = c2b + 64;
+      const float* fc2 = fc0 + L.R * 64;
+      if ((rc = pack_conv(c1w, 64, 64, 1, 0, kr + rr.w1, st))) return rc;
+      if ((rc = pack_conv(c2w, 64, 64, 1, 0, kr + rr.w2, st))) return rc;
+      if ((rc = pack_vec(c1b, 64, 64, 1, 0, kr + rr.b1, st))) return rc;
+      if ((rc = pack_vec(sl, 64, 64, 1, 0, kr + rr.slope, st))) return rc;
+      if ((rc = pack_vec(c2b, 64, 64, 1, 0, kr + rr.b2, st))) return rc;
+      if ((rc = pack_vec(fc0, L.R * 64, L.R * 64, 1, 0, kr + rr.fc0, st))) return rc;
+      if ((rc = pack_vec(fc2, L.R * 64, L.R * 64, 1, 0, kr + rr.fc2, st))) return rc;
+    }
+    uint8_t* kg = k + L.k_gconv0 + g * L.k_gconv_stride;
+    if ((rc = pack_conv(pg + L.p_gconv_w_in_group, 64, 64, 1, 0, kg, st))) return rc;
+    if ((rc = pack_vec(pg + L.p_gconv_w_in_group + kConvW, 64, 64, 1, 0, kg + kConvWBytes, st))) return rc;
+  }
+  if ((rc = pack_conv(params + L.p_after_w, 64, 64, 1, 0, k + L.k_after, st))) return rc;
+  if ((rc = pack_vec(params + L.p_after_b, 64, 64, 1, 0, k + L.k_after + kConvWBytes, st))) return rc;
+  for (int s = 0; s < 2; ++s) {
+    const float* pu = params + L.p_up[s];
+    uint8_t* ku = k + L.k_up[s];
+    if ((rc = pack_conv(pu, 256, 64, 4, 1, ku, st))) return rc;
+    if ((rc = pack_vec(pu + 4 * kConvW, 256, 64, 4, 1, ku + 4 * kConvWBytes, st))) return rc;
+    if ((rc = pack_vec(pu + 4 * kConvW + 256, 64, 64, 1, 0, ku + 4 * kConvWBytes + 1024, st))) return rc;
+  }
+  if ((rc = pack_conv(params + L.p_last_w, 3, 16, 1, 0, k + L.k_last, st))) return rc;
+  if ((rc = pack_vec(params + L.p_last_b, 3, 16, 1, 0, k + L.k_last + 9 * 16 * 64 * 2, st))) return rc;
+  return FEN_OK;
+}
+
+int64_t fen_forward_workspace_bytes(const fen_config* cfg, int B, int H, int W) {
+  Layout L;
+  if (make_layout(cfg, &L)) return FEN_EINVAL;
+  if (B < 1 || H < 1 || W < 1) { fail(FEN_EINVAL, "bad batch / size"); return FEN_EINVAL; }
+  Workspace ws;
+  make_workspace(L, B, H, W, &ws);
+  return ws.total;
+}
+
+int fen_conv3x3_c64(const void* x, const void* w_packed, const float* bias, const float* slope,
+                    const void* residual, float* sums, void* out, int B, int H, int W, int epilogue,
+                    void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  g_launches = 0;
+  if (!x || !w_packed || !out) return fail(FEN_EINVAL, "fen_conv3x3_c64: null pointer");
+  if (epilogue == kEpiShuffle || epilogue == kEpiLast || epilogue < 0 || epilogue > kEpiBias)
+    return fail(FEN_EINVAL, "fen_conv3x3_c64: unsupported epilogue");
+  if (epilogue == kEpiResidual && !residual) return fail(FEN_EINVAL, "fen_conv3x3_c64: residual required");
+  if (epilogue == kEpiSum && !sums) return fail(FEN_EINVAL, "fen_conv3x3_c64: sums required");
+  ConvArgs a{};
+  a.x = x; a.w = w_packed; a.n = 64; a.groups = 1;
+  a.p.B = B; a.p.H = H; a.p.W = W; a.p.epi = epilogue; a.p.bias = bias; a.p.slope = slope;
+  a.p.residual = static_cast<const bf16*>(residual); a.p.out = static_cast<bf16*>(out); a.p.sums = sums;
+  return launch_conv(a, static_cast<cudaStream_t>(stream));
+}
+
+int fen_forward(const fen_config* cfg, const void* packed, const float* x, float* out, int B, int H,
+                int W, int training, void* workspace, int64_t workspace_bytes, float* se_out,
+                void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  g_launches = 0;
+  Layout L;
+  if ((rc = make_layout(cfg, &L))) return rc;
+  if (!packed || !x || !out || !workspace) return fail(FEN_EINVAL, "fen_forward: null pointer");
+  if (B < 1 || H < 64 || W < 64 || H % 64 || W % 64)
+    return fail(FEN_EINVAL, "fen_forward: H and W must be positive multiples of 64 (no fallback path)");
+  Workspace ws;
+  make_workspace(L, B, H, W, &ws);
+  if (workspace_bytes < ws.total) return fail(FEN_ENOMEM, "fen_forward: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* wsb = static_cast<uint8_t*>(workspace);
+  const uint8_t* k = static_cast<const uint8_t*>(packed);
+  const RcabRec rr = rcab_rec(L.R);
+  auto act = [&](int64_t off) { return reinterpret_cast<bf16*>(wsb + off); };
+  float* sums = reinterpret_cast<float*>(wsb + ws.sums);
+  FEN_CUDA(cudaMemsetAsync(sums, 0, size_t(L.n_rcab) * B * 64 * 4, st));
+
+  conv_first_kernel<<<dim3(H, B), 256, 0, st>>>(x, reinterpret_cast<const float*>(k + L.k_first_w),
+                                                reinterpret_cast<const float*>(k + L.k_first_b), act(ws.f0), H, W);
+  FEN_CUDA(cudaGetLastError());
+  ++g_launches;
+
+  auto conv = [&](const bf16* in, const uint8_t* w, const float* bias, const float* slope, const bf16* res,
+                  float* sm, bf16* o, int epi, int h, int w_) -> int {
+    ConvArgs a{};
+    a.x = in; a.w = w; a.n = 64; a.groups = (epi == kEpiShuffle) ? 4 : 1;
+    a.p.B = B; a.p.H = h; a.p.W = w_; a.p.epi = epi; a.p.bias = bias; a.p.slope = slope; a.p.residual = res;
+    a.p.out = o; a.p.sums = sm;
+    return launch_conv(a, st);
+  };
+
+  const int hw = H * W;
+  const int se_chunks = 4;
+  const bf16* cur = act(ws.f0);
+  for (int g = 0; g < L.G; ++g) {
+    const bf16* gin = cur;
+    for (int b = 0; b < L.Bk; ++b) {
+      const int r = g * L.Bk + b;
+      const uint8_t* kr = k + L.k_rcab0 + int64_t(r) * L.k_rcab_stride;
+      float* sm = sums + size_t(r) * B * 64;
+      if ((rc = conv(cur, kr + rr.w1, reinterpret_cast<const float*>(kr + rr.b1),
+                     reinterpret_cast<const float*>(kr + rr.slope), nullptr, nullptr, act(ws.h), kEpiPrelu, H, W)))
+        return rc;
+      if ((rc = conv(act(ws.h), kr + rr.w2, reinterpret_cast<const float*>(kr + rr.b2), nullptr, nullptr, sm,
+                     act(ws.o), kEpiSum, H, W)))
+        return rc;
+      bf16* nxt = act(ws.x[b & 1]);
+      se_residual_kernel<<<dim3(se_chunks, B), 256, 0, st>>>(
+          cur, act(ws.o), sm, reinterpret_cast<const float*>(kr + rr.fc0), reinterpret_cast<const float*>(kr + rr.fc2),
+          L.R, 1.f / float(hw), cfg->res_scale, nxt, se_out ? se_out + size_t(r) * 64 : nullptr, L.n_rcab * 64, hw);
+      FEN_CUDA(cudaGetLastError());
+      ++g_launches;
+      cur = nxt;
+    }
+    const uint8_t* kg = k + L.k_gconv0 + g * L.k_gconv_stride;
+    bf16* gout = act(ws.grp0 + g * ws.grp_stride);
+    if ((rc = conv(cur, kg, reinterpret_cast<const float*>(kg + kConvWBytes), nullptr, gin, nullptr, gout,
+                   kEpiResidual, H, W)))
+      return rc;
+    cur = gout;
+  }
+  // conv_after_body + long skip -> x[0]
+  if ((rc = conv(cur, k + L.k_after, reinterpret_cast<const float*>(k + L.k_after + kConvWBytes), nullptr,
+                 act(ws.f0), nullptr, act(ws.x[0]), kEpiResidual, H, W)))
+    return rc;
+  // upsample stages
+  {
+    const uint8_t* ku = k + L.k_up[0];
+    if ((rc = conv(act(ws.x[0]), ku, reinterpret_cast<const float*>(ku + 4 * kConvWBytes),
+                   reinterpret_cast<const float*>(ku + 4 * kConvWBytes + 1024), nullptr, nullptr, act(ws.u0),
+                   kEpiShuffle, H, W)))
+      return rc;
+    ku = k + L.k_up[1];
+    if ((rc = conv(act(ws.u0), ku, reinterpret_cast<const float*>(ku + 4 * kConvWBytes),
+                   reinterpret_cast<const float*>(ku + 4 * kConvWBytes + 1024), nullptr, nullptr, act(ws.u1),
+                   kEpiShuffle, 2 * H, 2 * W)))
+      return rc;
+  }
+  // conv_last + bicubic skip + clamp
+  {
+    ConvArgs a{};
+    a.x = act(ws.u1); a.w = k + L.k_last; a.n = 16; a.groups = 1;
+    a.p.B = B; a.p.H = 4 * H; a.p.W = 4 * W; a.p.epi = kEpiLast; a.p.training = training;
+    a.p.bias = reinterpret_cast<const float*>(k + L.k_last + 9 * 16 * 64 * 2);
+    a.p.lr = x; a.p.out_f32 = out;
+    if ((rc = launch_conv(a, st))) return rc;
+  }
+  return FEN_OK;
+}
+
+int64_t fen_forward_tap(const fen_config* cfg, const void* workspace, int B, int H, int W, int which,
+                        int index, const void** ptr) {
+  Layout L;
+  if (make_layout(cfg, &L)) return FEN_EINVAL;
+  if (!workspace || !ptr) return fail(FEN_EINVAL, "fen_forward_tap: null pointer");
+  Workspace ws;
+  make_workspace(L, B, H, W, &ws);
+  const uint8_t* b = static_cast<const uint8_t*>(workspace);
+  const int64_t act = int64_t(B) * H * W * 64 * 2;
+  switch (which) {
+    case 0: *ptr = b + ws.f0; return act;
+    case 1: *ptr = b + ws.x[0]; return act;
+    case 2: *ptr = b + ws.u0; return 4 * act;
+    case 3: *ptr = b + ws.u1; return 16 * act;
+    case 4:
+      if (index < 0 || index >= L.G) return fail(FEN_EINVAL, "fen_forward_tap: bad group index");
+      *ptr = b + ws.grp0 + index * ws.grp_stride;
+      return act;
+    default: return fail(FEN_EINVAL, "fen_forward_tap: unknown tap");
+  }
+}
+
+int fen_lr_from_hr_u8(const uint8_t* hr, uint8_t* lr_u8, float* lr_f32, int B, int H, int W, int C,
+                      void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  g_launches = 0;
+  if (!hr || (!lr_u8 && !lr_f32)) return fail(FEN_EINVAL, "fen_lr_from_hr_u8: null pointer");
+  if (B < 0 || H < 4 || W < 4 || (H & 3) || (W & 3)) return fail(FEN_EINVAL, "fen_lr_from_hr_u8: H and W must be multiples of 4");
+  if (C < 1 || C > 4) return fail(FEN_EINVAL, "fen_lr_from_hr_u8: C must be in 1..4");
+  if (B == 0) return FEN_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t total = size_t(B) * (H / 4) * (W / 4);
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = size_t(num_sms()) * 32;
+  if (blocks > cap) blocks = cap;
+  switch (C) {
+    case 1: lr_from_hr_kernel<1><<<unsigned(blocks), 256, 0, st>>>(hr, lr_u8, lr_f32, B, H, W); break;
+    case 2: lr_from_hr_kernel<2><<<unsigned(blocks), 256, 0, st>>>(hr, lr_u8, lr_f32, B, H, W); break;
+    case 3: lr_from_hr_kernel<3><<<unsigned(blocks), 256, 0, st>>>(hr, lr_u8, lr_f32, B, H, W); break;
+    default: lr_from_hr_kernel<4><<<unsigned(blocks), 256, 0, st>>>(hr, lr_u8, lr_f32, B, H, W); break;
+  }
+  FEN_CUDA(cudaGetLastError());
+  ++g_launches;
+  return FEN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,51 @@
+// Shared declarations for the FaceEnhanceNet sm_100a kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+
+namespace fen {
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------ geometry of the conv kernel
+constexpr int kC = 64;                               // feature channels (K per tap)
+constexpr int kTileM = 128;                          // output pixels per UMMA tile (TMEM lanes)
+constexpr int kStripW = 64;                          // image columns handled by one strip
+constexpr int kPitch = kStripW + 2;                  // strip row pitch in shared memory (halo cols)
+constexpr int kBoxRows = 4;                          // image rows per TMA box / ring slot
+constexpr int kBoxPx = kBoxRows * kPitch;            // 264 pixels
+constexpr int kSlotBytes = kBoxPx * kC * 2;          // 33792 B (= 33 * 1024: swizzle-atom aligned)
+constexpr int kRingSlots = 3;                        // + 1 mirror slot after the last one
+constexpr int kRingBytes = (kRingSlots + 1) * kSlotBytes;
+constexpr int kMaxShift = 2 * kPitch + 2;            // largest tap offset in the strip-linear space
+constexpr int kConvThreads = 192;                    // warp0 TMA, warp1 MMA, warps2-5 epilogue
+
+enum EpilogueKind : int {
+  kEpiPrelu = 0,     // out = prelu(acc + bias)                       (RCAB conv1)
+  kEpiSum = 1,       // out = acc + bias ; per-image channel sums     (RCAB conv2 -> SE pool)
+  kEpiResidual = 2,  // out = acc + bias + residual                   (group conv, conv_after_body)
+  kEpiShuffle = 3,   // out[2y+i,2x+j,c] = prelu(acc + bias), sub-pixel = blockIdx.y (upsample conv)
+  kEpiLast = 4,      // out_f32 NCHW = [clamp](acc + bias + bicubic_x4(lr))   (conv_last)
+  kEpiBias = 5,      // out = acc + bias
+};
+
+struct ConvParams {
+  int B, H, W;            // input spatial size (W a multiple of 64)
+  int strips;             // W / 64
+  int tiles_per_seg;      // ceil(H * 66 / 128); a segment = one strip of one image
+  int total_tiles;        // B * strips * tiles_per_seg
+  int tiles_per_cta;
+  int epi;                // EpilogueKind
+  int training;           // kEpiLast: no clamp when non-zero
+  const float* bias;      // [gridDim.y][N]
+  const float* slope;     // [64] PReLU slopes or nullptr
+  const bf16* residual;   // NHWC, same shape as out (kEpiResidual)
+  bf16* out;              // NHWC bf16 output
+  float* sums;            // [B][64] fp32, accumulated with atomics (kEpiSum)
+  const float* lr;        // [B][3][H/4][W/4] fp32 network input (kEpiLast)
+  float* out_f32;         // [B][3][H][W] fp32 (kEpiLast)
+};
+
+}  // namespace fen

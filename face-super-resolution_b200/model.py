@@ -1,0 +1,209 @@
+"""FaceEnhanceNet: drop-in for the reference's model API (src/models/custom.py), with the forward
+pass executed by hand-written sm_100a kernels through the C ABI of include/fen_b200.h.
+
+Same constructor (`FaceEnhanceNet(config=None, **kwargs)`), dataclass fields, attributes, sub-module
+tree and therefore the same `state_dict()` keys / shapes (load_state_dict(strict=True) round-trips
+with the reference).  forward(x: [B,3,H,W] fp32 CUDA in [0,1]) -> [B,3,4H,4W] fp32, clamped to
+[0,1] iff not self.training (custom.py:187-188).
+
+There is no CPU path and no cuDNN dispatch: CPU tensors, non-64-channel configs or a missing CUDA
+library raise.  Backward is not implemented in this build (forward returns a tensor without a grad
+graph; calling it in train mode with grad enabled raises).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Any, Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .blocks import ResidualGroup, UpsampleModule
+
+
+@dataclass
+class FaceEnhanceNetConfig:
+    """Same fields and defaults as the reference dataclass (custom.py:22-43)."""
+    num_channels: int = 64
+    num_groups: int = 3
+    blocks_per_group: int = 4
+    kernel_size: int = 3
+    reduction_ratio: int = 4
+    scale_factor: int = 4
+    res_scale: float = 0.2
+    in_channels: int = 3
+    out_channels: int = 3
+    init_scale: float = 0.1
+    num_rcab_blocks: int = 8
+
+
+class FaceEnhanceNet(nn.Module):
+    def __init__(self, config: Optional[FaceEnhanceNetConfig] = None, **kwargs):
+        super().__init__()
+        if config is None:
+            config = FaceEnhanceNetConfig()
+        for key, value in kwargs.items():  # kwargs override dataclass fields (custom.py:78-80)
+            if hasattr(config, key):
+                setattr(config, key, value)
+        self.config = config
+        self.scale_factor = config.scale_factor
+        self.num_channels = config.num_channels
+        k, pad = config.kernel_size, config.kernel_size // 2
+        self.conv_first = nn.Conv2d(config.in_channels, config.num_channels, k, padding=pad)
+        self.residual_groups = nn.ModuleList([
+            ResidualGroup(config.num_channels, config.blocks_per_group, k, config.reduction_ratio,
+                          config.res_scale) for _ in range(config.num_groups)])
+        self.conv_after_body = nn.Conv2d(config.num_channels, config.num_channels, k, padding=pad)
+        self.upsample = UpsampleModule(config.num_channels, config.scale_factor)
+        self.conv_last = nn.Conv2d(config.num_channels, config.out_channels, k, padding=pad)
+        self._initialize_weights()
+        # derived kernel-side state (never part of state_dict)
+        self._packed: Optional[torch.Tensor] = None
+        self._packed_key = None
+        self._workspaces: Dict[Any, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ init (custom.py:128-145)
+    def _initialize_weights(self) -> None:
+        for m in self.modules():
+            if isinstance(m, (nn.Conv2d, nn.Linear)):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+        nn.init.zeros_(self.conv_last.weight)
+        nn.init.zeros_(self.conv_last.bias)
+
+    # ------------------------------------------------------------------ kernel-side plumbing
+    def _c_config(self) -> _lib.FenConfig:
+        c = self.config
+        if (c.kernel_size != 3 or c.in_channels != 3 or c.out_channels != 3):
+            raise ValueError("unsupported config for the B200 path: kernel_size must be 3 and "
+                             "in_channels == out_channels == 3 (no fallback path)")
+        return _lib.FenConfig(c.num_channels, c.num_groups, c.blocks_per_group, c.reduction_ratio,
+                              c.scale_factor, float(c.res_scale))
+
+    def _params_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _ensure_packed(self, device: torch.device, stream_ptr: int) -> torch.Tensor:
+        key = (str(device), self._params_key())
+        if self._packed is not None and self._packed_key == key:
+            return self._packed
+        lib, cfg = _lib.load(), self._c_config()
+        nbytes = lib.fen_packed_bytes(C.byref(cfg))
+        _lib.check(nbytes, "fen_packed_bytes")
+        flat = torch.cat([p.detach().reshape(-1).to(torch.float32) for p in self.parameters()])
+        n_expected = lib.fen_param_count(C.byref(cfg))
+        if flat.numel() != n_expected:
+            raise RuntimeError(f"parameter count {flat.numel()} != kernel layout {n_expected}")
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _lib.check(lib.fen_pack_weights(C.byref(cfg), flat.data_ptr(), packed.data_ptr(), stream_ptr),
+                   "fen_pack_weights")
+        self._packed, self._packed_key = packed, key
+        return packed
+
+    def _run(self, x: torch.Tensor, want_se: bool):
+        if not isinstance(x, torch.Tensor) or x.dim() != 4 or x.shape[1] != 3:
+            raise RuntimeError(f"expected input [B,3,H,W], got {tuple(getattr(x, 'shape', ()))}")
+        if not x.is_cuda:
+            raise RuntimeError("FaceEnhanceNet (B200 path) needs a CUDA tensor: there is no CPU fallback")
+        if next(self.parameters()).device != x.device:
+            raise RuntimeError("input and parameters are on different devices")
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise RuntimeError("backward is not implemented in this build of the B200 path; "
+                               "call forward under torch.no_grad() or in eval() mode")
+        lib, cfg = _lib.load(), self._c_config()
+        x = x.detach().to(torch.float32).contiguous()
+        B, _, H, W = x.shape
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            packed = self._ensure_packed(x.device, stream)
+            wkey = (str(x.device), B, H, W)
+            ws = self._workspaces.get(wkey)
+            if ws is None:
+                nbytes = lib.fen_forward_workspace_bytes(C.byref(cfg), B, H, W)
+                _lib.check(nbytes, "fen_forward_workspace_bytes")
+                self._workspaces.clear()
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+                self._workspaces[wkey] = ws
+            s = self.scale_factor
+            out = torch.empty((B, 3, H * s, W * s), dtype=torch.float32, device=x.device)
+            n_rcab = self.config.num_groups * self.config.blocks_per_group
+            se = torch.empty((B, n_rcab, 64), dtype=torch.float32, device=x.device) if want_se else None
+            rc = lib.fen_forward(C.byref(cfg), packed.data_ptr(), x.data_ptr(), out.data_ptr(), B, H, W,
+                                 1 if self.training else 0, ws.data_ptr(), ws.numel(),
+                                 se.data_ptr() if se is not None else None, stream)
+            _lib.check(rc, "fen_forward")
+        return out, se
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """custom.py:147-190."""
+        return self._run(x, want_se=False)[0]
+
+    def get_attention_maps(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """custom.py:192-230: {'group{g}_rcab{b}': [B, C] sigmoid channel weights}.  Served natively
+        from the fused path (sub-module hooks do not fire there)."""
+        with torch.no_grad():
+            _, se = self._run(x, want_se=True)
+        maps = {}
+        for g in range(self.config.num_groups):
+            for b in range(self.config.blocks_per_group):
+                maps[f"group{g}_rcab{b}"] = se[:, g * self.config.blocks_per_group + b]
+        return maps
+
+    def feature_tap(self, x_shape, which: int, index: int = 0) -> torch.Tensor:
+        """Parity/debug helper: NHWC bf16 intermediate of the last forward with input shape x_shape."""
+        lib, cfg = _lib.load(), self._c_config()
+        B, _, H, W = x_shape
+        ws = next(iter(self._workspaces.values()))
+        ptr = C.c_void_p()
+        n = lib.fen_forward_tap(C.byref(cfg), ws.data_ptr(), B, H, W, which, index, C.byref(ptr))
+        _lib.check(n, "fen_forward_tap")
+        off = ptr.value - ws.data_ptr()
+        mult = {0: 1, 1: 1, 2: 2, 3: 4, 4: 1}[which]
+        return ws[off:off + n].view(torch.bfloat16).view(B, H * mult, W * mult, 64)
+
+    def get_model_info(self) -> Dict[str, Any]:
+        """custom.py:232-256 (same keys)."""
+        total = sum(p.numel() for p in self.parameters())
+        trainable = sum(p.numel() for p in self.parameters() if p.requires_grad)
+        c = self.config
+        return {
+            "name": "FaceEnhanceNet", "total_params": total, "trainable_params": trainable,
+            "size_mb": total * 4 / (1024 ** 2), "num_groups": c.num_groups,
+            "blocks_per_group": c.blocks_per_group, "total_rcab_blocks": c.num_groups * c.blocks_per_group,
+            "num_channels": c.num_channels, "scale_factor": self.scale_factor,
+            "input_size": "64x64", "output_size": f"{64 * self.scale_factor}x{64 * self.scale_factor}",
+        }
+
+    @classmethod
+    def from_pretrained(cls, checkpoint_path: str, device: Optional[str] = None) -> "FaceEnhanceNet":
+        """custom.py:258-292: accepts {'config', 'model_state_dict' | 'state_dict'} or a bare state_dict."""
+        ckpt = torch.load(checkpoint_path, map_location="cpu")
+        config = FaceEnhanceNetConfig(**ckpt["config"]) if isinstance(ckpt, dict) and "config" in ckpt \
+            else FaceEnhanceNetConfig()
+        model = cls(config)
+        if "model_state_dict" in ckpt:
+            model.load_state_dict(ckpt["model_state_dict"])
+        elif "state_dict" in ckpt:
+            model.load_state_dict(ckpt["state_dict"])
+        else:
+            model.load_state_dict(ckpt)
+        return model.to(device) if device else model
+
+
+def create_face_enhance_net(num_rcab_blocks: int = 8, num_channels: int = 64, scale_factor: int = 4,
+                            **kwargs) -> FaceEnhanceNet:
+    """custom.py:295-319."""
+    return FaceEnhanceNet(FaceEnhanceNetConfig(num_rcab_blocks=num_rcab_blocks, num_channels=num_channels,
+                                               scale_factor=scale_factor, **kwargs))
+
+
+class FaceEnhanceNetLite(FaceEnhanceNet):
+    """custom.py:323-333 (32 channels).  Constructible for state_dict compatibility; its forward raises
+    because the kernels are built for 64 channels only."""
+
+    def __init__(self, **kwargs):
+        super().__init__(FaceEnhanceNetConfig(num_channels=32, num_rcab_blocks=4, reduction_ratio=2, **kwargs))

@@ -1,0 +1,110 @@
+/* fen_b200.h - C ABI of the B200-native FaceEnhanceNet forward path.
+ *
+ * The reference (tomasz-pres/face-super-resolution) has no FFI layer: its boundary for this path is
+ * the Python nn.Module API.  Every entry point below replaces one piece of that boundary; the
+ * Python host (face-super-resolution_b200/model.py, data.py) binds them with ctypes and keeps the
+ * reference's names, arguments and error behaviour.  INTEGRATION.md shows the binding a maintainer
+ * of the reference would add.
+ *
+ * Conventions: plain pointers and sizes only (all pointers are DEVICE pointers unless named
+ * host_*), `stream` is a cudaStream_t passed as void*, every function returns 0 on success or a
+ * negative FEN_E* code, never throws and never allocates device memory (the caller passes a
+ * workspace sized by fen_forward_workspace_bytes).  fen_last_error() returns a thread-local
+ * message for the last failure.  There is no CPU fallback: without a sm_100 device every compute
+ * entry point returns FEN_ENODEV.
+ */
+#ifndef FEN_B200_H
+#define FEN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FEN_ABI_VERSION 1
+
+#define FEN_OK 0
+#define FEN_EINVAL (-1)   /* bad argument / unsupported configuration (e.g. channels != 64) */
+#define FEN_ENODEV (-2)   /* no sm_100 CUDA device */
+#define FEN_ENOMEM (-3)   /* workspace too small */
+#define FEN_ECUDA (-4)    /* CUDA runtime / driver error, see fen_last_error() */
+
+/* Model hyper-parameters; mirrors FaceEnhanceNetConfig (reference src/models/custom.py:22-43).
+ * Supported by the kernels: num_channels == 64, kernel_size == 3, scale_factor == 4,
+ * in_channels == out_channels == 3, SE hidden width max(64 / reduction_ratio, 8) <= 64. */
+typedef struct fen_config {
+  int32_t num_channels;
+  int32_t num_groups;
+  int32_t blocks_per_group;
+  int32_t reduction_ratio;
+  int32_t scale_factor;
+  float res_scale;
+} fen_config;
+
+int fen_abi_version(void);
+const char* fen_last_error(void);
+
+/* Number of fp32 elements of the flat parameter vector: the state_dict tensors of
+ * FaceEnhanceNet concatenated in registration order (custom.py:88-124). */
+int64_t fen_param_count(const fen_config* cfg);
+
+/* Bytes of the packed (kernel-ready) weight blob. */
+int64_t fen_packed_bytes(const fen_config* cfg);
+
+/* Replaces nothing in the reference (weights are consumed in place by cuDNN there): turns the fp32
+ * OIHW state_dict tensors (flat vector, see fen_param_count) into the layout the kernels read -
+ * bf16 [tap][Cout][Cin] K-major conv weights (upsample convs permuted to PixelShuffle sub-pixel
+ * groups, conv_last padded to 16 outputs), fp32 biases / PReLU slopes / SE matrices.
+ * Call after construction, load_state_dict and every optimiser step. */
+int fen_pack_weights(const fen_config* cfg, const float* params, void* packed, void* stream);
+
+/* Workspace bytes fen_forward needs for a batch of B images of H x W (LR size). */
+int64_t fen_forward_workspace_bytes(const fen_config* cfg, int B, int H, int W);
+
+/* Replaces FaceEnhanceNet.forward (reference src/models/custom.py:147-190).
+ *   x        [B,3,H,W]   fp32 NCHW in [0,1]
+ *   out      [B,3,4H,4W] fp32 NCHW; clamped to [0,1] unless `training` (custom.py:187-188)
+ *   se_out   optional [B, num_groups*blocks_per_group, 64] fp32: the channel-attention scales of
+ *            every RCAB (what get_attention_maps, custom.py:192-230, returns); may be NULL
+ * H and W must be multiples of 64 (the benchmark uses 64 x 64). */
+int fen_forward(const fen_config* cfg, const void* packed, const float* x, float* out, int B, int H,
+                int W, int training, void* workspace, int64_t workspace_bytes, float* se_out,
+                void* stream);
+
+/* Debug / parity taps: copies of intermediate NHWC bf16 feature maps of the LAST fen_forward on this
+ * workspace.  which: 0 = conv_first output, 1 = body output (after conv_after_body + long skip),
+ * 2 = upsample stage 0 output, 3 = upsample stage 1 output, 4 = residual stream after group g
+ * (g = `index`).  Returns the tap's byte size, or a negative error. */
+int64_t fen_forward_tap(const fen_config* cfg, const void* workspace, int B, int H, int W, int which,
+                        int index, const void** ptr);
+
+/* Replaces the LR generator of src/data: cv2.resize(hr, (W/4, H/4), interpolation=cv2.INTER_CUBIC)
+ * (reference src/data/dataset.py:292-296, src/data/prepare_data.py:36-39) followed, optionally, by
+ * to_tensor (src/data/transforms.py:260-279).  Integer arithmetic, bit-exact.
+ *   hr       [B,H,W,C] uint8 HWC, H and W multiples of 4, C in 1..4
+ *   lr_u8    optional [B,H/4,W/4,C] uint8 HWC
+ *   lr_f32   optional [B,C,H/4,W/4] fp32 CHW, value / 255.0f */
+int fen_lr_from_hr_u8(const uint8_t* hr, uint8_t* lr_u8, float* lr_f32, int B, int H, int W, int C,
+                      void* stream);
+
+/* One 3x3 / pad-1 convolution with 64 input and 64 output channels on NHWC bf16 tensors
+ * (the RCAB building block, reference src/models/blocks.py:122-130): out = epilogue(conv(x) + bias).
+ *   w_packed [9][64][64] bf16 (tap, cout, cin), as produced by fen_pack_conv3x3
+ *   epilogue 0: prelu(slope)  1: none + channel sums into sums[B][64]  2: + residual  5: none
+ * Used by the single-layer parity tests and the RCAB micro-benchmark. */
+int fen_conv3x3_c64(const void* x, const void* w_packed, const float* bias, const float* slope,
+                    const void* residual, float* sums, void* out, int B, int H, int W, int epilogue,
+                    void* stream);
+
+/* fp32 OIHW [cout][cin=64][3][3] -> bf16 [tap][cout_pad][64]; rows >= cout are zero. */
+int fen_pack_conv3x3(const float* w_oihw, int cout, int cout_pad, void* w_packed, void* stream);
+
+/* Kernels launched by the last fen_forward / fen_conv3x3_c64 / fen_lr_from_hr_u8 call of this thread. */
+int fen_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEN_B200_H */
