@@ -1,0 +1,65 @@
+"""Generates the committed golden fixtures.  Run HERE (the authoring container), where
+/root/reference and cv2 exist:   python tests/golden/make_golden.py
+
+  lr_golden.npz   outputs of cv2.resize(hr, (W/4, H/4), interpolation=cv2.INTER_CUBIC) - the call the
+                  reference makes at src/data/dataset.py:296 / prepare_data.py:38 - for the inputs
+                  of cases.LR_CASES (cv2 version recorded in the file).
+  fen_golden.npz  outputs of the UNMODIFIED reference module `src.models.FaceEnhanceNet` (imported
+                  from /root/reference) with weights from oracle/weights.py loaded by
+                  load_state_dict(strict=True) in train() mode (unclamped; the eval() output is exactly its clamp to
+                  [0,1], asserted at generation time), plus its get_attention_maps.
+Nothing at test time reads /root/reference."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, HERE)
+import cases  # noqa: E402
+from oracle import weights  # noqa: E402
+
+
+def make_lr():
+    import cv2
+    out = {"cv2_version": np.array(cv2.__version__)}
+    for name, (H, W, C), _ in cases.LR_CASES:
+        hr = cases.lr_input(name)
+        src = hr[:, :, 0] if C == 1 else hr
+        lr = cv2.resize(src, (W // 4, H // 4), interpolation=cv2.INTER_CUBIC)
+        out[name] = lr.reshape(H // 4, W // 4, C)
+    np.savez_compressed(os.path.join(HERE, "lr_golden.npz"), **out)
+    print("lr_golden.npz:", {k: v.shape for k, v in out.items() if k != "cv2_version"})
+
+
+def make_fen():
+    sys.path.insert(0, "/root/reference")
+    from src.models import FaceEnhanceNet
+    torch.set_num_threads(8)
+    out = {"torch_version": np.array(torch.__version__)}
+    for name, cfg, tier, seed, batch in cases.FEN_CASES:
+        sd = weights.make_state_dict(seed, tier, **cfg)
+        m = FaceEnhanceNet(num_channels=64, scale_factor=4, **cfg)
+        m.load_state_dict(sd, strict=True)
+        x = torch.from_numpy(cases.fen_input(name))
+        with torch.no_grad():
+            m.eval()
+            y_eval = m(x)
+            att = m.get_attention_maps(x)
+            m.train()
+            y_train = m(x)
+        assert torch.equal(y_eval, y_train.clamp(0.0, 1.0))  # eval output is exactly clamp(train output)
+        out[name + "/train"] = y_train.numpy().astype(np.float32)
+        out[name + "/se"] = np.stack([att[f"group{g}_rcab{b}"].numpy() for g in range(cfg["num_groups"])
+                                      for b in range(cfg["blocks_per_group"])], 1)
+        print(name, y_eval.shape, float(y_eval.min()), float(y_eval.max()), float(y_train.min()), float(y_train.max()))
+    np.savez_compressed(os.path.join(HERE, "fen_golden.npz"), **out)
+
+
+if __name__ == "__main__":
+    make_lr()
+    make_fen()
+    for f in ("lr_golden.npz", "fen_golden.npz"):
+        print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

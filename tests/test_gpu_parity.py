@@ -1,0 +1,255 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes), against the CPU oracle, the
+committed golden vectors (made from the real reference / cv2) and size-independent properties.
+Run on a B200 with `pytest -m gpu`.
+
+Tolerances: LR generator bit-exact.  SR output: PSNR >= 50 dB and max-abs <= 2e-2 on [0,1] against the
+fp32 reference output (BASELINE.json north_star), weight tier T1."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cases
+import fsr_b200
+from fsr_b200 import _lib
+from oracle import fen_oracle, lr_oracle, weights
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+LR_GOLD = np.load(os.path.join(HERE, "golden", "lr_golden.npz"))
+FEN_GOLD = np.load(os.path.join(HERE, "golden", "fen_golden.npz"))
+PSNR_BAR, MAXABS_BAR = 50.0, 2e-2
+
+
+@pytest.fixture(scope="module")
+def dev(built_lib):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+# ------------------------------------------------------------------ LR generator (bit-exact)
+@pytest.mark.parametrize("name", [c[0] for c in cases.LR_CASES])
+def test_lr_kernel_matches_cv2_golden(name, dev):
+    hr = cases.lr_input(name)
+    u8, f32 = fsr_b200.lr_from_hr(torch.from_numpy(hr).to(dev).unsqueeze(0))
+    assert np.array_equal(u8[0].cpu().numpy(), LR_GOLD[name])
+    assert np.array_equal(f32[0].cpu().numpy(), lr_oracle.to_tensor_chw(LR_GOLD[name]))
+
+
+def test_lr_kernel_large_batch_against_oracle(dev):
+    rng = np.random.default_rng(11)
+    hr = rng.integers(0, 256, (96, 256, 256, 3), dtype=np.uint8)
+    hr[7] = (rng.integers(0, 8, (256, 256, 3)) * 32).astype(np.uint8)   # tie-heavy image
+    hr[8] = (rng.integers(0, 2, (256, 256, 3)) * 255).astype(np.uint8)  # saturating image
+    u8, f32 = fsr_b200.lr_from_hr(torch.from_numpy(hr).to(dev))
+    ref = lr_oracle.lr_from_hr_u8(hr)
+    assert np.array_equal(u8.cpu().numpy(), ref)
+    assert np.array_equal(f32.cpu().numpy(), lr_oracle.to_tensor_chw(ref))
+
+
+def test_lr_kernel_properties_and_edges(dev):
+    # constant 4x4 blocks are fixed points; empty batch; single output; only-one-output requests
+    blocks = torch.from_numpy(cases.lr_input("blocks_256")).to(dev).unsqueeze(0)
+    u8, _ = fsr_b200.lr_from_hr(blocks, want_f32=False)
+    assert torch.equal(u8[0], blocks[0, ::4, ::4])
+    e_u8, e_f32 = fsr_b200.lr_from_hr(torch.zeros(0, 8, 8, 3, dtype=torch.uint8, device=dev))
+    assert e_u8.shape == (0, 2, 2, 3) and e_f32.shape == (0, 3, 2, 2)
+    one = torch.full((1, 4, 4, 1), 200, dtype=torch.uint8, device=dev)
+    assert fsr_b200.lr_from_hr(one)[0].item() == 200
+    with pytest.raises(ValueError):
+        fsr_b200.lr_from_hr(torch.zeros(1, 6, 8, 3, dtype=torch.uint8, device=dev))
+    with pytest.raises(ValueError):
+        fsr_b200.lr_from_hr(torch.zeros(1, 8, 8, 5, dtype=torch.uint8, device=dev))
+
+
+def test_create_lr_image_numpy_boundary(dev):
+    hr = cases.lr_input("random_256")
+    out = fsr_b200.create_lr_image(hr, lr_size=64, method="bicubic")
+    assert out.dtype == np.uint8 and np.array_equal(out, LR_GOLD["random_256"])
+
+
+# ------------------------------------------------------------------ single convolution (C ABI)
+def _conv_call(dev, x, w, bias, slope, res, epi):
+    lib = _lib.load()
+    B, _, H, W = x.shape
+    to_nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).to(dev)
+    xd, rd = to_nhwc(x), to_nhwc(res)
+    wd, bd, sd = w.to(dev).contiguous(), bias.to(dev), slope.to(dev)
+    wp = torch.empty(9 * 64 * 64, dtype=torch.bfloat16, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.fen_pack_conv3x3(wd.data_ptr(), 64, 64, wp.data_ptr(), st), "fen_pack_conv3x3")
+    out = torch.full((B, H, W, 64), float("nan"), dtype=torch.bfloat16, device=dev)
+    sums = torch.zeros(B, 64, dtype=torch.float32, device=dev)
+    rc = lib.fen_conv3x3_c64(xd.data_ptr(), wp.data_ptr(), bd.data_ptr(), sd.data_ptr(), rd.data_ptr(),
+                             sums.data_ptr(), out.data_ptr(), B, H, W, epi, st)
+    _lib.check(rc, "fen_conv3x3_c64")
+    torch.cuda.synchronize()
+    return out.float().cpu().permute(0, 3, 1, 2), sums.cpu()
+
+
+@pytest.mark.parametrize("B,H,W,epi", [(1, 64, 64, 5), (2, 64, 64, 0), (3, 64, 64, 1), (2, 64, 64, 2),
+                                       (1, 128, 128, 0), (1, 64, 192, 2), (5, 128, 64, 1), (150, 64, 64, 1)])
+def test_conv3x3_against_fp32_reference(B, H, W, epi, dev):
+    g = torch.Generator().manual_seed(B * 1000 + H + epi)
+    bf = lambda t: t.to(torch.bfloat16).float()      # operands are bf16 on the device
+    x = bf(torch.randn(B, 64, H, W, generator=g) * 0.5)
+    w = bf(torch.randn(64, 64, 3, 3, generator=g) * 0.06)
+    bias = torch.randn(64, generator=g) * 0.1
+    slope = torch.rand(64, generator=g) * 0.4 + 0.05
+    res = bf(torch.randn(B, 64, H, W, generator=g) * 0.5)
+    ref = F.conv2d(x, w, bias, padding=1)            # plain PyTorch fp32 reference of the same op
+    sums_ref = ref.sum(dim=(2, 3))
+    if epi == 0:
+        ref = F.prelu(ref, slope)
+    elif epi == 2:
+        ref = ref + res
+    got, sums = _conv_call(dev, x, w, bias, slope, res, epi)
+    assert not torch.isnan(got).any()
+    # fp32 accumulate, bf16 store: error <= half a bf16 ulp of the result (+ accumulation order)
+    tol = ref.abs().clamp(min=1.0) * 2.0 ** -8 + 1e-3
+    assert ((got - ref).abs() <= tol).all(), (got - ref).abs().max().item()
+    if epi == 1:
+        assert (sums - sums_ref).abs().max().item() <= 1e-3 * sums_ref.abs().max().item() + 1e-2
+
+
+def test_conv3x3_zero_padding_and_linearity(dev):
+    # all-ones input, centre-tap-only weights -> identity; all-ones weights -> border counts 4/6/9
+    x = torch.ones(1, 64, 64, 64)
+    z = torch.zeros(64)
+    w_id = torch.zeros(64, 64, 3, 3)
+    w_id[torch.arange(64), torch.arange(64), 1, 1] = 1.0
+    got, _ = _conv_call(dev, x, w_id, z, z, x, 5)
+    assert torch.equal(got, x)
+    w_cnt = torch.zeros(64, 64, 3, 3)
+    w_cnt[:, 0] = 1.0
+    got, _ = _conv_call(dev, x, w_cnt, z, z, x, 5)
+    assert got[0, 0, 0, 0] == 4 and got[0, 5, 0, 7] == 6 and got[0, 9, 31, 0] == 6 and got[0, 3, 20, 20] == 9
+    assert got[0, 63, 63, 63] == 4 and got[0, 1, 63, 30] == 6
+
+
+def test_conv3x3_rejects_bad_arguments(dev):
+    lib = _lib.load()
+    t = torch.zeros(64 * 64 * 64, dtype=torch.bfloat16, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    rc = lib.fen_conv3x3_c64(t.data_ptr(), t.data_ptr(), None, None, None, None, t.data_ptr(), 1, 64, 60, 5, st)
+    assert rc == _lib.FEN_EINVAL
+    rc = lib.fen_conv3x3_c64(t.data_ptr(), t.data_ptr(), None, None, None, None, t.data_ptr(), 1, 64, 64, 2, st)
+    assert rc == _lib.FEN_EINVAL and b"residual" in lib.fen_last_error()
+    rc = lib.fen_conv3x3_c64(t.data_ptr(), t.data_ptr(), None, None, None, None, t.data_ptr(), 1, 64, 64, 3, st)
+    assert rc == _lib.FEN_EINVAL
+
+
+# ------------------------------------------------------------------ whole network
+def _model(cfg, sd, dev, train=False):
+    m = fsr_b200.FaceEnhanceNet(**cfg)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev)
+    return m.train() if train else m.eval()
+
+
+@pytest.mark.parametrize("name", [c[0] for c in cases.FEN_CASES])
+def test_forward_matches_reference_golden(name, dev):
+    _, cfg, tier, seed, _ = [c for c in cases.FEN_CASES if c[0] == name][0]
+    sd = weights.make_state_dict(seed, tier, **cfg)
+    x = torch.from_numpy(cases.fen_input(name)).to(dev)
+    g_train = torch.from_numpy(FEN_GOLD[name + "/train"])
+    with torch.no_grad():
+        y_eval = _model(cfg, sd, dev)(x).cpu()
+        y_train = _model(cfg, sd, dev, train=True)(x).cpu()
+    for got, ref in ((y_eval, g_train.clamp(0, 1)), (y_train, g_train)):
+        assert got.shape == ref.shape and got.dtype == torch.float32
+        assert fen_oracle.psnr(got, ref) >= PSNR_BAR
+        assert (got - ref).abs().max().item() <= MAXABS_BAR
+    assert y_eval.min() >= 0 and y_eval.max() <= 1
+    assert y_train.min() < 0 and y_train.max() > 1        # train mode really is unclamped
+    if tier == "T0":  # conv_last == 0: output is the bicubic skip alone, fp32 all the way
+        assert (y_train - g_train).abs().max().item() <= 2e-6
+
+
+def test_forward_batch64_full_model_against_oracle(dev):
+    """BASELINE.json config 2: bf16 inference, batch 64, 6 x 10 x 64 model, tier T1."""
+    cfg = dict(num_groups=6, blocks_per_group=10)
+    sd = weights.make_state_dict(0, "T1", **cfg)
+    x = torch.rand(64, 3, 64, 64, generator=torch.Generator().manual_seed(5))
+    m = _model(cfg, sd, dev)
+    with torch.no_grad():
+        y = m(x.to(dev)).cpu()
+    idx = [0, 1, 31, 62, 63]
+    taps = {}
+    ref = fen_oracle.fen_forward(sd, x[idx], taps=taps)
+    psnr, max_abs = fen_oracle.psnr(y[idx], ref), (y[idx] - ref).abs().max().item()
+    print(f"\nbatch-64 parity: PSNR {psnr:.2f} dB, max|err| {max_abs:.3e}")
+    assert psnr >= PSNR_BAR and max_abs <= MAXABS_BAR
+    assert not torch.isnan(y).any()
+    # intermediate feature maps: bf16 rounding grows slowly; > 5 % would be a bug
+    body = m.feature_tap(x.shape, 1)[idx].float().cpu().permute(0, 3, 1, 2)
+    rel = ((body - taps["body"]).norm() / taps["body"].norm()).item()
+    assert rel < 0.05, rel
+    # batch independence: image 31 alone gives the same answer (SE sums use atomics -> tiny fp32 jitter)
+    with torch.no_grad():
+        y1 = m(x[31:32].to(dev)).cpu()
+    assert (y1[0] - y[31]).abs().max().item() <= 2e-3
+
+
+def test_attention_maps_match_reference(dev):
+    name = "small_T1"
+    _, cfg, tier, seed, _ = [c for c in cases.FEN_CASES if c[0] == name][0]
+    sd = weights.make_state_dict(seed, tier, **cfg)
+    x = torch.from_numpy(cases.fen_input(name)).to(dev)
+    maps = _model(cfg, sd, dev).get_attention_maps(x)
+    assert sorted(maps) == ["group0_rcab0", "group0_rcab1"]
+    gold = torch.from_numpy(FEN_GOLD[name + "/se"])
+    got = torch.stack([maps["group0_rcab0"], maps["group0_rcab1"]], 1).cpu()
+    assert got.shape == gold.shape
+    assert (got - gold).abs().max().item() <= 5e-3
+
+
+def test_forward_other_shapes_and_repacking(dev):
+    cfg = dict(num_groups=1, blocks_per_group=1)
+    sd = weights.make_state_dict(4, "T1", **cfg)
+    m = _model(cfg, sd, dev)
+    x = torch.rand(2, 3, 128, 64, generator=torch.Generator().manual_seed(9))   # fully convolutional
+    with torch.no_grad():
+        y = m(x.to(dev)).cpu()
+    ref = fen_oracle.fen_forward(sd, x)
+    assert y.shape == (2, 3, 512, 256)
+    assert fen_oracle.psnr(y, ref) >= PSNR_BAR and (y - ref).abs().max().item() <= MAXABS_BAR
+    # in-place weight update must invalidate the packed copy
+    with torch.no_grad():
+        m.conv_last.weight.mul_(3.0)
+        y2 = m(x.to(dev)).cpu()
+    sd2 = {k: v.clone() for k, v in sd.items()}
+    sd2["conv_last.weight"] = sd2["conv_last.weight"] * 3.0
+    ref2 = fen_oracle.fen_forward(sd2, x)
+    assert (y2 - ref2).abs().max().item() <= MAXABS_BAR and (y2 - y).abs().max().item() > 1e-4
+
+
+def test_forward_error_behaviour(dev):
+    m = _model(dict(num_groups=1, blocks_per_group=1), weights.make_state_dict(0, "T0", num_groups=1, blocks_per_group=1), dev)
+    with pytest.raises(ValueError, match="multiples of 64"):
+        m(torch.rand(1, 3, 48, 64, device=dev))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.rand(1, 3, 64, 64))
+    m.train()
+    with pytest.raises(RuntimeError, match="backward is not implemented"):
+        m(torch.rand(1, 3, 64, 64, device=dev))
+    lite = fsr_b200.FaceEnhanceNetLite().to(dev).eval()
+    with pytest.raises(ValueError, match="num_channels must be 64"):
+        lite(torch.rand(1, 3, 64, 64, device=dev))
+
+
+def test_lr_generator_feeds_the_model(dev):
+    """Config 4's chain: uint8 HR -> integer LR kernel -> forward, vs the oracle chain."""
+    hr = cases.lr_input("smooth_256")[None]
+    cfg = dict(num_groups=1, blocks_per_group=2)
+    sd = weights.make_state_dict(2, "T1", **cfg)
+    _, lr = fsr_b200.lr_from_hr(torch.from_numpy(hr).to(dev))
+    with torch.no_grad():
+        y = _model(cfg, sd, dev)(lr).cpu()
+    ref_lr = torch.from_numpy(lr_oracle.to_tensor_chw(lr_oracle.lr_from_hr_u8(hr)))
+    assert torch.equal(lr.cpu(), ref_lr)
+    ref = fen_oracle.fen_forward(sd, ref_lr)
+    assert fen_oracle.psnr(y, ref) >= PSNR_BAR and (y - ref).abs().max().item() <= MAXABS_BAR

@@ -1,0 +1,89 @@
+"""Pins the fp32 network oracle (oracle/fen_oracle.py) against outputs of the UNMODIFIED reference
+module (tests/golden/fen_golden.npz, made by tests/golden/make_golden.py from /root/reference)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cases
+from oracle import fen_oracle, weights
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, "golden", "fen_golden.npz"))
+TOL = 2e-5  # fp32 reassociation only (the oracle calls the same ATen ops)
+
+
+@pytest.mark.parametrize("name", [c[0] for c in cases.FEN_CASES])
+def test_oracle_matches_reference_golden(name):
+    _, cfg, tier, seed, _ = [c for c in cases.FEN_CASES if c[0] == name][0]
+    sd = weights.make_state_dict(seed, tier, **cfg)
+    x = torch.from_numpy(cases.fen_input(name))
+    taps = {}
+    y_train = fen_oracle.fen_forward(sd, x, training=True, taps=taps)
+    y_eval = fen_oracle.fen_forward(sd, x, training=False)
+    g_train = torch.from_numpy(GOLD[name + "/train"])
+    assert (y_train - g_train).abs().max().item() <= TOL
+    assert (y_eval - g_train.clamp(0, 1)).abs().max().item() <= TOL
+    assert y_eval.min() >= 0 and y_eval.max() <= 1
+    assert (taps["se"] - torch.from_numpy(GOLD[name + "/se"])).abs().max().item() <= 1e-5
+
+
+def test_literal_init_is_vacuous_without_the_weight_recipe():
+    # trap 1 of SURVEY.md: conv_last == 0  =>  forward == clamp(bicubic_up(x))
+    cfg = dict(num_groups=1, blocks_per_group=1)
+    sd = weights.make_state_dict(3, "T0", **cfg)
+    x = torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(0))
+    y = fen_oracle.fen_forward(sd, x)
+    bic = F.interpolate(x, scale_factor=4, mode="bicubic", align_corners=False).clamp(0, 1)
+    assert torch.equal(y, bic)
+    sd1 = weights.make_state_dict(3, "T1", **cfg)
+    assert (fen_oracle.fen_forward(sd1, x) - bic).abs().max() > 1e-3
+
+
+def test_bicubic_phase_filters_match_interpolate():
+    # the integer/2048 phase filters the CUDA epilogue uses (custom.py:158-161)
+    w, off = fen_oracle.bicubic_x4_weights()
+    x = torch.rand(1, 1, 9, 11, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+    ref = F.interpolate(x, scale_factor=4, mode="bicubic", align_corners=False)[0, 0]
+    h, wd = x.shape[2:]
+    got = torch.zeros_like(ref)
+    for Y in range(4 * h):
+        for X in range(4 * wd):
+            qy, ry, qx, rx = Y // 4, Y % 4, X // 4, X % 4
+            acc = 0.0
+            for i in range(4):
+                yy = min(max(qy + off[ry] - 1 + i, 0), h - 1)
+                for j in range(4):
+                    xx = min(max(qx + off[rx] - 1 + j, 0), wd - 1)
+                    acc += w[ry][i] * w[rx][j] * x[0, 0, yy, xx].item()
+            got[Y, X] = acc / (2048.0 * 2048.0)
+    assert (got - ref).abs().max().item() < 1e-12
+
+
+def test_schema_matches_survey_counts():
+    s = weights.state_dict_schema()
+    assert len(s) == 444
+    assert sum(int(np.prod(v)) for v in s.values()) == 5_115_651
+    assert s["residual_groups.5.blocks.9.channel_attention.fc.0.weight"] == (16, 64)
+    assert s["upsample.stages.1.conv.weight"] == (256, 64, 3, 3)
+    assert fen_oracle.count_groups_blocks(weights.make_state_dict(0, "T0", num_groups=2, blocks_per_group=3)) == (2, 3)
+
+
+def test_weight_recipe_is_deterministic_and_tiered():
+    a = weights.make_state_dict(7, "T1", num_groups=1, blocks_per_group=1)
+    b = weights.make_state_dict(7, "T1", num_groups=1, blocks_per_group=1)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    t0 = weights.make_state_dict(7, "T0", num_groups=1, blocks_per_group=1)
+    assert t0["conv_last.weight"].abs().max() == 0 and t0["conv_first.bias"].abs().max() == 0
+    assert torch.all(t0["residual_groups.0.blocks.0.prelu.weight"] == 0.25)
+    assert a["conv_last.weight"].std() < 2e-3 and a["conv_last.weight"].abs().max() > 0
+    with pytest.raises(ValueError):
+        weights.make_state_dict(0, "T9")
+
+
+def test_psnr_formula():
+    a = torch.zeros(4, 4)
+    assert fen_oracle.psnr(a, a) == float("inf")
+    assert abs(fen_oracle.psnr(a, a + 0.1) - 20.0) < 1e-4
