@@ -630,10 +630,10 @@ int fen_lr_from_hr_u8(const uint8_t* hr, uint8_t* lr_u8, float* lr_f32, int B, i
   int rc = check_device();
   if (rc) return rc;
   g_launches = 0;
+  if (B == 0) return FEN_OK;  // empty batch: nothing to do (pointers may be null)
   if (!hr || (!lr_u8 && !lr_f32)) return fail(FEN_EINVAL, "fen_lr_from_hr_u8: null pointer");
   if (B < 0 || H < 4 || W < 4 || (H & 3) || (W & 3)) return fail(FEN_EINVAL, "fen_lr_from_hr_u8: H and W must be multiples of 4");
   if (C < 1 || C > 4) return fail(FEN_EINVAL, "fen_lr_from_hr_u8: C must be in 1..4");
-  if (B == 0) return FEN_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t total = size_t(B) * (H / 4) * (W / 4);
   size_t blocks = (total + 255) / 256;

@@ -188,10 +188,13 @@ def test_forward_batch64_full_model_against_oracle(dev):
     body = m.feature_tap(x.shape, 1)[idx].float().cpu().permute(0, 3, 1, 2)
     rel = ((body - taps["body"]).norm() / taps["body"].norm()).item()
     assert rel < 0.05, rel
-    # batch independence: image 31 alone gives the same answer (SE sums use atomics -> tiny fp32 jitter)
+    # batch independence: image 31 alone gives the same answer up to fp32 summation order of the SE
+    # pool (different tile->CTA split), which bf16 re-rounding amplifies to the parity-noise level;
+    # any cross-image leak would show up at the 0.3 level of the conv_last residual
     with torch.no_grad():
         y1 = m(x[31:32].to(dev)).cpu()
-    assert (y1[0] - y[31]).abs().max().item() <= 2e-3
+    assert (y1[0] - y[31]).abs().max().item() <= MAXABS_BAR
+    assert fen_oracle.psnr(y1[0], y[31]) >= PSNR_BAR
 
 
 def test_attention_maps_match_reference(dev):
