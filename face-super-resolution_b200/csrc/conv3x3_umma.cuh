@@ -15,11 +15,14 @@
 // columns and are discarded by the epilogue (3 % of MMA work).
 //
 // Pipeline.  warp 0: TMA producer (4-row boxes into a 3-slot ring + a mirror slot that keeps views
-// contiguous across the ring wrap).  warp 1: single-thread tcgen05.mma issuer, 9 taps x 4 k-steps
-// per tile, fp32 accumulators double-buffered in TMEM.  warps 2-5: epilogue, TMEM -> registers ->
-// bias / PReLU / residual / SE partial sums / PixelShuffle / bicubic skip -> global, written
-// straight from registers so shared-memory bandwidth (the binding resource: every MMA re-reads
-// its A and B operands) is left to the tensor core.
+// contiguous across the ring wrap).  warps 1-2: tcgen05.mma issuers (one elected lane each), 9 taps
+// x 4 k-steps per tile, alternating tiles: the tensor pipe accepts only ~1-2 queued MMAs, so the
+// ~800 cycles of barrier checks between two tiles of one issuer are covered by the other issuer's
+// MMAs.  fp32 accumulators live in TMEM, 4 buffers (2 per issuer).  warps 3..: epilogue, TMEM ->
+// registers -> bias / PReLU / residual / SE partial sums / PixelShuffle / bicubic skip -> global,
+// written straight from registers (256-bit stores) so shared-memory bandwidth - the binding
+// resource: every MMA re-reads its A and B operands, tools/umma_probe2.cu - is left to the tensor
+// core.
 #pragma once
 #include "fen_common.cuh"
 #include "ptx_sm100.cuh"
@@ -59,9 +62,16 @@ __device__ __forceinline__ Unit make_unit(const ConvParams& p, int g, int g_end)
 }
 
 template <int N>
-struct ConvSmem {
+struct ConvCfg {
   static constexpr int kWBytes = 9 * N * kC * 2;
   static constexpr int kDynBytes = kWBytes + kRingBytes + 1024;  // + alignment slack
+  // epilogue warps: N = 64 -> 8 (lane quarter x column half), N = 16 -> 4
+  static constexpr int kEpiWarps = (N == 64) ? 8 : 4;
+  static constexpr int kMmaWarps = 2;
+  static constexpr int kFirstEpiWarp = 1 + kMmaWarps;
+  static constexpr int kThreads = 32 * (1 + kMmaWarps + kEpiWarps);
+  static constexpr int kAccBufs = 4;
+  static constexpr int kColsPerWarp = (N == 64) ? 32 : N;
 };
 
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
@@ -69,6 +79,17 @@ __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v &
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_nc_256(const void* ptr, uint32_t (&v)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                 "=r"(v[7])
+               : "l"(ptr));
 }
 
 // Cubic-convolution phase filters of F.interpolate(scale_factor=4, mode='bicubic',
@@ -79,34 +100,37 @@ __device__ __constant__ float c_bicubic_w[4][4] = {{-135.f / 2048.f, 873.f / 204
                                                    {-225.f / 2048.f, 1535.f / 2048.f, 873.f / 2048.f, -135.f / 2048.f}};
 
 template <int N>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(ConvCfg<N>::kThreads, 1)
 conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w,
                     const ConvParams p) {
+  using Cfg = ConvCfg<N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_smem = smem;                                   // [9][N][64] bf16, SWIZZLE_128B
-  uint8_t* ring = smem + ConvSmem<N>::kWBytes;              // (kRingSlots + 1) x kSlotBytes
-  __shared__ uint64_t bar_w, bar_full[kRingSlots], bar_empty[kRingSlots], bar_acc_full[2], bar_acc_empty[2];
+  uint8_t* ring = smem + Cfg::kWBytes;                      // (kRingSlots + 1) x kSlotBytes
+  __shared__ uint64_t bar_w[9], bar_full[kRingSlots], bar_empty[kRingSlots], bar_acc_full[Cfg::kAccBufs], bar_acc_empty[Cfg::kAccBufs];
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_bias[N], s_slope[kC];
+  __shared__ __align__(16) float s_bias[N];
+  __shared__ __align__(16) float s_slope[kC];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr uint32_t kTmemCols = (2 * N < 32) ? 32 : 2 * N;  // two accumulators
+  constexpr uint32_t kTmemCols = Cfg::kAccBufs * N;  // accumulator buffers (power of two >= 32)
+  static_assert(kTmemCols >= 32 && (kTmemCols & (kTmemCols - 1)) == 0 && kTmemCols <= 512, "TMEM columns");
 
   const int g_begin = blockIdx.x * p.tiles_per_cta;
   const int g_end = min(p.total_tiles, g_begin + p.tiles_per_cta);
 
   if (warp == 1) tmem_alloc(&tmem_slot, kTmemCols);
   if (tid == 0) {
-    mbar_init(&bar_w, 1);
-    for (int i = 0; i < kRingSlots; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], 4); }
+    for (int i = 0; i < 9; ++i) mbar_init(&bar_w[i], 1);
+    for (int i = 0; i < kRingSlots; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], Cfg::kMmaWarps); }
+    for (int i = 0; i < Cfg::kAccBufs; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], Cfg::kEpiWarps); }
     fence_mbar_init();
     tma_prefetch_desc(&tm_in);
     tma_prefetch_desc(&tm_w);
   }
-  for (int i = tid; i < N; i += kConvThreads) s_bias[i] = p.bias ? p.bias[blockIdx.y * N + i] : 0.f;
-  for (int i = tid; i < kC; i += kConvThreads) s_slope[i] = p.slope ? p.slope[i] : 1.f;
+  for (int i = tid; i < N; i += Cfg::kThreads) s_bias[i] = p.bias ? p.bias[blockIdx.y * N + i] : 0.f;
+  for (int i = tid; i < kC; i += Cfg::kThreads) s_slope[i] = p.slope ? p.slope[i] : 1.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -115,9 +139,11 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
   if (warp == 0) {
     // ============================================================ TMA producer
     if (lane == 0 && g_begin < g_end) {
-      mbar_expect_tx(&bar_w, ConvSmem<N>::kWBytes);
-      for (int tap = 0; tap < 9; ++tap)
-        tma_load_2d(&tm_w, &bar_w, w_smem + tap * N * 128, 0, (blockIdx.y * 9 + tap) * N);
+      // weights arrive tap by tap (one barrier each) so the first MMAs need not wait for all 9
+      for (int tap = 0; tap < 9; ++tap) {
+        mbar_expect_tx(&bar_w[tap], N * kC * 2);
+        tma_load_2d(&tm_w, &bar_w[tap], w_smem + tap * N * 128, 0, (blockIdx.y * 9 + tap) * N);
+      }
       uint32_t gb = 0;  // running box counter of this CTA
       for (int g = g_begin; g < g_end;) {
         const Unit u = make_unit(p, g, g_end);
@@ -136,78 +162,114 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
         g += u.t1 - u.t0;
       }
     }
-  } else if (warp == 1) {
-    // ============================================================ MMA issuer (one thread)
-    if (lane == 0 && g_begin < g_end) {
+  } else if (warp < Cfg::kFirstEpiWarp) {
+    // ============================================================ MMA issuers
+    // Both issuer warps walk every tile (same bookkeeping, both arrive on the ring's empty barriers)
+    // but issue MMAs only for the tiles of their parity.  The whole warp runs the (warp-uniform)
+    // control flow so address math stays on the uniform datapath; one elected lane issues
+    // tcgen05.mma / tcgen05.commit.  Per MMA only the low
+    // descriptor word changes (start address); the high word (SBO = 1024 B, version 1, SWIZZLE_128B)
+    // is a constant.
+    if (g_begin < g_end) {
       constexpr uint32_t idesc = umma_idesc_bf16(kTileM, N);
-      const uint32_t ring_u32 = smem_u32(ring), w_u32 = smem_u32(w_smem);
-      mbar_wait(&bar_w, 0);
+      constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      constexpr uint32_t kLbo = 1u << 16;
+      const uint32_t ring_lo = (smem_u32(ring) >> 4) | kLbo;
+      const uint32_t w_lo = (smem_u32(w_smem) >> 4) | kLbo;
+      const bool leader = elect_one();
+      const uint32_t my_parity = warp - 1;
+      bool first = true;
+      long long dbg_t0 = p.dbg ? clock64() : 0, dbg_acc = 0, dbg_full = 0, dbg_issue = 0;
       uint32_t gb_base = 0, tile_ctr = 0;
       for (int g = g_begin; g < g_end;) {
         const Unit u = make_unit(p, g, g_end);
         int waited = 0, released = 0;
         for (int t = u.t0; t < u.t1; ++t, ++tile_ctr) {
-          const uint32_t acc = tile_ctr & 1;
-          mbar_wait(&bar_acc_empty[acc], ((tile_ctr >> 1) & 1) ^ 1);
+          const uint32_t acc = tile_ctr & (Cfg::kAccBufs - 1);
+          const bool mine = (tile_ctr & 1) == my_parity;
+          long long tw = p.dbg ? clock64() : 0;
+          if (mine) mbar_wait(&bar_acc_empty[acc], ((tile_ctr / Cfg::kAccBufs) & 1) ^ 1);
+          if (p.dbg) { const long long n = clock64(); dbg_acc += n - tw; tw = n; }
           const int base = kTileM * t - kPitch * u.ra;
           const int need_last = min((base + kTileM + kMaxShift - 1) / kBoxPx, u.nboxes - 1);
-          while (waited <= need_last) {
+          while (mine && waited <= need_last) {   // each issuer confirms every box it reads itself
             const uint32_t gb = gb_base + waited;
             mbar_wait(&bar_full[gb % kRingSlots], (gb / kRingSlots) & 1);
             ++waited;
           }
+          if (p.dbg) dbg_full += clock64() - tw;
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * N;
+          // views of this tile start in box lb0 or lb0 + 1 (tap offsets are < one box)
+          const int lb0 = base / kBoxPx, r0 = base - lb0 * kBoxPx;
+          const uint32_t slot0 = (gb_base + lb0) % kRingSlots;
+          const uint32_t slot1 = (slot0 + 1 == kRingSlots) ? 0 : slot0 + 1;
+          const uint32_t a0 = ring_lo + slot0 * (kSlotBytes >> 4) + r0 * 8;
+          const uint32_t a1 = ring_lo + slot1 * (kSlotBytes >> 4) + (r0 - kBoxPx) * 8;
+          const long long dbg_i0 = p.dbg ? clock64() : 0;
+          if (leader && mine) {
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const int px = base + (tap / 3) * kPitch + (tap % 3);
-            const int lb = px / kBoxPx, within = px - lb * kBoxPx;
-            const uint32_t slot = (gb_base + lb) % kRingSlots;
-            const uint32_t a_addr = ring_u32 + slot * kSlotBytes + within * 128;
-            const uint32_t b_addr = w_u32 + tap * N * 128;
+            for (int tap = 0; tap < 9; ++tap) {
+              if (first) mbar_wait(&bar_w[tap], 0);
+              const int off = (tap / 3) * kPitch + (tap % 3);
+              const uint32_t a_lo = ((r0 + off < kBoxPx) ? a0 : a1) + off * 8;
+              const uint32_t b_lo = w_lo + tap * (N * 128 >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = umma_smem_desc(a_addr + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
-              const uint64_t bd = umma_smem_desc(b_addr + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
-              umma_bf16_ss(d_tmem, ad, bd, idesc, (tap | k) != 0);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_ss_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, kDescHi, idesc, (tap | k) != 0);
             }
           }
+          __syncwarp();
+          if (p.dbg) dbg_issue += clock64() - dbg_i0;
           // boxes that no later tile of this unit will read can go back to the producer
           const int next_first = (t + 1 < u.t1) ? (base + kTileM) / kBoxPx : u.nboxes;
           while (released < next_first) {
-            umma_commit(&bar_empty[(gb_base + released) % kRingSlots]);
+            if (leader) umma_commit(&bar_empty[(gb_base + released) % kRingSlots]);
             ++released;
           }
-          umma_commit(&bar_acc_full[acc]);
+          if (leader && mine) umma_commit(&bar_acc_full[acc]);
+          if (mine) first = false;
+          __syncwarp();
         }
         gb_base += u.nboxes;
         g += u.t1 - u.t0;
       }
+      if (p.dbg && leader && warp == 1) {
+        p.dbg[blockIdx.x * 8 + 2] = dbg_acc;               // waiting for a free accumulator
+        p.dbg[blockIdx.x * 8 + 3] = dbg_full;              // waiting for TMA data
+        p.dbg[blockIdx.x * 8 + 4] = clock64() - dbg_t0;    // MMA warp total
+        p.dbg[blockIdx.x * 8 + 5] = tile_ctr;
+        p.dbg[blockIdx.x * 8 + 1] = dbg_issue;             // inside the 36-MMA issue loops
+      }
     }
   } else {
-    // ============================================================ epilogue (4 warps, 128 threads)
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    // ============================================================ epilogue
+    // thread <-> one TMEM lane (= one output pixel of the tile); a warp may only touch the lane
+    // quarter (warp % 4); for N = 64 two warps share a quarter and take 32 columns each.
+    constexpr int CW = Cfg::kColsPerWarp;
+    const int q = warp & 3;
+    const int half = (N == 64) ? ((warp - Cfg::kFirstEpiWarp) >> 2) : 0;
+    const int col0 = half * CW;
     const int row_in_tile = q * 32 + lane;
     uint32_t tile_ctr = 0;
+    long long dbg_e0 = p.dbg ? clock64() : 0, dbg_ewait = 0, dbg_etail = 0;
     for (int g = g_begin; g < g_end;) {
       const Unit u = make_unit(p, g, g_end);
-      float csum[(N == kC) ? kC : 1];
-      if (N == kC) {
+      float csum[CW];
 #pragma unroll
-        for (int c = 0; c < ((N == kC) ? kC : 1); ++c) csum[c] = 0.f;
-      }
+      for (int c = 0; c < CW; ++c) csum[c] = 0.f;
       for (int t = u.t0; t < u.t1; ++t, ++tile_ctr) {
-        const uint32_t acc = tile_ctr & 1;
-        mbar_wait(&bar_acc_full[acc], (tile_ctr >> 1) & 1);
+        const uint32_t acc = tile_ctr & (Cfg::kAccBufs - 1);
+        long long dbg_w0 = p.dbg ? clock64() : 0;
+        mbar_wait(&bar_acc_full[acc], (tile_ctr / Cfg::kAccBufs) & 1);
+        if (p.dbg) dbg_ewait += clock64() - dbg_w0;
         tc_fence_after();
-        uint32_t v[N];
-        const uint32_t taddr = tmem_base + acc * N + (uint32_t(q * 32) << 16);
-        if constexpr (N == 16) {
-          tmem_ld_32x16(taddr, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        uint32_t v[CW];
+        const uint32_t taddr = tmem_base + acc * N + col0 + (uint32_t(q * 32) << 16);
+        if constexpr (CW == 16) {
+          tmem_ld_32x16(taddr, v);
         } else {
-#pragma unroll
-          for (int h = 0; h < N / 32; ++h)
-            tmem_ld_32x32(taddr + h * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[h * 32]));
+          tmem_ld_32x32(taddr, v);
         }
         tmem_ld_wait();
         tc_fence_before();
@@ -246,17 +308,29 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
             }
           }
         } else {
-          float f[N];
+          float f[CW];
 #pragma unroll
-          for (int c = 0; c < N; ++c) f[c] = __uint_as_float(v[c]) + s_bias[c];
+          for (int j = 0; j < CW / 4; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[col0 + 4 * j]);
+            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4.x;
+            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z;
+            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+          }
           if (p.epi == kEpiSum) {
             if (valid) {
 #pragma unroll
-              for (int c = 0; c < N; ++c) csum[c & ((N == kC) ? 63 : 0)] += f[c];
+              for (int c = 0; c < CW; ++c) csum[c] += f[c];
             }
           } else if (p.epi == kEpiPrelu || p.epi == kEpiShuffle) {
 #pragma unroll
-            for (int c = 0; c < N; ++c) f[c] = f[c] > 0.f ? f[c] : f[c] * s_slope[c];
+            for (int j = 0; j < CW / 4; ++j) {
+              const float4 s4 = *reinterpret_cast<const float4*>(&s_slope[col0 + 4 * j]);
+              f[4 * j + 0] = f[4 * j + 0] > 0.f ? f[4 * j + 0] : f[4 * j + 0] * s4.x;
+              f[4 * j + 1] = f[4 * j + 1] > 0.f ? f[4 * j + 1] : f[4 * j + 1] * s4.y;
+              f[4 * j + 2] = f[4 * j + 2] > 0.f ? f[4 * j + 2] : f[4 * j + 2] * s4.z;
+              f[4 * j + 3] = f[4 * j + 3] > 0.f ? f[4 * j + 3] : f[4 * j + 3] * s4.w;
+            }
           }
           if (valid) {
             size_t opix;
@@ -266,46 +340,56 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
             } else {
               opix = (size_t(u.n) * p.H + y) * p.W + x;
             }
-            uint4* dst = reinterpret_cast<uint4*>(p.out + opix * kC);
+            bf16* dst = p.out + opix * kC + col0;
             if (p.epi == kEpiResidual) {
-              const uint4* rsd = reinterpret_cast<const uint4*>(p.residual + opix * kC);
+              const bf16* rsd = p.residual + opix * kC + col0;
 #pragma unroll
-              for (int j = 0; j < N / 8; ++j) {
-                const uint4 r = __ldg(rsd + j);
-                f[8 * j + 0] += bf16lo(r.x); f[8 * j + 1] += bf16hi(r.x);
-                f[8 * j + 2] += bf16lo(r.y); f[8 * j + 3] += bf16hi(r.y);
-                f[8 * j + 4] += bf16lo(r.z); f[8 * j + 5] += bf16hi(r.z);
-                f[8 * j + 6] += bf16lo(r.w); f[8 * j + 7] += bf16hi(r.w);
+              for (int j = 0; j < CW / 16; ++j) {
+                uint32_t r[8];
+                ld_global_nc_256(rsd + 16 * j, r);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  f[16 * j + 2 * e] += bf16lo(r[e]);
+                  f[16 * j + 2 * e + 1] += bf16hi(r[e]);
+                }
               }
             }
 #pragma unroll
-            for (int j = 0; j < N / 8; ++j) {
-              uint4 o;
-              o.x = pack_bf16(f[8 * j + 0], f[8 * j + 1]);
-              o.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
-              o.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
-              o.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
-              dst[j] = o;
+            for (int j = 0; j < CW / 16; ++j) {
+              uint32_t o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = pack_bf16(f[16 * j + 2 * e], f[16 * j + 2 * e + 1]);
+              st_global_256(dst + 16 * j, o);
             }
           }
         }
       }
+      long long dbg_t2 = p.dbg ? clock64() : 0;
       if constexpr (N == kC) {
         if (p.epi == kEpiSum) {
-          // per-image channel sums for the squeeze-and-excitation pool: warp reduce, then atomics
+          // Per-image channel sums for the squeeze-and-excitation pool.  Reduce-scatter butterfly
+          // over the warp: 16+8+4+2+1 shuffles leave lane l with the total of channel col0 + l
+          // (the lane bits 16,8,4,2,1 select the upper/lower half kept at each level).
 #pragma unroll
-          for (int c = 0; c < kC; ++c) {
-            float s = csum[c];
-            s += __shfl_xor_sync(0xffffffffu, s, 16);
-            s += __shfl_xor_sync(0xffffffffu, s, 8);
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            if (lane == (c & 31)) atomicAdd(p.sums + size_t(u.n) * kC + c, s);
+          for (int d = 16, len = CW; d >= 1; d >>= 1, len >>= 1) {
+            const bool hi = (lane & d) != 0;
+#pragma unroll
+            for (int i = 0; i < len / 2; ++i) {
+              const float send = hi ? csum[i] : csum[i + len / 2];
+              const float keep = hi ? csum[i + len / 2] : csum[i];
+              csum[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+            }
           }
+          atomicAdd(p.sums + size_t(u.n) * kC + col0 + lane, csum[0]);
         }
       }
+      if (p.dbg) dbg_etail += clock64() - dbg_t2;
       g += u.t1 - u.t0;
+    }
+    if (p.dbg && tid == 32 * Cfg::kFirstEpiWarp) {
+      p.dbg[blockIdx.x * 8 + 0] = dbg_etail;               // unit-end reduction
+      p.dbg[blockIdx.x * 8 + 6] = dbg_ewait;               // epilogue warp waiting for accumulators
+      p.dbg[blockIdx.x * 8 + 7] = clock64() - dbg_e0;      // epilogue warp total
     }
   }
 

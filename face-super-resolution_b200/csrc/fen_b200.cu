@@ -14,6 +14,7 @@ namespace fen {
 // ===================================================================== error plumbing
 static thread_local std::string g_err;
 static thread_local int g_launches = 0;
+static long long* g_dbg = nullptr;  // developer hook: per-CTA cycle counters of fen_conv3x3_c64
 
 static int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -110,7 +111,7 @@ static int launch_conv_n(const ConvArgs& a, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     FEN_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  ConvSmem<N>::kDynBytes));
+                                  ConvCfg<N>::kDynBytes));
     attr_set = true;
   }
   CUtensorMap tm_in, tm_w;
@@ -128,7 +129,7 @@ static int launch_conv_n(const ConvArgs& a, cudaStream_t st) {
   p.tiles_per_cta = (p.total_tiles + ctas_x - 1) / ctas_x;
   ctas_x = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
   dim3 grid(ctas_x, ctas_y);
-  conv3x3_umma_kernel<N><<<grid, kConvThreads, ConvSmem<N>::kDynBytes, st>>>(tm_in, tm_w, p);
+  conv3x3_umma_kernel<N><<<grid, ConvCfg<N>::kThreads, ConvCfg<N>::kDynBytes, st>>>(tm_in, tm_w, p);
   FEN_CUDA(cudaGetLastError());
   ++g_launches;
   return FEN_OK;
@@ -416,6 +417,8 @@ extern "C" {
 int fen_abi_version(void) { return FEN_ABI_VERSION; }
 const char* fen_last_error(void) { return g_err.c_str(); }
 int fen_last_launch_count(void) { return g_launches; }
+// developer hook (not in the public header): device buffer [ctas][8] of int64 cycle counters, or null
+void fen_debug_set_counters(void* dev_buf) { g_dbg = static_cast<long long*>(dev_buf); }
 
 int64_t fen_param_count(const fen_config* cfg) {
   Layout L;
@@ -505,6 +508,7 @@ int fen_conv3x3_c64(const void* x, const void* w_packed, const float* bias, cons
   a.x = x; a.w = w_packed; a.n = 64; a.groups = 1;
   a.p.B = B; a.p.H = H; a.p.W = W; a.p.epi = epilogue; a.p.bias = bias; a.p.slope = slope;
   a.p.residual = static_cast<const bf16*>(residual); a.p.out = static_cast<bf16*>(out); a.p.sums = sums;
+  a.p.dbg = g_dbg;
   return launch_conv(a, static_cast<cudaStream_t>(stream));
 }
 

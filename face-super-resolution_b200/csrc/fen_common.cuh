@@ -20,7 +20,6 @@ constexpr int kSlotBytes = kBoxPx * kC * 2;          // 33792 B (= 33 * 1024: sw
 constexpr int kRingSlots = 3;                        // + 1 mirror slot after the last one
 constexpr int kRingBytes = (kRingSlots + 1) * kSlotBytes;
 constexpr int kMaxShift = 2 * kPitch + 2;            // largest tap offset in the strip-linear space
-constexpr int kConvThreads = 192;                    // warp0 TMA, warp1 MMA, warps2-5 epilogue
 
 enum EpilogueKind : int {
   kEpiPrelu = 0,     // out = prelu(acc + bias)                       (RCAB conv1)
@@ -46,6 +45,7 @@ struct ConvParams {
   float* sums;            // [B][64] fp32, accumulated with atomics (kEpiSum)
   const float* lr;        // [B][3][H/4][W/4] fp32 network input (kEpiLast)
   float* out_f32;         // [B][3][H][W] fp32 (kEpiLast)
+  long long* dbg;         // optional [gridDim.x][8] cycle counters (developer builds), else nullptr
 };
 
 }  // namespace fen

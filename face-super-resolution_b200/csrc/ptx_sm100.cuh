@@ -192,6 +192,38 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, ui
       : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with both descriptors given as (low word, shared high word): the high word of a K-major
+// SWIZZLE_128B descriptor is a constant, only the start address in the low word moves.
+__device__ __forceinline__ void umma_bf16_ss_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo,
+                                                  uint32_t desc_hi, uint32_t idesc, bool accumulate) {
+  if (accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b64 da, db;\n\t"
+        ".reg .pred p;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.eq.u32 p, 1, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .b64 da, db;\n\t"
+        ".reg .pred p;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.eq.u32 p, 1, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+        "}\n"
+        :
+        : "r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+        : "memory");
+  }
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
