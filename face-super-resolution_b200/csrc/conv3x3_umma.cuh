@@ -139,11 +139,13 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
   if (warp == 0) {
     // ============================================================ TMA producer
     if (lane == 0 && g_begin < g_end) {
-      // weights arrive tap by tap (one barrier each) so the first MMAs need not wait for all 9
-      for (int tap = 0; tap < 9; ++tap) {
+      // Weights arrive tap by tap (one barrier each) so the first MMAs need not wait for all 9;
+      // the first activation box goes out right behind tap 0.
+      auto load_w = [&](int tap) {
         mbar_expect_tx(&bar_w[tap], N * kC * 2);
         tma_load_2d(&tm_w, &bar_w[tap], w_smem + tap * N * 128, 0, (blockIdx.y * 9 + tap) * N);
-      }
+      };
+      load_w(0);
       uint32_t gb = 0;  // running box counter of this CTA
       for (int g = g_begin; g < g_end;) {
         const Unit u = make_unit(p, g, g_end);
@@ -158,6 +160,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
           if (mirror)
             tma_load_4d(&tm_in, &bar_full[slot], smem_u32(ring + kRingSlots * kSlotBytes), 0, x0,
                         y0 + kBoxRows, u.n);
+          if (gb == 0)
+            for (int tap = 1; tap < 9; ++tap) load_w(tap);
         }
         g += u.t1 - u.t0;
       }
@@ -252,7 +256,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
     const int col0 = half * CW;
     const int row_in_tile = q * 32 + lane;
     uint32_t tile_ctr = 0;
-    long long dbg_e0 = p.dbg ? clock64() : 0, dbg_ewait = 0, dbg_etail = 0;
+    long long dbg_e0 = p.dbg ? clock64() : 0, dbg_ewait = 0, dbg_etail = 0, dbg_eld = 0;
     for (int g = g_begin; g < g_end;) {
       const Unit u = make_unit(p, g, g_end);
       float csum[CW];
@@ -262,7 +266,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
         const uint32_t acc = tile_ctr & (Cfg::kAccBufs - 1);
         long long dbg_w0 = p.dbg ? clock64() : 0;
         mbar_wait(&bar_acc_full[acc], (tile_ctr / Cfg::kAccBufs) & 1);
-        if (p.dbg) dbg_ewait += clock64() - dbg_w0;
+        const long long dbg_w1 = p.dbg ? clock64() : 0;
+        if (p.dbg) dbg_ewait += dbg_w1 - dbg_w0;
         tc_fence_after();
         uint32_t v[CW];
         const uint32_t taddr = tmem_base + acc * N + col0 + (uint32_t(q * 32) << 16);
@@ -275,6 +280,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_acc_empty[acc]);
+        if (p.dbg) dbg_eld += clock64() - dbg_w1;
 
         const int lin = kTileM * t + row_in_tile;       // strip-linear output pixel
         const int y = lin / kPitch, xs = lin - y * kPitch;
@@ -387,7 +393,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
       g += u.t1 - u.t0;
     }
     if (p.dbg && tid == 32 * Cfg::kFirstEpiWarp) {
-      p.dbg[blockIdx.x * 8 + 0] = dbg_etail;               // unit-end reduction
+      p.dbg[blockIdx.x * 8 + 0] = dbg_eld;                 // TMEM load + release of the accumulator
       p.dbg[blockIdx.x * 8 + 6] = dbg_ewait;               // epilogue warp waiting for accumulators
       p.dbg[blockIdx.x * 8 + 7] = clock64() - dbg_e0;      // epilogue warp total
     }

@@ -549,7 +549,7 @@ int fen_forward(const fen_config* cfg, const void* packed, const float* x, float
   };
 
   const int hw = H * W;
-  const int se_chunks = 4;
+  const int se_chunks = 32;
   const bf16* cur = act(ws.f0);
   for (int g = 0; g < L.G; ++g) {
     const bf16* gin = cur;

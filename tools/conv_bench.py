@@ -35,6 +35,6 @@ if os.environ.get("FEN_DBG"):
     once(0); torch.cuda.synchronize()
     lib.fen_debug_set_counters(None)
     d = dbg.cpu()[:141].double()
-    names = ["epi unit-end reduce", "MMA issue loops", "MMA wait acc_empty", "MMA wait TMA full", "MMA thread total", "tiles", "epi wait acc_full", "epi total"]
+    names = ["epi tmem ld+release", "MMA issue loops", "MMA wait acc_empty", "MMA wait TMA full", "MMA thread total", "tiles", "epi wait acc_full", "epi total"]
     for i, n in enumerate(names):
         print(f"  {n:22s} mean {d[:, i].mean().item():9.0f}  max {d[:, i].max().item():9.0f}")
