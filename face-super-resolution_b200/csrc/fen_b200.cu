@@ -2,12 +2,14 @@
 // Host orchestration + the small CUDA-core kernels; the tensor-core convolution lives in
 // conv3x3_umma.cuh.  Build: see face-super-resolution_b200/build.py (nvcc, sm_100a only).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "../../include/fen_b200.h"
 #include "conv3x3_umma.cuh"
+#include "body_umma.cuh"
 
 namespace fen {
 
@@ -323,7 +325,11 @@ struct Layout {
   int64_t p_first_w, p_first_b, p_rcab0, p_rcab_stride, p_group_stride, p_gconv_w_in_group, p_after_w, p_after_b,
       p_up[2], p_last_w, p_last_b, p_total;
   // packed blob offsets (bytes)
-  int64_t k_first_w, k_first_b, k_rcab0, k_rcab_stride, k_gconv0, k_gconv_stride, k_after, k_up[2], k_last, k_total;
+  int64_t k_first_w, k_first_b, k_rcab0, k_rcab_stride, k_gconv0, k_gconv_stride, k_after, k_up[2], k_last, k_cvec,
+      k_total;
+  // bias / slope table for the persistent body kernel (copied to __constant__ c_vec): per RCAB
+  // [b1 64][slope 64][b2 64], then per group conv [b 64], then conv_after_body [b 64]
+  int cv_rcab0, cv_gconv0, cv_after, cv_total;
 };
 // per-RCAB flat params: conv1.w conv1.b prelu conv2.w conv2.b fc0 fc2
 static constexpr int64_t kConvW = 64 * 64 * 9;
@@ -374,6 +380,9 @@ static int make_layout(const fen_config* cfg, Layout* L) {
   L->k_after = k; k += kPlainRec;
   for (int s = 0; s < 2; ++s) { L->k_up[s] = k; k += kUpRec; }
   L->k_last = k; k += kLastRec;
+  L->cv_rcab0 = 0; L->cv_gconv0 = L->n_rcab * 192; L->cv_after = L->cv_gconv0 + L->G * 64;
+  L->cv_total = L->cv_after + 64;
+  L->k_cvec = align256(k); k = L->k_cvec + int64_t(L->cv_total) * 4;
   L->k_total = align256(k);
   return FEN_OK;
 }
@@ -392,7 +401,7 @@ static int pack_vec(const float* src, int count, int n_grp, int groups, int perm
 
 // ===================================================================== workspace
 struct Workspace {
-  int64_t f0, x[2], h, o, grp0, grp_stride, u0, u1, sums, total;
+  int64_t f0, x[2], h, o, grp0, grp_stride, u0, u1, sums, flags, total;
 };
 static void make_workspace(const Layout& L, int B, int H, int W, Workspace* ws) {
   const int64_t act = align256(int64_t(B) * H * W * 64 * 2);
@@ -404,7 +413,65 @@ static void make_workspace(const Layout& L, int B, int H, int W, Workspace* ws) 
   ws->u0 = o; o += 4 * act;
   ws->u1 = o; o += 16 * act;
   ws->sums = o; o += align256(int64_t(L.n_rcab) * B * 64 * 4);
+  ws->flags = o; o += 4096;   // one int per CTA of the persistent body kernel
   ws->total = o;
+}
+
+
+// ===================================================================== persistent body kernel launcher
+static bool body_kernel_usable(const Layout& L, int W) {
+  static int disabled = -1;
+  if (disabled < 0) {
+    const char* e = getenv("FEN_DISABLE_BODY_KERNEL");
+    disabled = (e && e[0] == '1') ? 1 : 0;
+  }
+  return !disabled && W == kStripW && L.cv_total <= kConstVecFloats && L.G <= kBodyMaxBufs - 5;
+}
+
+static int launch_body(const fen_config* cfg, const Layout& L, const Workspace& ws, uint8_t* wsb, const uint8_t* k,
+                       int B, int H, int W, float* se_out, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    FEN_CUDA(cudaFuncSetAttribute(body_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBodyDynBytes));
+    attr_set = true;
+  }
+  const RcabRec rr = rcab_rec(L.R);
+  BodyMaps maps;
+  BodyParams p{};
+  p.B = B; p.H = H; p.W = W; p.G = L.G; p.Bk = L.Bk; p.R = L.R;
+  p.n_layers = L.G * (2 * L.Bk + 1) + 1;
+  p.tiles_per_seg = (H * kPitch + kTileM - 1) / kTileM;
+  p.total_tiles = B * p.tiles_per_seg;
+  p.tiles_per_cta = (p.total_tiles + num_sms() - 1) / num_sms();
+  const int ctas = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  p.res_scale = cfg->res_scale; p.inv_hw = 1.f / float(H * W);
+  const int nbuf = 5 + L.G;
+  int64_t offs[kBodyMaxBufs];
+  offs[kBufF0] = ws.f0; offs[kBufX0] = ws.x[0]; offs[kBufX1] = ws.x[1]; offs[kBufH] = ws.h; offs[kBufO] = ws.o;
+  for (int g = 0; g < L.G; ++g) offs[kBufG0 + g] = ws.grp0 + g * ws.grp_stride;
+  for (int i = 0; i < nbuf; ++i) {
+    p.buf[i] = reinterpret_cast<bf16*>(wsb + offs[i]);
+    int rc = make_act_map(&maps.act[i], p.buf[i], B, H, W);
+    if (rc) return rc;
+  }
+  for (int i = nbuf; i < kBodyMaxBufs; ++i) maps.act[i] = maps.act[0];
+  int rc = make_w_map(&maps.w, k, int(L.k_total / 128), kC);
+  if (rc) return rc;
+  p.packed = k;
+  p.k_rcab0 = L.k_rcab0; p.k_rcab_stride = L.k_rcab_stride; p.k_rcab_w2 = rr.w2; p.k_rcab_fc0 = rr.fc0; p.k_rcab_fc2 = rr.fc2;
+  p.k_gconv0 = L.k_gconv0; p.k_gconv_stride = L.k_gconv_stride; p.k_after = L.k_after;
+  p.cv_rcab0 = L.cv_rcab0; p.cv_gconv0 = L.cv_gconv0; p.cv_after = L.cv_after;
+  p.sums = reinterpret_cast<float*>(wsb + ws.sums);
+  p.se_out = se_out;
+  p.flags = reinterpret_cast<int*>(wsb + ws.flags);
+  p.dbg = g_dbg;
+  FEN_CUDA(cudaMemsetAsync(p.flags, 0, 4096, st));
+  FEN_CUDA(cudaMemcpyToSymbolAsync(c_vec, k + L.k_cvec, size_t(L.cv_total) * 4, 0, cudaMemcpyDeviceToDevice, st));
+  void* args[] = {&maps, &p};
+  FEN_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(body_umma_kernel), dim3(ctas), dim3(kBodyThreads), args,
+                                       kBodyDynBytes, st));
+  ++g_launches;
+  return FEN_OK;
 }
 
 }  // namespace fen
@@ -465,13 +532,22 @@ int fen_pack_weights(const fen_config* cfg, const float* params, void* packed, v
       if ((rc = pack_vec(c2b, 64, 64, 1, 0, kr + rr.b2, st))) return rc;
       if ((rc = pack_vec(fc0, L.R * 64, L.R * 64, 1, 0, kr + rr.fc0, st))) return rc;
       if ((rc = pack_vec(fc2, L.R * 64, L.R * 64, 1, 0, kr + rr.fc2, st))) return rc;
+      float* cv = reinterpret_cast<float*>(k + L.k_cvec) + L.cv_rcab0 + (g * L.Bk + b) * 192;
+      if ((rc = pack_vec(c1b, 64, 64, 1, 0, cv, st))) return rc;
+      if ((rc = pack_vec(sl, 64, 64, 1, 0, cv + 64, st))) return rc;
+      if ((rc = pack_vec(c2b, 64, 64, 1, 0, cv + 128, st))) return rc;
     }
     uint8_t* kg = k + L.k_gconv0 + g * L.k_gconv_stride;
     if ((rc = pack_conv(pg + L.p_gconv_w_in_group, 64, 64, 1, 0, kg, st))) return rc;
     if ((rc = pack_vec(pg + L.p_gconv_w_in_group + kConvW, 64, 64, 1, 0, kg + kConvWBytes, st))) return rc;
+    if ((rc = pack_vec(pg + L.p_gconv_w_in_group + kConvW, 64, 64, 1, 0,
+                       reinterpret_cast<float*>(k + L.k_cvec) + L.cv_gconv0 + g * 64, st)))
+      return rc;
   }
   if ((rc = pack_conv(params + L.p_after_w, 64, 64, 1, 0, k + L.k_after, st))) return rc;
   if ((rc = pack_vec(params + L.p_after_b, 64, 64, 1, 0, k + L.k_after + kConvWBytes, st))) return rc;
+  if ((rc = pack_vec(params + L.p_after_b, 64, 64, 1, 0, reinterpret_cast<float*>(k + L.k_cvec) + L.cv_after, st)))
+    return rc;
   for (int s = 0; s < 2; ++s) {
     const float* pu = params + L.p_up[s];
     uint8_t* ku = k + L.k_up[s];
@@ -548,40 +624,44 @@ int fen_forward(const fen_config* cfg, const void* packed, const float* x, float
     return launch_conv(a, st);
   };
 
-  const int hw = H * W;
-  const int se_chunks = 32;
-  const bf16* cur = act(ws.f0);
-  for (int g = 0; g < L.G; ++g) {
-    const bf16* gin = cur;
-    for (int b = 0; b < L.Bk; ++b) {
-      const int r = g * L.Bk + b;
-      const uint8_t* kr = k + L.k_rcab0 + int64_t(r) * L.k_rcab_stride;
-      float* sm = sums + size_t(r) * B * 64;
-      if ((rc = conv(cur, kr + rr.w1, reinterpret_cast<const float*>(kr + rr.b1),
-                     reinterpret_cast<const float*>(kr + rr.slope), nullptr, nullptr, act(ws.h), kEpiPrelu, H, W)))
+  if (body_kernel_usable(L, W)) {
+    if ((rc = launch_body(cfg, L, ws, wsb, k, B, H, W, se_out, st))) return rc;
+  } else {
+    const int hw = H * W;
+    const int se_chunks = 32;
+    const bf16* cur = act(ws.f0);
+    for (int g = 0; g < L.G; ++g) {
+      const bf16* gin = cur;
+      for (int b = 0; b < L.Bk; ++b) {
+        const int r = g * L.Bk + b;
+        const uint8_t* kr = k + L.k_rcab0 + int64_t(r) * L.k_rcab_stride;
+        float* sm = sums + size_t(r) * B * 64;
+        if ((rc = conv(cur, kr + rr.w1, reinterpret_cast<const float*>(kr + rr.b1),
+                       reinterpret_cast<const float*>(kr + rr.slope), nullptr, nullptr, act(ws.h), kEpiPrelu, H, W)))
+          return rc;
+        if ((rc = conv(act(ws.h), kr + rr.w2, reinterpret_cast<const float*>(kr + rr.b2), nullptr, nullptr, sm,
+                       act(ws.o), kEpiSum, H, W)))
+          return rc;
+        bf16* nxt = act(ws.x[b & 1]);
+        se_residual_kernel<<<dim3(se_chunks, B), 256, 0, st>>>(
+            cur, act(ws.o), sm, reinterpret_cast<const float*>(kr + rr.fc0), reinterpret_cast<const float*>(kr + rr.fc2),
+            L.R, 1.f / float(hw), cfg->res_scale, nxt, se_out ? se_out + size_t(r) * 64 : nullptr, L.n_rcab * 64, hw);
+        FEN_CUDA(cudaGetLastError());
+        ++g_launches;
+        cur = nxt;
+      }
+      const uint8_t* kg = k + L.k_gconv0 + g * L.k_gconv_stride;
+      bf16* gout = act(ws.grp0 + g * ws.grp_stride);
+      if ((rc = conv(cur, kg, reinterpret_cast<const float*>(kg + kConvWBytes), nullptr, gin, nullptr, gout,
+                     kEpiResidual, H, W)))
         return rc;
-      if ((rc = conv(act(ws.h), kr + rr.w2, reinterpret_cast<const float*>(kr + rr.b2), nullptr, nullptr, sm,
-                     act(ws.o), kEpiSum, H, W)))
-        return rc;
-      bf16* nxt = act(ws.x[b & 1]);
-      se_residual_kernel<<<dim3(se_chunks, B), 256, 0, st>>>(
-          cur, act(ws.o), sm, reinterpret_cast<const float*>(kr + rr.fc0), reinterpret_cast<const float*>(kr + rr.fc2),
-          L.R, 1.f / float(hw), cfg->res_scale, nxt, se_out ? se_out + size_t(r) * 64 : nullptr, L.n_rcab * 64, hw);
-      FEN_CUDA(cudaGetLastError());
-      ++g_launches;
-      cur = nxt;
+      cur = gout;
     }
-    const uint8_t* kg = k + L.k_gconv0 + g * L.k_gconv_stride;
-    bf16* gout = act(ws.grp0 + g * ws.grp_stride);
-    if ((rc = conv(cur, kg, reinterpret_cast<const float*>(kg + kConvWBytes), nullptr, gin, nullptr, gout,
-                   kEpiResidual, H, W)))
+    // conv_after_body + long skip -> x[0]
+    if ((rc = conv(cur, k + L.k_after, reinterpret_cast<const float*>(k + L.k_after + kConvWBytes), nullptr,
+                   act(ws.f0), nullptr, act(ws.x[0]), kEpiResidual, H, W)))
       return rc;
-    cur = gout;
   }
-  // conv_after_body + long skip -> x[0]
-  if ((rc = conv(cur, k + L.k_after, reinterpret_cast<const float*>(k + L.k_after + kConvWBytes), nullptr,
-                 act(ws.f0), nullptr, act(ws.x[0]), kEpiResidual, H, W)))
-    return rc;
   // upsample stages
   {
     const uint8_t* ku = k + L.k_up[0];
