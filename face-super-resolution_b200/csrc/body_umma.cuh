@@ -9,13 +9,14 @@
 // with it ("peers": halo rows + the per-image SE pool) through release/acquire flags in global
 // memory.  Launched cooperatively with one CTA per SM, so all CTAs are co-resident.
 //
-// Per layer the tile pipeline is the one of conv3x3_umma.cuh (ring of 4-row boxes with a mirror
-// slot, two tcgen05.mma issuer warps, 8 epilogue warps, TMEM accumulators).  Differences:
-//   * warps 0-7 are producers.  Plain layers: lane 0 of warp 0 issues TMA boxes.  Fused layers
-//     (conv1 of RCAB b > 0, group conv): the 256 producer threads read x and o (conv2 output of
-//     the previous block) from global memory, compute x' = x + (res_scale * s[c]) * o in fp32,
-//     write it as bf16 into the ring (SWIZZLE_128B pattern by hand), and write the rows they own
-//     back to global memory as the next residual stream - no standalone elementwise pass exists.
+// Per layer the tile pipeline is the one of conv3x3_umma.cuh (ring of boxes with a mirror slot -
+// here 2-row boxes, 7 slots -, two tcgen05.mma issuer warps, 8 epilogue warps, TMEM accumulators).  Differences:
+//   * warp 0 issues all TMA loads.  Fused layers (conv1 of RCAB b > 0, group conv): TMA brings x
+//     into the ring slot, the 256 transform threads (warps 1-8) read o (conv2 output of the
+//     previous block) from global memory one box ahead, update the slot in place with
+//     x' = x + (res_scale * s[c]) * o (fp32 math, bf16 store, SWIZZLE_128B pattern by hand) and
+//     write the rows they own back to global memory as the next residual stream - no standalone
+//     elementwise pass exists.
 //   * the SE vector s = sigmoid(W2 relu(W0 mean(o))) is recomputed per CTA from the per-image
 //     channel sums the conv2 epilogue accumulated (2 KMAC, fp32).
 //   * biases and PReLU slopes come from __constant__ memory (the epilogue must stay off shared
@@ -31,15 +32,23 @@ namespace fen {
 #endif
 #define BDBG (FEN_BODY_DEBUG && p.dbg)
 
-constexpr int kBodyProducerWarps = 8;
+constexpr int kBodyXformWarps = 8;                    // warps 1..8: x' = x + s*o transform (fused layers)
 constexpr int kBodyMmaWarps = 2;
 constexpr int kBodyEpiWarps = 8;
-constexpr int kBodyThreads = 32 * (kBodyProducerWarps + kBodyMmaWarps + kBodyEpiWarps);  // 576
-constexpr int kBodyFirstMmaWarp = kBodyProducerWarps;
-constexpr int kBodyFirstEpiWarp = kBodyProducerWarps + kBodyMmaWarps;
+constexpr int kBodyFirstXformWarp = 1;                // warp 0: TMA issuer
+constexpr int kBodyFirstMmaWarp = 1 + kBodyXformWarps;
+constexpr int kBodyFirstEpiWarp = kBodyFirstMmaWarp + kBodyMmaWarps;
+constexpr int kBodyThreads = 32 * (kBodyFirstEpiWarp + kBodyEpiWarps);   // 608
 constexpr int kBodyAccBufs = 4;
 constexpr int kBodyWBytes = 9 * kC * kC * 2;
-constexpr int kBodyDynBytes = kBodyWBytes + kRingBytes + 1024;
+// activation ring: 2-row boxes (132 px, 16 896 B; TMA SWIZZLE_128B only needs 128 B alignment, the
+// swizzle follows absolute address bits - tools/umma_probe4.cu), 7 slots + 1 mirror slot
+constexpr int kBBoxRows = 2;
+constexpr int kBBoxPx = kBBoxRows * kPitch;           // 132
+constexpr int kBSlotBytes = kBBoxPx * kC * 2;         // 16896
+constexpr int kBSlots = 7;
+constexpr int kBRingBytes = (kBSlots + 1) * kBSlotBytes;
+constexpr int kBodyDynBytes = kBodyWBytes + kBRingBytes + 1024;
 constexpr int kConstVecFloats = 15872;   // 62 KB of __constant__ for biases + slopes
 
 __device__ __constant__ float c_vec[kConstVecFloats];
@@ -121,6 +130,18 @@ __device__ __forceinline__ BodyLayer body_layer(const BodyParams& p, int L) {
   return l;
 }
 
+struct BUnit { int n, t0, t1, ra, nboxes; };
+__device__ __forceinline__ BUnit body_unit(const BodyParams& p, int g, int g_end) {
+  BUnit u;
+  u.n = g / p.tiles_per_seg;
+  u.t0 = g - u.n * p.tiles_per_seg;
+  u.t1 = min(p.tiles_per_seg, u.t0 + (g_end - g));
+  u.ra = (kTileM * u.t0) / kPitch;                              // first staged row (row 0 = image row -1)
+  const int rb = min((kTileM * u.t1 + kMaxShift - 1) / kPitch, p.H + 1);
+  u.nboxes = (rb - u.ra) / kBBoxRows + 1;
+  return u;
+}
+
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -172,13 +193,14 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_smem = smem;
   uint8_t* ring = smem + kBodyWBytes;
-  __shared__ uint64_t bar_w[9], bar_wfree[9], bar_full[kRingSlots], bar_empty[kRingSlots];
+  __shared__ uint64_t bar_w[9], bar_wfree[9], bar_x[kBSlots], bar_full[kBSlots], bar_empty[kBSlots];
   __shared__ uint64_t bar_acc_full[kBodyAccBufs], bar_acc_empty[kBodyAccBufs], bar_done;
   __shared__ uint32_t tmem_slot;
   __shared__ float s_mean[2][kC], s_hid[2][kC], s_scale[2][kC];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr uint32_t kTmemCols = kBodyAccBufs * N;
+  constexpr int kFrontThreads = 32 * kBodyFirstMmaWarp;   // TMA warp + transform warps (named barrier 1)
 
   const int g_begin = blockIdx.x * p.tiles_per_cta;
   const int g_end = min(p.total_tiles, g_begin + p.tiles_per_cta);
@@ -191,9 +213,13 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
   if (warp == kBodyFirstMmaWarp) tmem_alloc(&tmem_slot, kTmemCols);
   if (tid == 0) {
     for (int i = 0; i < 9; ++i) { mbar_init(&bar_w[i], 1); mbar_init(&bar_wfree[i], kBodyMmaWarps); }
-    for (int i = 0; i < kRingSlots; ++i) { mbar_init(&bar_full[i], kBodyProducerWarps + 1); mbar_init(&bar_empty[i], kBodyMmaWarps); }
+    for (int i = 0; i < kBSlots; ++i) {
+      mbar_init(&bar_x[i], 1);
+      mbar_init(&bar_full[i], kBodyXformWarps + 1);     // 8 transform warps + the TMA issuer, every box
+      mbar_init(&bar_empty[i], kBodyMmaWarps);
+    }
     for (int i = 0; i < kBodyAccBufs; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], kBodyEpiWarps); }
-    mbar_init(&bar_done, kBodyProducerWarps + kBodyEpiWarps);
+    mbar_init(&bar_done, kBodyXformWarps + kBodyEpiWarps);
     fence_mbar_init();
     tma_prefetch_desc(&maps.w);
   }
@@ -203,37 +229,74 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
   const uint32_t tmem_base = tmem_slot;
   if (n_tiles <= 0) return;   // never happens with the host's grid sizing (all CTAs have tiles)
 
-  if (warp < kBodyProducerWarps) {
-    // ============================================================ producers (256 threads)
-    constexpr int kPT = 32 * kBodyProducerWarps;
-    const int ptid = tid;                      // 0..255
-    const int chunk = ptid & 7;                // 16-byte channel chunk this thread always handles
-    uint32_t gb = 0;                           // running box counter
-    long long d_wfree = 0, d_flag = 0, d_se = 0, d_fused = 0, d_plain = 0, d_t = BDBG ? clock64() : 0;
-    const long long d_start = d_t;
-#define DBG_LAP(acc) if (BDBG) { const long long n_ = clock64(); acc += n_ - d_t; d_t = n_; }
+  if (warp == 0) {
+    // ============================================================ TMA issuer (one lane)
+    uint32_t gb = 0;   // running box counter
     for (int L = 0; L < p.n_layers; ++L) {
       const BodyLayer ly = body_layer(p, L);
-      DBG_LAP(d_plain)
-      // ---- weights of this layer, tap by tap, as soon as the previous layer released the tap
-      if (ptid == 0) {
+      if (lane == 0) {
+        // weights of this layer, tap by tap, as soon as the previous layer released the tap
         for (int tap = 0; tap < 9; ++tap) {
           if (L > 0) mbar_wait(&bar_wfree[tap], (L - 1) & 1);
           mbar_expect_tx(&bar_w[tap], N * kC * 2);
           tma_load_2d(&maps.w, &bar_w[tap], w_smem + tap * N * 128, 0, ly.w_row + tap * N);
         }
       }
-      DBG_LAP(d_wfree)
+      __syncwarp();
+      if (L > 0) named_bar_sync(1, kFrontThreads);       // peers have finished layer L-1 (polled by warp 1)
+      if (ly.fused) named_bar_sync(1, kFrontThreads);    // keeps the barrier sequence of the transform warps (SE)
+      if (lane == 0) {
+        const uint64_t pol = (ly.fused || ly.in == kBufH || ly.epi == kEpiResidual) ? kPolicyEvictFirst
+                                                                                   : 0x1000000000000000ull;
+        for (int g = g_begin; g < g_end;) {
+          const BUnit u = body_unit(p, g, g_end);
+          for (int j = 0; j < u.nboxes; ++j, ++gb) {
+            const uint32_t slot = gb % kBSlots, ph = (gb / kBSlots) & 1;
+            const int y0 = u.ra - 1 + j * kBBoxRows;
+            mbar_wait(&bar_empty[slot], ph ^ 1);
+            const uint32_t dst = smem_u32(ring + slot * kBSlotBytes);
+            if (ly.fused) {
+              // x goes to the slot; the transform warps finish the box (and the mirror copy)
+              mbar_expect_tx(&bar_x[slot], kBSlotBytes);
+              tma_load_4d_hint(&maps.act[ly.in], &bar_x[slot], dst, 0, -1, y0, u.n, pol);
+              mbar_arrive(&bar_full[slot]);
+            } else {
+              const bool mirror = (slot == 0) && (j > 0);
+              mbar_expect_tx(&bar_full[slot], mirror ? 2 * kBSlotBytes : kBSlotBytes);
+              tma_load_4d_hint(&maps.act[ly.in], &bar_full[slot], dst, 0, -1, y0, u.n, pol);
+              if (mirror)
+                tma_load_4d_hint(&maps.act[ly.in], &bar_full[slot], smem_u32(ring + kBSlots * kBSlotBytes), 0, -1, y0,
+                                 u.n, pol);
+            }
+          }
+          g += u.t1 - u.t0;
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp < kBodyFirstMmaWarp) {
+    // ============================================================ transform warps (256 threads)
+    constexpr int kXT = 32 * kBodyXformWarps;
+    const int xt = tid - 32 * kBodyFirstXformWarp;      // 0..255
+    const int chunk = xt & 7;                           // 16-byte channel chunk this thread always handles
+    uint32_t gb = 0;                                    // running box counter (same sequence as the issuer)
+    uint32_t x_phase = 0;                               // bar_x completes only in fused layers: one parity bit per slot
+    long long d_flag = 0, d_se = 0, d_fused = 0, d_plain = 0, d_t = BDBG ? clock64() : 0;
+    const long long d_start = d_t;
+#define DBG_LAP(acc) if (BDBG) { const long long n_ = clock64(); acc += n_ - d_t; d_t = n_; }
+    for (int L = 0; L < p.n_layers; ++L) {
+      const BodyLayer ly = body_layer(p, L);
+      DBG_LAP(d_plain)
       // ---- wait until every peer finished layer L-1 (their outputs are my inputs / halos, and my
       //      outputs of this layer overwrite buffers they were still reading in L-1)
       if (L > 0) {
-        if (warp == 0) {
+        if (warp == kBodyFirstXformWarp) {
           for (int k = peer0 + lane; k <= peer1; k += 32)
             while (ld_acquire_gpu(p.flags + k) < L) { __nanosleep(32); }
           __syncwarp();
           fence_proxy_async_all();
         }
-        named_bar_sync(1, kPT);
+        named_bar_sync(1, kFrontThreads);
       }
       DBG_LAP(d_flag)
       // ---- SE vectors of the (at most two) images of this CTA
@@ -242,17 +305,17 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
         const uint8_t* rec = p.packed + p.k_rcab0 + int64_t(ly.rcab_in) * p.k_rcab_stride;
         const float* fc0 = reinterpret_cast<const float*>(rec + p.k_rcab_fc0);
         const float* fc2 = reinterpret_cast<const float*>(rec + p.k_rcab_fc2);
-        const int u = (ptid >> 6) & 1, c = ptid & 63;     // unit (image) slot, channel; threads >= 128 idle here
+        const int u = (xt >> 6) & 1, c = xt & 63;         // unit (image) slot, channel; threads >= 128 idle here
         const int n = min(img0 + u, img1);
-        if (ptid < 128) s_mean[u][c] = ld_cg_f32(sums + size_t(n) * kC + c) * p.inv_hw;
-        named_bar_sync(1, kPT);
-        if (ptid < 128 && c < p.R) {
+        if (xt < 128) s_mean[u][c] = ld_cg_f32(sums + size_t(n) * kC + c) * p.inv_hw;
+        named_bar_sync(2, kXT);
+        if (xt < 128 && c < p.R) {
           float a = 0.f;
           for (int k = 0; k < kC; ++k) a = fmaf(__ldg(fc0 + c * kC + k), s_mean[u][k], a);
           s_hid[u][c] = fmaxf(a, 0.f);
         }
-        named_bar_sync(1, kPT);
-        if (ptid < 128) {
+        named_bar_sync(2, kXT);
+        if (xt < 128) {
           float a = 0.f;
           for (int j = 0; j < p.R; ++j) a = fmaf(__ldg(fc2 + c * p.R + j), s_hid[u][j], a);
           const float s = 1.f / (1.f + expf(-a));
@@ -261,98 +324,85 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
           if (p.se_out && (img0 + u <= img1) && (n * p.tiles_per_seg >= g_begin) && (n * p.tiles_per_seg < g_end))
             p.se_out[(size_t(n) * (p.G * p.Bk) + ly.rcab_in) * kC + c] = s;
         }
-        named_bar_sync(1, kPT);
+        named_bar_sync(1, kFrontThreads);               // also releases the TMA issuer into the box loop
       }
       DBG_LAP(d_se)
-      // ---- stream the input boxes
-      const bf16* xin = p.buf[ly.in];
+      // ---- boxes
       const bf16* oin = p.buf[kBufO];
       bf16* xout = ly.xout >= 0 ? p.buf[ly.xout] : nullptr;
+      constexpr int kSteps = (kBBoxPx * 8 + kXT - 1) / kXT;            // 5 (last one: 32 threads)
       for (int g = g_begin; g < g_end;) {
-        ConvParams cp;  // only the fields make_unit reads
-        cp.tiles_per_seg = p.tiles_per_seg; cp.strips = 1; cp.H = p.H;
-        const Unit u = make_unit(cp, g, g_end);
-        for (int j = 0; j < u.nboxes; ++j, ++gb) {
-          const uint32_t slot = gb % kRingSlots, ph = (gb / kRingSlots) & 1;
-          const int y0 = u.ra - 1 + j * kBoxRows;
-          mbar_wait(&bar_empty[slot], ph ^ 1);
-          if (!ly.fused) {
-            // every producer warp arrives once per box (the barrier counts 8 warps + the TMA issuer)
-            if (ptid == 0) {
-              const bool mirror = (slot == kRingSlots - 1) && (j + 1 < u.nboxes);
-              mbar_expect_tx(&bar_full[slot], mirror ? 2 * kSlotBytes : kSlotBytes);
-              // h (conv2 input) and the last group output are read for the last time here
-              const uint64_t pol = (ly.in == kBufH || ly.epi == kEpiResidual) ? kPolicyEvictFirst : 0x1000000000000000ull;
-              tma_load_4d_hint(&maps.act[ly.in], &bar_full[slot], smem_u32(ring + slot * kSlotBytes), 0, -1, y0, u.n, pol);
-              if (mirror)
-                tma_load_4d_hint(&maps.act[ly.in], &bar_full[slot], smem_u32(ring + kRingSlots * kSlotBytes), 0, -1,
-                                 y0 + kBoxRows, u.n, pol);
-            }
+        const BUnit u = body_unit(p, g, g_end);
+        if (!ly.fused) {
+          // every transform warp arrives once per box so the full barrier always counts 9
+          for (int j = 0; j < u.nboxes; ++j, ++gb) {
+            const uint32_t slot = gb % kBSlots, ph = (gb / kBSlots) & 1;
+            mbar_wait(&bar_empty[slot], ph ^ 1);
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_full[slot]);
-          } else {
-            // x' = x + s * o for the 4 x 66 pixels of this box; a thread owns one 16-byte channel chunk of
-            // 8-9 pixels and keeps ALL its loads of the box in flight at once
-            uint8_t* dst = ring + slot * kSlotBytes;
-            uint8_t* dst_mirror = (slot == 0 && j > 0) ? ring + kRingSlots * kSlotBytes : nullptr;
-            const int us = u.n - img0;                                   // which s_scale row
-            float sc[8];
+          }
+        } else {
+          const int us = u.n - img0;                                     // which s_scale row
+          float sc[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) sc[e] = s_scale[us][chunk * 8 + e];
-            const int lo = kTileM * u.t0, hi = kTileM * u.t1;            // owned strip-linear range
-            // two half boxes (2 rows = 132 px each), 5 steps of 256 chunks: 10 loads in flight per thread
-            constexpr int kHalfPx = kBoxPx / 2;
-            constexpr int kSteps = (kHalfPx * 8 + kPT - 1) / kPT;        // 5 (last one partial)
-#pragma unroll 1
-            for (int hb = 0; hb < 2; ++hb) {
-              uint4 xv[kSteps], ov[kSteps];
-              uint32_t inb = 0;
+          for (int e = 0; e < 8; ++e) sc[e] = s_scale[us][chunk * 8 + e];
+          const int lo = kTileM * u.t0, hi = kTileM * u.t1;              // owned strip-linear range
+          // o of a box is loaded one box ahead of its use
+          uint4 ov[kSteps];
+          auto load_o = [&](int j, uint4 (&dst)[kSteps]) {
+            const int y0 = u.ra - 1 + j * kBBoxRows;
 #pragma unroll
-              for (int q = 0; q < kSteps; ++q) {
-                const int hp = (q * kPT + ptid) >> 3;                    // pixel within the half box
-                const int px = hb * kHalfPx + hp;
-                const int row = px / kPitch, col = px - row * kPitch;
-                const int iy = y0 + row, ix = col - 1;
-                const bool ok = (hp < kHalfPx) && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-                if (ok) {
-                  const size_t off = ((size_t(u.n) * p.H + iy) * p.W + ix) * kC + chunk * 8;
-                  xv[q] = ld_cg_128_hint(xin + off, kPolicyEvictFirst);
-                  ov[q] = ld_cg_128_hint(oin + off, kPolicyEvictFirst);
-                  inb |= 1u << q;
-                } else {
-                  xv[q] = make_uint4(0, 0, 0, 0);
-                  ov[q] = make_uint4(0, 0, 0, 0);
+            for (int q = 0; q < kSteps; ++q) {
+              const int px = (q * kXT + xt) >> 3;
+              const int row = px / kPitch, col = px - row * kPitch;
+              const int iy = y0 + row, ix = col - 1;
+              const bool ok = (px < kBBoxPx) && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+              dst[q] = ok ? ld_cg_128_hint(oin + ((size_t(u.n) * p.H + iy) * p.W + ix) * kC + chunk * 8, kPolicyEvictFirst)
+                          : make_uint4(0, 0, 0, 0);
+            }
+          };
+          load_o(0, ov);
+          for (int j = 0; j < u.nboxes; ++j, ++gb) {
+            const uint32_t slot = gb % kBSlots;
+            const int y0 = u.ra - 1 + j * kBBoxRows;
+            uint4 on[kSteps];
+            if (j + 1 < u.nboxes) load_o(j + 1, on);
+            mbar_wait(&bar_x[slot], (x_phase >> slot) & 1);              // x has landed in the slot
+            x_phase ^= 1u << slot;
+            uint8_t* dst = ring + slot * kBSlotBytes;
+            uint8_t* dst_mirror = (slot == 0 && j > 0) ? ring + kBSlots * kBSlotBytes : nullptr;
+#pragma unroll
+            for (int q = 0; q < kSteps; ++q) {
+              const int px = (q * kXT + xt) >> 3;
+              if (px < kBBoxPx) {
+                // SWIZZLE_128B: 16-byte chunk index XOR (128-byte row index of the absolute address mod 8)
+                const uint32_t lin_b = uint32_t(slot) * kBSlotBytes + uint32_t(px) * 128u;   // ring is 1024-aligned
+                const uint32_t so = uint32_t(px) * 128u + (uint32_t(chunk ^ ((lin_b >> 7) & 7)) << 4);
+                const uint4 xv = *reinterpret_cast<const uint4*>(dst + so);
+                uint4 r;
+                r.x = pack_bf16(fmaf(bf16lo(ov[q].x), sc[0], bf16lo(xv.x)), fmaf(bf16hi(ov[q].x), sc[1], bf16hi(xv.x)));
+                r.y = pack_bf16(fmaf(bf16lo(ov[q].y), sc[2], bf16lo(xv.y)), fmaf(bf16hi(ov[q].y), sc[3], bf16hi(xv.y)));
+                r.z = pack_bf16(fmaf(bf16lo(ov[q].z), sc[4], bf16lo(xv.z)), fmaf(bf16hi(ov[q].z), sc[5], bf16hi(xv.z)));
+                r.w = pack_bf16(fmaf(bf16lo(ov[q].w), sc[6], bf16lo(xv.w)), fmaf(bf16hi(ov[q].w), sc[7], bf16hi(xv.w)));
+                *reinterpret_cast<uint4*>(dst + so) = r;
+                if (dst_mirror) {
+                  const uint32_t lin_m = uint32_t(kBSlots) * kBSlotBytes + uint32_t(px) * 128u;
+                  *reinterpret_cast<uint4*>(dst_mirror + uint32_t(px) * 128u + (uint32_t(chunk ^ ((lin_m >> 7) & 7)) << 4)) = r;
                 }
-              }
-#pragma unroll
-              for (int q = 0; q < kSteps; ++q) {
-                const int hp = (q * kPT + ptid) >> 3;
-                const int px = hb * kHalfPx + hp;
-                if (hp < kHalfPx) {
-                  uint4 r;
-                  r.x = pack_bf16(fmaf(bf16lo(ov[q].x), sc[0], bf16lo(xv[q].x)), fmaf(bf16hi(ov[q].x), sc[1], bf16hi(xv[q].x)));
-                  r.y = pack_bf16(fmaf(bf16lo(ov[q].y), sc[2], bf16lo(xv[q].y)), fmaf(bf16hi(ov[q].y), sc[3], bf16hi(xv[q].y)));
-                  r.z = pack_bf16(fmaf(bf16lo(ov[q].z), sc[4], bf16lo(xv[q].z)), fmaf(bf16hi(ov[q].z), sc[5], bf16hi(xv[q].z)));
-                  r.w = pack_bf16(fmaf(bf16lo(ov[q].w), sc[6], bf16lo(xv[q].w)), fmaf(bf16hi(ov[q].w), sc[7], bf16hi(xv[q].w)));
-                  // SWIZZLE_128B: 16-byte chunk index XOR (128-byte row index mod 8); slots are 1024-aligned
-                  const uint32_t so = uint32_t(px) * 128u + (uint32_t(chunk ^ (px & 7)) << 4);
-                  *reinterpret_cast<uint4*>(dst + so) = r;
-                  if (dst_mirror) *reinterpret_cast<uint4*>(dst_mirror + so) = r;
-                  if (xout && ((inb >> q) & 1)) {
-                    const int row = px / kPitch, col = px - row * kPitch;
-                    const int lin = (y0 + row) * kPitch + (col - 1);     // strip-linear output index of the pixel
-                    if (lin >= lo && lin < hi) {
-                      const size_t off = ((size_t(u.n) * p.H + (y0 + row)) * p.W + (col - 1)) * kC + chunk * 8;
-                      *reinterpret_cast<uint4*>(xout + off) = r;
-                    }
-                  }
+                if (xout) {
+                  const int row = px / kPitch, col = px - row * kPitch;
+                  const int iy = y0 + row, ix = col - 1;
+                  const int lin = iy * kPitch + ix;                      // strip-linear output index of the pixel
+                  if (ix >= 0 && ix < p.W && lin >= lo && lin < hi)
+                    *reinterpret_cast<uint4*>(xout + ((size_t(u.n) * p.H + iy) * p.W + ix) * kC + chunk * 8) = r;
                 }
               }
             }
             fence_proxy_async_smem();          // generic-proxy smem writes -> visible to tcgen05.mma
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_full[slot]);
-            if (ptid == 0) mbar_arrive(&bar_full[slot]);   // the 9th arrival (the TMA issuer's in plain layers)
+#pragma unroll
+            for (int q = 0; q < kSteps; ++q) ov[q] = on[q];
           }
         }
         g += u.t1 - u.t0;
@@ -363,9 +413,9 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_done);
     }
-    if (BDBG && ptid == 0) {
+    if (BDBG && xt == 0) {
       long long* d = p.dbg + blockIdx.x * 16;
-      d[0] = d_wfree; d[1] = d_flag; d[2] = d_se; d[3] = d_fused; d[4] = d_plain; d[5] = clock64() - d_start;
+      d[0] = 0; d[1] = d_flag; d[2] = d_se; d[3] = d_fused; d[4] = d_plain; d[5] = clock64() - d_start;
     }
   } else if (warp < kBodyFirstEpiWarp) {
     // ============================================================ MMA issuers (2 warps)
@@ -392,9 +442,7 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
       }
       int i_layer = 0;
       for (int g = g_begin; g < g_end;) {
-        ConvParams cp;
-        cp.tiles_per_seg = p.tiles_per_seg; cp.strips = 1; cp.H = p.H;
-        const Unit u = make_unit(cp, g, g_end);
+        const BUnit u = body_unit(p, g, g_end);
         int waited = 0, released = 0;
         for (int t = u.t0; t < u.t1; ++t, ++tile_ctr, ++i_layer) {
           const uint32_t acc = tile_ctr & (kBodyAccBufs - 1);
@@ -403,27 +451,30 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
           if (mine) mbar_wait(&bar_acc_empty[acc], ((tile_ctr / kBodyAccBufs) & 1) ^ 1);
           if (BDBG) { const long long n_ = clock64(); m_acc += n_ - m_t; m_t = n_; }
           const int base = kTileM * t - kPitch * u.ra;
-          const int need_last = min((base + kTileM + kMaxShift - 1) / kBoxPx, u.nboxes - 1);
+          const int need_last = min((base + kTileM + kMaxShift - 1) / kBBoxPx, u.nboxes - 1);
           while (mine && waited <= need_last) {
             const uint32_t gb = gb_base + waited;
-            mbar_wait(&bar_full[gb % kRingSlots], (gb / kRingSlots) & 1);
+            mbar_wait(&bar_full[gb % kBSlots], (gb / kBSlots) & 1);
             ++waited;
           }
           if (BDBG) { const long long n_ = clock64(); m_full += n_ - m_t; m_t = n_; }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * N;
-          const int lb0 = base / kBoxPx, r0 = base - lb0 * kBoxPx;
-          const uint32_t slot0 = (gb_base + lb0) % kRingSlots;
-          const uint32_t slot1 = (slot0 + 1 == kRingSlots) ? 0 : slot0 + 1;
-          const uint32_t a0 = ring_lo + slot0 * (kSlotBytes >> 4) + r0 * 8;
-          const uint32_t a1 = ring_lo + slot1 * (kSlotBytes >> 4) + (r0 - kBoxPx) * 8;
+          // a view starts in box lb0, lb0 + 1 or lb0 + 2 (tap offsets reach 134 px, a box is 132)
+          const int lb0 = base / kBBoxPx, r0 = base - lb0 * kBBoxPx;
+          const uint32_t slot0 = (gb_base + lb0) % kBSlots;
+          const uint32_t slot1 = (slot0 + 1 >= kBSlots) ? slot0 + 1 - kBSlots : slot0 + 1;
+          const uint32_t slot2 = (slot0 + 2 >= kBSlots) ? slot0 + 2 - kBSlots : slot0 + 2;
+          const uint32_t a0 = ring_lo + slot0 * (kBSlotBytes >> 4) + r0 * 8;
+          const uint32_t a1 = ring_lo + slot1 * (kBSlotBytes >> 4) + (r0 - kBBoxPx) * 8;
+          const uint32_t a2 = ring_lo + slot2 * (kBSlotBytes >> 4) + (r0 - 2 * kBBoxPx) * 8;
           const bool w_first = (i_layer == first_mine), w_last = (i_layer == last_mine);
           if (leader && mine) {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               if (w_first) mbar_wait(&bar_w[tap], L & 1);
               const int off = (tap / 3) * kPitch + (tap % 3);
-              const uint32_t a_lo = ((r0 + off < kBoxPx) ? a0 : a1) + off * 8;
+              const uint32_t a_lo = ((r0 + off < kBBoxPx) ? a0 : (r0 + off < 2 * kBBoxPx) ? a1 : a2) + off * 8;
               const uint32_t b_lo = w_lo + tap * (N * 128 >> 4);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
@@ -433,9 +484,9 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
           }
           __syncwarp();
           if (BDBG) { const long long n_ = clock64(); m_issue += n_ - m_t; m_t = n_; }
-          const int next_first = (t + 1 < u.t1) ? (base + kTileM) / kBoxPx : u.nboxes;
+          const int next_first = (t + 1 < u.t1) ? (base + kTileM) / kBBoxPx : u.nboxes;
           while (released < next_first) {
-            if (leader) umma_commit(&bar_empty[(gb_base + released) % kRingSlots]);
+            if (leader) umma_commit(&bar_empty[(gb_base + released) % kBSlots]);
             ++released;
           }
           if (leader && mine) umma_commit(&bar_acc_full[acc]);
@@ -469,9 +520,7 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
       const float* cbias = c_vec + ly.cv_bias + col0;
       const float* cslope = c_vec + ly.cv_slope + col0;
       for (int g = g_begin; g < g_end;) {
-        ConvParams cp;
-        cp.tiles_per_seg = p.tiles_per_seg; cp.strips = 1; cp.H = p.H;
-        const Unit u = make_unit(cp, g, g_end);
+        const BUnit u = body_unit(p, g, g_end);
         float csum[CW];
 #pragma unroll
         for (int c = 0; c < CW; ++c) csum[c] = 0.f;
