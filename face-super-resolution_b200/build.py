@@ -10,7 +10,6 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libfen_b200.so")
 SOURCES = ["fen_b200.cu"]
-HEADERS = ["conv3x3_umma.cuh", "fen_common.cuh", "ptx_sm100.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC",
@@ -28,7 +27,7 @@ def is_stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
     deps.append(os.path.join(os.path.dirname(PKG_DIR), "include", "fen_b200.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 

@@ -1,7 +1,7 @@
 // Persistent "body" kernel: ALL 64->64 3x3 convolutions of the residual body
 // (num_groups x (2 x blocks_per_group + 1) + conv_after_body = 127 layers for the 6 x 10 model)
-// in ONE launch, with the squeeze-and-excitation scale and the RCAB residual folded into the
-// producer of the following conv.  Reference: src/models/custom.py:167-175 (body loop, long skip),
+// in ONE launch, with the squeeze-and-excitation scale and the RCAB residual fused into the conv2
+// epilogue.  Reference: src/models/custom.py:167-175 (body loop, long skip),
 // src/models/blocks.py:135-153 (RCAB), :75-92 (ChannelAttention), :185-189 (ResidualGroup).
 //
 // Every CTA owns the same run of output tiles in every layer (all body layers share one geometry),
@@ -9,19 +9,22 @@
 // with it ("peers": halo rows + the per-image SE pool) through release/acquire flags in global
 // memory.  Launched cooperatively with one CTA per SM, so all CTAs are co-resident.
 //
+// SE without a second pass.  The reference computes s = sigmoid(W2' relu(W0' mean_hw(o))) from the
+// conv2 OUTPUT o and then x' = o*s*0.2 + x, which would force o through memory.  But mean_hw(o) is
+// linear in conv2's INPUT h:  mean(o)[c] = b2[c] + 1/HW * sum_{tap,ci} W2[c,ci,tap] * S_tap[ci], where
+// S_tap[ci] is the sum of h[ci] over the window the tap sees = (total) - (excluded border row)
+// - (excluded border column) + (corner).  The conv1 epilogue accumulates those 9 sums of the
+// bf16-rounded h per image (total, first/last row, first/last column, 4 corners); at the start of
+// the conv2 layer four auxiliary warps turn them into s (a 64x576 mat-vec + the two tiny FC layers,
+// fp32) while the first tiles' MMAs already run; the conv2 epilogue then writes
+// x' = x + (0.2 s[c]) * (acc + b2[c]) directly.  o is never materialised and no elementwise pass or
+// transform producer exists: every layer is a plain TMA-fed convolution.
+//
 // Per layer the tile pipeline is the one of conv3x3_umma.cuh (ring of boxes with a mirror slot -
-// here 2-row boxes, 7 slots -, two tcgen05.mma issuer warps, 8 epilogue warps, TMEM accumulators).  Differences:
-//   * warp 0 issues all TMA loads.  Fused layers (conv1 of RCAB b > 0, group conv): TMA brings x
-//     into the ring slot, the 256 transform threads (warps 1-8) read o (conv2 output of the
-//     previous block) from global memory one box ahead, update the slot in place with
-//     x' = x + (res_scale * s[c]) * o (fp32 math, bf16 store, SWIZZLE_128B pattern by hand) and
-//     write the rows they own back to global memory as the next residual stream - no standalone
-//     elementwise pass exists.
-//   * the SE vector s = sigmoid(W2 relu(W0 mean(o))) is recomputed per CTA from the per-image
-//     channel sums the conv2 epilogue accumulated (2 KMAC, fp32).
-//   * biases and PReLU slopes come from __constant__ memory (the epilogue must stay off shared
-//     memory, whose bandwidth the tensor core needs), weights of the next layer are loaded tap by
-//     tap as soon as the current layer has issued its last MMA on that tap.
+// here 2-row boxes, 7 slots -, two tcgen05.mma issuer warps, 8 epilogue warps, TMEM accumulators).
+// Biases and PReLU slopes come from __constant__ memory and s through warp shuffles (the epilogue
+// must stay off shared memory, whose bandwidth the tensor core needs); the weights of the next
+// layer are loaded tap by tap as soon as the current layer has issued its last MMA on that tap.
 #pragma once
 #include "conv3x3_umma.cuh"
 
@@ -32,13 +35,14 @@ namespace fen {
 #endif
 #define BDBG (FEN_BODY_DEBUG && p.dbg)
 
-constexpr int kBodyXformWarps = 8;                    // warps 1..8: x' = x + s*o transform (fused layers)
+constexpr int kBodyAuxWarps = 4;                      // warps 1..4: peer flags + SE vector
 constexpr int kBodyMmaWarps = 2;
 constexpr int kBodyEpiWarps = 8;
-constexpr int kBodyFirstXformWarp = 1;                // warp 0: TMA issuer
-constexpr int kBodyFirstMmaWarp = 1 + kBodyXformWarps;
+constexpr int kBodyFirstAuxWarp = 1;                  // warp 0: TMA issuer
+constexpr int kBodyFirstMmaWarp = 1 + kBodyAuxWarps;
 constexpr int kBodyFirstEpiWarp = kBodyFirstMmaWarp + kBodyMmaWarps;
-constexpr int kBodyThreads = 32 * (kBodyFirstEpiWarp + kBodyEpiWarps);   // 608
+constexpr int kBodyThreads = 32 * (kBodyFirstEpiWarp + kBodyEpiWarps);   // 480
+constexpr int kBodyMaxUnits = 4;                      // images a CTA may touch in one layer (host caps the batch per launch)
 constexpr int kBodyAccBufs = 4;
 constexpr int kBodyWBytes = 9 * kC * kC * 2;
 // activation ring: 2-row boxes (132 px, 16 896 B; TMA SWIZZLE_128B only needs 128 B alignment, the
@@ -53,7 +57,9 @@ constexpr int kConstVecFloats = 15872;   // 62 KB of __constant__ for biases + s
 
 __device__ __constant__ float c_vec[kConstVecFloats];
 
-enum BodyBuf : int { kBufF0 = 0, kBufX0 = 1, kBufX1 = 2, kBufH = 3, kBufO = 4, kBufG0 = 5 };  // G0.. = group outputs
+enum BodyBuf : int { kBufF0 = 0, kBufX0 = 1, kBufX1 = 2, kBufH = 3, kBufO = 4 /* unused */, kBufG0 = 5 };  // G0.. = group outputs
+enum BodyEpi : int { kBEpiPreluHsum = 0, kBEpiSeResidual = 1, kBEpiResidual = 2 };
+enum HSum : int { kHsTotal = 0, kHsRow0, kHsRowL, kHsCol0, kHsColL, kHsC00, kHsC0L, kHsCL0, kHsCLL, kHsCount };
 constexpr int kBodyMaxBufs = 5 + 16;
 
 struct BodyMaps {
@@ -72,22 +78,21 @@ struct BodyParams {
   int64_t k_rcab0, k_rcab_stride, k_rcab_w2, k_rcab_fc0, k_rcab_fc2;   // byte offsets in the blob
   int64_t k_gconv0, k_gconv_stride, k_after;
   int cv_rcab0, cv_gconv0, cv_after;   // float offsets in c_vec: per RCAB [b1 64][slope 64][b2 64]; per plain conv [b 64]
-  float* sums;                     // [n_rcab][B][64]
+  float* hsum;                     // [n_rcab][B][64]: per-image channel sums of the bf16-rounded h
   float* se_out;                   // [B][n_rcab][64] or nullptr
   int* flags;                      // [gridDim.x], zeroed before launch
   long long* dbg;
 };
 
 struct BodyLayer {
-  int fused;        // producer transforms x' = x + s*o instead of a TMA load
-  int epi;          // kEpiPrelu / kEpiSum / kEpiResidual
-  int in;           // input buffer (plain) or x buffer (fused)
-  int xout;         // fused: buffer receiving x' (-1: do not store)
-  int res;          // residual buffer (kEpiResidual)
+  int epi;          // BodyEpi
+  int in;           // input buffer
+  int res;          // residual buffer (kBEpiSeResidual: x of the block, kBEpiResidual: skip) or -1
   int out;          // output buffer
-  int rcab_in;      // fused: RCAB index whose SE vector scales o
-  int rcab_out;     // kEpiSum: RCAB index receiving the channel sums
+  int rcab;         // RCAB index (h sums written by conv1, consumed by conv2) or -1
+  int last_use;     // the input is dead after this layer (L2 evict-first hint)
   int w_row;        // first row (128 B units) of this layer's weights in the blob
+  int64_t w_off;    // byte offset of those weights in the blob (conv2: read again for the SE mat-vec)
   int cv_bias, cv_slope;   // offsets in c_vec
 };
 
@@ -95,38 +100,30 @@ __device__ __forceinline__ BodyLayer body_layer(const BodyParams& p, int L) {
   BodyLayer l;
   const int per_group = 2 * p.Bk + 1;
   const int g = L / per_group, r = L - g * per_group;
-  l.fused = 0; l.xout = -1; l.res = -1; l.rcab_in = -1; l.rcab_out = -1; l.cv_slope = 0;
+  l.res = -1; l.rcab = -1; l.cv_slope = 0; l.last_use = 1;
   if (g == p.G) {                                  // conv_after_body + long skip -> X0
-    l.epi = kEpiResidual; l.in = kBufG0 + p.G - 1; l.res = kBufF0; l.out = kBufX0;
-    l.w_row = int(p.k_after >> 7); l.cv_bias = p.cv_after;
-    return l;
-  }
-  const int gin = (g == 0) ? kBufF0 : kBufG0 + g - 1;
-  if (r == 2 * p.Bk) {                             // group conv: input x' of the last block, + group input
-    l.fused = 1; l.epi = kEpiResidual;
-    l.in = (p.Bk == 1) ? gin : kBufX0 + ((p.Bk - 2) & 1);
-    l.rcab_in = g * p.Bk + p.Bk - 1;
-    l.res = gin; l.out = kBufG0 + g;
-    l.w_row = int((p.k_gconv0 + g * p.k_gconv_stride) >> 7); l.cv_bias = p.cv_gconv0 + g * 64;
-    return l;
-  }
-  const int b = r >> 1, rc = g * p.Bk + b;
-  const int64_t rec = p.k_rcab0 + int64_t(rc) * p.k_rcab_stride;
-  if ((r & 1) == 0) {                              // conv1 (+ PReLU) -> H
-    l.epi = kEpiPrelu; l.out = kBufH;
-    if (b == 0) {
-      l.in = gin;
-    } else {                                       // x' = X_{b-1} + s_{b-1} * o_{b-1}, stored to X[(b-1)&1]
-      l.fused = 1;
-      l.in = (b == 1) ? gin : kBufX0 + ((b - 2) & 1);
-      l.xout = kBufX0 + ((b - 1) & 1);
-      l.rcab_in = rc - 1;
+    l.epi = kBEpiResidual; l.in = kBufG0 + p.G - 1; l.res = kBufF0; l.out = kBufX0;
+    l.w_off = p.k_after; l.cv_bias = p.cv_after;
+  } else {
+    const int gin = (g == 0) ? kBufF0 : kBufG0 + g - 1;
+    if (r == 2 * p.Bk) {                           // group conv on the last block's output, + group input
+      l.epi = kBEpiResidual; l.in = kBufX0 + ((p.Bk - 1) & 1); l.res = gin; l.out = kBufG0 + g;
+      l.w_off = p.k_gconv0 + g * p.k_gconv_stride; l.cv_bias = p.cv_gconv0 + g * 64;
+    } else {
+      const int b = r >> 1, rc = g * p.Bk + b;
+      const int xb = (b == 0) ? gin : kBufX0 + ((b - 1) & 1);          // input of block b
+      const int64_t rec = p.k_rcab0 + int64_t(rc) * p.k_rcab_stride;
+      l.rcab = rc;
+      if ((r & 1) == 0) {                          // conv1 + PReLU -> H, plus the 9 channel sums of h
+        l.epi = kBEpiPreluHsum; l.in = xb; l.out = kBufH; l.last_use = 0;   // xb is read again as conv2's residual
+        l.w_off = rec; l.cv_bias = p.cv_rcab0 + rc * 192; l.cv_slope = l.cv_bias + 64;
+      } else {                                     // conv2, SE scale, residual -> X[b & 1]
+        l.epi = kBEpiSeResidual; l.in = kBufH; l.res = xb; l.out = kBufX0 + (b & 1);
+        l.w_off = rec + p.k_rcab_w2; l.cv_bias = p.cv_rcab0 + rc * 192 + 128;
+      }
     }
-    l.w_row = int(rec >> 7); l.cv_bias = p.cv_rcab0 + rc * 192; l.cv_slope = l.cv_bias + 64;
-  } else {                                         // conv2 -> O, channel sums
-    l.epi = kEpiSum; l.in = kBufH; l.out = kBufO; l.rcab_out = rc;
-    l.w_row = int((rec + p.k_rcab_w2) >> 7); l.cv_bias = p.cv_rcab0 + rc * 192 + 128;
   }
+  l.w_row = int(l.w_off >> 7);
   return l;
 }
 
@@ -193,14 +190,18 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_smem = smem;
   uint8_t* ring = smem + kBodyWBytes;
-  __shared__ uint64_t bar_w[9], bar_wfree[9], bar_x[kBSlots], bar_full[kBSlots], bar_empty[kBSlots];
-  __shared__ uint64_t bar_acc_full[kBodyAccBufs], bar_acc_empty[kBodyAccBufs], bar_done;
+  __shared__ uint64_t bar_w[9], bar_wfree[9], bar_full[kBSlots], bar_empty[kBSlots];
+  __shared__ uint64_t bar_acc_full[kBodyAccBufs], bar_acc_empty[kBodyAccBufs], bar_done, bar_s;
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_mean[2][kC], s_hid[2][kC], s_scale[2][kC];
+  __shared__ float s_scale[kBodyMaxUnits][kC];            // res_scale * s per image of this CTA
+  __shared__ __align__(16) float s_S[9][kC];
+  __shared__ float s_q[kHsCount][kC], s_part[2][kC], s_mean[kC], s_hid[kC], s_red[kBodyAuxWarps][4][kC];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr uint32_t kTmemCols = kBodyAccBufs * N;
-  constexpr int kFrontThreads = 32 * kBodyFirstMmaWarp;   // TMA warp + transform warps (named barrier 1)
+  constexpr int kFrontThreads = 32 * kBodyFirstMmaWarp;   // TMA warp + aux warps (named barrier 1)
+  constexpr int kAuxThreads = 32 * kBodyAuxWarps;         // named barrier 2
+  constexpr int kEpiThreads = 32 * kBodyEpiWarps;         // named barrier 3
 
   const int g_begin = blockIdx.x * p.tiles_per_cta;
   const int g_end = min(p.total_tiles, g_begin + p.tiles_per_cta);
@@ -213,13 +214,10 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
   if (warp == kBodyFirstMmaWarp) tmem_alloc(&tmem_slot, kTmemCols);
   if (tid == 0) {
     for (int i = 0; i < 9; ++i) { mbar_init(&bar_w[i], 1); mbar_init(&bar_wfree[i], kBodyMmaWarps); }
-    for (int i = 0; i < kBSlots; ++i) {
-      mbar_init(&bar_x[i], 1);
-      mbar_init(&bar_full[i], kBodyXformWarps + 1);     // 8 transform warps + the TMA issuer, every box
-      mbar_init(&bar_empty[i], kBodyMmaWarps);
-    }
+    for (int i = 0; i < kBSlots; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], kBodyMmaWarps); }
     for (int i = 0; i < kBodyAccBufs; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], kBodyEpiWarps); }
-    mbar_init(&bar_done, kBodyXformWarps + kBodyEpiWarps);
+    mbar_init(&bar_done, kBodyEpiWarps);
+    mbar_init(&bar_s, 1);
     fence_mbar_init();
     tma_prefetch_desc(&maps.w);
   }
@@ -244,30 +242,20 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
       }
       __syncwarp();
       if (L > 0) named_bar_sync(1, kFrontThreads);       // peers have finished layer L-1 (polled by warp 1)
-      if (ly.fused) named_bar_sync(1, kFrontThreads);    // keeps the barrier sequence of the transform warps (SE)
       if (lane == 0) {
-        const uint64_t pol = (ly.fused || ly.in == kBufH || ly.epi == kEpiResidual) ? kPolicyEvictFirst
-                                                                                   : 0x1000000000000000ull;
+        const uint64_t pol = ly.last_use ? kPolicyEvictFirst : 0x1000000000000000ull;
         for (int g = g_begin; g < g_end;) {
           const BUnit u = body_unit(p, g, g_end);
           for (int j = 0; j < u.nboxes; ++j, ++gb) {
             const uint32_t slot = gb % kBSlots, ph = (gb / kBSlots) & 1;
             const int y0 = u.ra - 1 + j * kBBoxRows;
             mbar_wait(&bar_empty[slot], ph ^ 1);
-            const uint32_t dst = smem_u32(ring + slot * kBSlotBytes);
-            if (ly.fused) {
-              // x goes to the slot; the transform warps finish the box (and the mirror copy)
-              mbar_expect_tx(&bar_x[slot], kBSlotBytes);
-              tma_load_4d_hint(&maps.act[ly.in], &bar_x[slot], dst, 0, -1, y0, u.n, pol);
-              mbar_arrive(&bar_full[slot]);
-            } else {
-              const bool mirror = (slot == 0) && (j > 0);
-              mbar_expect_tx(&bar_full[slot], mirror ? 2 * kBSlotBytes : kBSlotBytes);
-              tma_load_4d_hint(&maps.act[ly.in], &bar_full[slot], dst, 0, -1, y0, u.n, pol);
-              if (mirror)
-                tma_load_4d_hint(&maps.act[ly.in], &bar_full[slot], smem_u32(ring + kBSlots * kBSlotBytes), 0, -1, y0,
-                                 u.n, pol);
-            }
+            const bool mirror = (slot == 0) && (j > 0);
+            mbar_expect_tx(&bar_full[slot], mirror ? 2 * kBSlotBytes : kBSlotBytes);
+            tma_load_4d_hint(&maps.act[ly.in], &bar_full[slot], smem_u32(ring + slot * kBSlotBytes), 0, -1, y0, u.n, pol);
+            if (mirror)
+              tma_load_4d_hint(&maps.act[ly.in], &bar_full[slot], smem_u32(ring + kBSlots * kBSlotBytes), 0, -1, y0,
+                               u.n, pol);
           }
           g += u.t1 - u.t0;
         }
@@ -275,22 +263,17 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
       __syncwarp();
     }
   } else if (warp < kBodyFirstMmaWarp) {
-    // ============================================================ transform warps (256 threads)
-    constexpr int kXT = 32 * kBodyXformWarps;
-    const int xt = tid - 32 * kBodyFirstXformWarp;      // 0..255
-    const int chunk = xt & 7;                           // 16-byte channel chunk this thread always handles
-    uint32_t gb = 0;                                    // running box counter (same sequence as the issuer)
-    uint32_t x_phase = 0;                               // bar_x completes only in fused layers: one parity bit per slot
-    long long d_flag = 0, d_se = 0, d_fused = 0, d_plain = 0, d_t = BDBG ? clock64() : 0;
+    // ============================================================ aux warps (128 threads): peer flags + SE vector
+    const int at = tid - 32 * kBodyFirstAuxWarp;        // 0..127
+    long long d_flag = 0, d_se = 0, d_t = BDBG ? clock64() : 0;
     const long long d_start = d_t;
 #define DBG_LAP(acc) if (BDBG) { const long long n_ = clock64(); acc += n_ - d_t; d_t = n_; }
     for (int L = 0; L < p.n_layers; ++L) {
       const BodyLayer ly = body_layer(p, L);
-      DBG_LAP(d_plain)
       // ---- wait until every peer finished layer L-1 (their outputs are my inputs / halos, and my
       //      outputs of this layer overwrite buffers they were still reading in L-1)
       if (L > 0) {
-        if (warp == kBodyFirstXformWarp) {
+        if (warp == kBodyFirstAuxWarp) {
           for (int k = peer0 + lane; k <= peer1; k += 32)
             while (ld_acquire_gpu(p.flags + k) < L) { __nanosleep(32); }
           __syncwarp();
@@ -299,123 +282,138 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
         named_bar_sync(1, kFrontThreads);
       }
       DBG_LAP(d_flag)
-      // ---- SE vectors of the (at most two) images of this CTA
-      if (ly.fused) {
-        const float* sums = p.sums + size_t(ly.rcab_in) * p.B * kC;
-        const uint8_t* rec = p.packed + p.k_rcab0 + int64_t(ly.rcab_in) * p.k_rcab_stride;
-        const float* fc0 = reinterpret_cast<const float*>(rec + p.k_rcab_fc0);
-        const float* fc2 = reinterpret_cast<const float*>(rec + p.k_rcab_fc2);
-        const int u = (xt >> 6) & 1, c = xt & 63;         // unit (image) slot, channel; threads >= 128 idle here
-        const int n = min(img0 + u, img1);
-        if (xt < 128) s_mean[u][c] = ld_cg_f32(sums + size_t(n) * kC + c) * p.inv_hw;
-        named_bar_sync(2, kXT);
-        if (xt < 128 && c < p.R) {
-          float a = 0.f;
-          for (int k = 0; k < kC; ++k) a = fmaf(__ldg(fc0 + c * kC + k), s_mean[u][k], a);
-          s_hid[u][c] = fmaxf(a, 0.f);
+      if (ly.epi != kBEpiSeResidual) continue;
+#ifdef FEN_EXP_NO_SE
+      if (at == 0) mbar_arrive(&bar_s);
+      continue;
+#endif
+      // ---- SE vector of every image of this CTA, from the sums of h that the conv1 layer left
+      const bf16* w2 = reinterpret_cast<const bf16*>(p.packed + ly.w_off);        // [tap][c][ci] bf16
+      const uint8_t* rec = p.packed + p.k_rcab0 + int64_t(ly.rcab) * p.k_rcab_stride;
+      const float* fc0 = reinterpret_cast<const float*>(rec + p.k_rcab_fc0);
+      const float* fc2 = reinterpret_cast<const float*>(rec + p.k_rcab_fc2);
+      for (int n = img0; n <= img1; ++n) {
+        const int us = n - img0;
+        // total sum of h: accumulated by the conv1 epilogue; the border rows / columns / corners are
+        // re-read here from h itself (a few KB per image, L2-resident) - atomics from the epilogue,
+        // shared or global, would queue behind the tensor core's operand traffic
+        const float* hs = p.hsum + (size_t(ly.rcab) * p.B + n) * kC;
+        const bf16* hb = p.buf[kBufH] + size_t(n) * p.H * p.W * kC;
+        {
+          const int chunk = at & 7, pg = at >> 3;            // 8 channels of every 16th border pixel
+          float a4[4][8];
+#pragma unroll
+          for (int qn = 0; qn < 4; ++qn)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a4[qn][e] = 0.f;
+          const int npix = max(p.H, p.W);
+          for (int px = pg; px < npix; px += 16) {
+            uint4 v[4];
+            v[0] = (px < p.W) ? ld_cg_128(hb + (size_t(0) * p.W + px) * kC + chunk * 8) : make_uint4(0, 0, 0, 0);
+            v[1] = (px < p.W) ? ld_cg_128(hb + (size_t(p.H - 1) * p.W + px) * kC + chunk * 8) : make_uint4(0, 0, 0, 0);
+            v[2] = (px < p.H) ? ld_cg_128(hb + (size_t(px) * p.W + 0) * kC + chunk * 8) : make_uint4(0, 0, 0, 0);
+            v[3] = (px < p.H) ? ld_cg_128(hb + (size_t(px) * p.W + p.W - 1) * kC + chunk * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int qn = 0; qn < 4; ++qn) {
+              a4[qn][0] += bf16lo(v[qn].x); a4[qn][1] += bf16hi(v[qn].x);
+              a4[qn][2] += bf16lo(v[qn].y); a4[qn][3] += bf16hi(v[qn].y);
+              a4[qn][4] += bf16lo(v[qn].z); a4[qn][5] += bf16hi(v[qn].z);
+              a4[qn][6] += bf16lo(v[qn].w); a4[qn][7] += bf16hi(v[qn].w);
+            }
+          }
+          // reduce over the 4 pixel groups of this warp (lane bits 3, 4), then over the 4 warps in smem
+#pragma unroll
+          for (int qn = 0; qn < 4; ++qn)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float t = a4[qn][e];
+              t += __shfl_xor_sync(0xffffffffu, t, 8);
+              t += __shfl_xor_sync(0xffffffffu, t, 16);
+              a4[qn][e] = t;
+            }
+          const int aw = at >> 5;
+          if ((at & 31) < 8) {
+#pragma unroll
+            for (int qn = 0; qn < 4; ++qn)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) s_red[aw][qn][chunk * 8 + e] = a4[qn][e];
+          }
+          // corners: 4 pixels x 8 chunks = 32 threads
+          if (at < 32) {
+            const int cy = (at >> 4) & 1, cx = (at >> 3) & 1;
+            const uint4 v = ld_cg_128(hb + (size_t(cy ? p.H - 1 : 0) * p.W + (cx ? p.W - 1 : 0)) * kC + chunk * 8);
+            float* d = &s_q[kHsC00 + 2 * cy + cx][chunk * 8];
+            d[0] = bf16lo(v.x); d[1] = bf16hi(v.x); d[2] = bf16lo(v.y); d[3] = bf16hi(v.y);
+            d[4] = bf16lo(v.z); d[5] = bf16hi(v.z); d[6] = bf16lo(v.w); d[7] = bf16hi(v.w);
+          }
+          if (at < kC) s_q[kHsTotal][at] = ld_cg_f32(hs + at);
         }
-        named_bar_sync(2, kXT);
-        if (xt < 128) {
+        named_bar_sync(2, kAuxThreads);
+        for (int i = at; i < 4 * kC; i += kAuxThreads) {
+          const int qn = i >> 6, c = i & 63;
+          s_q[kHsRow0 + qn][c] = s_red[0][qn][c] + s_red[1][qn][c] + s_red[2][qn][c] + s_red[3][qn][c];
+        }
+        named_bar_sync(2, kAuxThreads);
+        // S_tap = total - excluded border row - excluded border column + corner (dy = tap/3 - 1, dx = tap%3 - 1)
+        for (int i = at; i < 9 * kC; i += kAuxThreads) {
+          const int tap = i >> 6, ci = i & 63, dy = tap / 3 - 1, dx = tap % 3 - 1;
+          float v = s_q[kHsTotal][ci];
+          if (dy == 1) v -= s_q[kHsRow0][ci];
+          if (dy == -1) v -= s_q[kHsRowL][ci];
+          if (dx == 1) v -= s_q[kHsCol0][ci];
+          if (dx == -1) v -= s_q[kHsColL][ci];
+          if (dy == 1 && dx == 1) v += s_q[kHsC00][ci];
+          if (dy == 1 && dx == -1) v += s_q[kHsC0L][ci];
+          if (dy == -1 && dx == 1) v += s_q[kHsCL0][ci];
+          if (dy == -1 && dx == -1) v += s_q[kHsCLL][ci];
+          s_S[tap][ci] = v;
+        }
+        named_bar_sync(2, kAuxThreads);
+        {  // mat-vec: thread (c, half) sums 32 input channels of all 9 taps
+          const int c = at & 63, hf = at >> 6;
           float a = 0.f;
-          for (int j = 0; j < p.R; ++j) a = fmaf(__ldg(fc2 + c * p.R + j), s_hid[u][j], a);
-          const float s = 1.f / (1.f + expf(-a));
-          s_scale[u][c] = s * p.res_scale;
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint4* wp = reinterpret_cast<const uint4*>(w2 + (size_t(tap) * kC + c) * kC + hf * 32);
+            const float* sp = &s_S[tap][hf * 32];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 w = __ldg(wp + j);
+              const float4 s0 = *reinterpret_cast<const float4*>(sp + 8 * j);
+              const float4 s1 = *reinterpret_cast<const float4*>(sp + 8 * j + 4);
+              a = fmaf(bf16lo(w.x), s0.x, a); a = fmaf(bf16hi(w.x), s0.y, a);
+              a = fmaf(bf16lo(w.y), s0.z, a); a = fmaf(bf16hi(w.y), s0.w, a);
+              a = fmaf(bf16lo(w.z), s1.x, a); a = fmaf(bf16hi(w.z), s1.y, a);
+              a = fmaf(bf16lo(w.w), s1.z, a); a = fmaf(bf16hi(w.w), s1.w, a);
+            }
+          }
+          s_part[hf][c] = a;
+        }
+        named_bar_sync(2, kAuxThreads);
+        if (at < kC) s_mean[at] = c_vec[ly.cv_bias + at] + (s_part[0][at] + s_part[1][at]) * p.inv_hw;
+        named_bar_sync(2, kAuxThreads);
+        if (at < p.R) {
+          float a = 0.f;
+          for (int k = 0; k < kC; ++k) a = fmaf(__ldg(fc0 + at * kC + k), s_mean[k], a);
+          s_hid[at] = fmaxf(a, 0.f);
+        }
+        named_bar_sync(2, kAuxThreads);
+        if (at < kC) {
+          float a = 0.f;
+          for (int j = 0; j < p.R; ++j) a = fmaf(__ldg(fc2 + at * p.R + j), s_hid[j], a);
+          const float sv = 1.f / (1.f + expf(-a));
+          s_scale[us][at] = sv * p.res_scale;
           // the CTA owning tile 0 of the image publishes the attention vector
-          if (p.se_out && (img0 + u <= img1) && (n * p.tiles_per_seg >= g_begin) && (n * p.tiles_per_seg < g_end))
-            p.se_out[(size_t(n) * (p.G * p.Bk) + ly.rcab_in) * kC + c] = s;
+          if (p.se_out && (n * p.tiles_per_seg >= g_begin) && (n * p.tiles_per_seg < g_end))
+            p.se_out[(size_t(n) * (p.G * p.Bk) + ly.rcab) * kC + at] = sv;
         }
-        named_bar_sync(1, kFrontThreads);               // also releases the TMA issuer into the box loop
+        named_bar_sync(2, kAuxThreads);
       }
+      if (at == 0) mbar_arrive(&bar_s);                  // the epilogue may now read s_scale
       DBG_LAP(d_se)
-      // ---- boxes
-      const bf16* oin = p.buf[kBufO];
-      bf16* xout = ly.xout >= 0 ? p.buf[ly.xout] : nullptr;
-      constexpr int kSteps = (kBBoxPx * 8 + kXT - 1) / kXT;            // 5 (last one: 32 threads)
-      for (int g = g_begin; g < g_end;) {
-        const BUnit u = body_unit(p, g, g_end);
-        if (!ly.fused) {
-          // every transform warp arrives once per box so the full barrier always counts 9
-          for (int j = 0; j < u.nboxes; ++j, ++gb) {
-            const uint32_t slot = gb % kBSlots, ph = (gb / kBSlots) & 1;
-            mbar_wait(&bar_empty[slot], ph ^ 1);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_full[slot]);
-          }
-        } else {
-          const int us = u.n - img0;                                     // which s_scale row
-          float sc[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) sc[e] = s_scale[us][chunk * 8 + e];
-          const int lo = kTileM * u.t0, hi = kTileM * u.t1;              // owned strip-linear range
-          // o of a box is loaded one box ahead of its use
-          uint4 ov[kSteps];
-          auto load_o = [&](int j, uint4 (&dst)[kSteps]) {
-            const int y0 = u.ra - 1 + j * kBBoxRows;
-#pragma unroll
-            for (int q = 0; q < kSteps; ++q) {
-              const int px = (q * kXT + xt) >> 3;
-              const int row = px / kPitch, col = px - row * kPitch;
-              const int iy = y0 + row, ix = col - 1;
-              const bool ok = (px < kBBoxPx) && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
-              dst[q] = ok ? ld_cg_128_hint(oin + ((size_t(u.n) * p.H + iy) * p.W + ix) * kC + chunk * 8, kPolicyEvictFirst)
-                          : make_uint4(0, 0, 0, 0);
-            }
-          };
-          load_o(0, ov);
-          for (int j = 0; j < u.nboxes; ++j, ++gb) {
-            const uint32_t slot = gb % kBSlots;
-            const int y0 = u.ra - 1 + j * kBBoxRows;
-            uint4 on[kSteps];
-            if (j + 1 < u.nboxes) load_o(j + 1, on);
-            mbar_wait(&bar_x[slot], (x_phase >> slot) & 1);              // x has landed in the slot
-            x_phase ^= 1u << slot;
-            uint8_t* dst = ring + slot * kBSlotBytes;
-            uint8_t* dst_mirror = (slot == 0 && j > 0) ? ring + kBSlots * kBSlotBytes : nullptr;
-#pragma unroll
-            for (int q = 0; q < kSteps; ++q) {
-              const int px = (q * kXT + xt) >> 3;
-              if (px < kBBoxPx) {
-                // SWIZZLE_128B: 16-byte chunk index XOR (128-byte row index of the absolute address mod 8)
-                const uint32_t lin_b = uint32_t(slot) * kBSlotBytes + uint32_t(px) * 128u;   // ring is 1024-aligned
-                const uint32_t so = uint32_t(px) * 128u + (uint32_t(chunk ^ ((lin_b >> 7) & 7)) << 4);
-                const uint4 xv = *reinterpret_cast<const uint4*>(dst + so);
-                uint4 r;
-                r.x = pack_bf16(fmaf(bf16lo(ov[q].x), sc[0], bf16lo(xv.x)), fmaf(bf16hi(ov[q].x), sc[1], bf16hi(xv.x)));
-                r.y = pack_bf16(fmaf(bf16lo(ov[q].y), sc[2], bf16lo(xv.y)), fmaf(bf16hi(ov[q].y), sc[3], bf16hi(xv.y)));
-                r.z = pack_bf16(fmaf(bf16lo(ov[q].z), sc[4], bf16lo(xv.z)), fmaf(bf16hi(ov[q].z), sc[5], bf16hi(xv.z)));
-                r.w = pack_bf16(fmaf(bf16lo(ov[q].w), sc[6], bf16lo(xv.w)), fmaf(bf16hi(ov[q].w), sc[7], bf16hi(xv.w)));
-                *reinterpret_cast<uint4*>(dst + so) = r;
-                if (dst_mirror) {
-                  const uint32_t lin_m = uint32_t(kBSlots) * kBSlotBytes + uint32_t(px) * 128u;
-                  *reinterpret_cast<uint4*>(dst_mirror + uint32_t(px) * 128u + (uint32_t(chunk ^ ((lin_m >> 7) & 7)) << 4)) = r;
-                }
-                if (xout) {
-                  const int row = px / kPitch, col = px - row * kPitch;
-                  const int iy = y0 + row, ix = col - 1;
-                  const int lin = iy * kPitch + ix;                      // strip-linear output index of the pixel
-                  if (ix >= 0 && ix < p.W && lin >= lo && lin < hi)
-                    *reinterpret_cast<uint4*>(xout + ((size_t(u.n) * p.H + iy) * p.W + ix) * kC + chunk * 8) = r;
-                }
-              }
-            }
-            fence_proxy_async_smem();          // generic-proxy smem writes -> visible to tcgen05.mma
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_full[slot]);
-#pragma unroll
-            for (int q = 0; q < kSteps; ++q) ov[q] = on[q];
-          }
-        }
-        g += u.t1 - u.t0;
-      }
-      if (ly.fused) { DBG_LAP(d_fused) } else { DBG_LAP(d_plain) }
-      // ---- this warp's global writes (x') are complete: fence, then count the warp as done
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_done);
     }
-    if (BDBG && xt == 0) {
+    if (BDBG && at == 0) {
       long long* d = p.dbg + blockIdx.x * 16;
-      d[0] = 0; d[1] = d_flag; d[2] = d_se; d[3] = d_fused; d[4] = d_plain; d[5] = clock64() - d_start;
+      d[0] = 0; d[1] = d_flag; d[2] = d_se; d[3] = 0; d[4] = 0; d[5] = clock64() - d_start;
     }
   } else if (warp < kBodyFirstEpiWarp) {
     // ============================================================ MMA issuers (2 warps)
@@ -432,7 +430,7 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
     for (int L = 0; L < p.n_layers; ++L) {
       const long long m_l0 = BDBG ? clock64() : 0;
       const long long m_full0 = m_full;
-      const bool m_is_fused = body_layer(p, L).fused != 0;
+      const bool m_is_fused = body_layer(p, L).epi == kBEpiSeResidual;
       // index (within the layer) of this warp's first / last tile
       const int first_mine = ((tile_ctr & 1) == my_parity) ? 0 : 1;
       const int last_mine = (((tile_ctr + n_tiles - 1) & 1) == my_parity) ? n_tiles - 1 : n_tiles - 2;
@@ -509,8 +507,9 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
     const int half = (warp - kBodyFirstEpiWarp) >> 2;
     const int col0 = half * CW;
     const int row_in_tile = q * 32 + lane;
+    const int et = tid - 32 * kBodyFirstEpiWarp;         // 0..255
     const bool flag_writer = (warp == kBodyFirstEpiWarp);
-    uint32_t tile_ctr = 0;
+    uint32_t tile_ctr = 0, se_layers = 0;
     long long e_wait = 0, e_done = 0, e_t = 0;
     const long long e_start = BDBG ? clock64() : 0;
     for (int L = 0; L < p.n_layers; ++L) {
@@ -519,11 +518,17 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
       const bf16* resp = ly.res >= 0 ? p.buf[ly.res] : nullptr;
       const float* cbias = c_vec + ly.cv_bias + col0;
       const float* cslope = c_vec + ly.cv_slope + col0;
+      if (ly.epi == kBEpiSeResidual) {                   // s of this layer is ready
+        mbar_wait(&bar_s, se_layers & 1);
+        ++se_layers;
+      }
       for (int g = g_begin; g < g_end;) {
         const BUnit u = body_unit(p, g, g_end);
+        const int us = u.n - img0;
         float csum[CW];
 #pragma unroll
         for (int c = 0; c < CW; ++c) csum[c] = 0.f;
+        const float sreg = (ly.epi == kBEpiSeResidual) ? s_scale[us][col0 + lane] : 0.f;   // lane <-> channel
         for (int t = u.t0; t < u.t1; ++t, ++tile_ctr) {
           const uint32_t acc = tile_ctr & (kBodyAccBufs - 1);
           if (BDBG) e_t = clock64();
@@ -547,35 +552,45 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
             float f[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) f[c] = __uint_as_float(v[c]) + cbias[16 * hp + c];
-            if (ly.epi == kEpiSum) {
-              if (valid) {
-#pragma unroll
-                for (int c = 0; c < 16; ++c) csum[16 * hp + c] += f[c];
-              }
-            } else if (ly.epi == kEpiPrelu) {
+            if (ly.epi == kBEpiPreluHsum) {
 #pragma unroll
               for (int c = 0; c < 16; ++c) f[c] = f[c] > 0.f ? f[c] : f[c] * cslope[16 * hp + c];
+            } else if (ly.epi == kBEpiSeResidual) {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) f[c] *= __shfl_sync(0xffffffffu, sreg, 16 * hp + c);
+            }
+            if (valid && ly.epi != kBEpiPreluHsum) {     // + x (RCAB residual) or + skip (group / long skip)
+              const bf16* rsd = resp + opix * kC + col0 + 16 * hp;
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint4 r = ld_cg_128_hint(rsd + 8 * j, kPolicyEvictFirst);
+                f[8 * j + 0] += bf16lo(r.x); f[8 * j + 1] += bf16hi(r.x);
+                f[8 * j + 2] += bf16lo(r.y); f[8 * j + 3] += bf16hi(r.y);
+                f[8 * j + 4] += bf16lo(r.z); f[8 * j + 5] += bf16hi(r.z);
+                f[8 * j + 6] += bf16lo(r.w); f[8 * j + 7] += bf16hi(r.w);
+              }
             }
             if (valid) {
-              if (ly.epi == kEpiResidual) {
-                const bf16* rsd = resp + opix * kC + col0 + 16 * hp;
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                  const uint4 r = ld_cg_128(rsd + 8 * j);
-                  f[8 * j + 0] += bf16lo(r.x); f[8 * j + 1] += bf16hi(r.x);
-                  f[8 * j + 2] += bf16lo(r.y); f[8 * j + 3] += bf16hi(r.y);
-                  f[8 * j + 4] += bf16lo(r.z); f[8 * j + 5] += bf16hi(r.z);
-                  f[8 * j + 6] += bf16lo(r.w); f[8 * j + 7] += bf16hi(r.w);
-                }
-              }
               uint32_t o[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) o[e] = pack_bf16(f[2 * e], f[2 * e + 1]);
               st_global_256(outp + opix * kC + col0 + 16 * hp, o);
+              if (ly.epi == kBEpiPreluHsum) {
+                // sums of the bf16-ROUNDED h (what conv2 will read): total in registers, borders in smem
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  f[2 * e] = bf16lo(o[e]);
+                  f[2 * e + 1] = bf16hi(o[e]);
+                  csum[16 * hp + 2 * e] += f[2 * e];
+                  csum[16 * hp + 2 * e + 1] += f[2 * e + 1];
+                }
+              }
             }
           }
         }
-        if (ly.epi == kEpiSum) {
+        if (ly.epi == kBEpiPreluHsum) {
+          float* hs = p.hsum + (size_t(ly.rcab) * p.B + u.n) * kC;
+          // total: reduce-scatter butterfly over the warp, lane l ends with channel col0 + l
 #pragma unroll
           for (int d = 16, len = CW; d >= 1; d >>= 1, len >>= 1) {
             const bool hi = (lane & d) != 0;
@@ -586,7 +601,7 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
               csum[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
             }
           }
-          atomicAdd(p.sums + (size_t(ly.rcab_out) * p.B + u.n) * kC + col0 + lane, csum[0]);
+          atomicAdd(hs + col0 + lane, csum[0]);
         }
         g += u.t1 - u.t0;
       }

@@ -43,6 +43,17 @@ static int check_device() {
   return FEN_OK;
 }
 
+// Developer aid: FEN_SYNC_EACH=1 synchronises after every stage of fen_forward and names the stage
+// whose kernel faulted.
+static int stage_check(const char* name, cudaStream_t st) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("FEN_SYNC_EACH"); on = (e && e[0] == '1') ? 1 : 0; }
+  if (!on) return FEN_OK;
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return fail(FEN_ECUDA, std::string("stage '") + name + "': " + cudaGetErrorString(e));
+  return FEN_OK;
+}
+
 // ===================================================================== tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -401,7 +412,7 @@ static int pack_vec(const float* src, int count, int n_grp, int groups, int perm
 
 // ===================================================================== workspace
 struct Workspace {
-  int64_t f0, x[2], h, o, grp0, grp_stride, u0, u1, sums, flags, total;
+  int64_t f0, x[2], h, o, grp0, grp_stride, u0, u1, sums, hsum, flags, total;
 };
 static void make_workspace(const Layout& L, int B, int H, int W, Workspace* ws) {
   const int64_t act = align256(int64_t(B) * H * W * 64 * 2);
@@ -413,19 +424,24 @@ static void make_workspace(const Layout& L, int B, int H, int W, Workspace* ws) 
   ws->u0 = o; o += 4 * act;
   ws->u1 = o; o += 16 * act;
   ws->sums = o; o += align256(int64_t(L.n_rcab) * B * 64 * 4);
+  ws->hsum = o; o += align256(int64_t(L.n_rcab) * B * 9 * 64 * 4);   // body kernel: 9 channel sums of h per RCAB, image
   ws->flags = o; o += 4096;   // one int per CTA of the persistent body kernel
   ws->total = o;
 }
 
 
 // ===================================================================== persistent body kernel launcher
-static bool body_kernel_usable(const Layout& L, int W) {
+static bool body_kernel_usable(const Layout& L, int B, int H, int W) {
   static int disabled = -1;
   if (disabled < 0) {
     const char* e = getenv("FEN_DISABLE_BODY_KERNEL");
     disabled = (e && e[0] == '1') ? 1 : 0;
   }
-  return !disabled && W == kStripW && L.cv_total <= kConstVecFloats && L.G <= kBodyMaxBufs - 5;
+  if (disabled || W != kStripW || L.cv_total > kConstVecFloats || L.G > kBodyMaxBufs - 5) return false;
+  // a CTA must not touch more than kBodyMaxUnits images per layer
+  const int tps = (H * kPitch + kTileM - 1) / kTileM;
+  const int tpc = (B * tps + num_sms() - 1) / num_sms();
+  return (tpc + tps - 2) / tps + 1 <= kBodyMaxUnits;
 }
 
 static int launch_body(const fen_config* cfg, const Layout& L, const Workspace& ws, uint8_t* wsb, const uint8_t* k,
@@ -461,11 +477,12 @@ static int launch_body(const fen_config* cfg, const Layout& L, const Workspace& 
   p.k_rcab0 = L.k_rcab0; p.k_rcab_stride = L.k_rcab_stride; p.k_rcab_w2 = rr.w2; p.k_rcab_fc0 = rr.fc0; p.k_rcab_fc2 = rr.fc2;
   p.k_gconv0 = L.k_gconv0; p.k_gconv_stride = L.k_gconv_stride; p.k_after = L.k_after;
   p.cv_rcab0 = L.cv_rcab0; p.cv_gconv0 = L.cv_gconv0; p.cv_after = L.cv_after;
-  p.sums = reinterpret_cast<float*>(wsb + ws.sums);
+  p.hsum = reinterpret_cast<float*>(wsb + ws.hsum);
   p.se_out = se_out;
   p.flags = reinterpret_cast<int*>(wsb + ws.flags);
   p.dbg = g_dbg;
   FEN_CUDA(cudaMemsetAsync(p.flags, 0, 4096, st));
+  FEN_CUDA(cudaMemsetAsync(p.hsum, 0, size_t(L.n_rcab) * B * 9 * 64 * 4, st));
   FEN_CUDA(cudaMemcpyToSymbolAsync(c_vec, k + L.k_cvec, size_t(L.cv_total) * 4, 0, cudaMemcpyDeviceToDevice, st));
   void* args[] = {&maps, &p};
   FEN_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(body_umma_kernel), dim3(ctas), dim3(kBodyThreads), args,
@@ -624,8 +641,10 @@ int fen_forward(const fen_config* cfg, const void* packed, const float* x, float
     return launch_conv(a, st);
   };
 
-  if (body_kernel_usable(L, W)) {
+  if ((rc = stage_check("conv_first", st))) return rc;
+  if (body_kernel_usable(L, B, H, W)) {
     if ((rc = launch_body(cfg, L, ws, wsb, k, B, H, W, se_out, st))) return rc;
+    if ((rc = stage_check("body kernel", st))) return rc;
   } else {
     const int hw = H * W;
     const int se_chunks = 32;
@@ -675,6 +694,7 @@ int fen_forward(const fen_config* cfg, const void* packed, const float* x, float
                    kEpiShuffle, 2 * H, 2 * W)))
       return rc;
   }
+  if ((rc = stage_check("upsample convs", st))) return rc;
   // conv_last + bicubic skip + clamp
   {
     ConvArgs a{};
@@ -684,6 +704,7 @@ int fen_forward(const fen_config* cfg, const void* packed, const float* x, float
     a.p.lr = x; a.p.out_f32 = out;
     if ((rc = launch_conv(a, st))) return rc;
   }
+  if ((rc = stage_check("conv_last", st))) return rc;
   return FEN_OK;
 }
 
