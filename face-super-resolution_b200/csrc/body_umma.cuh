@@ -14,17 +14,19 @@
 // linear in conv2's INPUT h:  mean(o)[c] = b2[c] + 1/HW * sum_{tap,ci} W2[c,ci,tap] * S_tap[ci], where
 // S_tap[ci] is the sum of h[ci] over the window the tap sees = (total) - (excluded border row)
 // - (excluded border column) + (corner).  The conv1 epilogue accumulates those 9 sums of the
-// bf16-rounded h per image (total, first/last row, first/last column, 4 corners); at the start of
-// the conv2 layer four auxiliary warps turn them into s (a 64x576 mat-vec + the two tiny FC layers,
-// fp32) while the first tiles' MMAs already run; the conv2 epilogue then writes
+// bf16-rounded h per image (the total; border rows / columns / corners are re-read from h, a few
+// KB per image); at the start of the conv2 layer the epilogue warps turn them into s (a 64x576
+// mat-vec + the two tiny FC layers, fp32) while the first tiles' MMAs already run into the 8
+// TMEM accumulator buffers; the conv2 epilogue then writes
 // x' = x + (0.2 s[c]) * (acc + b2[c]) directly.  o is never materialised and no elementwise pass or
 // transform producer exists: every layer is a plain TMA-fed convolution.
 //
 // Per layer the tile pipeline is the one of conv3x3_umma.cuh (ring of boxes with a mirror slot -
 // here 2-row boxes, 7 slots -, two tcgen05.mma issuer warps, 8 epilogue warps, TMEM accumulators).
-// Biases and PReLU slopes come from __constant__ memory and s through warp shuffles (the epilogue
-// must stay off shared memory, whose bandwidth the tensor core needs); the weights of the next
-// layer are loaded tap by tap as soon as the current layer has issued its last MMA on that tap.
+// The epilogue keeps bias, PReLU slope and SE scale of its 32 columns in registers (loaded once per
+// layer from __constant__ memory): it must stay off shared memory, whose bandwidth the tensor core
+// needs, and indexed constant loads per tile starve its two warps per scheduler.  The weights of the
+// next layer are loaded tap by tap as soon as the current layer has issued its last MMA on that tap.
 #pragma once
 #include "conv3x3_umma.cuh"
 
@@ -35,15 +37,13 @@ namespace fen {
 #endif
 #define BDBG (FEN_BODY_DEBUG && p.dbg)
 
-constexpr int kBodyAuxWarps = 4;                      // warps 1..4: peer flags + SE vector
 constexpr int kBodyMmaWarps = 2;
 constexpr int kBodyEpiWarps = 8;
-constexpr int kBodyFirstAuxWarp = 1;                  // warp 0: TMA issuer
-constexpr int kBodyFirstMmaWarp = 1 + kBodyAuxWarps;
+constexpr int kBodyFirstMmaWarp = 1;                  // warp 0: TMA issuer + peer-flag poller
 constexpr int kBodyFirstEpiWarp = kBodyFirstMmaWarp + kBodyMmaWarps;
-constexpr int kBodyThreads = 32 * (kBodyFirstEpiWarp + kBodyEpiWarps);   // 480
+constexpr int kBodyThreads = 32 * (kBodyFirstEpiWarp + kBodyEpiWarps);   // 352 -> up to 186 registers per thread
 constexpr int kBodyMaxUnits = 4;                      // images a CTA may touch in one layer (host caps the batch per launch)
-constexpr int kBodyAccBufs = 4;
+constexpr int kBodyAccBufs = 8;                        // 8 x 64 = all 512 TMEM columns: the MMAs can run 8 tiles ahead of the SE vector
 constexpr int kBodyWBytes = 9 * kC * kC * 2;
 // activation ring: 2-row boxes (132 px, 16 896 B; TMA SWIZZLE_128B only needs 128 B alignment, the
 // swizzle follows absolute address bits - tools/umma_probe4.cu), 7 slots + 1 mirror slot
@@ -163,6 +163,11 @@ __device__ __forceinline__ uint4 ld_cg_128_hint(const void* p, uint64_t policy) 
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(policy));
   return v;
 }
+__device__ __forceinline__ void ld_cg_256_hint(const void* p, uint64_t policy, uint32_t (&v)[8]) {
+  asm volatile("ld.global.cg.L2::cache_hint.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p), "l"(policy));
+}
 __device__ __forceinline__ void tma_load_4d_hint(const CUtensorMap* m, uint64_t* bar, uint32_t dst_smem, int c0, int c1,
                                                  int c2, int c3, uint64_t policy) {
   asm volatile(
@@ -191,17 +196,15 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
   uint8_t* w_smem = smem;
   uint8_t* ring = smem + kBodyWBytes;
   __shared__ uint64_t bar_w[9], bar_wfree[9], bar_full[kBSlots], bar_empty[kBSlots];
-  __shared__ uint64_t bar_acc_full[kBodyAccBufs], bar_acc_empty[kBodyAccBufs], bar_done, bar_s;
+  __shared__ uint64_t bar_acc_full[kBodyAccBufs], bar_acc_empty[kBodyAccBufs], bar_done, bar_flags;
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_scale[kBodyMaxUnits][kC];            // res_scale * s per image of this CTA
   __shared__ __align__(16) float s_S[9][kC];
-  __shared__ float s_q[kHsCount][kC], s_part[2][kC], s_mean[kC], s_hid[kC], s_red[kBodyAuxWarps][4][kC];
+  __shared__ __align__(16) float s_scale[kBodyMaxUnits][kC];   // res_scale * s per image of this CTA
+  __shared__ float s_q[kHsCount][kC], s_part[4][kC], s_mean[kC], s_hid[kC], s_red[kBodyEpiWarps][4][kC];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr uint32_t kTmemCols = kBodyAccBufs * N;
-  constexpr int kFrontThreads = 32 * kBodyFirstMmaWarp;   // TMA warp + aux warps (named barrier 1)
-  constexpr int kAuxThreads = 32 * kBodyAuxWarps;         // named barrier 2
-  constexpr int kEpiThreads = 32 * kBodyEpiWarps;         // named barrier 3
+  constexpr int kEpiThreads = 32 * kBodyEpiWarps;         // named barrier 1
 
   const int g_begin = blockIdx.x * p.tiles_per_cta;
   const int g_end = min(p.total_tiles, g_begin + p.tiles_per_cta);
@@ -217,7 +220,7 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
     for (int i = 0; i < kBSlots; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], kBodyMmaWarps); }
     for (int i = 0; i < kBodyAccBufs; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], kBodyEpiWarps); }
     mbar_init(&bar_done, kBodyEpiWarps);
-    mbar_init(&bar_s, 1);
+    mbar_init(&bar_flags, 1);
     fence_mbar_init();
     tma_prefetch_desc(&maps.w);
   }
@@ -228,7 +231,7 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
   if (n_tiles <= 0) return;   // never happens with the host's grid sizing (all CTAs have tiles)
 
   if (warp == 0) {
-    // ============================================================ TMA issuer (one lane)
+    // ============================================================ TMA issuer + peer-flag poller
     uint32_t gb = 0;   // running box counter
     for (int L = 0; L < p.n_layers; ++L) {
       const BodyLayer ly = body_layer(p, L);
@@ -241,7 +244,15 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
         }
       }
       __syncwarp();
-      if (L > 0) named_bar_sync(1, kFrontThreads);       // peers have finished layer L-1 (polled by warp 1)
+      // wait until every peer finished layer L-1 (their outputs are my inputs / halos, and my outputs of
+      // this layer overwrite buffers they were still reading in L-1)
+      if (L > 0) {
+        for (int k = peer0 + lane; k <= peer1; k += 32)
+          while (ld_acquire_gpu(p.flags + k) < L) { __nanosleep(32); }
+        __syncwarp();
+        fence_proxy_async_all();
+        if (lane == 0) mbar_arrive(&bar_flags);          // the epilogue may read peers' h / sums (SE vector)
+      }
       if (lane == 0) {
         const uint64_t pol = ly.last_use ? kPolicyEvictFirst : 0x1000000000000000ull;
         for (int g = g_begin; g < g_end;) {
@@ -261,159 +272,6 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
         }
       }
       __syncwarp();
-    }
-  } else if (warp < kBodyFirstMmaWarp) {
-    // ============================================================ aux warps (128 threads): peer flags + SE vector
-    const int at = tid - 32 * kBodyFirstAuxWarp;        // 0..127
-    long long d_flag = 0, d_se = 0, d_t = BDBG ? clock64() : 0;
-    const long long d_start = d_t;
-#define DBG_LAP(acc) if (BDBG) { const long long n_ = clock64(); acc += n_ - d_t; d_t = n_; }
-    for (int L = 0; L < p.n_layers; ++L) {
-      const BodyLayer ly = body_layer(p, L);
-      // ---- wait until every peer finished layer L-1 (their outputs are my inputs / halos, and my
-      //      outputs of this layer overwrite buffers they were still reading in L-1)
-      if (L > 0) {
-        if (warp == kBodyFirstAuxWarp) {
-          for (int k = peer0 + lane; k <= peer1; k += 32)
-            while (ld_acquire_gpu(p.flags + k) < L) { __nanosleep(32); }
-          __syncwarp();
-          fence_proxy_async_all();
-        }
-        named_bar_sync(1, kFrontThreads);
-      }
-      DBG_LAP(d_flag)
-      if (ly.epi != kBEpiSeResidual) continue;
-#ifdef FEN_EXP_NO_SE
-      if (at == 0) mbar_arrive(&bar_s);
-      continue;
-#endif
-      // ---- SE vector of every image of this CTA, from the sums of h that the conv1 layer left
-      const bf16* w2 = reinterpret_cast<const bf16*>(p.packed + ly.w_off);        // [tap][c][ci] bf16
-      const uint8_t* rec = p.packed + p.k_rcab0 + int64_t(ly.rcab) * p.k_rcab_stride;
-      const float* fc0 = reinterpret_cast<const float*>(rec + p.k_rcab_fc0);
-      const float* fc2 = reinterpret_cast<const float*>(rec + p.k_rcab_fc2);
-      for (int n = img0; n <= img1; ++n) {
-        const int us = n - img0;
-        // total sum of h: accumulated by the conv1 epilogue; the border rows / columns / corners are
-        // re-read here from h itself (a few KB per image, L2-resident) - atomics from the epilogue,
-        // shared or global, would queue behind the tensor core's operand traffic
-        const float* hs = p.hsum + (size_t(ly.rcab) * p.B + n) * kC;
-        const bf16* hb = p.buf[kBufH] + size_t(n) * p.H * p.W * kC;
-        {
-          const int chunk = at & 7, pg = at >> 3;            // 8 channels of every 16th border pixel
-          float a4[4][8];
-#pragma unroll
-          for (int qn = 0; qn < 4; ++qn)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) a4[qn][e] = 0.f;
-          const int npix = max(p.H, p.W);
-          for (int px = pg; px < npix; px += 16) {
-            uint4 v[4];
-            v[0] = (px < p.W) ? ld_cg_128(hb + (size_t(0) * p.W + px) * kC + chunk * 8) : make_uint4(0, 0, 0, 0);
-            v[1] = (px < p.W) ? ld_cg_128(hb + (size_t(p.H - 1) * p.W + px) * kC + chunk * 8) : make_uint4(0, 0, 0, 0);
-            v[2] = (px < p.H) ? ld_cg_128(hb + (size_t(px) * p.W + 0) * kC + chunk * 8) : make_uint4(0, 0, 0, 0);
-            v[3] = (px < p.H) ? ld_cg_128(hb + (size_t(px) * p.W + p.W - 1) * kC + chunk * 8) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-            for (int qn = 0; qn < 4; ++qn) {
-              a4[qn][0] += bf16lo(v[qn].x); a4[qn][1] += bf16hi(v[qn].x);
-              a4[qn][2] += bf16lo(v[qn].y); a4[qn][3] += bf16hi(v[qn].y);
-              a4[qn][4] += bf16lo(v[qn].z); a4[qn][5] += bf16hi(v[qn].z);
-              a4[qn][6] += bf16lo(v[qn].w); a4[qn][7] += bf16hi(v[qn].w);
-            }
-          }
-          // reduce over the 4 pixel groups of this warp (lane bits 3, 4), then over the 4 warps in smem
-#pragma unroll
-          for (int qn = 0; qn < 4; ++qn)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float t = a4[qn][e];
-              t += __shfl_xor_sync(0xffffffffu, t, 8);
-              t += __shfl_xor_sync(0xffffffffu, t, 16);
-              a4[qn][e] = t;
-            }
-          const int aw = at >> 5;
-          if ((at & 31) < 8) {
-#pragma unroll
-            for (int qn = 0; qn < 4; ++qn)
-#pragma unroll
-              for (int e = 0; e < 8; ++e) s_red[aw][qn][chunk * 8 + e] = a4[qn][e];
-          }
-          // corners: 4 pixels x 8 chunks = 32 threads
-          if (at < 32) {
-            const int cy = (at >> 4) & 1, cx = (at >> 3) & 1;
-            const uint4 v = ld_cg_128(hb + (size_t(cy ? p.H - 1 : 0) * p.W + (cx ? p.W - 1 : 0)) * kC + chunk * 8);
-            float* d = &s_q[kHsC00 + 2 * cy + cx][chunk * 8];
-            d[0] = bf16lo(v.x); d[1] = bf16hi(v.x); d[2] = bf16lo(v.y); d[3] = bf16hi(v.y);
-            d[4] = bf16lo(v.z); d[5] = bf16hi(v.z); d[6] = bf16lo(v.w); d[7] = bf16hi(v.w);
-          }
-          if (at < kC) s_q[kHsTotal][at] = ld_cg_f32(hs + at);
-        }
-        named_bar_sync(2, kAuxThreads);
-        for (int i = at; i < 4 * kC; i += kAuxThreads) {
-          const int qn = i >> 6, c = i & 63;
-          s_q[kHsRow0 + qn][c] = s_red[0][qn][c] + s_red[1][qn][c] + s_red[2][qn][c] + s_red[3][qn][c];
-        }
-        named_bar_sync(2, kAuxThreads);
-        // S_tap = total - excluded border row - excluded border column + corner (dy = tap/3 - 1, dx = tap%3 - 1)
-        for (int i = at; i < 9 * kC; i += kAuxThreads) {
-          const int tap = i >> 6, ci = i & 63, dy = tap / 3 - 1, dx = tap % 3 - 1;
-          float v = s_q[kHsTotal][ci];
-          if (dy == 1) v -= s_q[kHsRow0][ci];
-          if (dy == -1) v -= s_q[kHsRowL][ci];
-          if (dx == 1) v -= s_q[kHsCol0][ci];
-          if (dx == -1) v -= s_q[kHsColL][ci];
-          if (dy == 1 && dx == 1) v += s_q[kHsC00][ci];
-          if (dy == 1 && dx == -1) v += s_q[kHsC0L][ci];
-          if (dy == -1 && dx == 1) v += s_q[kHsCL0][ci];
-          if (dy == -1 && dx == -1) v += s_q[kHsCLL][ci];
-          s_S[tap][ci] = v;
-        }
-        named_bar_sync(2, kAuxThreads);
-        {  // mat-vec: thread (c, half) sums 32 input channels of all 9 taps
-          const int c = at & 63, hf = at >> 6;
-          float a = 0.f;
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint4* wp = reinterpret_cast<const uint4*>(w2 + (size_t(tap) * kC + c) * kC + hf * 32);
-            const float* sp = &s_S[tap][hf * 32];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 w = __ldg(wp + j);
-              const float4 s0 = *reinterpret_cast<const float4*>(sp + 8 * j);
-              const float4 s1 = *reinterpret_cast<const float4*>(sp + 8 * j + 4);
-              a = fmaf(bf16lo(w.x), s0.x, a); a = fmaf(bf16hi(w.x), s0.y, a);
-              a = fmaf(bf16lo(w.y), s0.z, a); a = fmaf(bf16hi(w.y), s0.w, a);
-              a = fmaf(bf16lo(w.z), s1.x, a); a = fmaf(bf16hi(w.z), s1.y, a);
-              a = fmaf(bf16lo(w.w), s1.z, a); a = fmaf(bf16hi(w.w), s1.w, a);
-            }
-          }
-          s_part[hf][c] = a;
-        }
-        named_bar_sync(2, kAuxThreads);
-        if (at < kC) s_mean[at] = c_vec[ly.cv_bias + at] + (s_part[0][at] + s_part[1][at]) * p.inv_hw;
-        named_bar_sync(2, kAuxThreads);
-        if (at < p.R) {
-          float a = 0.f;
-          for (int k = 0; k < kC; ++k) a = fmaf(__ldg(fc0 + at * kC + k), s_mean[k], a);
-          s_hid[at] = fmaxf(a, 0.f);
-        }
-        named_bar_sync(2, kAuxThreads);
-        if (at < kC) {
-          float a = 0.f;
-          for (int j = 0; j < p.R; ++j) a = fmaf(__ldg(fc2 + at * p.R + j), s_hid[j], a);
-          const float sv = 1.f / (1.f + expf(-a));
-          s_scale[us][at] = sv * p.res_scale;
-          // the CTA owning tile 0 of the image publishes the attention vector
-          if (p.se_out && (n * p.tiles_per_seg >= g_begin) && (n * p.tiles_per_seg < g_end))
-            p.se_out[(size_t(n) * (p.G * p.Bk) + ly.rcab) * kC + at] = sv;
-        }
-        named_bar_sync(2, kAuxThreads);
-      }
-      if (at == 0) mbar_arrive(&bar_s);                  // the epilogue may now read s_scale
-      DBG_LAP(d_se)
-    }
-    if (BDBG && at == 0) {
-      long long* d = p.dbg + blockIdx.x * 16;
-      d[0] = 0; d[1] = d_flag; d[2] = d_se; d[3] = 0; d[4] = 0; d[5] = clock64() - d_start;
     }
   } else if (warp < kBodyFirstEpiWarp) {
     // ============================================================ MMA issuers (2 warps)
@@ -497,93 +355,241 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
     }
     if (BDBG && leader && warp == kBodyFirstMmaWarp) {
       long long* d = p.dbg + blockIdx.x * 16;
-      d[13] = m_fl; d[14] = m_pl; d[15] = m_ffull;
+      d[15] = m_fl;
       d[6] = m_acc; d[7] = m_full; d[8] = m_issue; d[9] = clock64() - m_start;
     }
   } else {
-    // ============================================================ epilogue (8 warps)
+    // ============================================================ epilogue (8 warps, 256 threads)
     constexpr int CW = 32;
     const int q = warp & 3;
     const int half = (warp - kBodyFirstEpiWarp) >> 2;
     const int col0 = half * CW;
     const int row_in_tile = q * 32 + lane;
     const int et = tid - 32 * kBodyFirstEpiWarp;         // 0..255
+    const int ew = et >> 5;
     const bool flag_writer = (warp == kBodyFirstEpiWarp);
-    uint32_t tile_ctr = 0, se_layers = 0;
-    long long e_wait = 0, e_done = 0, e_t = 0;
+    uint32_t tile_ctr = 0;
+    long long e_wait = 0, e_done = 0, e_t = 0, e_swait = 0, e_c2 = 0, e_c2w = 0, e_c1 = 0, e_c1w = 0, e_se = 0;
     const long long e_start = BDBG ? clock64() : 0;
     for (int L = 0; L < p.n_layers; ++L) {
       const BodyLayer ly = body_layer(p, L);
       bf16* outp = p.buf[ly.out];
       const bf16* resp = ly.res >= 0 ? p.buf[ly.res] : nullptr;
-      const float* cbias = c_vec + ly.cv_bias + col0;
-      const float* cslope = c_vec + ly.cv_slope + col0;
-      if (ly.epi == kBEpiSeResidual) {                   // s of this layer is ready
-        mbar_wait(&bar_s, se_layers & 1);
-        ++se_layers;
+      // per-layer constants of this thread's 32 columns, in registers
+      float bias[CW], slope[CW];
+#pragma unroll
+      for (int j = 0; j < CW / 4; ++j) {
+        const float4 b4 = *reinterpret_cast<const float4*>(c_vec + ly.cv_bias + col0 + 4 * j);
+        bias[4 * j] = b4.x; bias[4 * j + 1] = b4.y; bias[4 * j + 2] = b4.z; bias[4 * j + 3] = b4.w;
       }
+      if (ly.epi == kBEpiPreluHsum) {
+#pragma unroll
+        for (int j = 0; j < CW / 4; ++j) {
+          const float4 s4 = *reinterpret_cast<const float4*>(c_vec + ly.cv_slope + col0 + 4 * j);
+          slope[4 * j] = s4.x; slope[4 * j + 1] = s4.y; slope[4 * j + 2] = s4.z; slope[4 * j + 3] = s4.w;
+        }
+      }
+      if (ly.epi == kBEpiSeResidual) {
+        // ---- SE vector of every image of this CTA, from the sums of h that the conv1 layer left
+        if (BDBG) e_t = clock64();
+        mbar_wait(&bar_flags, (L - 1) & 1);              // peers have finished the conv1 layer
+        if (BDBG) { const long long n_ = clock64(); e_swait += n_ - e_t; e_t = n_; }
+        const bf16* w2 = reinterpret_cast<const bf16*>(p.packed + ly.w_off);        // [tap][c][ci] bf16
+        const uint8_t* rec = p.packed + p.k_rcab0 + int64_t(ly.rcab) * p.k_rcab_stride;
+        const float* fc0 = reinterpret_cast<const float*>(rec + p.k_rcab_fc0);
+        const float* fc2 = reinterpret_cast<const float*>(rec + p.k_rcab_fc2);
+        for (int n = img0; n <= img1; ++n) {
+          const int us = n - img0;
+          // total sum of h: accumulated by the conv1 epilogue; the border rows / columns / corners are
+          // re-read here from h itself (a few KB per image, L2-resident) - atomics from the epilogue,
+          // shared or global, would queue behind the tensor core's operand traffic
+          const float* hs = p.hsum + (size_t(ly.rcab) * p.B + n) * kC;
+          const bf16* hb = p.buf[kBufH] + size_t(n) * p.H * p.W * kC;
+          {
+            const int chunk = et & 7, pg = et >> 3;          // 8 channels of every 32nd border pixel
+            float a4[4][8];
+#pragma unroll
+            for (int qn = 0; qn < 4; ++qn)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) a4[qn][e] = 0.f;
+            const int npix = max(p.H, p.W);
+            for (int px = pg; px < npix; px += 32) {
+              uint4 v[4];
+              v[0] = (px < p.W) ? ld_cg_128(hb + (size_t(0) * p.W + px) * kC + chunk * 8) : make_uint4(0, 0, 0, 0);
+              v[1] = (px < p.W) ? ld_cg_128(hb + (size_t(p.H - 1) * p.W + px) * kC + chunk * 8) : make_uint4(0, 0, 0, 0);
+              v[2] = (px < p.H) ? ld_cg_128(hb + (size_t(px) * p.W + 0) * kC + chunk * 8) : make_uint4(0, 0, 0, 0);
+              v[3] = (px < p.H) ? ld_cg_128(hb + (size_t(px) * p.W + p.W - 1) * kC + chunk * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+              for (int qn = 0; qn < 4; ++qn) {
+                a4[qn][0] += bf16lo(v[qn].x); a4[qn][1] += bf16hi(v[qn].x);
+                a4[qn][2] += bf16lo(v[qn].y); a4[qn][3] += bf16hi(v[qn].y);
+                a4[qn][4] += bf16lo(v[qn].z); a4[qn][5] += bf16hi(v[qn].z);
+                a4[qn][6] += bf16lo(v[qn].w); a4[qn][7] += bf16hi(v[qn].w);
+              }
+            }
+            // reduce over the 4 pixel groups of this warp (lane bits 3, 4), then over the 8 warps in smem
+#pragma unroll
+            for (int qn = 0; qn < 4; ++qn)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float t = a4[qn][e];
+                t += __shfl_xor_sync(0xffffffffu, t, 8);
+                t += __shfl_xor_sync(0xffffffffu, t, 16);
+                a4[qn][e] = t;
+              }
+            if (lane < 8) {
+#pragma unroll
+              for (int qn = 0; qn < 4; ++qn)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s_red[ew][qn][chunk * 8 + e] = a4[qn][e];
+            }
+            // corners: 4 pixels x 8 chunks = 32 threads
+            if (et < 32) {
+              const int cy = (et >> 4) & 1, cx = (et >> 3) & 1;
+              const uint4 v = ld_cg_128(hb + (size_t(cy ? p.H - 1 : 0) * p.W + (cx ? p.W - 1 : 0)) * kC + chunk * 8);
+              float* d = &s_q[kHsC00 + 2 * cy + cx][chunk * 8];
+              d[0] = bf16lo(v.x); d[1] = bf16hi(v.x); d[2] = bf16lo(v.y); d[3] = bf16hi(v.y);
+              d[4] = bf16lo(v.z); d[5] = bf16hi(v.z); d[6] = bf16lo(v.w); d[7] = bf16hi(v.w);
+            }
+            if (et < kC) s_q[kHsTotal][et] = ld_cg_f32(hs + et);
+          }
+          named_bar_sync(1, kEpiThreads);
+          {
+            const int qn = et >> 6, c = et & 63;           // 4 border quantities x 64 channels = 256 threads
+            float t = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < kBodyEpiWarps; ++w8) t += s_red[w8][qn][c];
+            s_q[kHsRow0 + qn][c] = t;
+          }
+          named_bar_sync(1, kEpiThreads);
+          // S_tap = total - excluded border row - excluded border column + corner (dy = tap/3 - 1, dx = tap%3 - 1)
+          for (int i = et; i < 9 * kC; i += kEpiThreads) {
+            const int tap = i >> 6, ci = i & 63, dy = tap / 3 - 1, dx = tap % 3 - 1;
+            float v = s_q[kHsTotal][ci];
+            if (dy == 1) v -= s_q[kHsRow0][ci];
+            if (dy == -1) v -= s_q[kHsRowL][ci];
+            if (dx == 1) v -= s_q[kHsCol0][ci];
+            if (dx == -1) v -= s_q[kHsColL][ci];
+            if (dy == 1 && dx == 1) v += s_q[kHsC00][ci];
+            if (dy == 1 && dx == -1) v += s_q[kHsC0L][ci];
+            if (dy == -1 && dx == 1) v += s_q[kHsCL0][ci];
+            if (dy == -1 && dx == -1) v += s_q[kHsCLL][ci];
+            s_S[tap][ci] = v;
+          }
+          named_bar_sync(1, kEpiThreads);
+          {  // mat-vec: thread (c, quarter) sums 16 input channels of all 9 taps
+            const int c = et & 63, qt = et >> 6;
+            float a = 0.f;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint4* wp = reinterpret_cast<const uint4*>(w2 + (size_t(tap) * kC + c) * kC + qt * 16);
+              const float* sp = &s_S[tap][qt * 16];
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint4 w = __ldg(wp + j);
+                const float4 s0 = *reinterpret_cast<const float4*>(sp + 8 * j);
+                const float4 s1 = *reinterpret_cast<const float4*>(sp + 8 * j + 4);
+                a = fmaf(bf16lo(w.x), s0.x, a); a = fmaf(bf16hi(w.x), s0.y, a);
+                a = fmaf(bf16lo(w.y), s0.z, a); a = fmaf(bf16hi(w.y), s0.w, a);
+                a = fmaf(bf16lo(w.z), s1.x, a); a = fmaf(bf16hi(w.z), s1.y, a);
+                a = fmaf(bf16lo(w.w), s1.z, a); a = fmaf(bf16hi(w.w), s1.w, a);
+              }
+            }
+            s_part[qt][c] = a;
+          }
+          named_bar_sync(1, kEpiThreads);
+          if (et < kC)
+            s_mean[et] = c_vec[ly.cv_bias + et] + (s_part[0][et] + s_part[1][et] + s_part[2][et] + s_part[3][et]) * p.inv_hw;
+          named_bar_sync(1, kEpiThreads);
+          if (et < p.R) {
+            float a = 0.f;
+            for (int k = 0; k < kC; ++k) a = fmaf(__ldg(fc0 + et * kC + k), s_mean[k], a);
+            s_hid[et] = fmaxf(a, 0.f);
+          }
+          named_bar_sync(1, kEpiThreads);
+          if (et < kC) {
+            float a = 0.f;
+            for (int j = 0; j < p.R; ++j) a = fmaf(__ldg(fc2 + et * p.R + j), s_hid[j], a);
+            const float sv = 1.f / (1.f + expf(-a));
+            s_scale[us][et] = sv * p.res_scale;
+            // the CTA owning tile 0 of the image publishes the attention vector
+            if (p.se_out && (n * p.tiles_per_seg >= g_begin) && (n * p.tiles_per_seg < g_end))
+              p.se_out[(size_t(n) * (p.G * p.Bk) + ly.rcab) * kC + et] = sv;
+          }
+          named_bar_sync(1, kEpiThreads);
+        }
+        if (BDBG) e_se += clock64() - e_t;
+      }
+      const long long e_l0 = BDBG ? clock64() : 0;
+      const long long e_w0 = e_wait;
       for (int g = g_begin; g < g_end;) {
         const BUnit u = body_unit(p, g, g_end);
-        const int us = u.n - img0;
         float csum[CW];
 #pragma unroll
         for (int c = 0; c < CW; ++c) csum[c] = 0.f;
-        const float sreg = (ly.epi == kBEpiSeResidual) ? s_scale[us][col0 + lane] : 0.f;   // lane <-> channel
+        if (ly.epi == kBEpiSeResidual) {                  // `slope` doubles as the SE scale of this image
+          const int us = u.n - img0;
+#pragma unroll
+          for (int j = 0; j < CW / 4; ++j) {
+            const float4 s4 = *reinterpret_cast<const float4*>(&s_scale[us][col0 + 4 * j]);
+            slope[4 * j] = s4.x; slope[4 * j + 1] = s4.y; slope[4 * j + 2] = s4.z; slope[4 * j + 3] = s4.w;
+          }
+        }
         for (int t = u.t0; t < u.t1; ++t, ++tile_ctr) {
           const uint32_t acc = tile_ctr & (kBodyAccBufs - 1);
-          if (BDBG) e_t = clock64();
-          mbar_wait(&bar_acc_full[acc], (tile_ctr / kBodyAccBufs) & 1);
-          if (BDBG) e_wait += clock64() - e_t;
-          tc_fence_after();
           const int lin = kTileM * t + row_in_tile;
           const int y = lin / kPitch, x = lin - y * kPitch;
           const bool valid = (x < kStripW) && (y < p.H);
           const size_t opix = (size_t(u.n) * p.H + y) * p.W + x;
+          // residual / skip values of this pixel: requested before waiting for the accumulator so the
+          // L2 round trip overlaps the MMAs of the tile
+          uint32_t rv[16];                          // 32 bf16, two 256-bit loads (one L1 line lookup each per lane)
+          if (valid && ly.epi != kBEpiPreluHsum) {
+            const bf16* rsd = resp + opix * kC + col0;
+            ld_cg_256_hint(rsd, kPolicyEvictFirst, *reinterpret_cast<uint32_t(*)[8]>(&rv[0]));
+            ld_cg_256_hint(rsd + 16, kPolicyEvictFirst, *reinterpret_cast<uint32_t(*)[8]>(&rv[8]));
+          } else {
 #pragma unroll
-          for (int hp = 0; hp < 2; ++hp) {      // two passes of 16 columns keep the live register set small
-            uint32_t v[16];
-            tmem_ld_32x16(tmem_base + acc * N + col0 + 16 * hp + (uint32_t(q * 32) << 16), v);
-            tmem_ld_wait();
-            if (hp == 1) {                      // accumulator fully read: hand it back to the MMA issuers
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&bar_acc_empty[acc]);
+            for (int j = 0; j < 16; ++j) rv[j] = 0u;
+          }
+          if (BDBG) e_t = clock64();
+          mbar_wait(&bar_acc_full[acc], (tile_ctr / kBodyAccBufs) & 1);
+          if (BDBG) e_wait += clock64() - e_t;
+          tc_fence_after();
+          uint32_t v[CW];
+          tmem_ld_32x32(tmem_base + acc * N + col0 + (uint32_t(q * 32) << 16), v);
+          tmem_ld_wait();
+          tc_fence_before();                       // accumulator read: hand it back to the MMA issuers
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_acc_empty[acc]);
+          float f[CW];
+#pragma unroll
+          for (int c = 0; c < CW; ++c) f[c] = __uint_as_float(v[c]) + bias[c];
+          if (ly.epi == kBEpiPreluHsum) {
+#pragma unroll
+            for (int c = 0; c < CW; ++c) f[c] = fmaxf(f[c], 0.f) + slope[c] * fminf(f[c], 0.f);
+          } else {
+            if (ly.epi == kBEpiSeResidual) {
+#pragma unroll
+              for (int c = 0; c < CW; ++c) f[c] *= slope[c];
             }
-            float f[16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) f[c] = __uint_as_float(v[c]) + cbias[16 * hp + c];
-            if (ly.epi == kBEpiPreluHsum) {
-#pragma unroll
-              for (int c = 0; c < 16; ++c) f[c] = f[c] > 0.f ? f[c] : f[c] * cslope[16 * hp + c];
-            } else if (ly.epi == kBEpiSeResidual) {
-#pragma unroll
-              for (int c = 0; c < 16; ++c) f[c] *= __shfl_sync(0xffffffffu, sreg, 16 * hp + c);
+            for (int j = 0; j < 16; ++j) {          // + x (RCAB residual) or + skip (group / long skip)
+              f[2 * j] += bf16lo(rv[j]);
+              f[2 * j + 1] += bf16hi(rv[j]);
             }
-            if (valid && ly.epi != kBEpiPreluHsum) {     // + x (RCAB residual) or + skip (group / long skip)
-              const bf16* rsd = resp + opix * kC + col0 + 16 * hp;
+          }
+          if (valid) {
+            uint32_t o[16];
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const uint4 r = ld_cg_128_hint(rsd + 8 * j, kPolicyEvictFirst);
-                f[8 * j + 0] += bf16lo(r.x); f[8 * j + 1] += bf16hi(r.x);
-                f[8 * j + 2] += bf16lo(r.y); f[8 * j + 3] += bf16hi(r.y);
-                f[8 * j + 4] += bf16lo(r.z); f[8 * j + 5] += bf16hi(r.z);
-                f[8 * j + 6] += bf16lo(r.w); f[8 * j + 7] += bf16hi(r.w);
-              }
-            }
-            if (valid) {
-              uint32_t o[8];
+            for (int e = 0; e < 16; ++e) o[e] = pack_bf16(f[2 * e], f[2 * e + 1]);
+            st_global_256(outp + opix * kC + col0, *reinterpret_cast<uint32_t(*)[8]>(&o[0]));
+            st_global_256(outp + opix * kC + col0 + 16, *reinterpret_cast<uint32_t(*)[8]>(&o[8]));
+            if (ly.epi == kBEpiPreluHsum) {          // sum of the bf16-ROUNDED h (what conv2 will read)
 #pragma unroll
-              for (int e = 0; e < 8; ++e) o[e] = pack_bf16(f[2 * e], f[2 * e + 1]);
-              st_global_256(outp + opix * kC + col0 + 16 * hp, o);
-              if (ly.epi == kBEpiPreluHsum) {
-                // sums of the bf16-ROUNDED h (what conv2 will read): total in registers, borders in smem
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  f[2 * e] = bf16lo(o[e]);
-                  f[2 * e + 1] = bf16hi(o[e]);
-                  csum[16 * hp + 2 * e] += f[2 * e];
-                  csum[16 * hp + 2 * e + 1] += f[2 * e + 1];
-                }
+              for (int e = 0; e < 16; ++e) {
+                csum[2 * e] += bf16lo(o[e]);
+                csum[2 * e + 1] += bf16hi(o[e]);
               }
             }
           }
@@ -605,6 +611,10 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
         }
         g += u.t1 - u.t0;
       }
+      if (BDBG) {
+        if (ly.epi == kBEpiSeResidual) { e_c2 += clock64() - e_l0; e_c2w += e_wait - e_w0; }
+        else { e_c1 += clock64() - e_l0; e_c1w += e_wait - e_w0; }
+      }
       // ---- layer done for this warp: make its global writes visible, then publish the CTA's flag
       __threadfence();
       __syncwarp();
@@ -624,6 +634,7 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
     if (BDBG && flag_writer && lane == 0) {
       long long* d = p.dbg + blockIdx.x * 16;
       d[10] = e_wait; d[11] = e_done; d[12] = clock64() - e_start;
+      d[0] = e_swait; d[2] = e_se; d[3] = e_c2; d[4] = e_c2w; d[13] = e_c1; d[14] = e_c1w;
     }
   }
 

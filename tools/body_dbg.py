@@ -16,12 +16,11 @@ with torch.no_grad():
     lib.fen_debug_set_counters(ctypes.c_void_p(dbg.data_ptr()))
     m(x); torch.cuda.synchronize()
     lib.fen_debug_set_counters(None)
-d = dbg.cpu().double(); d = d[d[:, 5] > 0]
-names = ["prod wait wfree", "prod wait flags", "prod SE compute", "prod fused boxes", "prod plain/other", "prod total",
-         "mma wait acc_empty", "mma wait full/w", "mma issue", "mma total", "epi wait acc_full", "epi wait done", "epi total", "mma fused layers", "mma plain layers", "mma fused wait full"]
-print(f"{len(d)} CTAs, 127 layers; cycles per layer (mean over CTAs / max CTA):")
+d = dbg.cpu().double(); d = d[d[:, 12] > 0]
+names = ["epi wait flags", "(unused)", "epi SE compute", "epi conv2 tile loops", "epi conv2 acc waits", "aux total",
+         "mma wait acc_empty", "mma wait full/w", "mma issue", "mma total", "epi wait acc_full", "epi wait done", "epi total",
+         "epi other tile loops", "epi other acc waits", "mma conv2 layers"]
+print(f"{len(d)} CTAs, 127 layers (60 conv2 = SE layers, 67 others); cycles per layer, mean over CTAs:")
 for i, n in enumerate(names):
-    print(f"  {n:20s} {d[:, i].mean().item() / 127:9.0f} {d[:, i].max().item() / 127:9.0f}")
-nf = 6 * 10  # fused layers: 9 conv1 + 1 group conv per group
-print(f"per FUSED layer (60): mma {d[:, 13].mean().item() / nf:.0f} cycles (waiting for data {d[:, 15].mean().item() / nf:.0f}); "
-      f"per PLAIN layer (67): mma {d[:, 14].mean().item() / 67:.0f} (waiting {(d[:, 7] - d[:, 15]).mean().item() / 67:.0f})")
+    div = 60 if i in (0, 2, 3, 4, 15) else 67 if i in (13, 14) else 127
+    print(f"  {n:22s} {d[:, i].mean().item() / div:9.0f}   (per {'conv2 layer' if div == 60 else 'other layer' if div == 67 else 'layer'})")
