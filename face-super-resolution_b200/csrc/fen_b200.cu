@@ -412,7 +412,7 @@ static int pack_vec(const float* src, int count, int n_grp, int groups, int perm
 
 // ===================================================================== workspace
 struct Workspace {
-  int64_t f0, x[2], h, o, grp0, grp_stride, u0, u1, sums, hsum, flags, total;
+  int64_t f0, x[2], h, o, grp0, grp_stride, u0, u1, sums, hsum, flags, scratch, total;
 };
 static void make_workspace(const Layout& L, int B, int H, int W, Workspace* ws) {
   const int64_t act = align256(int64_t(B) * H * W * 64 * 2);
@@ -426,6 +426,7 @@ static void make_workspace(const Layout& L, int B, int H, int W, Workspace* ws) 
   ws->sums = o; o += align256(int64_t(L.n_rcab) * B * 64 * 4);
   ws->hsum = o; o += align256(int64_t(L.n_rcab) * B * 9 * 64 * 4);   // body kernel: 9 channel sums of h per RCAB, image
   ws->flags = o; o += 4096;   // one int per CTA of the persistent body kernel
+  ws->scratch = o; o += align256(int64_t(160) * kScrFloats * 4);   // per-CTA SE work area
   ws->total = o;
 }
 
@@ -480,6 +481,7 @@ static int launch_body(const fen_config* cfg, const Layout& L, const Workspace& 
   p.hsum = reinterpret_cast<float*>(wsb + ws.hsum);
   p.se_out = se_out;
   p.flags = reinterpret_cast<int*>(wsb + ws.flags);
+  p.scratch = reinterpret_cast<float*>(wsb + ws.scratch);
   p.dbg = g_dbg;
   FEN_CUDA(cudaMemsetAsync(p.flags, 0, 4096, st));
   FEN_CUDA(cudaMemsetAsync(p.hsum, 0, size_t(L.n_rcab) * B * 9 * 64 * 4, st));
