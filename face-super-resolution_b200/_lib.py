@@ -36,6 +36,8 @@ SIGNATURES = {
                                   C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fen_pack_conv3x3": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "fen_last_launch_count": (C.c_int, []),
+    "fen_profile_body": (C.c_int, [C.c_int]),
+    "fen_last_body_ms": (C.c_float, []),
 }
 
 _lib = None

@@ -36,21 +36,14 @@ namespace fen {
 #define FEN_BODY_DEBUG 0   // 1: per-CTA cycle counters into BodyParams::dbg (developer builds)
 #endif
 #define BDBG (FEN_BODY_DEBUG && p.dbg)
+// timeline trace (FEN_BODY_DEBUG=2): event e of layer L of CTA 70 -> dbg[4096 + L*16 + e]
+#define BTRACE(L, e) do { if (FEN_BODY_DEBUG == 2 && p.dbg && blockIdx.x == 70) p.dbg[4096 + (L) * 16 + (e)] = clock64(); } while (0)
 
 constexpr int kBodyMmaWarps = 2;
 constexpr int kBodyEpiWarps = 8;
 constexpr int kBodyFirstMmaWarp = 1;                  // warp 0: TMA issuer + peer-flag poller
 constexpr int kBodyFirstEpiWarp = kBodyFirstMmaWarp + kBodyMmaWarps;
 constexpr int kBodyThreads = 32 * (kBodyFirstEpiWarp + kBodyEpiWarps);   // 352 -> up to 186 registers per thread
-// per-CTA scratch in GLOBAL memory for the SE computation (shared memory loads would queue for
-// microseconds behind the tensor core's operand reads; L2 round trips are pipelined and ~1 us)
-constexpr int kScrQ = 0;                                   // [2][9][64] sums of h
-constexpr int kScrS = kScrQ + 2 * 9 * 64;                  // [2][9][64] S_tap
-constexpr int kScrPart = kScrS + 2 * 9 * 64;               // [2][4][64] mat-vec partials
-constexpr int kScrMean = kScrPart + 2 * 4 * 64;            // [2][64]
-constexpr int kScrHid = kScrMean + 2 * 64;                 // [2][64]
-constexpr int kScrScale = kScrHid + 2 * 64;                // [kBodyMaxUnits][64] res_scale * s
-constexpr int kScrFloats = kScrScale + 4 * 64;             // 3328 floats per CTA
 constexpr int kBodyMaxUnits = 4;                      // images a CTA may touch in one layer (host caps the batch per launch)
 constexpr int kBodyAccBufs = 8;                        // 8 x 64 = all 512 TMEM columns: the MMAs can run 8 tiles ahead of the SE vector
 constexpr int kBodyWBytes = 9 * kC * kC * 2;
@@ -90,7 +83,6 @@ struct BodyParams {
   float* hsum;                     // [n_rcab][B][64]: per-image channel sums of the bf16-rounded h
   float* se_out;                   // [B][n_rcab][64] or nullptr
   int* flags;                      // [gridDim.x], zeroed before launch
-  float* scratch;                  // [gridDim.x][kScrFloats] SE work area
   long long* dbg;
 };
 
@@ -193,11 +185,6 @@ __device__ __forceinline__ float ld_cg_f32(const float* p) {
   asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
-__device__ __forceinline__ float4 ld_cg_f32x4(const float* p) {
-  float4 v;
-  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -213,6 +200,9 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
   __shared__ uint64_t bar_w[9], bar_wfree[9], bar_full[kBSlots], bar_empty[kBSlots];
   __shared__ uint64_t bar_acc_full[kBodyAccBufs], bar_acc_empty[kBodyAccBufs], bar_done, bar_flags;
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_S[9][kC];
+  __shared__ __align__(16) float s_scale[kBodyMaxUnits][kC];   // res_scale * s per image of this CTA
+  __shared__ float s_q[kHsCount][kC], s_part[4][kC], s_mean[kC], s_hid[kC], s_red[kBodyEpiWarps][4][kC];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr uint32_t kTmemCols = kBodyAccBufs * N;
@@ -265,6 +255,7 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
         fence_proxy_async_all();
         if (lane == 0) mbar_arrive(&bar_flags);          // the epilogue may read peers' h / sums (SE vector)
       }
+      if (lane == 0) BTRACE(L, 0);   // flags passed, first box about to be issued
       if (lane == 0) {
         const uint64_t pol = ly.last_use ? kPolicyEvictFirst : 0x1000000000000000ull;
         for (int g = g_begin; g < g_end;) {
@@ -326,6 +317,7 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
             ++waited;
           }
           if (BDBG) { const long long n_ = clock64(); m_full += n_ - m_t; m_t = n_; }
+          if (leader && i_layer == 0) BTRACE(L, 1);   // data for the first tile of the layer present
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * N;
           // a view starts in box lb0, lb0 + 1 or lb0 + 2 (tap offsets reach 134 px, a box is 132)
@@ -358,6 +350,7 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
             ++released;
           }
           if (leader && mine) umma_commit(&bar_acc_full[acc]);
+          if (leader && i_layer >= n_tiles - 2) BTRACE(L, 2 + (i_layer == n_tiles - 1));   // last two tiles issued
           __syncwarp();
         }
         gb_base += u.nboxes;
@@ -387,171 +380,6 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
       const BodyLayer ly = body_layer(p, L);
       bf16* outp = p.buf[ly.out];
       const bf16* resp = ly.res >= 0 ? p.buf[ly.res] : nullptr;
-      if (ly.epi == kBEpiSeResidual) {
-        // ---- SE vector of every image of this CTA, from the sums of h that the conv1 layer left.
-        // Latency matters (the MMAs can only run 8 tiles ahead): data-independent loads are issued
-        // before the peer-flag wait, images are handled two at a time, every phase is one barrier.
-        if (BDBG) e_t = clock64();
-        const bf16* w2 = reinterpret_cast<const bf16*>(p.packed + ly.w_off);        // [tap][c][ci] bf16
-        const uint8_t* rec = p.packed + p.k_rcab0 + int64_t(ly.rcab) * p.k_rcab_stride;
-        const float* fc0 = reinterpret_cast<const float*>(rec + p.k_rcab_fc0);
-        const float* fc2 = reinterpret_cast<const float*>(rec + p.k_rcab_fc2);
-        float* scr = p.scratch + size_t(blockIdx.x) * kScrFloats;
-        float* g_q = scr + kScrQ;        // [li][9][64]
-        float* g_S = scr + kScrS;        // [li][9][64]
-        float* g_part = scr + kScrPart;  // [li][4][64]
-        float* g_mean = scr + kScrMean;  // [li][64]
-        float* g_hid = scr + kScrHid;    // [li][64]
-        float* g_scale = scr + kScrScale;
-        const int mc = et & 63, mq = et >> 6;              // mat-vec: output channel, quarter of the input channels
-        uint4 wreg[18];
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const uint4* wp = reinterpret_cast<const uint4*>(w2 + (size_t(tap) * kC + mc) * kC + mq * 16);
-          wreg[2 * tap] = __ldg(wp);
-          wreg[2 * tap + 1] = __ldg(wp + 1);
-        }
-        mbar_wait(&bar_flags, (L - 1) & 1);              // peers have finished the conv1 layer
-        if (BDBG) { const long long n_ = clock64(); e_swait += n_ - e_t; e_t = n_; }
-        for (int u0 = 0; img0 + u0 <= img1; u0 += 2) {
-          const int nimg = min(2, img1 - (img0 + u0) + 1);
-          // -- border rows / columns of h: one warp per (image, quantity); corners; totals
-          {
-            const int li = ew >> 2, qn = ew & 3;
-            if (li < nimg) {
-              const bf16* hb = p.buf[kBufH] + size_t(img0 + u0 + li) * p.H * p.W * kC;
-              const int chunk = lane & 7, pg = lane >> 3;
-              const int npix = (qn < 2) ? p.W : p.H;
-              float a8[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) a8[e] = 0.f;
-#pragma unroll 4
-              for (int px = pg; px < npix; px += 4) {
-                const size_t pix = (qn == 0) ? size_t(px) : (qn == 1) ? size_t(p.H - 1) * p.W + px
-                                 : (qn == 2) ? size_t(px) * p.W : size_t(px) * p.W + p.W - 1;
-                const uint4 v = ld_cg_128(hb + pix * kC + chunk * 8);
-                a8[0] += bf16lo(v.x); a8[1] += bf16hi(v.x); a8[2] += bf16lo(v.y); a8[3] += bf16hi(v.y);
-                a8[4] += bf16lo(v.z); a8[5] += bf16hi(v.z); a8[6] += bf16lo(v.w); a8[7] += bf16hi(v.w);
-              }
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                a8[e] += __shfl_xor_sync(0xffffffffu, a8[e], 8);
-                a8[e] += __shfl_xor_sync(0xffffffffu, a8[e], 16);
-              }
-              if (lane < 8) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) g_q[(li * 9 + kHsRow0 + qn) * kC + chunk * 8 + e] = a8[e];
-              }
-            }
-            if (et < 64) {                                  // corners: 2 images x 4 pixels x 8 chunks
-              const int cl = et >> 5, cy = (et >> 4) & 1, cx = (et >> 3) & 1, chunk = et & 7;
-              if (cl < nimg) {
-                const bf16* hb = p.buf[kBufH] + size_t(img0 + u0 + cl) * p.H * p.W * kC;
-                const uint4 v = ld_cg_128(hb + (size_t(cy ? p.H - 1 : 0) * p.W + (cx ? p.W - 1 : 0)) * kC + chunk * 8);
-                float* d = g_q + (cl * 9 + kHsC00 + 2 * cy + cx) * kC + chunk * 8;
-                d[0] = bf16lo(v.x); d[1] = bf16hi(v.x); d[2] = bf16lo(v.y); d[3] = bf16hi(v.y);
-                d[4] = bf16lo(v.z); d[5] = bf16hi(v.z); d[6] = bf16lo(v.w); d[7] = bf16hi(v.w);
-              }
-            } else if (et >= 128) {                         // totals accumulated by the conv1 epilogue
-              const int tl = (et - 128) >> 6, c = et & 63;
-              if (tl < nimg) g_q[(tl * 9 + kHsTotal) * kC + c] = ld_cg_f32(p.hsum + (size_t(ly.rcab) * p.B + img0 + u0 + tl) * kC + c);
-            }
-          }
-          __threadfence();
-          named_bar_sync(1, kEpiThreads);
-          // -- S_tap = total - excluded border row - excluded border column + corner
-          for (int i = et; i < nimg * 9 * kC; i += kEpiThreads) {
-            const int li = i / (9 * kC), r = i - li * 9 * kC;
-            const int tap = r >> 6, ci = r & 63, dy = tap / 3 - 1, dx = tap % 3 - 1;
-            const float* qq = g_q + li * 9 * kC + ci;
-            float v = ld_cg_f32(qq + kHsTotal * kC);
-            if (dy == 1) v -= ld_cg_f32(qq + kHsRow0 * kC);
-            if (dy == -1) v -= ld_cg_f32(qq + kHsRowL * kC);
-            if (dx == 1) v -= ld_cg_f32(qq + kHsCol0 * kC);
-            if (dx == -1) v -= ld_cg_f32(qq + kHsColL * kC);
-            if (dy == 1 && dx == 1) v += ld_cg_f32(qq + kHsC00 * kC);
-            if (dy == 1 && dx == -1) v += ld_cg_f32(qq + kHsC0L * kC);
-            if (dy == -1 && dx == 1) v += ld_cg_f32(qq + kHsCL0 * kC);
-            if (dy == -1 && dx == -1) v += ld_cg_f32(qq + kHsCLL * kC);
-            g_S[i] = v;
-          }
-          __threadfence();
-          named_bar_sync(1, kEpiThreads);
-          // -- mat-vec: thread (c, quarter) sums 16 input channels of all 9 taps, for both images
-          {
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const uint4 w = wreg[2 * tap + j];
-                const float wf[8] = {bf16lo(w.x), bf16hi(w.x), bf16lo(w.y), bf16hi(w.y),
-                                     bf16lo(w.z), bf16hi(w.z), bf16lo(w.w), bf16hi(w.w)};
-                const float4 p0 = ld_cg_f32x4(g_S + tap * kC + mq * 16 + 8 * j);
-                const float4 p1 = ld_cg_f32x4(g_S + tap * kC + mq * 16 + 8 * j + 4);
-                a0 = fmaf(wf[0], p0.x, a0); a0 = fmaf(wf[1], p0.y, a0); a0 = fmaf(wf[2], p0.z, a0); a0 = fmaf(wf[3], p0.w, a0);
-                a0 = fmaf(wf[4], p1.x, a0); a0 = fmaf(wf[5], p1.y, a0); a0 = fmaf(wf[6], p1.z, a0); a0 = fmaf(wf[7], p1.w, a0);
-                if (nimg > 1) {
-                  const float4 r0 = ld_cg_f32x4(g_S + 9 * kC + tap * kC + mq * 16 + 8 * j);
-                  const float4 r1 = ld_cg_f32x4(g_S + 9 * kC + tap * kC + mq * 16 + 8 * j + 4);
-                  a1 = fmaf(wf[0], r0.x, a1); a1 = fmaf(wf[1], r0.y, a1); a1 = fmaf(wf[2], r0.z, a1); a1 = fmaf(wf[3], r0.w, a1);
-                  a1 = fmaf(wf[4], r1.x, a1); a1 = fmaf(wf[5], r1.y, a1); a1 = fmaf(wf[6], r1.z, a1); a1 = fmaf(wf[7], r1.w, a1);
-                }
-              }
-            }
-            g_part[(0 * 4 + mq) * kC + mc] = a0;
-            g_part[(1 * 4 + mq) * kC + mc] = a1;
-          }
-          __threadfence();
-          named_bar_sync(1, kEpiThreads);
-          if (et < 128) {                                   // mean of o = b2 + (W2 . S) / HW
-            const int li = et >> 6, c = et & 63;
-            const float* pp = g_part + li * 4 * kC + c;
-            g_mean[li * kC + c] = c_vec[ly.cv_bias + c] +
-                                  (ld_cg_f32(pp) + ld_cg_f32(pp + kC) + ld_cg_f32(pp + 2 * kC) + ld_cg_f32(pp + 3 * kC)) * p.inv_hw;
-          }
-          __threadfence();
-          named_bar_sync(1, kEpiThreads);
-          // -- FC1 + ReLU: thread (j, part) sums 4 of the 64 inputs of hidden unit j (+16, +32.. if R > 16)
-          for (int j = et >> 4; j < p.R; j += 16) {
-            const int part = et & 15;
-            const float4 w4 = __ldg(reinterpret_cast<const float4*>(fc0 + j * kC + part * 4));
-#pragma unroll
-            for (int li = 0; li < 2; ++li) {
-              const float4 m4 = ld_cg_f32x4(g_mean + li * kC + part * 4);
-              float a = w4.x * m4.x + w4.y * m4.y + w4.z * m4.z + w4.w * m4.w;
-              a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2);
-              a += __shfl_xor_sync(0xffffffffu, a, 4); a += __shfl_xor_sync(0xffffffffu, a, 8);
-              if (part == 0) g_hid[li * kC + j] = fmaxf(a, 0.f);
-            }
-          }
-          __threadfence();
-          named_bar_sync(1, kEpiThreads);
-          // -- FC2 + sigmoid: thread (c, part) sums a quarter of the R hidden units
-          {
-            const int c = et >> 2, part = et & 3, rq = p.R >> 2;
-            float a0 = 0.f, a1 = 0.f;
-            for (int j = part * rq; j < (part + 1) * rq; ++j) {
-              const float w = __ldg(fc2 + c * p.R + j);
-              a0 = fmaf(w, ld_cg_f32(g_hid + j), a0);
-              a1 = fmaf(w, ld_cg_f32(g_hid + kC + j), a1);
-            }
-            a0 += __shfl_xor_sync(0xffffffffu, a0, 1); a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
-            a1 += __shfl_xor_sync(0xffffffffu, a1, 1); a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
-            if (part < nimg) {                              // lane `part` finishes image `part` of the pair
-              const int n = img0 + u0 + part;
-              const float sv = 1.f / (1.f + expf(-(part == 0 ? a0 : a1)));
-              g_scale[(u0 + part) * kC + c] = sv * p.res_scale;
-              // the CTA owning tile 0 of the image publishes the attention vector
-              if (p.se_out && (n * p.tiles_per_seg >= g_begin) && (n * p.tiles_per_seg < g_end))
-                p.se_out[(size_t(n) * (p.G * p.Bk) + ly.rcab) * kC + c] = sv;
-            }
-          }
-          __threadfence();
-          named_bar_sync(1, kEpiThreads);
-        }
-        if (BDBG) e_se += clock64() - e_t;
-      }
       // per-layer constants of this thread's 32 columns, in registers
       float bias[CW], slope[CW];
 #pragma unroll
@@ -566,6 +394,138 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
           slope[4 * j] = s4.x; slope[4 * j + 1] = s4.y; slope[4 * j + 2] = s4.z; slope[4 * j + 3] = s4.w;
         }
       }
+      if (ly.epi == kBEpiSeResidual) {
+        // ---- SE vector of every image of this CTA, from the sums of h that the conv1 layer left
+        if (BDBG) e_t = clock64();
+        mbar_wait(&bar_flags, (L - 1) & 1);              // peers have finished the conv1 layer
+        if (BDBG) { const long long n_ = clock64(); e_swait += n_ - e_t; e_t = n_; }
+        const bf16* w2 = reinterpret_cast<const bf16*>(p.packed + ly.w_off);        // [tap][c][ci] bf16
+        const uint8_t* rec = p.packed + p.k_rcab0 + int64_t(ly.rcab) * p.k_rcab_stride;
+        const float* fc0 = reinterpret_cast<const float*>(rec + p.k_rcab_fc0);
+        const float* fc2 = reinterpret_cast<const float*>(rec + p.k_rcab_fc2);
+        for (int n = img0; n <= img1; ++n) {
+          const int us = n - img0;
+          // total sum of h: accumulated by the conv1 epilogue; the border rows / columns / corners are
+          // re-read here from h itself (a few KB per image, L2-resident) - atomics from the epilogue,
+          // shared or global, would queue behind the tensor core's operand traffic
+          const float* hs = p.hsum + (size_t(ly.rcab) * p.B + n) * kC;
+          const bf16* hb = p.buf[kBufH] + size_t(n) * p.H * p.W * kC;
+          {
+            const int chunk = et & 7, pg = et >> 3;          // 8 channels of every 32nd border pixel
+            float a4[4][8];
+#pragma unroll
+            for (int qn = 0; qn < 4; ++qn)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) a4[qn][e] = 0.f;
+            const int npix = max(p.H, p.W);
+            for (int px = pg; px < npix; px += 32) {
+              uint4 v[4];
+              v[0] = (px < p.W) ? ld_cg_128(hb + (size_t(0) * p.W + px) * kC + chunk * 8) : make_uint4(0, 0, 0, 0);
+              v[1] = (px < p.W) ? ld_cg_128(hb + (size_t(p.H - 1) * p.W + px) * kC + chunk * 8) : make_uint4(0, 0, 0, 0);
+              v[2] = (px < p.H) ? ld_cg_128(hb + (size_t(px) * p.W + 0) * kC + chunk * 8) : make_uint4(0, 0, 0, 0);
+              v[3] = (px < p.H) ? ld_cg_128(hb + (size_t(px) * p.W + p.W - 1) * kC + chunk * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+              for (int qn = 0; qn < 4; ++qn) {
+                a4[qn][0] += bf16lo(v[qn].x); a4[qn][1] += bf16hi(v[qn].x);
+                a4[qn][2] += bf16lo(v[qn].y); a4[qn][3] += bf16hi(v[qn].y);
+                a4[qn][4] += bf16lo(v[qn].z); a4[qn][5] += bf16hi(v[qn].z);
+                a4[qn][6] += bf16lo(v[qn].w); a4[qn][7] += bf16hi(v[qn].w);
+              }
+            }
+            // reduce over the 4 pixel groups of this warp (lane bits 3, 4), then over the 8 warps in smem
+#pragma unroll
+            for (int qn = 0; qn < 4; ++qn)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float t = a4[qn][e];
+                t += __shfl_xor_sync(0xffffffffu, t, 8);
+                t += __shfl_xor_sync(0xffffffffu, t, 16);
+                a4[qn][e] = t;
+              }
+            if (lane < 8) {
+#pragma unroll
+              for (int qn = 0; qn < 4; ++qn)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s_red[ew][qn][chunk * 8 + e] = a4[qn][e];
+            }
+            // corners: 4 pixels x 8 chunks = 32 threads
+            if (et < 32) {
+              const int cy = (et >> 4) & 1, cx = (et >> 3) & 1;
+              const uint4 v = ld_cg_128(hb + (size_t(cy ? p.H - 1 : 0) * p.W + (cx ? p.W - 1 : 0)) * kC + chunk * 8);
+              float* d = &s_q[kHsC00 + 2 * cy + cx][chunk * 8];
+              d[0] = bf16lo(v.x); d[1] = bf16hi(v.x); d[2] = bf16lo(v.y); d[3] = bf16hi(v.y);
+              d[4] = bf16lo(v.z); d[5] = bf16hi(v.z); d[6] = bf16lo(v.w); d[7] = bf16hi(v.w);
+            }
+            if (et < kC) s_q[kHsTotal][et] = ld_cg_f32(hs + et);
+          }
+          named_bar_sync(1, kEpiThreads);
+          {
+            const int qn = et >> 6, c = et & 63;           // 4 border quantities x 64 channels = 256 threads
+            float t = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < kBodyEpiWarps; ++w8) t += s_red[w8][qn][c];
+            s_q[kHsRow0 + qn][c] = t;
+          }
+          named_bar_sync(1, kEpiThreads);
+          // S_tap = total - excluded border row - excluded border column + corner (dy = tap/3 - 1, dx = tap%3 - 1)
+          for (int i = et; i < 9 * kC; i += kEpiThreads) {
+            const int tap = i >> 6, ci = i & 63, dy = tap / 3 - 1, dx = tap % 3 - 1;
+            float v = s_q[kHsTotal][ci];
+            if (dy == 1) v -= s_q[kHsRow0][ci];
+            if (dy == -1) v -= s_q[kHsRowL][ci];
+            if (dx == 1) v -= s_q[kHsCol0][ci];
+            if (dx == -1) v -= s_q[kHsColL][ci];
+            if (dy == 1 && dx == 1) v += s_q[kHsC00][ci];
+            if (dy == 1 && dx == -1) v += s_q[kHsC0L][ci];
+            if (dy == -1 && dx == 1) v += s_q[kHsCL0][ci];
+            if (dy == -1 && dx == -1) v += s_q[kHsCLL][ci];
+            s_S[tap][ci] = v;
+          }
+          named_bar_sync(1, kEpiThreads);
+          {  // mat-vec: thread (c, quarter) sums 16 input channels of all 9 taps
+            const int c = et & 63, qt = et >> 6;
+            float a = 0.f;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint4* wp = reinterpret_cast<const uint4*>(w2 + (size_t(tap) * kC + c) * kC + qt * 16);
+              const float* sp = &s_S[tap][qt * 16];
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const uint4 w = __ldg(wp + j);
+                const float4 s0 = *reinterpret_cast<const float4*>(sp + 8 * j);
+                const float4 s1 = *reinterpret_cast<const float4*>(sp + 8 * j + 4);
+                a = fmaf(bf16lo(w.x), s0.x, a); a = fmaf(bf16hi(w.x), s0.y, a);
+                a = fmaf(bf16lo(w.y), s0.z, a); a = fmaf(bf16hi(w.y), s0.w, a);
+                a = fmaf(bf16lo(w.z), s1.x, a); a = fmaf(bf16hi(w.z), s1.y, a);
+                a = fmaf(bf16lo(w.w), s1.z, a); a = fmaf(bf16hi(w.w), s1.w, a);
+              }
+            }
+            s_part[qt][c] = a;
+          }
+          named_bar_sync(1, kEpiThreads);
+          if (et < kC)
+            s_mean[et] = c_vec[ly.cv_bias + et] + (s_part[0][et] + s_part[1][et] + s_part[2][et] + s_part[3][et]) * p.inv_hw;
+          named_bar_sync(1, kEpiThreads);
+          if (et < p.R) {
+            float a = 0.f;
+            for (int k = 0; k < kC; ++k) a = fmaf(__ldg(fc0 + et * kC + k), s_mean[k], a);
+            s_hid[et] = fmaxf(a, 0.f);
+          }
+          named_bar_sync(1, kEpiThreads);
+          if (et < kC) {
+            float a = 0.f;
+            for (int j = 0; j < p.R; ++j) a = fmaf(__ldg(fc2 + et * p.R + j), s_hid[j], a);
+            const float sv = 1.f / (1.f + expf(-a));
+            s_scale[us][et] = sv * p.res_scale;
+            // the CTA owning tile 0 of the image publishes the attention vector
+            if (p.se_out && (n * p.tiles_per_seg >= g_begin) && (n * p.tiles_per_seg < g_end))
+              p.se_out[(size_t(n) * (p.G * p.Bk) + ly.rcab) * kC + et] = sv;
+          }
+          named_bar_sync(1, kEpiThreads);
+        }
+        if (BDBG) e_se += clock64() - e_t;
+        if (et == 0) BTRACE(L, 4);   // SE vector ready
+      }
       const long long e_l0 = BDBG ? clock64() : 0;
       const long long e_w0 = e_wait;
       for (int g = g_begin; g < g_end;) {
@@ -577,7 +537,7 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
           const int us = u.n - img0;
 #pragma unroll
           for (int j = 0; j < CW / 4; ++j) {
-            const float4 s4 = ld_cg_f32x4(p.scratch + size_t(blockIdx.x) * kScrFloats + kScrScale + us * kC + col0 + 4 * j);
+            const float4 s4 = *reinterpret_cast<const float4*>(&s_scale[us][col0 + 4 * j]);
             slope[4 * j] = s4.x; slope[4 * j + 1] = s4.y; slope[4 * j + 2] = s4.z; slope[4 * j + 3] = s4.w;
           }
         }
@@ -601,6 +561,7 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
           if (BDBG) e_t = clock64();
           mbar_wait(&bar_acc_full[acc], (tile_ctr / kBodyAccBufs) & 1);
           if (BDBG) e_wait += clock64() - e_t;
+          if (et == 0 && tile_ctr % n_tiles == 0) BTRACE(L, 5);   // first accumulator of the layer ready
           tc_fence_after();
           uint32_t v[CW];
           tmem_ld_32x32(tmem_base + acc * N + col0 + (uint32_t(q * 32) << 16), v);
@@ -661,6 +622,7 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
         if (ly.epi == kBEpiSeResidual) { e_c2 += clock64() - e_l0; e_c2w += e_wait - e_w0; }
         else { e_c1 += clock64() - e_l0; e_c1w += e_wait - e_w0; }
       }
+      if (et == 0) BTRACE(L, 6);     // last tile stored
       // ---- layer done for this warp: make its global writes visible, then publish the CTA's flag
       __threadfence();
       __syncwarp();
@@ -670,9 +632,8 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
         mbar_wait(&bar_done, L & 1);
         if (BDBG) e_done += clock64() - e_t;
         if (lane == 0) {
-          fence_proxy_async_all();
-          __threadfence();
           st_release_gpu(p.flags + blockIdx.x, L + 1);
+          BTRACE(L, 7);                // flag published
         }
         __syncwarp();
       }

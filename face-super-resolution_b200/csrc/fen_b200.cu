@@ -16,7 +16,9 @@ namespace fen {
 // ===================================================================== error plumbing
 static thread_local std::string g_err;
 static thread_local int g_launches = 0;
-static long long* g_dbg = nullptr;  // developer hook: per-CTA cycle counters of fen_conv3x3_c64
+static long long* g_dbg = nullptr;
+static int g_time_body = 0;           // fen_profile_body(1): CUDA events around the persistent body kernel
+static cudaEvent_t g_body_ev[2] = {nullptr, nullptr};  // developer hook: per-CTA cycle counters of fen_conv3x3_c64
 
 static int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -412,7 +414,7 @@ static int pack_vec(const float* src, int count, int n_grp, int groups, int perm
 
 // ===================================================================== workspace
 struct Workspace {
-  int64_t f0, x[2], h, o, grp0, grp_stride, u0, u1, sums, hsum, flags, scratch, total;
+  int64_t f0, x[2], h, o, grp0, grp_stride, u0, u1, sums, hsum, flags, total;
 };
 static void make_workspace(const Layout& L, int B, int H, int W, Workspace* ws) {
   const int64_t act = align256(int64_t(B) * H * W * 64 * 2);
@@ -426,7 +428,6 @@ static void make_workspace(const Layout& L, int B, int H, int W, Workspace* ws) 
   ws->sums = o; o += align256(int64_t(L.n_rcab) * B * 64 * 4);
   ws->hsum = o; o += align256(int64_t(L.n_rcab) * B * 9 * 64 * 4);   // body kernel: 9 channel sums of h per RCAB, image
   ws->flags = o; o += 4096;   // one int per CTA of the persistent body kernel
-  ws->scratch = o; o += align256(int64_t(160) * kScrFloats * 4);   // per-CTA SE work area
   ws->total = o;
 }
 
@@ -481,14 +482,18 @@ static int launch_body(const fen_config* cfg, const Layout& L, const Workspace& 
   p.hsum = reinterpret_cast<float*>(wsb + ws.hsum);
   p.se_out = se_out;
   p.flags = reinterpret_cast<int*>(wsb + ws.flags);
-  p.scratch = reinterpret_cast<float*>(wsb + ws.scratch);
   p.dbg = g_dbg;
   FEN_CUDA(cudaMemsetAsync(p.flags, 0, 4096, st));
   FEN_CUDA(cudaMemsetAsync(p.hsum, 0, size_t(L.n_rcab) * B * 9 * 64 * 4, st));
   FEN_CUDA(cudaMemcpyToSymbolAsync(c_vec, k + L.k_cvec, size_t(L.cv_total) * 4, 0, cudaMemcpyDeviceToDevice, st));
   void* args[] = {&maps, &p};
+  if (g_time_body) {
+    if (!g_body_ev[0]) { FEN_CUDA(cudaEventCreate(&g_body_ev[0])); FEN_CUDA(cudaEventCreate(&g_body_ev[1])); }
+    FEN_CUDA(cudaEventRecord(g_body_ev[0], st));
+  }
   FEN_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(body_umma_kernel), dim3(ctas), dim3(kBodyThreads), args,
                                        kBodyDynBytes, st));
+  if (g_time_body) FEN_CUDA(cudaEventRecord(g_body_ev[1], st));
   ++g_launches;
   return FEN_OK;
 }
@@ -503,6 +508,14 @@ extern "C" {
 int fen_abi_version(void) { return FEN_ABI_VERSION; }
 const char* fen_last_error(void) { return g_err.c_str(); }
 int fen_last_launch_count(void) { return g_launches; }
+int fen_profile_body(int enable) { g_time_body = enable ? 1 : 0; return FEN_OK; }
+float fen_last_body_ms(void) {
+  if (!g_body_ev[0] || !g_body_ev[1]) return -1.f;
+  if (cudaEventSynchronize(g_body_ev[1]) != cudaSuccess) { cudaGetLastError(); return -1.f; }
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, g_body_ev[0], g_body_ev[1]) != cudaSuccess) { cudaGetLastError(); return -1.f; }
+  return ms;
+}
 // developer hook (not in the public header): device buffer [ctas][8] of int64 cycle counters, or null
 void fen_debug_set_counters(void* dev_buf) { g_dbg = static_cast<long long*>(dev_buf); }
 

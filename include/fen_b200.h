@@ -104,6 +104,12 @@ int fen_pack_conv3x3(const float* w_oihw, int cout, int cout_pad, void* w_packed
 /* Kernels launched by the last fen_forward / fen_conv3x3_c64 / fen_lr_from_hr_u8 call of this thread. */
 int fen_last_launch_count(void);
 
+/* Measurement hooks for bench.py's roofline: fen_profile_body(1) makes fen_forward record CUDA events
+ * on its launch stream around the persistent body kernel (all 64->64 convolutions of the residual
+ * body); fen_last_body_ms() waits for the last one and returns its duration (-1 if none). */
+int fen_profile_body(int enable);
+float fen_last_body_ms(void);
+
 #ifdef __cplusplus
 }
 #endif
