@@ -185,6 +185,11 @@ __device__ __forceinline__ float ld_cg_f32(const float* p) {
   asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
+__device__ __forceinline__ float4 ld_cg_f32x4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -198,11 +203,11 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
   uint8_t* w_smem = smem;
   uint8_t* ring = smem + kBodyWBytes;
   __shared__ uint64_t bar_w[9], bar_wfree[9], bar_full[kBSlots], bar_empty[kBSlots];
-  __shared__ uint64_t bar_acc_full[kBodyAccBufs], bar_acc_empty[kBodyAccBufs], bar_done, bar_flags;
+  __shared__ uint64_t bar_acc_full[kBodyAccBufs], bar_acc_empty[kBodyAccBufs], bar_done, bar_flags, bar_se;
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(16) float s_S[9][kC];
   __shared__ __align__(16) float s_scale[kBodyMaxUnits][kC];   // res_scale * s per image of this CTA
-  __shared__ float s_q[kHsCount][kC], s_part[4][kC], s_mean[kC], s_hid[kC], s_red[kBodyEpiWarps][4][kC];
+  __shared__ __align__(16) float s_S[2][9][kC], s_q[2][kHsCount][kC], s_mean[2][kC], s_hid[2][kC];   // SE work arrays
+  __shared__ float s_part[2][4][kC];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr uint32_t kTmemCols = kBodyAccBufs * N;
@@ -223,6 +228,7 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
     for (int i = 0; i < kBodyAccBufs; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], kBodyEpiWarps); }
     mbar_init(&bar_done, kBodyEpiWarps);
     mbar_init(&bar_flags, 1);
+    mbar_init(&bar_se, 1);
     fence_mbar_init();
     tma_prefetch_desc(&maps.w);
   }
@@ -285,10 +291,17 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
     const uint32_t w_lo = (smem_u32(w_smem) >> 4) | kLbo;
     const bool leader = elect_one();
     const uint32_t my_parity = warp - kBodyFirstMmaWarp;
-    uint32_t gb_base = 0, tile_ctr = 0;
+    uint32_t gb_base = 0, tile_ctr = 0, se_seen = 0;
     long long m_acc = 0, m_full = 0, m_issue = 0, m_t = 0, m_fl = 0, m_pl = 0, m_ffull = 0;
     const long long m_start = BDBG ? clock64() : 0;
     for (int L = 0; L < p.n_layers; ++L) {
+      // SE layers: the shuffles / loads of the SE chain crawl while MMAs saturate the shared-memory pipe
+      // (40k cycles instead of a few k), so the issuers hold back until the vector is ready; TMA keeps
+      // filling the ring meanwhile.
+      if (body_layer(p, L).epi == kBEpiSeResidual) {
+        mbar_wait(&bar_se, se_seen & 1);
+        ++se_seen;
+      }
       const long long m_l0 = BDBG ? clock64() : 0;
       const long long m_full0 = m_full;
       const bool m_is_fused = body_layer(p, L).epi == kBEpiSeResidual;
@@ -395,134 +408,189 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
         }
       }
       if (ly.epi == kBEpiSeResidual) {
-        // ---- SE vector of every image of this CTA, from the sums of h that the conv1 layer left
+        // ---- SE vector of every image of this CTA, from the sums of h that the conv1 layer left.
+        // There is no L1 left beside 226 KB of shared memory, so every global load is an L2 round trip
+        // (~1k cycles): all weight loads are data-independent and are requested BEFORE waiting for the
+        // peers; after the wait the chain is one round trip (border pixels of h) plus six short phases.
         if (BDBG) e_t = clock64();
-        mbar_wait(&bar_flags, (L - 1) & 1);              // peers have finished the conv1 layer
-        if (BDBG) { const long long n_ = clock64(); e_swait += n_ - e_t; e_t = n_; }
         const bf16* w2 = reinterpret_cast<const bf16*>(p.packed + ly.w_off);        // [tap][c][ci] bf16
         const uint8_t* rec = p.packed + p.k_rcab0 + int64_t(ly.rcab) * p.k_rcab_stride;
         const float* fc0 = reinterpret_cast<const float*>(rec + p.k_rcab_fc0);
         const float* fc2 = reinterpret_cast<const float*>(rec + p.k_rcab_fc2);
-        for (int n = img0; n <= img1; ++n) {
-          const int us = n - img0;
-          // total sum of h: accumulated by the conv1 epilogue; the border rows / columns / corners are
-          // re-read here from h itself (a few KB per image, L2-resident) - atomics from the epilogue,
-          // shared or global, would queue behind the tensor core's operand traffic
-          const float* hs = p.hsum + (size_t(ly.rcab) * p.B + n) * kC;
-          const bf16* hb = p.buf[kBufH] + size_t(n) * p.H * p.W * kC;
+        const int mc = et & 63, mq = et >> 6;              // mat-vec: output channel, quarter of the input channels
+        const int f1j = et >> 4, f1p = et & 15;            // FC1: hidden unit, 4 of its 64 inputs
+        const int f2c = et >> 2, f2p = et & 3;             // FC2: channel, quarter of the hidden units
+        const bool fast_fc = (p.R == 16);
+        float4 f1 = make_float4(0.f, 0.f, 0.f, 0.f), f2 = f1;
+        if (fast_fc) {
+          f1 = __ldg(reinterpret_cast<const float4*>(fc0 + f1j * kC + f1p * 4));
+          f2 = __ldg(reinterpret_cast<const float4*>(fc2 + f2c * 16 + f2p * 4));
+        }
+        mbar_wait(&bar_flags, (L - 1) & 1);              // peers have finished the conv1 layer
+        if (BDBG) { const long long n_ = clock64(); e_swait += n_ - e_t; e_t = n_; }
+        if (et == 0) BTRACE(L, 8);
+        for (int u0 = 0; img0 + u0 <= img1; u0 += 2) {
+          const int nimg = min(2, img1 - (img0 + u0) + 1);
+          // -- P1: border rows / columns of h (one warp per image and quantity), corners, totals.
+          // Every lane issues ALL its loads before touching any result (one L2 round trip): divergent
+          // branches with a load each would serialise into one round trip per branch.
           {
-            const int chunk = et & 7, pg = et >> 3;          // 8 channels of every 32nd border pixel
-            float a4[4][8];
+            const int li = ew >> 2, qn = ew & 3;
+            if (li < nimg) {
+              const bf16* hb = p.buf[kBufH] + size_t(img0 + u0 + li) * p.H * p.W * kC;
+              const int chunk = lane & 7, pg = lane >> 3;
+              const int npix = (qn < 2) ? p.W : p.H;
+              // extra load of this lane: warps qn<2 -> corner pixels of their row (lanes 8..23); warps qn>=2 ->
+              // totals from the conv1 epilogue (lanes 24..31); other lanes re-read pixel 0 (ignored)
+              const bool is_corner = (qn < 2) && (lane >= 8) && (lane < 24);
+              const bool is_total = (qn >= 2) && (lane >= 24);
+              const int cx = (lane >= 16) ? p.W - 1 : 0;
+              const uint4 xv = ld_cg_128(hb + (size_t((qn & 1) ? p.H - 1 : 0) * p.W + (is_corner ? cx : 0)) * kC + chunk * 8);
+              const int c4 = ((qn & 1) * 8 + (lane & 7)) * 4;
+              const float4 t4 = ld_cg_f32x4(p.hsum + (size_t(ly.rcab) * p.B + img0 + u0 + li) * kC + c4);
+              float a8[8];
 #pragma unroll
-            for (int qn = 0; qn < 4; ++qn)
-#pragma unroll
-              for (int e = 0; e < 8; ++e) a4[qn][e] = 0.f;
-            const int npix = max(p.H, p.W);
-            for (int px = pg; px < npix; px += 32) {
-              uint4 v[4];
-              v[0] = (px < p.W) ? ld_cg_128(hb + (size_t(0) * p.W + px) * kC + chunk * 8) : make_uint4(0, 0, 0, 0);
-              v[1] = (px < p.W) ? ld_cg_128(hb + (size_t(p.H - 1) * p.W + px) * kC + chunk * 8) : make_uint4(0, 0, 0, 0);
-              v[2] = (px < p.H) ? ld_cg_128(hb + (size_t(px) * p.W + 0) * kC + chunk * 8) : make_uint4(0, 0, 0, 0);
-              v[3] = (px < p.H) ? ld_cg_128(hb + (size_t(px) * p.W + p.W - 1) * kC + chunk * 8) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-              for (int qn = 0; qn < 4; ++qn) {
-                a4[qn][0] += bf16lo(v[qn].x); a4[qn][1] += bf16hi(v[qn].x);
-                a4[qn][2] += bf16lo(v[qn].y); a4[qn][3] += bf16hi(v[qn].y);
-                a4[qn][4] += bf16lo(v[qn].z); a4[qn][5] += bf16hi(v[qn].z);
-                a4[qn][6] += bf16lo(v[qn].w); a4[qn][7] += bf16hi(v[qn].w);
+              for (int e = 0; e < 8; ++e) a8[e] = 0.f;
+#pragma unroll 16
+              for (int px = pg; px < npix; px += 4) {
+                const size_t pix = (qn == 0) ? size_t(px) : (qn == 1) ? size_t(p.H - 1) * p.W + px
+                                 : (qn == 2) ? size_t(px) * p.W : size_t(px) * p.W + p.W - 1;
+                const uint4 v = ld_cg_128(hb + pix * kC + chunk * 8);
+                a8[0] += bf16lo(v.x); a8[1] += bf16hi(v.x); a8[2] += bf16lo(v.y); a8[3] += bf16hi(v.y);
+                a8[4] += bf16lo(v.z); a8[5] += bf16hi(v.z); a8[6] += bf16lo(v.w); a8[7] += bf16hi(v.w);
               }
-            }
-            // reduce over the 4 pixel groups of this warp (lane bits 3, 4), then over the 8 warps in smem
-#pragma unroll
-            for (int qn = 0; qn < 4; ++qn)
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
-                float t = a4[qn][e];
-                t += __shfl_xor_sync(0xffffffffu, t, 8);
-                t += __shfl_xor_sync(0xffffffffu, t, 16);
-                a4[qn][e] = t;
+                a8[e] += __shfl_xor_sync(0xffffffffu, a8[e], 8);
+                a8[e] += __shfl_xor_sync(0xffffffffu, a8[e], 16);
               }
-            if (lane < 8) {
-#pragma unroll
-              for (int qn = 0; qn < 4; ++qn)
-#pragma unroll
-                for (int e = 0; e < 8; ++e) s_red[ew][qn][chunk * 8 + e] = a4[qn][e];
+              if (lane < 8) {
+                float4* d = reinterpret_cast<float4*>(&s_q[li][kHsRow0 + qn][chunk * 8]);
+                d[0] = make_float4(a8[0], a8[1], a8[2], a8[3]);
+                d[1] = make_float4(a8[4], a8[5], a8[6], a8[7]);
+              } else if (is_corner) {                       // (row qn ? H-1 : 0, column cx)
+                float4* d = reinterpret_cast<float4*>(&s_q[li][kHsC00 + 2 * qn + (lane >= 16 ? 1 : 0)][chunk * 8]);
+                d[0] = make_float4(bf16lo(xv.x), bf16hi(xv.x), bf16lo(xv.y), bf16hi(xv.y));
+                d[1] = make_float4(bf16lo(xv.z), bf16hi(xv.z), bf16lo(xv.w), bf16hi(xv.w));
+              } else if (is_total) {
+                *reinterpret_cast<float4*>(&s_q[li][kHsTotal][c4]) = t4;
+              }
             }
-            // corners: 4 pixels x 8 chunks = 32 threads
-            if (et < 32) {
-              const int cy = (et >> 4) & 1, cx = (et >> 3) & 1;
-              const uint4 v = ld_cg_128(hb + (size_t(cy ? p.H - 1 : 0) * p.W + (cx ? p.W - 1 : 0)) * kC + chunk * 8);
-              float* d = &s_q[kHsC00 + 2 * cy + cx][chunk * 8];
-              d[0] = bf16lo(v.x); d[1] = bf16hi(v.x); d[2] = bf16lo(v.y); d[3] = bf16hi(v.y);
-              d[4] = bf16lo(v.z); d[5] = bf16hi(v.z); d[6] = bf16lo(v.w); d[7] = bf16hi(v.w);
-            }
-            if (et < kC) s_q[kHsTotal][et] = ld_cg_f32(hs + et);
+          }
+          // mat-vec weights (this thread's 16 input channels x 9 taps of output channel mc): requested now,
+          // consumed in P3 - their L2 round trip hides behind P2 (not earlier: P1 needs the registers)
+          uint4 wreg[18];
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint4* wp = reinterpret_cast<const uint4*>(w2 + (size_t(tap) * kC + mc) * kC + mq * 16);
+            wreg[2 * tap] = __ldg(wp);
+            wreg[2 * tap + 1] = __ldg(wp + 1);
+          }
+          if (et == 0) BTRACE(L, 9);
+          named_bar_sync(1, kEpiThreads);
+          if (et == 0) BTRACE(L, 10);
+          // -- P2: S_tap = total - excluded border row - excluded border column + corner
+          for (int i = et; i < nimg * 9 * kC; i += kEpiThreads) {
+            const int li = i / (9 * kC), r = i - li * 9 * kC;
+            const int tap = r >> 6, ci = r & 63, dy = tap / 3 - 1, dx = tap % 3 - 1;
+            float v = s_q[li][kHsTotal][ci];
+            if (dy == 1) v -= s_q[li][kHsRow0][ci];
+            if (dy == -1) v -= s_q[li][kHsRowL][ci];
+            if (dx == 1) v -= s_q[li][kHsCol0][ci];
+            if (dx == -1) v -= s_q[li][kHsColL][ci];
+            if (dy == 1 && dx == 1) v += s_q[li][kHsC00][ci];
+            if (dy == 1 && dx == -1) v += s_q[li][kHsC0L][ci];
+            if (dy == -1 && dx == 1) v += s_q[li][kHsCL0][ci];
+            if (dy == -1 && dx == -1) v += s_q[li][kHsCLL][ci];
+            s_S[li][tap][ci] = v;
           }
           named_bar_sync(1, kEpiThreads);
+          if (et == 0) BTRACE(L, 11);
+          // -- P3: mat-vec, thread (c, quarter): 16 input channels of all 9 taps, both images
           {
-            const int qn = et >> 6, c = et & 63;           // 4 border quantities x 64 channels = 256 threads
-            float t = 0.f;
-#pragma unroll
-            for (int w8 = 0; w8 < kBodyEpiWarps; ++w8) t += s_red[w8][qn][c];
-            s_q[kHsRow0 + qn][c] = t;
-          }
-          named_bar_sync(1, kEpiThreads);
-          // S_tap = total - excluded border row - excluded border column + corner (dy = tap/3 - 1, dx = tap%3 - 1)
-          for (int i = et; i < 9 * kC; i += kEpiThreads) {
-            const int tap = i >> 6, ci = i & 63, dy = tap / 3 - 1, dx = tap % 3 - 1;
-            float v = s_q[kHsTotal][ci];
-            if (dy == 1) v -= s_q[kHsRow0][ci];
-            if (dy == -1) v -= s_q[kHsRowL][ci];
-            if (dx == 1) v -= s_q[kHsCol0][ci];
-            if (dx == -1) v -= s_q[kHsColL][ci];
-            if (dy == 1 && dx == 1) v += s_q[kHsC00][ci];
-            if (dy == 1 && dx == -1) v += s_q[kHsC0L][ci];
-            if (dy == -1 && dx == 1) v += s_q[kHsCL0][ci];
-            if (dy == -1 && dx == -1) v += s_q[kHsCLL][ci];
-            s_S[tap][ci] = v;
-          }
-          named_bar_sync(1, kEpiThreads);
-          {  // mat-vec: thread (c, quarter) sums 16 input channels of all 9 taps
-            const int c = et & 63, qt = et >> 6;
-            float a = 0.f;
+            float a0 = 0.f, a1 = 0.f;
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-              const uint4* wp = reinterpret_cast<const uint4*>(w2 + (size_t(tap) * kC + c) * kC + qt * 16);
-              const float* sp = &s_S[tap][qt * 16];
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
-                const uint4 w = __ldg(wp + j);
-                const float4 s0 = *reinterpret_cast<const float4*>(sp + 8 * j);
-                const float4 s1 = *reinterpret_cast<const float4*>(sp + 8 * j + 4);
-                a = fmaf(bf16lo(w.x), s0.x, a); a = fmaf(bf16hi(w.x), s0.y, a);
-                a = fmaf(bf16lo(w.y), s0.z, a); a = fmaf(bf16hi(w.y), s0.w, a);
-                a = fmaf(bf16lo(w.z), s1.x, a); a = fmaf(bf16hi(w.z), s1.y, a);
-                a = fmaf(bf16lo(w.w), s1.z, a); a = fmaf(bf16hi(w.w), s1.w, a);
+                const uint4 w = wreg[2 * tap + j];
+                const float4 p0 = *reinterpret_cast<const float4*>(&s_S[0][tap][mq * 16 + 8 * j]);
+                const float4 p1 = *reinterpret_cast<const float4*>(&s_S[0][tap][mq * 16 + 8 * j + 4]);
+                a0 = fmaf(bf16lo(w.x), p0.x, a0); a0 = fmaf(bf16hi(w.x), p0.y, a0);
+                a0 = fmaf(bf16lo(w.y), p0.z, a0); a0 = fmaf(bf16hi(w.y), p0.w, a0);
+                a0 = fmaf(bf16lo(w.z), p1.x, a0); a0 = fmaf(bf16hi(w.z), p1.y, a0);
+                a0 = fmaf(bf16lo(w.w), p1.z, a0); a0 = fmaf(bf16hi(w.w), p1.w, a0);
+                if (nimg > 1) {
+                  const float4 r0 = *reinterpret_cast<const float4*>(&s_S[1][tap][mq * 16 + 8 * j]);
+                  const float4 r1 = *reinterpret_cast<const float4*>(&s_S[1][tap][mq * 16 + 8 * j + 4]);
+                  a1 = fmaf(bf16lo(w.x), r0.x, a1); a1 = fmaf(bf16hi(w.x), r0.y, a1);
+                  a1 = fmaf(bf16lo(w.y), r0.z, a1); a1 = fmaf(bf16hi(w.y), r0.w, a1);
+                  a1 = fmaf(bf16lo(w.z), r1.x, a1); a1 = fmaf(bf16hi(w.z), r1.y, a1);
+                  a1 = fmaf(bf16lo(w.w), r1.z, a1); a1 = fmaf(bf16hi(w.w), r1.w, a1);
+                }
               }
             }
-            s_part[qt][c] = a;
+            s_part[0][mq][mc] = a0;
+            s_part[1][mq][mc] = a1;
           }
           named_bar_sync(1, kEpiThreads);
-          if (et < kC)
-            s_mean[et] = c_vec[ly.cv_bias + et] + (s_part[0][et] + s_part[1][et] + s_part[2][et] + s_part[3][et]) * p.inv_hw;
-          named_bar_sync(1, kEpiThreads);
-          if (et < p.R) {
-            float a = 0.f;
-            for (int k = 0; k < kC; ++k) a = fmaf(__ldg(fc0 + et * kC + k), s_mean[k], a);
-            s_hid[et] = fmaxf(a, 0.f);
+          if (et == 0) BTRACE(L, 12);
+          // -- P4: mean of o = b2 + (W2 . S) / HW
+          if (et < 128) {
+            const int li = et >> 6, c = et & 63;
+            s_mean[li][c] = c_vec[ly.cv_bias + c] +
+                            (s_part[li][0][c] + s_part[li][1][c] + s_part[li][2][c] + s_part[li][3][c]) * p.inv_hw;
           }
           named_bar_sync(1, kEpiThreads);
-          if (et < kC) {
+          if (et == 0) BTRACE(L, 13);
+          // -- P5: FC1 + ReLU
+          if (fast_fc) {
+#pragma unroll
+            for (int li = 0; li < 2; ++li) {
+              const float4 m4 = *reinterpret_cast<const float4*>(&s_mean[li][f1p * 4]);
+              float a = f1.x * m4.x + f1.y * m4.y + f1.z * m4.z + f1.w * m4.w;
+              a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2);
+              a += __shfl_xor_sync(0xffffffffu, a, 4); a += __shfl_xor_sync(0xffffffffu, a, 8);
+              if (f1p == 0) s_hid[li][f1j] = fmaxf(a, 0.f);
+            }
+          } else if (et < 2 * p.R) {
+            const int li = et / p.R, j = et - li * p.R;
             float a = 0.f;
-            for (int j = 0; j < p.R; ++j) a = fmaf(__ldg(fc2 + et * p.R + j), s_hid[j], a);
-            const float sv = 1.f / (1.f + expf(-a));
-            s_scale[us][et] = sv * p.res_scale;
-            // the CTA owning tile 0 of the image publishes the attention vector
-            if (p.se_out && (n * p.tiles_per_seg >= g_begin) && (n * p.tiles_per_seg < g_end))
-              p.se_out[(size_t(n) * (p.G * p.Bk) + ly.rcab) * kC + et] = sv;
+            for (int k = 0; k < kC; ++k) a = fmaf(__ldg(fc0 + j * kC + k), s_mean[li][k], a);
+            s_hid[li][j] = fmaxf(a, 0.f);
+          }
+          named_bar_sync(1, kEpiThreads);
+          if (et == 0) BTRACE(L, 14);
+          // -- P6: FC2 + sigmoid
+          {
+            float a0 = 0.f, a1 = 0.f;
+            if (fast_fc) {
+              const float4 h0 = *reinterpret_cast<const float4*>(&s_hid[0][f2p * 4]);
+              const float4 h1 = *reinterpret_cast<const float4*>(&s_hid[1][f2p * 4]);
+              a0 = f2.x * h0.x + f2.y * h0.y + f2.z * h0.z + f2.w * h0.w;
+              a1 = f2.x * h1.x + f2.y * h1.y + f2.z * h1.z + f2.w * h1.w;
+            } else {
+              const int rq = p.R >> 2;
+              for (int j = f2p * rq; j < (f2p + 1) * rq; ++j) {
+                const float w = __ldg(fc2 + f2c * p.R + j);
+                a0 = fmaf(w, s_hid[0][j], a0);
+                a1 = fmaf(w, s_hid[1][j], a1);
+              }
+            }
+            a0 += __shfl_xor_sync(0xffffffffu, a0, 1); a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, 1); a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+            if (f2p < nimg) {                               // lane `f2p` finishes image `f2p` of the pair
+              const int n = img0 + u0 + f2p;
+              const float sv = 1.f / (1.f + expf(-(f2p == 0 ? a0 : a1)));
+              s_scale[u0 + f2p][f2c] = sv * p.res_scale;
+              // the CTA owning tile 0 of the image publishes the attention vector
+              if (p.se_out && (n * p.tiles_per_seg >= g_begin) && (n * p.tiles_per_seg < g_end))
+                p.se_out[(size_t(n) * (p.G * p.Bk) + ly.rcab) * kC + f2c] = sv;
+            }
           }
           named_bar_sync(1, kEpiThreads);
         }
+        if (et == 0) mbar_arrive(&bar_se);                // release the MMA issuers (see there)
         if (BDBG) e_se += clock64() - e_t;
         if (et == 0) BTRACE(L, 4);   // SE vector ready
       }

@@ -23,3 +23,7 @@ for L in range(20, 32):
     base = t[L, 0]
     row = "  ".join(f"{(t[L, e] - base).item():12.0f}" if t[L, e] > 0 else f"{'-':>12s}" for e in range(8))
     print(f"{L:4d} {kind:6s} {row}   next layer starts at {(t[L + 1, 0] - base).item():.0f}")
+    if kind == "conv2":
+        tt = dbg.cpu()[4096:].view(128, 16)[L].double()
+        print("        SE phases (rel. flags ok): enter %d | P1 done %d | bar1 %d | P2+bar2 %d | P3+bar3 %d | P4+bar4 %d | P5+bar5 %d" %
+              tuple((tt[e] - base).item() for e in range(8, 15)))
