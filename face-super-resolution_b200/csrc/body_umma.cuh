@@ -32,6 +32,9 @@
 
 namespace fen {
 
+#ifndef FEN_SE_GATE
+#define FEN_SE_GATE 0   // 1: MMA issuers wait for the SE vector in conv2 layers (measured slower: 4.57 vs 4.35 ms)
+#endif
 #ifndef FEN_BODY_DEBUG
 #define FEN_BODY_DEBUG 0   // 1: per-CTA cycle counters into BodyParams::dbg (developer builds)
 #endif
@@ -298,7 +301,7 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
       // SE layers: the shuffles / loads of the SE chain crawl while MMAs saturate the shared-memory pipe
       // (40k cycles instead of a few k), so the issuers hold back until the vector is ready; TMA keeps
       // filling the ring meanwhile.
-      if (body_layer(p, L).epi == kBEpiSeResidual) {
+      if (FEN_SE_GATE && body_layer(p, L).epi == kBEpiSeResidual) {
         mbar_wait(&bar_se, se_seen & 1);
         ++se_seen;
       }
@@ -618,7 +621,11 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
           // residual / skip values of this pixel: requested before waiting for the accumulator so the
           // L2 round trip overlaps the MMAs of the tile
           uint32_t rv[16];                          // 32 bf16, two 256-bit loads (one L1 line lookup each per lane)
+#ifdef FEN_EXP_NORES
+          if (false) {
+#else
           if (valid && ly.epi != kBEpiPreluHsum) {
+#endif
             const bf16* rsd = resp + opix * kC + col0;
             ld_cg_256_hint(rsd, kPolicyEvictFirst, *reinterpret_cast<uint32_t(*)[8]>(&rv[0]));
             ld_cg_256_hint(rsd + 16, kPolicyEvictFirst, *reinterpret_cast<uint32_t(*)[8]>(&rv[8]));
@@ -658,8 +665,12 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
             uint32_t o[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) o[e] = pack_bf16(f[2 * e], f[2 * e + 1]);
+#ifndef FEN_EXP_NOSTORE
             st_global_256(outp + opix * kC + col0, *reinterpret_cast<uint32_t(*)[8]>(&o[0]));
             st_global_256(outp + opix * kC + col0 + 16, *reinterpret_cast<uint32_t(*)[8]>(&o[8]));
+#else
+            if (o[0] == 0x12345678u && o[9] == 0x9abcdef0u) st_global_256(outp + opix * kC + col0, *reinterpret_cast<uint32_t(*)[8]>(&o[0]));
+#endif
             if (ly.epi == kBEpiPreluHsum) {          // sum of the bf16-ROUNDED h (what conv2 will read)
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
