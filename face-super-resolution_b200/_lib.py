@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libfen_b200.so")
+# FEN_B200_LIB: developer override (e.g. a -DFEN_BODY_DEBUG build next to the product library)
+LIB_PATH = os.environ.get("FEN_B200_LIB") or os.path.join(PKG_DIR, "libfen_b200.so")
 
 FEN_OK, FEN_EINVAL, FEN_ENODEV, FEN_ENOMEM, FEN_ECUDA = 0, -1, -2, -3, -4
 

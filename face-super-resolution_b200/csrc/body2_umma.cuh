@@ -1,0 +1,648 @@
+// Persistent body kernel, second generation: all 64->64 3x3 convolutions of the residual body in
+// one cooperative launch (see body_umma.cuh for the layer chain and the references:
+// src/models/custom.py:167-175, src/models/blocks.py:75-92,135-153,185-189).
+//
+// What changed against body_umma.cuh, and why (B200 timelines in profiles/r01_body_trace.txt):
+//  * Table-driven issue loops.  Every layer has the same geometry, so the per-tile bookkeeping (ring
+//    position of the tile's view, boxes to wait for / to release, image of the tile) is computed ONCE
+//    into shared-memory tables.  The old issuer warps spent ~2500 cycles of scalar work per tile, in
+//    lock-step, against 1728 cycles of MMA time - the tensor pipe idled a third of every layer.
+//    Each issuer now only visits its own tiles (even / odd).
+//  * Two interleaved image sets.  The batch is split in two halves that are processed alternately
+//    (layer L set 0, layer L set 1, layer L+1 set 0, ...).  A layer boundary costs a release/acquire
+//    round trip between CTAs sharing an image (halo rows, SE pool); with two independent sets that
+//    round trip (and the SE vector) of one set hides behind the other set's tiles.
+//  * Squeeze-and-excitation on the tensor core.  mean_hw(conv2(h)) is linear in 9 border-corrected
+//    channel sums of h (see body_umma.cuh).  The conv1 epilogue now accumulates all 9 sums itself
+//    (no re-read of h), a dedicated SE warp turns them into a 8-row bf16 hi/lo-split operand in
+//    shared memory, and ONE extra batch of 36 tcgen05.mma against the conv2 weights that are in shared
+//    memory anyway produces the 64x576 mat-vec of up to 4 images.  The SE warp finishes with the two
+//    tiny FC layers + sigmoid.  The old 20k-cycle CUDA-core chain on the epilogue warps is gone.
+#pragma once
+#include "body_umma.cuh"
+
+namespace fen {
+
+#ifndef FEN_B2_TRACE
+#define FEN_B2_TRACE 0   // 1: pass-level timeline of CTA 70 into Body2Params::dbg (developer builds)
+#endif
+#ifndef FEN_B2_WATCH
+#define FEN_B2_WATCH 0   // 1: every role logs (stage, L, s, i) into Body2Params::dbg (host-mapped memory) - hang post-mortems
+#endif
+#define B2W(role, stage, L, s, i) do { if (FEN_B2_WATCH && p.dbg && lane == 0) { *(volatile long long*)(p.dbg + blockIdx.x * 8 + (role)) = (long long)(stage) | ((long long)(L) << 8) | ((long long)(s) << 20) | ((long long)(i) << 24); } } while (0)
+#define B2TRACE(P, e) do { if (FEN_B2_TRACE && p.dbg && blockIdx.x == 70 && (P) < 512) p.dbg[(P) * 8 + (e)] = clock64(); } while (0)
+
+constexpr int kB2Threads = 384;
+constexpr int kB2SeWarp = 0;                       // warp % 4 == 0: may read TMEM lanes 0..31 (the SE result rows)
+constexpr int kB2TmaWarp = 1;
+constexpr int kB2FirstMmaWarp = 2;                 // warps 2, 3
+constexpr int kB2FirstEpiWarp = 4;                 // warps 4..11
+constexpr int kB2EpiWarps = 8;
+constexpr int kB2AccBufs = 7;                      // 7 x 64 TMEM columns for conv tiles ...
+constexpr uint32_t kB2SeCol = kB2AccBufs * kC;     // ... + 64 columns for the SE mat-vec
+constexpr int kB2SBytes = 9 * 1024;                // SE operand: one 8-row SWIZZLE_128B atom per tap
+constexpr int kB2RingPx = kBSlots * kBBoxPx;       // 924 pixels, + the 132-pixel mirror slot
+constexpr int kB2DynBytes = kBodyWBytes + kB2SBytes + kBRingBytes + 1024;
+constexpr int kB2MaxTiles = 64;
+constexpr int kB2MaxBoxes = 96;
+
+struct B2Tile { uint16_t m; uint8_t wait_upto, rel_upto, unit, t; uint16_t pad; };
+struct B2Box { int16_t img; int8_t y0; uint8_t mirror; };
+struct B2Unit { int img, t0, t1, pad; };
+
+// BodyParams::B is the whole batch; total_tiles / tiles_per_cta count the tiles of ONE set.
+struct Body2Params : BodyParams {
+  int nset;      // 1 or 2 interleaved image sets
+  int set_B;     // images per set (B = nset * set_B)
+};
+
+__device__ __forceinline__ float2 ld_cg_f32x2(const float* p) {
+  float2 v;
+  asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_shared_u32(uint32_t saddr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(kB2Threads, 1)
+body2_umma_kernel(const __grid_constant__ BodyMaps maps, const Body2Params p) {
+  constexpr int N = kC;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_smem = smem;                              // [9][64][64] bf16, SWIZZLE_128B
+  uint8_t* s_buf = smem + kBodyWBytes;                 // [9] atoms of 8 rows x 128 B (rows 2u, 2u+1: hi / lo of unit u)
+  uint8_t* ring = s_buf + kB2SBytes;                   // 7 slots + mirror
+  __shared__ uint64_t bar_w[9], bar_wfree[9], bar_full[kBSlots], bar_empty[kBSlots];
+  __shared__ uint64_t bar_acc_full[kB2AccBufs], bar_acc_empty[kB2AccBufs];
+  __shared__ uint64_t bar_done, bar_s_ready, bar_s_free, bar_se_full, bar_se_empty, bar_scale[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ B2Tile tile_tab[kB2MaxTiles];
+  __shared__ B2Box box_tab[kB2MaxBoxes];
+  __shared__ B2Unit unit_tab[kBodyMaxUnits];
+  __shared__ int s_meta[4];                            // tiles, boxes, units, odd-use slot mask
+  __shared__ __align__(16) float s_scale[2][kBodyMaxUnits][kC];   // res_scale * s, per set and unit
+  __shared__ __align__(16) float s_mean[kBodyMaxUnits][kC], s_hid[kBodyMaxUnits][kC];
+  __shared__ __align__(16) uint32_t s_colx[kB2EpiWarps][2][16];   // per epilogue warp: one staged pixel (32 bf16) per border column
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t kTmemCols = 512;
+
+  const int g_begin = blockIdx.x * p.tiles_per_cta;
+  const int g_end = min(p.total_tiles, g_begin + p.tiles_per_cta);
+  // peers: CTAs owning tiles of the images this CTA touches (same for both sets)
+  const int img0 = g_begin / p.tiles_per_seg, img1 = (g_end - 1) / p.tiles_per_seg;
+  const int peer0 = (img0 * p.tiles_per_seg) / p.tiles_per_cta;
+  const int peer1 = min(int(gridDim.x) - 1, ((img1 + 1) * p.tiles_per_seg - 1) / p.tiles_per_cta);
+
+  if (warp == kB2FirstMmaWarp) tmem_alloc(&tmem_slot, kTmemCols);
+  if (tid == 0) {
+    // ---- per-pass tables (identical for every layer and both sets)
+    int first_box[kB2MaxTiles + 2];
+    int b_cum = 0, i = 0, u = 0;
+    for (int g = g_begin; g < g_end; ++u) {
+      const BUnit bu = body_unit(p, g, g_end);
+      unit_tab[u].img = bu.n; unit_tab[u].t0 = bu.t0; unit_tab[u].t1 = bu.t1; unit_tab[u].pad = 0;
+      for (int j = 0; j < bu.nboxes; ++j) {
+        B2Box e;
+        e.img = int16_t(bu.n); e.y0 = int8_t(bu.ra - 1 + j * kBBoxRows);
+        e.mirror = uint8_t(((b_cum + j) % kBSlots == 0) && j > 0);
+        box_tab[b_cum + j] = e;
+      }
+      for (int t = bu.t0; t < bu.t1; ++t, ++i) {
+        const int base = kTileM * t - kPitch * bu.ra;
+        first_box[i] = b_cum + base / kBBoxPx;
+        B2Tile e;
+        e.m = uint16_t((b_cum * kBBoxPx + base) % kB2RingPx);
+        e.wait_upto = uint8_t(b_cum + min((base + kTileM + kMaxShift - 1) / kBBoxPx, bu.nboxes - 1) + 1);
+        e.rel_upto = 0; e.unit = uint8_t(u); e.t = uint8_t(t); e.pad = 0;
+        tile_tab[i] = e;
+      }
+      b_cum += bu.nboxes;
+      g += bu.t1 - bu.t0;
+    }
+    for (int k = 0; k < i; ++k) tile_tab[k].rel_upto = uint8_t((k + 2 < i) ? first_box[k + 2] : b_cum);
+    int odd = 0;
+    for (int s = 0; s < kBSlots; ++s) {
+      const int uses = (b_cum > s) ? (b_cum - s + kBSlots - 1) / kBSlots : 0;
+      if (uses & 1) odd |= 1 << s;
+    }
+    s_meta[0] = i; s_meta[1] = b_cum; s_meta[2] = u; s_meta[3] = odd;
+    // ---- barriers.  A CTA with a single tile per pass has no odd tile: issuer warp 3 stays out of the
+    // ring / weight release protocol entirely (an issuer without MMAs could lap the other one).
+    const uint32_t n_issuers = (i >= 2) ? 2u : 1u;
+    for (int k = 0; k < 9; ++k) { mbar_init(&bar_w[k], 1); mbar_init(&bar_wfree[k], n_issuers); }
+    for (int k = 0; k < kBSlots; ++k) { mbar_init(&bar_full[k], 1); mbar_init(&bar_empty[k], n_issuers); }
+    for (int k = 0; k < kB2AccBufs; ++k) { mbar_init(&bar_acc_full[k], 1); mbar_init(&bar_acc_empty[k], kB2EpiWarps); }
+    mbar_init(&bar_done, kB2EpiWarps);
+    mbar_init(&bar_s_ready, 1); mbar_init(&bar_s_free, 1); mbar_init(&bar_se_full, 1); mbar_init(&bar_se_empty, 1);
+    mbar_init(&bar_scale[0], 1); mbar_init(&bar_scale[1], 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&maps.w);
+  }
+  for (int k = tid; k < kB2SBytes / 16; k += kB2Threads) reinterpret_cast<uint4*>(s_buf)[k] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int n_tiles = s_meta[0], n_boxes = s_meta[1], n_units = s_meta[2];
+  const uint32_t oddmask = uint32_t(s_meta[3]);
+  if (n_tiles <= 0) return;   // never happens with the host's grid sizing
+
+  if (warp == kB2TmaWarp) {
+    // ============================================================ TMA issuer + peer-flag poller
+    uint32_t P = 0;
+    for (int L = 0; L < p.n_layers; ++L) {
+      const BodyLayer ly = body_layer(p, L);
+      if (lane == 0) {
+        for (int tap = 0; tap < 9; ++tap) {     // weights, tap by tap, as soon as the previous layer released the tap
+          B2W(1, 1, L, 0, tap);
+          if (L > 0) mbar_wait(&bar_wfree[tap], (L - 1) & 1);
+          mbar_expect_tx(&bar_w[tap], N * kC * 2);
+          tma_load_2d(&maps.w, &bar_w[tap], w_smem + tap * N * 128, 0, ly.w_row + tap * N);
+        }
+      }
+      __syncwarp();
+      const uint64_t pol = ly.last_use ? kPolicyEvictFirst : 0x1000000000000000ull;
+      for (int s = 0; s < p.nset; ++s, ++P) {
+        // every peer must have finished layer L-1 of this set: their outputs are my inputs / halos
+        B2W(1, 2, L, s, 0);
+        if (L > 0) {
+          const int* fl = p.flags + s * int(gridDim.x);
+          for (int k = peer0 + lane; k <= peer1; k += 32)
+            while (ld_acquire_gpu(fl + k) < L) { __nanosleep(20); }
+          __syncwarp();
+          fence_proxy_async_all();
+        }
+        if (lane == 0) {
+          B2TRACE(P, 0);
+          const uint32_t passpar = (P & 1) ? oddmask : 0u;
+          const int img_base = s * p.set_B;
+          uint32_t slot = 0, k = 0;
+          for (int b = 0; b < n_boxes; ++b) {
+            const B2Box e = box_tab[b];
+            B2W(1, 3, L, s, b);
+            mbar_wait(&bar_empty[slot], ((passpar >> slot) ^ k ^ 1u) & 1u);
+            mbar_expect_tx(&bar_full[slot], e.mirror ? 2 * kBSlotBytes : kBSlotBytes);
+            tma_load_4d_hint(&maps.act[ly.in], &bar_full[slot], smem_u32(ring + slot * kBSlotBytes), 0, -1, e.y0,
+                             img_base + e.img, pol);
+            if (e.mirror)
+              tma_load_4d_hint(&maps.act[ly.in], &bar_full[slot], smem_u32(ring + kBSlots * kBSlotBytes), 0, -1, e.y0,
+                               img_base + e.img, pol);
+            if (++slot == kBSlots) { slot = 0; ++k; }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == kB2FirstMmaWarp || warp == kB2FirstMmaWarp + 1) {
+    // ============================================================ MMA issuers: warp 2 even tiles (+ SE batches), warp 3 odd tiles
+    constexpr uint32_t idesc = umma_idesc_bf16(kTileM, N);
+    constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    constexpr uint32_t kLbo = 1u << 16;
+    const uint32_t ring_lo = (smem_u32(ring) >> 4) | kLbo;
+    const uint32_t w_lo = (smem_u32(w_smem) >> 4) | kLbo;
+    const uint32_t s_lo = (smem_u32(s_buf) >> 4) | kLbo;
+    const bool leader = elect_one();
+    const int wi = warp - kB2FirstMmaWarp;
+    const int last_own = ((n_tiles - 1 - wi) >= 0) ? wi + 2 * ((n_tiles - 1 - wi) >> 1) : -1;
+    uint32_t P = 0, gbase = 0, se_n = 0;
+    for (int L = 0; L < (last_own >= 0 ? p.n_layers : 0); ++L) {
+      const bool conv2 = body_layer(p, L).epi == kBEpiSeResidual;
+      bool w_seen = false;
+      for (int s = 0; s < p.nset; ++s, ++P, gbase += n_tiles) {
+        const uint32_t passpar = (P & 1) ? oddmask : 0u;
+        const bool last_pass = (s == p.nset - 1);
+#ifdef FEN_B2_X2
+        bool se_pending = false;
+#else
+        bool se_pending = conv2 && (wi == 0);
+#endif
+        uint32_t waited = 0, released = 0;
+        // one SE batch: D[row, c] = sum_tap S_tap[row, :] . W2_tap[c, :] into the SE accumulator
+        auto issue_se = [&]() {
+          B2W(2 + wi, 5, L, s, se_n);
+          if (se_n >= 1) mbar_wait(&bar_se_empty, (se_n - 1) & 1);
+          tc_fence_after();
+          // The batch only starts once ALL taps of this layer's weights have landed, i.e. once no MMA of the
+          // previous layer is in flight any more.  Issued tap by tap behind the weight loads, interleaved
+          // with the other issuer's last tile of the previous layer, it raised "warp out-of-range address"
+          // on B200 for even tile counts (the only case where this warp enters a layer first).
+          if (!w_seen) {
+            for (int tap = 0; tap < 9; ++tap) mbar_wait(&bar_w[tap], L & 1);
+          }
+          if (leader) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t a_lo = s_lo + tap * (1024 >> 4);
+              const uint32_t b_lo = w_lo + tap * (N * 128 >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16_ss_lohi(tmem_base + kB2SeCol, a_lo + 2 * k, b_lo + 2 * k, kDescHi, idesc, (tap | k) != 0);
+              }
+            }
+            umma_commit(&bar_se_full);
+            umma_commit(&bar_s_free);
+          }
+          w_seen = true;
+          ++se_n;
+          se_pending = false;
+          __syncwarp();
+        };
+        for (int i = wi; i < n_tiles; i += 2) {
+          const B2Tile e = tile_tab[i];
+          const uint32_t G = gbase + i, acc = G % kB2AccBufs, aph = (G / kB2AccBufs) & 1;
+          B2W(2 + wi, 1, L, s, i);
+          if (se_pending) {
+            // The epilogue of this pass cannot free accumulators before the SE batch has run: never block on
+            // an accumulator while the batch is still owed.
+            if (i == last_own) {
+              mbar_wait(&bar_s_ready, se_n & 1);
+              issue_se();
+            } else {
+              for (;;) {
+                // (never as the first batch of a layer: see issue_se)
+                if (w_seen && __any_sync(0xffffffffu, mbar_try_wait(&bar_s_ready, se_n & 1))) { issue_se(); break; }
+                if (__any_sync(0xffffffffu, mbar_try_wait(&bar_acc_empty[acc], aph ^ 1))) break;
+              }
+            }
+          }
+          B2W(2 + wi, 2, L, s, i);
+          mbar_wait(&bar_acc_empty[acc], aph ^ 1);
+          B2W(2 + wi, 3, L, s, i);
+          while (waited < e.wait_upto) {
+            const uint32_t slot = waited % kBSlots, k = waited / kBSlots;
+            mbar_wait(&bar_full[slot], ((passpar >> slot) ^ k) & 1u);
+            ++waited;
+          }
+          if (leader && i == wi) B2TRACE(P, 1 + wi);
+          B2W(2 + wi, 4, L, s, i);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * N;
+          const uint32_t m = e.m;
+          const bool w_rel = last_pass && (i == last_own);
+          if (leader) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              if (!w_seen) mbar_wait(&bar_w[tap], L & 1);
+              const uint32_t off = (tap / 3) * kPitch + (tap % 3);
+              uint32_t pos = m + off;
+              if (pos >= uint32_t(kB2RingPx)) pos -= kB2RingPx;
+              const uint32_t a_lo = ring_lo + pos * 8;
+              const uint32_t b_lo = w_lo + tap * (N * 128 >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_ss_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, kDescHi, idesc, (tap | k) != 0);
+              if (w_rel) umma_commit(&bar_wfree[tap]);   // the next layer's tap may overwrite once these MMAs finish
+            }
+          }
+          w_seen = true;
+          __syncwarp();
+          // A box may only be handed back after THIS warp has seen it arrive (the last boxes of a pass are
+          // read by the other issuer alone): an arrival for a use that has not started yet would complete
+          // the slot's previous phase early.
+          while (waited < e.rel_upto) {
+            const uint32_t slot = waited % kBSlots, k = waited / kBSlots;
+            mbar_wait(&bar_full[slot], ((passpar >> slot) ^ k) & 1u);
+            ++waited;
+          }
+          while (released < e.rel_upto) {
+            if (leader) umma_commit(&bar_empty[released % kBSlots]);
+            ++released;
+          }
+          if (leader) umma_commit(&bar_acc_full[acc]);
+          if (leader && i == last_own) B2TRACE(P, 3 + wi);
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == kB2SeWarp) {
+    // ============================================================ SE warp
+    uint32_t se_n = 0, m_cnt = 0;
+    const uint32_t s_base = smem_u32(s_buf);
+#ifdef FEN_B2_X2
+    for (int L = 0; L < 0; ++L) {
+#else
+    for (int L = 0; L < p.n_layers; ++L) {
+#endif
+      const BodyLayer ly = body_layer(p, L);
+      if (ly.epi != kBEpiSeResidual) continue;
+      const uint8_t* rec = p.packed + p.k_rcab0 + int64_t(ly.rcab) * p.k_rcab_stride;
+      const float* fc0 = reinterpret_cast<const float*>(rec + p.k_rcab_fc0);
+      const float* fc2 = reinterpret_cast<const float*>(rec + p.k_rcab_fc2);
+      for (int s = 0; s < p.nset; ++s, ++se_n) {
+        // the conv1 layer (L - 1) of this set must be complete on every peer: its epilogues own the sums
+        B2W(0, 1, L, s, se_n);
+        {
+          const int* fl = p.flags + s * int(gridDim.x);
+          for (int k = peer0 + lane; k <= peer1; k += 32)
+            while (ld_acquire_gpu(fl + k) < L) { __nanosleep(20); }
+          __syncwarp();
+        }
+        const int img_base = s * p.set_B;
+        // 9 sums x 2 channels per lane and unit, all requested before the first use (one L2 round trip)
+        float2 qv[kBodyMaxUnits][kHsCount];
+#pragma unroll
+        for (int u = 0; u < kBodyMaxUnits; ++u) {
+          if (u < n_units) {
+            const float* hs = p.hsum + (size_t(ly.rcab) * p.B + img_base + unit_tab[u].img) * (kHsCount * kC) + 2 * lane;
+#pragma unroll
+            for (int k = 0; k < kHsCount; ++k) qv[u][k] = ld_cg_f32x2(hs + k * kC);
+          }
+        }
+        B2W(0, 2, L, s, se_n);
+        if (se_n >= 1) mbar_wait(&bar_s_free, (se_n - 1) & 1);   // the previous batch has consumed the operand
+#pragma unroll
+        for (int u = 0; u < kBodyMaxUnits; ++u) {
+          if (u < n_units) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+              float2 v = qv[u][kHsTotal];
+              if (dy == 1) { v.x -= qv[u][kHsRow0].x; v.y -= qv[u][kHsRow0].y; }
+              if (dy == -1) { v.x -= qv[u][kHsRowL].x; v.y -= qv[u][kHsRowL].y; }
+              if (dx == 1) { v.x -= qv[u][kHsCol0].x; v.y -= qv[u][kHsCol0].y; }
+              if (dx == -1) { v.x -= qv[u][kHsColL].x; v.y -= qv[u][kHsColL].y; }
+              if (dy == 1 && dx == 1) { v.x += qv[u][kHsC00].x; v.y += qv[u][kHsC00].y; }
+              if (dy == 1 && dx == -1) { v.x += qv[u][kHsC0L].x; v.y += qv[u][kHsC0L].y; }
+              if (dy == -1 && dx == 1) { v.x += qv[u][kHsCL0].x; v.y += qv[u][kHsCL0].y; }
+              if (dy == -1 && dx == -1) { v.x += qv[u][kHsCLL].x; v.y += qv[u][kHsCLL].y; }
+              // hi / lo bf16 split: hi + lo carries 16 mantissa bits of the fp32 sum
+              const uint32_t hi = pack_bf16(v.x, v.y);
+              const uint32_t lo = pack_bf16(v.x - bf16lo(hi), v.y - bf16hi(hi));
+              const uint32_t chunk = uint32_t(lane >> 2), inner = uint32_t(lane & 3) * 4;   // channels 2*lane, 2*lane+1
+              const uint32_t r0 = 2 * u, r1 = 2 * u + 1;
+              st_shared_u32(s_base + tap * 1024 + r0 * 128 + ((chunk ^ r0) << 4) + inner, hi);
+              st_shared_u32(s_base + tap * 1024 + r1 * 128 + ((chunk ^ r1) << 4) + inner, lo);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_s_ready);
+        // ---- result rows 0..7 of the SE accumulator: lane r holds row r
+        B2W(0, 3, L, s, se_n);
+        mbar_wait(&bar_se_full, se_n & 1);
+        B2W(0, 4, L, s, se_n);
+        tc_fence_after();
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(tmem_base + kB2SeCol, v0);
+        tmem_ld_32x32(tmem_base + kB2SeCol + 32, v1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_se_empty);
+        {
+          const int u = lane >> 1;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float a = __uint_as_float(v0[c]), b = __uint_as_float(v1[c]);
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            b += __shfl_xor_sync(0xffffffffu, b, 1);
+            if ((lane & 1) == 0 && u < n_units) {
+              s_mean[u][c] = c_vec[ly.cv_bias + c] + a * p.inv_hw;
+              s_mean[u][c + 32] = c_vec[ly.cv_bias + c + 32] + b * p.inv_hw;
+            }
+          }
+        }
+        __syncwarp();
+        for (int idx = lane; idx < n_units * p.R; idx += 32) {        // FC1 + ReLU
+          const int u = idx / p.R, j = idx - u * p.R;
+          float a = 0.f;
+#pragma unroll 16
+          for (int c = 0; c < kC; ++c) a = fmaf(__ldg(fc0 + j * kC + c), s_mean[u][c], a);
+          s_hid[u][j] = fmaxf(a, 0.f);
+        }
+        __syncwarp();
+        for (int idx = lane; idx < n_units * kC; idx += 32) {         // FC2 + sigmoid
+          const int u = idx >> 6, c = idx & 63;
+          float a = 0.f;
+          for (int j = 0; j < p.R; ++j) a = fmaf(__ldg(fc2 + c * p.R + j), s_hid[u][j], a);
+          const float sv = 1.f / (1.f + expf(-a));
+          s_scale[s][u][c] = sv * p.res_scale;
+          if (p.se_out && unit_tab[u].t0 == 0)      // the CTA owning tile 0 of the image publishes the attention vector
+            p.se_out[(size_t(img_base + unit_tab[u].img) * (p.G * p.Bk) + ly.rcab) * kC + c] = sv;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_scale[s]);
+      }
+      ++m_cnt;
+    }
+    (void)m_cnt;
+  } else {
+    // ============================================================ epilogue (8 warps)
+    constexpr int CW = 32;
+    const int q = warp & 3;
+    const int ew = warp - kB2FirstEpiWarp;
+    const int half = ew >> 2;
+    const int col0 = half * CW;
+    const int row_in_tile = q * 32 + lane;
+    const bool flag_writer = (ew == 0);
+    uint32_t G = 0, P = 0, m_cnt = 0;
+    for (int L = 0; L < p.n_layers; ++L) {
+      const BodyLayer ly = body_layer(p, L);
+      bf16* outp = p.buf[ly.out];
+      const bf16* resp = ly.res >= 0 ? p.buf[ly.res] : nullptr;
+      float bias[CW], slope[CW];
+#pragma unroll
+      for (int j = 0; j < CW / 4; ++j) {
+        const float4 b4 = *reinterpret_cast<const float4*>(c_vec + ly.cv_bias + col0 + 4 * j);
+        bias[4 * j] = b4.x; bias[4 * j + 1] = b4.y; bias[4 * j + 2] = b4.z; bias[4 * j + 3] = b4.w;
+      }
+      if (ly.epi == kBEpiPreluHsum) {
+#pragma unroll
+        for (int j = 0; j < CW / 4; ++j) {
+          const float4 s4 = *reinterpret_cast<const float4*>(c_vec + ly.cv_slope + col0 + 4 * j);
+          slope[4 * j] = s4.x; slope[4 * j + 1] = s4.y; slope[4 * j + 2] = s4.z; slope[4 * j + 3] = s4.w;
+        }
+      }
+      for (int s = 0; s < p.nset; ++s, ++P) {
+        const int img_base = s * p.set_B;
+        if (ew == 0) B2W(4, 1, L, s, 0);
+#ifndef FEN_B2_X2
+        if (ly.epi == kBEpiSeResidual) mbar_wait(&bar_scale[s], m_cnt & 1);
+#endif
+        int cur_unit = -1, img = 0;
+        float csum[CW], col0sum = 0.f, colLsum = 0.f;
+        float* hs = nullptr;
+        auto flush_unit = [&]() {
+          if (ly.epi != kBEpiPreluHsum || cur_unit < 0) return;
+          // total: reduce-scatter butterfly over the warp, lane l ends with channel col0 + l
+#pragma unroll
+          for (int d = 16, len = CW; d >= 1; d >>= 1, len >>= 1) {
+            const bool hi = (lane & d) != 0;
+#pragma unroll
+            for (int i = 0; i < len / 2; ++i) {
+              const float send = hi ? csum[i] : csum[i + len / 2];
+              const float keep = hi ? csum[i + len / 2] : csum[i];
+              csum[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+            }
+          }
+          atomicAdd(hs + kHsTotal * kC + col0 + lane, csum[0]);
+          atomicAdd(hs + kHsCol0 * kC + col0 + lane, col0sum);
+          atomicAdd(hs + kHsColL * kC + col0 + lane, colLsum);
+        };
+        for (int i = 0; i < n_tiles; ++i, ++G) {
+          const B2Tile e = tile_tab[i];
+          if (int(e.unit) != cur_unit) {
+            flush_unit();
+            cur_unit = e.unit;
+            img = img_base + unit_tab[cur_unit].img;
+#pragma unroll
+            for (int c = 0; c < CW; ++c) csum[c] = 0.f;
+            col0sum = 0.f; colLsum = 0.f;
+            if (ly.epi == kBEpiPreluHsum) hs = p.hsum + (size_t(ly.rcab) * p.B + img) * (kHsCount * kC);
+            if (ly.epi == kBEpiSeResidual) {             // `slope` doubles as the SE scale of this image
+#pragma unroll
+              for (int j = 0; j < CW / 4; ++j) {
+                const float4 s4 = *reinterpret_cast<const float4*>(&s_scale[s][cur_unit][col0 + 4 * j]);
+                slope[4 * j] = s4.x; slope[4 * j + 1] = s4.y; slope[4 * j + 2] = s4.z; slope[4 * j + 3] = s4.w;
+              }
+            }
+          }
+          const uint32_t acc = G % kB2AccBufs, aph = (G / kB2AccBufs) & 1;
+          const int lin = kTileM * int(e.t) + row_in_tile;
+          const int y = lin / kPitch, x = lin - y * kPitch;
+          const bool valid = (x < kStripW) && (y < p.H);
+          const size_t opix = (size_t(img) * p.H + y) * p.W + x;
+          // residual / skip values of this pixel: requested before waiting for the accumulator
+          uint32_t rv[16];
+          if (valid && ly.epi != kBEpiPreluHsum) {
+            const bf16* rsd = resp + opix * kC + col0;
+            ld_cg_256_hint(rsd, kPolicyEvictFirst, *reinterpret_cast<uint32_t(*)[8]>(&rv[0]));
+            ld_cg_256_hint(rsd + 16, kPolicyEvictFirst, *reinterpret_cast<uint32_t(*)[8]>(&rv[8]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rv[j] = 0u;
+          }
+          if (ew == 0) B2W(4, 2, L, s, i);
+          mbar_wait(&bar_acc_full[acc], aph);
+          if (ew == 0 && lane == 0 && i == 0) B2TRACE(P, 5);
+          tc_fence_after();
+          uint32_t v[CW];
+          tmem_ld_32x32(tmem_base + acc * N + col0 + (uint32_t(q * 32) << 16), v);
+          tmem_ld_wait();
+          tc_fence_before();                       // accumulator read: hand it back to the MMA issuers
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_acc_empty[acc]);
+          float f[CW];
+#pragma unroll
+          for (int c = 0; c < CW; ++c) f[c] = __uint_as_float(v[c]) + bias[c];
+          if (ly.epi == kBEpiPreluHsum) {
+#pragma unroll
+            for (int c = 0; c < CW; ++c) f[c] = fmaxf(f[c], 0.f) + slope[c] * fminf(f[c], 0.f);
+          } else {
+            if (ly.epi == kBEpiSeResidual) {
+#pragma unroll
+              for (int c = 0; c < CW; ++c) f[c] *= slope[c];
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {          // + x (RCAB residual) or + skip (group / long skip)
+              f[2 * j] += bf16lo(rv[j]);
+              f[2 * j + 1] += bf16hi(rv[j]);
+            }
+          }
+          uint32_t o[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) o[k] = pack_bf16(f[2 * k], f[2 * k + 1]);
+          if (valid) {
+            st_global_256(outp + opix * kC + col0, *reinterpret_cast<uint32_t(*)[8]>(&o[0]));
+            st_global_256(outp + opix * kC + col0 + 16, *reinterpret_cast<uint32_t(*)[8]>(&o[8]));
+          }
+          if (ly.epi == kBEpiPreluHsum) {
+            // ---- the 9 channel sums of the bf16-ROUNDED h (what conv2 will read) that the SE pool needs
+            if (valid) {
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                csum[2 * k] += bf16lo(o[k]);
+                csum[2 * k + 1] += bf16hi(o[k]);
+              }
+            }
+#if defined(FEN_B2_X1) || defined(FEN_B2_X4)
+            const unsigned mc0 = 0, mcl = 0;
+#else
+            // border columns: at most one pixel of each per warp and tile (a strip row is 66 > 32 pixels)
+            const unsigned mc0 = __ballot_sync(0xffffffffu, valid && x == 0);
+            const unsigned mcl = __ballot_sync(0xffffffffu, valid && x == p.W - 1);
+#endif
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+              const unsigned mk = side ? mcl : mc0;
+              if (mk) {
+                const int src = __ffs(mk) - 1;
+                if (lane == src) {
+                  uint4* d = reinterpret_cast<uint4*>(&s_colx[ew][side][0]);
+                  d[0] = make_uint4(o[0], o[1], o[2], o[3]);    d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                  d[2] = make_uint4(o[8], o[9], o[10], o[11]);  d[3] = make_uint4(o[12], o[13], o[14], o[15]);
+                }
+                __syncwarp();
+                const uint32_t wv = s_colx[ew][side][lane >> 1];
+                const float val = (lane & 1) ? bf16hi(wv) : bf16lo(wv);
+                const int ys = __shfl_sync(0xffffffffu, y, src);
+                if (side) colLsum += val; else col0sum += val;
+                if (ys == 0) atomicAdd(hs + (side ? kHsC0L : kHsC00) * kC + col0 + lane, val);
+                if (ys == p.H - 1) atomicAdd(hs + (side ? kHsCL0 + 1 : kHsCL0) * kC + col0 + lane, val);
+                __syncwarp();
+              }
+            }
+            // border rows: only the first and the last tiles of an image contain them
+#if defined(FEN_B2_X1) || defined(FEN_B2_X3)
+            const unsigned mr0 = 0, mrl = 0;
+#else
+            const unsigned mr0 = __ballot_sync(0xffffffffu, valid && y == 0);
+            const unsigned mrl = __ballot_sync(0xffffffffu, valid && y == p.H - 1);
+#endif
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+              const unsigned mk = side ? mrl : mr0;
+              if (mk) {
+                const bool in = (mk >> lane) & 1u;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                  f[2 * k] = in ? bf16lo(o[k]) : 0.f;
+                  f[2 * k + 1] = in ? bf16hi(o[k]) : 0.f;
+                }
+#pragma unroll
+                for (int d = 16, len = CW; d >= 1; d >>= 1, len >>= 1) {
+                  const bool hi = (lane & d) != 0;
+#pragma unroll
+                  for (int k = 0; k < len / 2; ++k) {
+                    const float send = hi ? f[k] : f[k + len / 2];
+                    const float keep = hi ? f[k + len / 2] : f[k];
+                    f[k] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+                  }
+                }
+                atomicAdd(hs + (side ? kHsRowL : kHsRow0) * kC + col0 + lane, f[0]);
+              }
+            }
+          }
+        }
+        flush_unit();
+        // ---- pass done for this warp: make its global writes visible, then publish the CTA's flag
+        __threadfence();
+        __syncwarp();
+        // arrivals of pass P may only start once pass P-1 is complete (a warp running ahead over short
+        // passes could otherwise complete a phase with two of its own arrivals)
+        if (P > 0) mbar_wait(&bar_done, (P - 1) & 1);
+        if (lane == 0) mbar_arrive(&bar_done);
+        if (flag_writer) {
+          B2W(4, 3, L, s, 0);
+          mbar_wait(&bar_done, P & 1);
+          if (lane == 0) {
+            st_release_gpu(p.flags + s * int(gridDim.x) + blockIdx.x, L + 1);
+            B2TRACE(P, 7);
+          }
+          __syncwarp();
+        }
+      }
+      if (ly.epi == kBEpiSeResidual) ++m_cnt;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kB2FirstMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace fen

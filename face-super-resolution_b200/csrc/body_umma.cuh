@@ -40,6 +40,8 @@ namespace fen {
 #endif
 #define BDBG (FEN_BODY_DEBUG && p.dbg)
 // timeline trace (FEN_BODY_DEBUG=2): event e of layer L of CTA 70 -> dbg[4096 + L*16 + e]
+// per-tile trace (FEN_BODY_DEBUG=2): layers 20..23 of CTA 70 -> dbg[8192 + (L-20)*256 + e*32 + i]
+#define BT2(L, e, i) do { if (FEN_BODY_DEBUG == 2 && p.dbg && blockIdx.x == 70 && (L) >= 20 && (L) < 24 && (i) < 32) p.dbg[8192 + ((L) - 20) * 512 + (e) * 32 + (i)] = clock64(); } while (0)
 #define BTRACE(L, e) do { if (FEN_BODY_DEBUG == 2 && p.dbg && blockIdx.x == 70) p.dbg[4096 + (L) * 16 + (e)] = clock64(); } while (0)
 
 constexpr int kBodyMmaWarps = 2;
@@ -265,6 +267,7 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
         if (lane == 0) mbar_arrive(&bar_flags);          // the epilogue may read peers' h / sums (SE vector)
       }
       if (lane == 0) BTRACE(L, 0);   // flags passed, first box about to be issued
+      const uint32_t gb_l0 = gb;
       if (lane == 0) {
         const uint64_t pol = ly.last_use ? kPolicyEvictFirst : 0x1000000000000000ull;
         for (int g = g_begin; g < g_end;) {
@@ -273,6 +276,7 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
             const uint32_t slot = gb % kBSlots, ph = (gb / kBSlots) & 1;
             const int y0 = u.ra - 1 + j * kBBoxRows;
             mbar_wait(&bar_empty[slot], ph ^ 1);
+            BT2(L, 4, int(gb - gb_l0));
             const bool mirror = (slot == 0) && (j > 0);
             mbar_expect_tx(&bar_full[slot], mirror ? 2 * kBSlotBytes : kBSlotBytes);
             tma_load_4d_hint(&maps.act[ly.in], &bar_full[slot], smem_u32(ring + slot * kBSlotBytes), 0, -1, y0, u.n, pol);
@@ -323,8 +327,11 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
           const uint32_t acc = tile_ctr & (kBodyAccBufs - 1);
           const bool mine = (tile_ctr & 1) == my_parity;
           if (BDBG) m_t = clock64();
+          if (leader && mine) BT2(L, 0, i_layer);
+          if (leader && !mine) BT2(L, 11, i_layer);
           if (mine) mbar_wait(&bar_acc_empty[acc], ((tile_ctr / kBodyAccBufs) & 1) ^ 1);
           if (BDBG) { const long long n_ = clock64(); m_acc += n_ - m_t; m_t = n_; }
+          if (leader && mine) BT2(L, 6, i_layer);
           const int base = kTileM * t - kPitch * u.ra;
           const int need_last = min((base + kTileM + kMaxShift - 1) / kBBoxPx, u.nboxes - 1);
           while (mine && waited <= need_last) {
@@ -334,7 +341,10 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
           }
           if (BDBG) { const long long n_ = clock64(); m_full += n_ - m_t; m_t = n_; }
           if (leader && i_layer == 0) BTRACE(L, 1);   // data for the first tile of the layer present
+          if (leader && mine) BT2(L, 5, i_layer);
+          if (leader && !mine) BT2(L, 12, i_layer);
           tc_fence_after();
+          if (leader && !mine) BT2(L, 13, i_layer);
           const uint32_t d_tmem = tmem_base + acc * N;
           // a view starts in box lb0, lb0 + 1 or lb0 + 2 (tap offsets reach 134 px, a box is 132)
           const int lb0 = base / kBBoxPx, r0 = base - lb0 * kBBoxPx;
@@ -359,13 +369,17 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
             }
           }
           __syncwarp();
+          if (leader && mine) BT2(L, 1, i_layer);
+          if (leader && !mine) BT2(L, 14, i_layer);
           if (BDBG) { const long long n_ = clock64(); m_issue += n_ - m_t; m_t = n_; }
           const int next_first = (t + 1 < u.t1) ? (base + kTileM) / kBBoxPx : u.nboxes;
           while (released < next_first) {
             if (leader) umma_commit(&bar_empty[(gb_base + released) % kBSlots]);
             ++released;
           }
+          if (leader) BT2(L, 9, i_layer);
           if (leader && mine) umma_commit(&bar_acc_full[acc]);
+          if (leader) BT2(L, 10, i_layer);
           if (leader && i_layer >= n_tiles - 2) BTRACE(L, 2 + (i_layer == n_tiles - 1));   // last two tiles issued
           __syncwarp();
         }
@@ -637,6 +651,7 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
           mbar_wait(&bar_acc_full[acc], (tile_ctr / kBodyAccBufs) & 1);
           if (BDBG) e_wait += clock64() - e_t;
           if (et == 0 && tile_ctr % n_tiles == 0) BTRACE(L, 5);   // first accumulator of the layer ready
+          if (et == 0) BT2(L, 2, int(tile_ctr % n_tiles));
           tc_fence_after();
           uint32_t v[CW];
           tmem_ld_32x32(tmem_base + acc * N + col0 + (uint32_t(q * 32) << 16), v);
@@ -679,6 +694,7 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
               }
             }
           }
+          if (et == 0) BT2(L, 3, int(tile_ctr % n_tiles));
         }
         if (ly.epi == kBEpiPreluHsum) {
           float* hs = p.hsum + (size_t(ly.rcab) * p.B + u.n) * kC;

@@ -10,6 +10,7 @@
 #include "../../include/fen_b200.h"
 #include "conv3x3_umma.cuh"
 #include "body_umma.cuh"
+#include "body2_umma.cuh"
 
 namespace fen {
 
@@ -498,6 +499,84 @@ static int launch_body(const fen_config* cfg, const Layout& L, const Workspace& 
   return FEN_OK;
 }
 
+// ===================================================================== second-generation body kernel launcher
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+// 2 interleaved image sets when the batch is even (FEN_BODY_NSET=1 forces one set)
+static int body2_nset(int B) {
+  static int forced = -1;
+  if (forced < 0) forced = env_int("FEN_BODY_NSET", 0);
+  if (forced == 1 || (B & 1)) return 1;
+  return 2;
+}
+static bool body2_usable(const Layout& L, int B, int H, int W) {
+  static int version = -1;
+  if (version < 0) version = env_int("FEN_BODY_KERNEL", 2);
+  if (version != 2 || W != kStripW || L.cv_total > kConstVecFloats || L.G > kBodyMaxBufs - 5) return false;
+  const int tps = (H * kPitch + kTileM - 1) / kTileM;
+  if (tps > 255) return false;
+  const int set_tiles = (B / body2_nset(B)) * tps;
+  const int tpc = (set_tiles + num_sms() - 1) / num_sms();
+  if (tpc > kB2MaxTiles - 8) return false;
+  return (tpc + tps - 2) / tps + 1 <= kBodyMaxUnits;
+}
+
+static int launch_body2(const fen_config* cfg, const Layout& L, const Workspace& ws, uint8_t* wsb, const uint8_t* k,
+                        int B, int H, int W, float* se_out, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    FEN_CUDA(cudaFuncSetAttribute(body2_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2DynBytes));
+    attr_set = true;
+  }
+  const RcabRec rr = rcab_rec(L.R);
+  BodyMaps maps;
+  Body2Params p{};
+  p.nset = body2_nset(B);
+  p.set_B = B / p.nset;
+  p.B = B; p.H = H; p.W = W; p.G = L.G; p.Bk = L.Bk; p.R = L.R;
+  p.n_layers = L.G * (2 * L.Bk + 1) + 1;
+  p.tiles_per_seg = (H * kPitch + kTileM - 1) / kTileM;
+  p.total_tiles = p.set_B * p.tiles_per_seg;
+  p.tiles_per_cta = (p.total_tiles + num_sms() - 1) / num_sms();
+  const int ctas = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  p.res_scale = cfg->res_scale; p.inv_hw = 1.f / float(H * W);
+  const int nbuf = 5 + L.G;
+  int64_t offs[kBodyMaxBufs];
+  offs[kBufF0] = ws.f0; offs[kBufX0] = ws.x[0]; offs[kBufX1] = ws.x[1]; offs[kBufH] = ws.h; offs[kBufO] = ws.o;
+  for (int g = 0; g < L.G; ++g) offs[kBufG0 + g] = ws.grp0 + g * ws.grp_stride;
+  for (int i = 0; i < nbuf; ++i) {
+    p.buf[i] = reinterpret_cast<bf16*>(wsb + offs[i]);
+    int rc = make_act_map(&maps.act[i], p.buf[i], B, H, W, kBBoxRows);
+    if (rc) return rc;
+  }
+  for (int i = nbuf; i < kBodyMaxBufs; ++i) maps.act[i] = maps.act[0];
+  int rc = make_w_map(&maps.w, k, int(L.k_total / 128), kC);
+  if (rc) return rc;
+  p.packed = k;
+  p.k_rcab0 = L.k_rcab0; p.k_rcab_stride = L.k_rcab_stride; p.k_rcab_w2 = rr.w2; p.k_rcab_fc0 = rr.fc0; p.k_rcab_fc2 = rr.fc2;
+  p.k_gconv0 = L.k_gconv0; p.k_gconv_stride = L.k_gconv_stride; p.k_after = L.k_after;
+  p.cv_rcab0 = L.cv_rcab0; p.cv_gconv0 = L.cv_gconv0; p.cv_after = L.cv_after;
+  p.hsum = reinterpret_cast<float*>(wsb + ws.hsum);
+  p.se_out = se_out;
+  p.flags = reinterpret_cast<int*>(wsb + ws.flags);
+  p.dbg = g_dbg;
+  FEN_CUDA(cudaMemsetAsync(p.flags, 0, 4096, st));
+  FEN_CUDA(cudaMemsetAsync(p.hsum, 0, size_t(L.n_rcab) * B * 9 * 64 * 4, st));
+  FEN_CUDA(cudaMemcpyToSymbolAsync(c_vec, k + L.k_cvec, size_t(L.cv_total) * 4, 0, cudaMemcpyDeviceToDevice, st));
+  void* args[] = {&maps, &p};
+  if (g_time_body) {
+    if (!g_body_ev[0]) { FEN_CUDA(cudaEventCreate(&g_body_ev[0])); FEN_CUDA(cudaEventCreate(&g_body_ev[1])); }
+    FEN_CUDA(cudaEventRecord(g_body_ev[0], st));
+  }
+  FEN_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(body2_umma_kernel), dim3(ctas), dim3(kB2Threads), args,
+                                       kB2DynBytes, st));
+  if (g_time_body) FEN_CUDA(cudaEventRecord(g_body_ev[1], st));
+  ++g_launches;
+  return FEN_OK;
+}
+
 }  // namespace fen
 
 using namespace fen;
@@ -657,7 +736,10 @@ int fen_forward(const fen_config* cfg, const void* packed, const float* x, float
   };
 
   if ((rc = stage_check("conv_first", st))) return rc;
-  if (body_kernel_usable(L, B, H, W)) {
+  if (body2_usable(L, B, H, W)) {
+    if ((rc = launch_body2(cfg, L, ws, wsb, k, B, H, W, se_out, st))) return rc;
+    if ((rc = stage_check("body kernel", st))) return rc;
+  } else if (body_kernel_usable(L, B, H, W)) {
     if ((rc = launch_body(cfg, L, ws, wsb, k, B, H, W, se_out, st))) return rc;
     if ((rc = stage_check("body kernel", st))) return rc;
   } else {
