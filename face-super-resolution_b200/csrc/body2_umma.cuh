@@ -30,6 +30,9 @@ namespace fen {
 #define FEN_B2_WATCH 0   // 1: every role logs (stage, L, s, i) into Body2Params::dbg (host-mapped memory) - hang post-mortems
 #endif
 #define B2W(role, stage, L, s, i) do { if (FEN_B2_WATCH && p.dbg && lane == 0) { *(volatile long long*)(p.dbg + blockIdx.x * 8 + (role)) = (long long)(stage) | ((long long)(L) << 8) | ((long long)(s) << 20) | ((long long)(i) << 24); } } while (0)
+// per-tile trace (FEN_B2_TRACE=1): passes 80..83 of CTA 70 -> dbg[4096 + (P-80)*512 + e*32 + i]
+#define B2T2(P, e, i) do { if (FEN_B2_TRACE && p.dbg && blockIdx.x == 70 && (P) >= 80 && (P) < 84 && (i) < 32) p.dbg[4096 + ((P) - 80) * 512 + (e) * 32 + (i)] = clock64(); } while (0)
+#define B2TS(P, e) do { if (FEN_B2_TRACE && p.dbg && blockIdx.x == 70 && (P) < 512 && lane == 0) p.dbg[6144 + (P) * 8 + (e)] = clock64(); } while (0)
 #define B2TRACE(P, e) do { if (FEN_B2_TRACE && p.dbg && blockIdx.x == 70 && (P) < 512) p.dbg[(P) * 8 + (e)] = clock64(); } while (0)
 
 constexpr int kB2Threads = 384;
@@ -41,8 +44,14 @@ constexpr int kB2EpiWarps = 8;
 constexpr int kB2AccBufs = 7;                      // 7 x 64 TMEM columns for conv tiles ...
 constexpr uint32_t kB2SeCol = kB2AccBufs * kC;     // ... + 64 columns for the SE mat-vec
 constexpr int kB2SBytes = 9 * 1024;                // SE operand: one 8-row SWIZZLE_128B atom per tap
-constexpr int kB2RingPx = kBSlots * kBBoxPx;       // 924 pixels, + the 132-pixel mirror slot
-constexpr int kB2DynBytes = kBodyWBytes + kB2SBytes + kBRingBytes + 1024;
+#ifndef FEN_B2_STAGED_STORE
+#define FEN_B2_STAGED_STORE 0   // 1: outputs go through a shared-memory transpose to coalesced stores (measured slower)
+#endif
+constexpr int kB2Slots = FEN_B2_STAGED_STORE ? 6 : 7;   // activation ring: two-row boxes, + 1 mirror slot
+constexpr int kB2RingPx = kB2Slots * kBBoxPx;      // 792 pixels, + the 132-pixel mirror slot
+constexpr int kB2RingBytes = (kB2Slots + 1) * kBSlotBytes;
+constexpr int kB2StageBytes = 2048;                // per epilogue warp: 32 pixels x 32 channels bf16, SWIZZLE_64B
+constexpr int kB2DynBytes = kBodyWBytes + kB2SBytes + kB2RingBytes + (FEN_B2_STAGED_STORE ? kB2EpiWarps * kB2StageBytes : 0) + 1024;
 constexpr int kB2MaxTiles = 64;
 constexpr int kB2MaxBoxes = 96;
 
@@ -51,6 +60,15 @@ struct B2Box { int16_t img; int8_t y0; uint8_t mirror; };
 struct B2Unit { int img, t0, t1, pad; };
 
 // BodyParams::B is the whole batch; total_tiles / tiles_per_cta count the tiles of ONE set.
+// Tensor maps (kernel parameters stay below 4 KB): per activation buffer one load map (box 64 ch x 66 px x
+// 2 rows, SWIZZLE_128B) and one store map (box 32 ch x 32 px, SWIZZLE_64B); the packed weights.
+constexpr int kB2MaxBufs = 12;   // 5 + num_groups <= 12
+struct Body2Maps {
+  CUtensorMap act[kB2MaxBufs];
+  CUtensorMap w;
+  CUtensorMap st[kB2MaxBufs];
+};
+
 struct Body2Params : BodyParams {
   int nset;      // 1 or 2 interleaved image sets
   int set_B;     // images per set (B = nset * set_B)
@@ -61,19 +79,37 @@ __device__ __forceinline__ float2 ld_cg_f32x2(const float* p) {
   asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
   return v;
 }
+__device__ __forceinline__ void st_shared_u128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_u128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void st_global_128(void* ptr, const uint4& v) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void st_shared_u32(uint32_t saddr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
 
 __global__ void __launch_bounds__(kB2Threads, 1)
-body2_umma_kernel(const __grid_constant__ BodyMaps maps, const Body2Params p) {
+body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
   constexpr int N = kC;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_smem = smem;                              // [9][64][64] bf16, SWIZZLE_128B
   uint8_t* s_buf = smem + kBodyWBytes;                 // [9] atoms of 8 rows x 128 B (rows 2u, 2u+1: hi / lo of unit u)
-  uint8_t* ring = s_buf + kB2SBytes;                   // 7 slots + mirror
-  __shared__ uint64_t bar_w[9], bar_wfree[9], bar_full[kBSlots], bar_empty[kBSlots];
+  uint8_t* ring = s_buf + kB2SBytes;                   // 6 slots + mirror
+  uint8_t* stage = ring + kB2RingBytes;                // 8 x 2 KB output staging (one per epilogue warp)
+  __shared__ uint64_t bar_w[9], bar_wfree[9], bar_full[kB2Slots], bar_empty[kB2Slots];
   __shared__ uint64_t bar_acc_full[kB2AccBufs], bar_acc_empty[kB2AccBufs];
   __shared__ uint64_t bar_done, bar_s_ready, bar_s_free, bar_se_full, bar_se_empty, bar_scale[2];
   __shared__ uint32_t tmem_slot;
@@ -83,6 +119,7 @@ body2_umma_kernel(const __grid_constant__ BodyMaps maps, const Body2Params p) {
   __shared__ int s_meta[4];                            // tiles, boxes, units, odd-use slot mask
   __shared__ __align__(16) float s_scale[2][kBodyMaxUnits][kC];   // res_scale * s, per set and unit
   __shared__ __align__(16) float s_mean[kBodyMaxUnits][kC], s_hid[kBodyMaxUnits][kC];
+  __shared__ __align__(16) float s_raw[2 * kBodyMaxUnits][kC];     // raw SE accumulator rows (hi / lo per unit)
   __shared__ __align__(16) uint32_t s_colx[kB2EpiWarps][2][16];   // per epilogue warp: one staged pixel (32 bf16) per border column
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -106,14 +143,14 @@ body2_umma_kernel(const __grid_constant__ BodyMaps maps, const Body2Params p) {
       for (int j = 0; j < bu.nboxes; ++j) {
         B2Box e;
         e.img = int16_t(bu.n); e.y0 = int8_t(bu.ra - 1 + j * kBBoxRows);
-        e.mirror = uint8_t(((b_cum + j) % kBSlots == 0) && j > 0);
+        e.mirror = uint8_t(j > 0);   // continues the previous box of its unit: mirrored when it lands in slot 0
         box_tab[b_cum + j] = e;
       }
       for (int t = bu.t0; t < bu.t1; ++t, ++i) {
         const int base = kTileM * t - kPitch * bu.ra;
         first_box[i] = b_cum + base / kBBoxPx;
         B2Tile e;
-        e.m = uint16_t((b_cum * kBBoxPx + base) % kB2RingPx);
+        e.m = uint16_t(b_cum * kBBoxPx + base);   // pixel position of the tile's view, relative to the pass's first box
         e.wait_upto = uint8_t(b_cum + min((base + kTileM + kMaxShift - 1) / kBBoxPx, bu.nboxes - 1) + 1);
         e.rel_upto = 0; e.unit = uint8_t(u); e.t = uint8_t(t); e.pad = 0;
         tile_tab[i] = e;
@@ -122,17 +159,13 @@ body2_umma_kernel(const __grid_constant__ BodyMaps maps, const Body2Params p) {
       g += bu.t1 - bu.t0;
     }
     for (int k = 0; k < i; ++k) tile_tab[k].rel_upto = uint8_t((k + 2 < i) ? first_box[k + 2] : b_cum);
-    int odd = 0;
-    for (int s = 0; s < kBSlots; ++s) {
-      const int uses = (b_cum > s) ? (b_cum - s + kBSlots - 1) / kBSlots : 0;
-      if (uses & 1) odd |= 1 << s;
-    }
+    const int odd = 0;
     s_meta[0] = i; s_meta[1] = b_cum; s_meta[2] = u; s_meta[3] = odd;
     // ---- barriers.  A CTA with a single tile per pass has no odd tile: issuer warp 3 stays out of the
     // ring / weight release protocol entirely (an issuer without MMAs could lap the other one).
     const uint32_t n_issuers = (i >= 2) ? 2u : 1u;
     for (int k = 0; k < 9; ++k) { mbar_init(&bar_w[k], 1); mbar_init(&bar_wfree[k], n_issuers); }
-    for (int k = 0; k < kBSlots; ++k) { mbar_init(&bar_full[k], 1); mbar_init(&bar_empty[k], n_issuers); }
+    for (int k = 0; k < kB2Slots; ++k) { mbar_init(&bar_full[k], 1); mbar_init(&bar_empty[k], n_issuers); }
     for (int k = 0; k < kB2AccBufs; ++k) { mbar_init(&bar_acc_full[k], 1); mbar_init(&bar_acc_empty[k], kB2EpiWarps); }
     mbar_init(&bar_done, kB2EpiWarps);
     mbar_init(&bar_s_ready, 1); mbar_init(&bar_s_free, 1); mbar_init(&bar_se_full, 1); mbar_init(&bar_se_empty, 1);
@@ -147,25 +180,18 @@ body2_umma_kernel(const __grid_constant__ BodyMaps maps, const Body2Params p) {
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   const int n_tiles = s_meta[0], n_boxes = s_meta[1], n_units = s_meta[2];
-  const uint32_t oddmask = uint32_t(s_meta[3]);
   if (n_tiles <= 0) return;   // never happens with the host's grid sizing
 
   if (warp == kB2TmaWarp) {
     // ============================================================ TMA issuer + peer-flag poller
-    uint32_t P = 0;
+    // The ring is one running sequence of boxes over all passes (box g -> slot g % kB2Slots, use g / kB2Slots),
+    // so the first boxes of a pass are prefetched while the previous pass still owns the other slots.
+    uint32_t P = 0, slot = 0, use = 0;
+    constexpr int kPre = 4;                       // boxes of a new layer requested BEFORE its weights
     for (int L = 0; L < p.n_layers; ++L) {
       const BodyLayer ly = body_layer(p, L);
-      if (lane == 0) {
-        for (int tap = 0; tap < 9; ++tap) {     // weights, tap by tap, as soon as the previous layer released the tap
-          B2W(1, 1, L, 0, tap);
-          if (L > 0) mbar_wait(&bar_wfree[tap], (L - 1) & 1);
-          mbar_expect_tx(&bar_w[tap], N * kC * 2);
-          tma_load_2d(&maps.w, &bar_w[tap], w_smem + tap * N * 128, 0, ly.w_row + tap * N);
-        }
-      }
-      __syncwarp();
       const uint64_t pol = ly.last_use ? kPolicyEvictFirst : 0x1000000000000000ull;
-      for (int s = 0; s < p.nset; ++s, ++P) {
+      auto wait_flags = [&](int s) {
         // every peer must have finished layer L-1 of this set: their outputs are my inputs / halos
         B2W(1, 2, L, s, 0);
         if (L > 0) {
@@ -175,24 +201,44 @@ body2_umma_kernel(const __grid_constant__ BodyMaps maps, const Body2Params p) {
           __syncwarp();
           fence_proxy_async_all();
         }
-        if (lane == 0) {
-          B2TRACE(P, 0);
-          const uint32_t passpar = (P & 1) ? oddmask : 0u;
-          const int img_base = s * p.set_B;
-          uint32_t slot = 0, k = 0;
-          for (int b = 0; b < n_boxes; ++b) {
-            const B2Box e = box_tab[b];
-            B2W(1, 3, L, s, b);
-            mbar_wait(&bar_empty[slot], ((passpar >> slot) ^ k ^ 1u) & 1u);
-            mbar_expect_tx(&bar_full[slot], e.mirror ? 2 * kBSlotBytes : kBSlotBytes);
-            tma_load_4d_hint(&maps.act[ly.in], &bar_full[slot], smem_u32(ring + slot * kBSlotBytes), 0, -1, e.y0,
+      };
+      auto issue_boxes = [&](int s, int b0, int b1) {     // lane 0 only
+        const int img_base = s * p.set_B;
+        for (int b = b0; b < b1; ++b) {
+          const B2Box e = box_tab[b];
+          B2T2(P, 9, b);
+          B2W(1, 3, L, s, b);
+          mbar_wait(&bar_empty[slot], (use & 1u) ^ 1u);
+          const bool mirror = e.mirror && slot == 0;
+          mbar_expect_tx(&bar_full[slot], mirror ? 2 * kBSlotBytes : kBSlotBytes);
+          tma_load_4d_hint(&maps.act[ly.in], &bar_full[slot], smem_u32(ring + slot * kBSlotBytes), 0, -1, e.y0,
+                           img_base + e.img, pol);
+          if (mirror)
+            tma_load_4d_hint(&maps.act[ly.in], &bar_full[slot], smem_u32(ring + kB2Slots * kBSlotBytes), 0, -1, e.y0,
                              img_base + e.img, pol);
-            if (e.mirror)
-              tma_load_4d_hint(&maps.act[ly.in], &bar_full[slot], smem_u32(ring + kBSlots * kBSlotBytes), 0, -1, e.y0,
-                               img_base + e.img, pol);
-            if (++slot == kBSlots) { slot = 0; ++k; }
-          }
+          B2T2(P, 10, b);
+          if (++slot == kB2Slots) { slot = 0; ++use; }
         }
+      };
+      const int pre = min(kPre, n_boxes);
+      wait_flags(0);
+      if (lane == 0) {
+        B2TRACE(P, 0);
+        issue_boxes(0, 0, pre);
+        for (int tap = 0; tap < 9; ++tap) {     // weights, tap by tap, as soon as the previous layer released the tap
+          B2W(1, 1, L, 0, tap);
+          if (L > 0) mbar_wait(&bar_wfree[tap], (L - 1) & 1);
+          mbar_expect_tx(&bar_w[tap], N * kC * 2);
+          tma_load_2d(&maps.w, &bar_w[tap], w_smem + tap * N * 128, 0, ly.w_row + tap * N);
+        }
+      }
+      __syncwarp();
+      for (int s = 0; s < p.nset; ++s, ++P) {
+        if (s > 0) {
+          wait_flags(s);
+          if (lane == 0) B2TRACE(P, 0);
+        }
+        if (lane == 0) issue_boxes(s, s == 0 ? pre : 0, n_boxes);
         __syncwarp();
       }
     }
@@ -211,14 +257,19 @@ body2_umma_kernel(const __grid_constant__ BodyMaps maps, const Body2Params p) {
     for (int L = 0; L < (last_own >= 0 ? p.n_layers : 0); ++L) {
       const bool conv2 = body_layer(p, L).epi == kBEpiSeResidual;
       bool w_seen = false;
+      int se_done = 0;
       for (int s = 0; s < p.nset; ++s, ++P, gbase += n_tiles) {
-        const uint32_t passpar = (P & 1) ? oddmask : 0u;
+        const uint32_t gb0 = P * uint32_t(n_boxes);                 // running index of the pass's first box
+        const uint32_t start_px = (gb0 % kB2Slots) * kBBoxPx;
         const bool last_pass = (s == p.nset - 1);
+        // SE batches of this layer still owed: the one of set s must run before this pass's epilogue can start,
+        // those of later sets may run as soon as their operand is ready (W2 is in shared memory all layer long)
 #ifdef FEN_B2_X2
-        bool se_pending = false;
+        const bool se_layer = false;
 #else
-        bool se_pending = conv2 && (wi == 0);
+        const bool se_layer = conv2 && (wi == 0);
 #endif
+        if (s == 0) se_done = 0;
         uint32_t waited = 0, released = 0;
         // one SE batch: D[row, c] = sum_tap S_tap[row, :] . W2_tap[c, :] into the SE accumulator
         auto issue_se = [&]() {
@@ -232,6 +283,7 @@ body2_umma_kernel(const __grid_constant__ BodyMaps maps, const Body2Params p) {
           if (!w_seen) {
             for (int tap = 0; tap < 9; ++tap) mbar_wait(&bar_w[tap], L & 1);
           }
+          __syncwarp();                            // converge after the spin-waits before any tcgen05 issue
           if (leader) {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
@@ -247,71 +299,97 @@ body2_umma_kernel(const __grid_constant__ BodyMaps maps, const Body2Params p) {
           }
           w_seen = true;
           ++se_n;
-          se_pending = false;
+          ++se_done;
           __syncwarp();
         };
         for (int i = wi; i < n_tiles; i += 2) {
           const B2Tile e = tile_tab[i];
           const uint32_t G = gbase + i, acc = G % kB2AccBufs, aph = (G / kB2AccBufs) & 1;
           B2W(2 + wi, 1, L, s, i);
-          if (se_pending) {
-            // The epilogue of this pass cannot free accumulators before the SE batch has run: never block on
-            // an accumulator while the batch is still owed.
+          if (se_layer && se_done <= s) {
+            // The epilogue of this pass cannot free accumulators before the SE batch of this set has run: never
+            // block on an accumulator while that batch is still owed.
             if (i == last_own) {
               mbar_wait(&bar_s_ready, se_n & 1);
               issue_se();
             } else {
               for (;;) {
                 // (never as the first batch of a layer: see issue_se)
-                if (w_seen && __any_sync(0xffffffffu, mbar_try_wait(&bar_s_ready, se_n & 1))) { issue_se(); break; }
-                if (__any_sync(0xffffffffu, mbar_try_wait(&bar_acc_empty[acc], aph ^ 1))) break;
+                if (w_seen && __any_sync(0xffffffffu, mbar_test_wait(&bar_s_ready, se_n & 1))) { issue_se(); break; }
+                if (__any_sync(0xffffffffu, mbar_test_wait(&bar_acc_empty[acc], aph ^ 1))) break;
               }
             }
           }
+#ifndef FEN_B2_NOEARLY
+          if (se_layer && se_done > s && se_done < p.nset && w_seen &&
+              __any_sync(0xffffffffu, mbar_test_wait(&bar_s_ready, se_n & 1)))
+            issue_se();                          // a later set's batch, ahead of time
+#endif
           B2W(2 + wi, 2, L, s, i);
+          if (leader) B2T2(P, 4, i);
           mbar_wait(&bar_acc_empty[acc], aph ^ 1);
+          if (leader) B2T2(P, 5, i);
           B2W(2 + wi, 3, L, s, i);
           while (waited < e.wait_upto) {
-            const uint32_t slot = waited % kBSlots, k = waited / kBSlots;
-            mbar_wait(&bar_full[slot], ((passpar >> slot) ^ k) & 1u);
+            const uint32_t g = gb0 + waited;
+            mbar_wait(&bar_full[g % kB2Slots], (g / kB2Slots) & 1u);
             ++waited;
           }
           if (leader && i == wi) B2TRACE(P, 1 + wi);
           B2W(2 + wi, 4, L, s, i);
+          if (leader) B2T2(P, 6, i);
+          __syncwarp();                            // converge after the spin-waits (see the commits below)
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * N;
-          const uint32_t m = e.m;
+          const uint32_t m = (uint32_t(e.m) + start_px) % kB2RingPx;
           const bool w_rel = last_pass && (i == last_own);
-          if (leader) {
+          // Elected-lane blocks hold straight-line tcgen05 code only: every wait is executed by the whole
+          // (converged) warp.  The first tile of a layer follows the weight loads tap by tap.
+          auto issue_tap = [&](int tap) {
+            const uint32_t off = (tap / 3) * kPitch + (tap % 3);
+            uint32_t pos = m + off;
+            if (pos >= uint32_t(kB2RingPx)) pos -= kB2RingPx;
+            const uint32_t a_lo = ring_lo + pos * 8;
+            const uint32_t b_lo = w_lo + tap * (N * 128 >> 4);
 #pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ss_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, kDescHi, idesc, (tap | k) != 0);
+            if (w_rel) umma_commit(&bar_wfree[tap]);   // the next layer's tap may overwrite once these MMAs finish
+          };
+          if (!w_seen) {
             for (int tap = 0; tap < 9; ++tap) {
-              if (!w_seen) mbar_wait(&bar_w[tap], L & 1);
-              const uint32_t off = (tap / 3) * kPitch + (tap % 3);
-              uint32_t pos = m + off;
-              if (pos >= uint32_t(kB2RingPx)) pos -= kB2RingPx;
-              const uint32_t a_lo = ring_lo + pos * 8;
-              const uint32_t b_lo = w_lo + tap * (N * 128 >> 4);
+              mbar_wait(&bar_w[tap], L & 1);
+              __syncwarp();
+              if (leader) issue_tap(tap);
+              __syncwarp();
+            }
+          } else {
+            if (leader) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16_ss_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, kDescHi, idesc, (tap | k) != 0);
-              if (w_rel) umma_commit(&bar_wfree[tap]);   // the next layer's tap may overwrite once these MMAs finish
+              for (int tap = 0; tap < 9; ++tap) issue_tap(tap);
             }
           }
           w_seen = true;
           __syncwarp();
+          if (leader) B2T2(P, 7, i);
           // A box may only be handed back after THIS warp has seen it arrive (the last boxes of a pass are
           // read by the other issuer alone): an arrival for a use that has not started yet would complete
           // the slot's previous phase early.
           while (waited < e.rel_upto) {
-            const uint32_t slot = waited % kBSlots, k = waited / kBSlots;
-            mbar_wait(&bar_full[slot], ((passpar >> slot) ^ k) & 1u);
+            const uint32_t g = gb0 + waited;
+            mbar_wait(&bar_full[g % kB2Slots], (g / kB2Slots) & 1u);
             ++waited;
           }
+          // Lanes leave a spin-wait at different times.  The commits below compile to warp-level UTCBAR
+          // instructions fed by predicated R2UR: executed by a diverged warp, the group WITHOUT the elected
+          // lane would repeat them with stale operands (spurious mbarrier arrivals -> "illegal instruction").
+          __syncwarp();
           while (released < e.rel_upto) {
-            if (leader) umma_commit(&bar_empty[released % kBSlots]);
+            if (leader) umma_commit(&bar_empty[(gb0 + released) % kB2Slots]);
             ++released;
           }
           if (leader) umma_commit(&bar_acc_full[acc]);
+          if (leader) B2T2(P, 8, i);
           if (leader && i == last_own) B2TRACE(P, 3 + wi);
           __syncwarp();
         }
@@ -331,9 +409,13 @@ body2_umma_kernel(const __grid_constant__ BodyMaps maps, const Body2Params p) {
       const uint8_t* rec = p.packed + p.k_rcab0 + int64_t(ly.rcab) * p.k_rcab_stride;
       const float* fc0 = reinterpret_cast<const float*>(rec + p.k_rcab_fc0);
       const float* fc2 = reinterpret_cast<const float*>(rec + p.k_rcab_fc2);
+      // the two FC matrices (contiguous, 2 * R * 64 floats) into L1 long before they are needed
+      for (int ofs = lane * 32; ofs < 2 * p.R * kC; ofs += 32 * 32)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(fc0 + ofs));
       for (int s = 0; s < p.nset; ++s, ++se_n) {
         // the conv1 layer (L - 1) of this set must be complete on every peer: its epilogues own the sums
         B2W(0, 1, L, s, se_n);
+        B2TS(L * p.nset + s, 0);
         {
           const int* fl = p.flags + s * int(gridDim.x);
           for (int k = peer0 + lane; k <= peer1; k += 32)
@@ -352,6 +434,7 @@ body2_umma_kernel(const __grid_constant__ BodyMaps maps, const Body2Params p) {
           }
         }
         B2W(0, 2, L, s, se_n);
+        B2TS(L * p.nset + s, 1);
         if (se_n >= 1) mbar_wait(&bar_s_free, (se_n - 1) & 1);   // the previous batch has consumed the operand
 #pragma unroll
         for (int u = 0; u < kBodyMaxUnits; ++u) {
@@ -381,51 +464,96 @@ body2_umma_kernel(const __grid_constant__ BodyMaps maps, const Body2Params p) {
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_s_ready);
-        // ---- result rows 0..7 of the SE accumulator: lane r holds row r
+        B2TS(L * p.nset + s, 2);
+        const bool fast_fc = (p.R == 16);   // lane l: hidden unit l & 15 of units (l >> 4), (l >> 4) + 2; channels l, l + 32
+        // ---- result rows 0..7 of the SE accumulator (lane r = row r = hi / lo part of unit r / 2) -> smem
         B2W(0, 3, L, s, se_n);
         mbar_wait(&bar_se_full, se_n & 1);
         B2W(0, 4, L, s, se_n);
+        B2TS(L * p.nset + s, 3);
         tc_fence_after();
-        uint32_t v0[32], v1[32];
-        tmem_ld_32x32(tmem_base + kB2SeCol, v0);
-        tmem_ld_32x32(tmem_base + kB2SeCol + 32, v1);
-        tmem_ld_wait();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + kB2SeCol + 32 * hf, v);
+          tmem_ld_wait();
+          if (lane < 2 * kBodyMaxUnits) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              *reinterpret_cast<uint4*>(&s_raw[lane][32 * hf + 4 * k]) = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          }
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_se_empty);
-        {
-          const int u = lane >> 1;
+        if (fast_fc) {
+          // FC1 + ReLU: mean[c] = b2[c] + (hi + lo)[c] / HW, folded into the dot product
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            float a = __uint_as_float(v0[c]), b = __uint_as_float(v1[c]);
-            a += __shfl_xor_sync(0xffffffffu, a, 1);
-            b += __shfl_xor_sync(0xffffffffu, b, 1);
-            if ((lane & 1) == 0 && u < n_units) {
-              s_mean[u][c] = c_vec[ly.cv_bias + c] + a * p.inv_hw;
-              s_mean[u][c + 32] = c_vec[ly.cv_bias + c + 32] + b * p.inv_hw;
+          for (int rep = 0; rep < 2; ++rep) {
+            const int u = (lane >> 4) + 2 * rep;
+            if (u < n_units) {
+              float acc = 0.f;
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                const float4 hi = *reinterpret_cast<const float4*>(&s_raw[2 * u][4 * k]);
+                const float4 lo = *reinterpret_cast<const float4*>(&s_raw[2 * u + 1][4 * k]);
+                const float4 b4 = *reinterpret_cast<const float4*>(c_vec + ly.cv_bias + 4 * k);
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(fc0 + (lane & 15) * kC) + k);   // L1 hit (prefetched)
+                acc = fmaf(w1.x, fmaf(hi.x + lo.x, p.inv_hw, b4.x), acc);
+                acc = fmaf(w1.y, fmaf(hi.y + lo.y, p.inv_hw, b4.y), acc);
+                acc = fmaf(w1.z, fmaf(hi.z + lo.z, p.inv_hw, b4.z), acc);
+                acc = fmaf(w1.w, fmaf(hi.w + lo.w, p.inv_hw, b4.w), acc);
+              }
+              s_hid[u][lane & 15] = fmaxf(acc, 0.f);
             }
+          }
+          __syncwarp();
+          // FC2 + sigmoid
+          for (int u = 0; u < n_units; ++u) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float4 h4 = *reinterpret_cast<const float4*>(&s_hid[u][4 * k]);
+              const float4 wa = __ldg(reinterpret_cast<const float4*>(fc2 + lane * 16) + k);
+              const float4 wb = __ldg(reinterpret_cast<const float4*>(fc2 + (lane + 32) * 16) + k);
+              a0 = fmaf(wa.x, h4.x, a0); a0 = fmaf(wa.y, h4.y, a0); a0 = fmaf(wa.z, h4.z, a0); a0 = fmaf(wa.w, h4.w, a0);
+              a1 = fmaf(wb.x, h4.x, a1); a1 = fmaf(wb.y, h4.y, a1); a1 = fmaf(wb.z, h4.z, a1); a1 = fmaf(wb.w, h4.w, a1);
+            }
+            const float sv0 = 1.f / (1.f + expf(-a0)), sv1 = 1.f / (1.f + expf(-a1));
+            s_scale[s][u][lane] = sv0 * p.res_scale;
+            s_scale[s][u][lane + 32] = sv1 * p.res_scale;
+            if (p.se_out && unit_tab[u].t0 == 0) {   // the CTA owning tile 0 of the image publishes the attention vector
+              float* so = p.se_out + (size_t(img_base + unit_tab[u].img) * (p.G * p.Bk) + ly.rcab) * kC;
+              so[lane] = sv0;
+              so[lane + 32] = sv1;
+            }
+          }
+        } else {
+          for (int idx = lane; idx < n_units * kC; idx += 32) {
+            const int u = idx >> 6, c = idx & 63;
+            s_mean[u][c] = c_vec[ly.cv_bias + c] + (s_raw[2 * u][c] + s_raw[2 * u + 1][c]) * p.inv_hw;
+          }
+          __syncwarp();
+          for (int idx = lane; idx < n_units * p.R; idx += 32) {        // FC1 + ReLU
+            const int u = idx / p.R, j = idx - u * p.R;
+            float a = 0.f;
+            for (int c = 0; c < kC; ++c) a = fmaf(__ldg(fc0 + j * kC + c), s_mean[u][c], a);
+            s_hid[u][j] = fmaxf(a, 0.f);
+          }
+          __syncwarp();
+          for (int idx = lane; idx < n_units * kC; idx += 32) {         // FC2 + sigmoid
+            const int u = idx >> 6, c = idx & 63;
+            float a = 0.f;
+            for (int j = 0; j < p.R; ++j) a = fmaf(__ldg(fc2 + c * p.R + j), s_hid[u][j], a);
+            const float sv = 1.f / (1.f + expf(-a));
+            s_scale[s][u][c] = sv * p.res_scale;
+            if (p.se_out && unit_tab[u].t0 == 0)
+              p.se_out[(size_t(img_base + unit_tab[u].img) * (p.G * p.Bk) + ly.rcab) * kC + c] = sv;
           }
         }
         __syncwarp();
-        for (int idx = lane; idx < n_units * p.R; idx += 32) {        // FC1 + ReLU
-          const int u = idx / p.R, j = idx - u * p.R;
-          float a = 0.f;
-#pragma unroll 16
-          for (int c = 0; c < kC; ++c) a = fmaf(__ldg(fc0 + j * kC + c), s_mean[u][c], a);
-          s_hid[u][j] = fmaxf(a, 0.f);
-        }
-        __syncwarp();
-        for (int idx = lane; idx < n_units * kC; idx += 32) {         // FC2 + sigmoid
-          const int u = idx >> 6, c = idx & 63;
-          float a = 0.f;
-          for (int j = 0; j < p.R; ++j) a = fmaf(__ldg(fc2 + c * p.R + j), s_hid[u][j], a);
-          const float sv = 1.f / (1.f + expf(-a));
-          s_scale[s][u][c] = sv * p.res_scale;
-          if (p.se_out && unit_tab[u].t0 == 0)      // the CTA owning tile 0 of the image publishes the attention vector
-            p.se_out[(size_t(img_base + unit_tab[u].img) * (p.G * p.Bk) + ly.rcab) * kC + c] = sv;
-        }
-        __syncwarp();
         if (lane == 0) mbar_arrive(&bar_scale[s]);
+        B2TS(L * p.nset + s, 4);
       }
       ++m_cnt;
     }
@@ -439,6 +567,7 @@ body2_umma_kernel(const __grid_constant__ BodyMaps maps, const Body2Params p) {
     const int col0 = half * CW;
     const int row_in_tile = q * 32 + lane;
     const bool flag_writer = (ew == 0);
+    const uint32_t pair_u32 = smem_u32(stage + q * 2 * kB2StageBytes);   // 4 KB per lane quarter
     uint32_t G = 0, P = 0, m_cnt = 0;
     for (int L = 0; L < p.n_layers; ++L) {
       const BodyLayer ly = body_layer(p, L);
@@ -508,7 +637,11 @@ body2_umma_kernel(const __grid_constant__ BodyMaps maps, const Body2Params p) {
           const size_t opix = (size_t(img) * p.H + y) * p.W + x;
           // residual / skip values of this pixel: requested before waiting for the accumulator
           uint32_t rv[16];
+#ifdef FEN_EXP_NORES
+          if (false) {
+#else
           if (valid && ly.epi != kBEpiPreluHsum) {
+#endif
             const bf16* rsd = resp + opix * kC + col0;
             ld_cg_256_hint(rsd, kPolicyEvictFirst, *reinterpret_cast<uint32_t(*)[8]>(&rv[0]));
             ld_cg_256_hint(rsd + 16, kPolicyEvictFirst, *reinterpret_cast<uint32_t(*)[8]>(&rv[8]));
@@ -517,8 +650,10 @@ body2_umma_kernel(const __grid_constant__ BodyMaps maps, const Body2Params p) {
             for (int j = 0; j < 16; ++j) rv[j] = 0u;
           }
           if (ew == 0) B2W(4, 2, L, s, i);
+          if (ew == 0 && lane == 0) B2T2(P, 0, i);
           mbar_wait(&bar_acc_full[acc], aph);
           if (ew == 0 && lane == 0 && i == 0) B2TRACE(P, 5);
+          if (ew == 0 && lane == 0) B2T2(P, 1, i);
           tc_fence_after();
           uint32_t v[CW];
           tmem_ld_32x32(tmem_base + acc * N + col0 + (uint32_t(q * 32) << 16), v);
@@ -526,6 +661,7 @@ body2_umma_kernel(const __grid_constant__ BodyMaps maps, const Body2Params p) {
           tc_fence_before();                       // accumulator read: hand it back to the MMA issuers
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_acc_empty[acc]);
+          if (ew == 0 && lane == 0) B2T2(P, 2, i);
           float f[CW];
 #pragma unroll
           for (int c = 0; c < CW; ++c) f[c] = __uint_as_float(v[c]) + bias[c];
@@ -546,10 +682,47 @@ body2_umma_kernel(const __grid_constant__ BodyMaps maps, const Body2Params p) {
           uint32_t o[16];
 #pragma unroll
           for (int k = 0; k < 16; ++k) o[k] = pack_bf16(f[2 * k], f[2 * k + 1]);
+#if FEN_B2_STAGED_STORE
+          {
+            // ---- output: registers -> staging of this lane quarter (32 px x 128 B, shared by the two warps
+            // that hold the two channel halves; 16 B chunks XOR-swizzled by the pixel index) -> coalesced
+            // 128-bit global stores, 4 full 128 B lines per instruction.  (Writing straight from the TMEM
+            // layout - one pixel per lane, 128 B apart - costs 16x the LSU wavefronts; TMA tensor stores
+            // cannot be used: a row-straddling warp needs a negative start coordinate, which faults.)
+            const uint32_t sw = uint32_t(lane) & 7u;
+            const uint32_t prow = pair_u32 + lane * 128;
+            st_shared_u128(prow + (((4u * half + 0u) ^ sw) << 4), o[0], o[1], o[2], o[3]);
+            st_shared_u128(prow + (((4u * half + 1u) ^ sw) << 4), o[4], o[5], o[6], o[7]);
+            st_shared_u128(prow + (((4u * half + 2u) ^ sw) << 4), o[8], o[9], o[10], o[11]);
+            st_shared_u128(prow + (((4u * half + 3u) ^ sw) << 4), o[12], o[13], o[14], o[15]);
+            named_bar_sync(1 + q, 64);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int px = 16 * half + 4 * k + (lane >> 3);
+              const uint32_t ch = uint32_t(lane) & 7u;
+              const uint4 v4 = ld_shared_u128(pair_u32 + px * 128 + ((ch ^ (uint32_t(px) & 7u)) << 4));
+              const int l2 = kTileM * int(e.t) + q * 32 + px;
+              const int y2 = l2 / kPitch, x2 = l2 - y2 * kPitch;
+#ifdef FEN_EXP_NOSTORE
+              if (x2 < kStripW && y2 < p.H && v4.x == 0x12345678u)
+#else
+              if (x2 < kStripW && y2 < p.H)
+#endif
+                st_global_128(outp + ((size_t(img) * p.H + y2) * p.W + x2) * kC + ch * 8, v4);
+            }
+            named_bar_sync(1 + q, 64);             // the staging may be overwritten again
+          }
+#else
+#ifdef FEN_EXP_NOSTORE
+          if (valid && o[0] == 0x12345678u && o[9] == 0x9abcdef0u) {
+#else
           if (valid) {
+#endif
             st_global_256(outp + opix * kC + col0, *reinterpret_cast<uint32_t(*)[8]>(&o[0]));
             st_global_256(outp + opix * kC + col0 + 16, *reinterpret_cast<uint32_t(*)[8]>(&o[8]));
           }
+#endif
+          if (ew == 0 && lane == 0) B2T2(P, 3, i);
           if (ly.epi == kBEpiPreluHsum) {
             // ---- the 9 channel sums of the bf16-ROUNDED h (what conv2 will read) that the SE pool needs
             if (valid) {

@@ -87,6 +87,23 @@ static int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, in
   if (r != CUDA_SUCCESS) return fail(FEN_ECUDA, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string(int(r)));
   return FEN_OK;
 }
+// NHWC bf16 activation [B][H][W][64] as a TMA STORE target: box = 32 ch x 32 px x 1 row, 64B swizzle
+// (the epilogue warps of the body kernel stage 32 pixels x 32 channels each).
+static int make_act_store_map(CUtensorMap* m, const void* ptr, int B, int H, int W) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(FEN_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[4] = {cuuint64_t(kC), cuuint64_t(W), cuuint64_t(H), cuuint64_t(B)};
+  cuuint64_t strides[3] = {cuuint64_t(kC) * 2, cuuint64_t(W) * kC * 2, cuuint64_t(H) * W * kC * 2};
+  cuuint32_t box[4] = {32, 32, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  const char* e1 = getenv("FEN_ST_SWZ"); const char* e2 = getenv("FEN_ST_L2");
+  CUtensorMapSwizzle swz = (e1 && e1[0] == '0') ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMapL2promotion l2 = (e2 && e2[0] == '0') ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FEN_ECUDA, "cuTensorMapEncodeTiled(store) failed: " + std::to_string(int(r)));
+  return FEN_OK;
+}
 // packed weights [rows][64] bf16, box = 64 x N rows.
 static int make_w_map(CUtensorMap* m, const void* ptr, int rows, int n) {
   EncodeTiledFn enc = get_encode();
@@ -514,7 +531,7 @@ static int body2_nset(int B) {
 static bool body2_usable(const Layout& L, int B, int H, int W) {
   static int version = -1;
   if (version < 0) version = env_int("FEN_BODY_KERNEL", 2);
-  if (version != 2 || W != kStripW || L.cv_total > kConstVecFloats || L.G > kBodyMaxBufs - 5) return false;
+  if (version != 2 || W != kStripW || L.cv_total > kConstVecFloats || L.G > kB2MaxBufs - 5) return false;
   const int tps = (H * kPitch + kTileM - 1) / kTileM;
   if (tps > 255) return false;
   const int set_tiles = (B / body2_nset(B)) * tps;
@@ -531,7 +548,7 @@ static int launch_body2(const fen_config* cfg, const Layout& L, const Workspace&
     attr_set = true;
   }
   const RcabRec rr = rcab_rec(L.R);
-  BodyMaps maps;
+  Body2Maps maps;
   Body2Params p{};
   p.nset = body2_nset(B);
   p.set_B = B / p.nset;
@@ -550,8 +567,9 @@ static int launch_body2(const fen_config* cfg, const Layout& L, const Workspace&
     p.buf[i] = reinterpret_cast<bf16*>(wsb + offs[i]);
     int rc = make_act_map(&maps.act[i], p.buf[i], B, H, W, kBBoxRows);
     if (rc) return rc;
+    if ((rc = make_act_store_map(&maps.st[i], p.buf[i], B, H, W))) return rc;
   }
-  for (int i = nbuf; i < kBodyMaxBufs; ++i) maps.act[i] = maps.act[0];
+  for (int i = nbuf; i < kB2MaxBufs; ++i) { maps.act[i] = maps.act[0]; maps.st[i] = maps.st[0]; }
   int rc = make_w_map(&maps.w, k, int(L.k_total / 128), kC);
   if (rc) return rc;
   p.packed = k;
