@@ -12,7 +12,7 @@ Prints ONE JSON line (rank 0):
   value     images/s with inputs resident in HBM (inputs rotate through a pool larger than L2)
   e2e       images/s through the public API with pinned HOST buffers: H2D of the LR batch, forward,
             D2H of the SR batch, every step inside the timed region
-  roofline  the dominant kernel (body_umma_kernel: the 127 64->64 3x3 convolutions of the body in one
+  roofline  the dominant kernel (body2_umma_kernel: the 127 64->64 3x3 convolutions of the body in one
             persistent launch): algorithmic FLOPs per launch / its average launch time (CUDA events on
             the launch stream), against the measured sustained bf16 peak
   cpu_baseline  the fp32 CPU oracle (a port of the reference's forward) on this box's host cores
@@ -37,6 +37,17 @@ FLOP_PER_IMAGE = 44.633e9          # 22 316 703 744 MAC x 2, forwa
 CONV64_FLOP_PER_IMAGE = 2.0 * 4096 * 64 * 64 * 9   # one 64->64 3x3 conv on a 64x64 map
 MODEL_CFG = dict(num_groups=6, blocks_per_group=10)
 WORKLOAD = "FaceEnhanceNet 6x10x64 bf16 inference, batch 64/GPU, synthetic 64x64 -> 256x256 (BASELINE config 2)"
+
+
+def ncu_traffic(batch: int):
+    """DRAM bytes per launch of the body kernel from the committed `ncu --set full` capture (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "body_kernel_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["dram_bytes_per_launch"]) if int(d.get("batch", -1)) == batch else None
+    except (OSError, ValueError, KeyError):
+        return None
 
 
 def measured_peaks():
@@ -250,7 +261,7 @@ def main():
     ms_e2e = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
 
-    # ---- roofline of the dominant kernel: body_umma_kernel (all 127 64->64 3x3 convs of the body in one
+    # ---- roofline of the dominant kernel: body2_umma_kernel (all 127 64->64 3x3 convs of the body in one
     # persistent launch, 86 % of the FLOPs).  Its launches are timed with CUDA events recorded on the
     # launch stream by the library itself (fen_profile_body) during extra forwards of the same workload.
     n_body_convs = MODEL_CFG["num_groups"] * (2 * MODEL_CFG["blocks_per_group"] + 1) + 1
@@ -264,7 +275,7 @@ def main():
     peaks = measured_peaks()
     if body_ms:
         k_ms = sum(body_ms) / len(body_ms)
-        k_name = "body_umma_kernel (127 x 64->64 3x3 conv + SE + residuals, batch %d)" % B
+        k_name = "body2_umma_kernel (127 x 64->64 3x3 conv + SE + residuals in one persistent launch, batch %d)" % B
         k_flop = CONV64_FLOP_PER_IMAGE * B * n_body_convs
     else:  # configurations the persistent kernel does not cover fall back to per-layer launches
         act = [torch.randn(B, 64, 64, 64, device=dev).mul_(0.3).to(torch.bfloat16) for _ in range(2)]
@@ -311,7 +322,7 @@ def main():
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "tensor", "kernel": k_name,
                      "achieved": conv_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": conv_tflops / peaks["bf16_sustained"], "traffic": None,
+                     "frac": conv_tflops / peaks["bf16_sustained"], "traffic": ncu_traffic(B) if body_ms else None,
                      "peak_source": peaks["source"] + " bf16_tflops_sustained", "us_per_launch": conv_ms * 1e3,
                      "step_achieved": step_tflops, "step_frac": step_tflops / peaks["bf16_sustained"]},
         "clocks": clocks,

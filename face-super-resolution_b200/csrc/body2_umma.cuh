@@ -345,29 +345,28 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           const bool w_rel = last_pass && (i == last_own);
           // Elected-lane blocks hold straight-line tcgen05 code only: every wait is executed by the whole
           // (converged) warp.  The first tile of a layer follows the weight loads tap by tap.
-          auto issue_tap = [&](int tap) {
-            const uint32_t off = (tap / 3) * kPitch + (tap % 3);
-            uint32_t pos = m + off;
-            if (pos >= uint32_t(kB2RingPx)) pos -= kB2RingPx;
-            const uint32_t a_lo = ring_lo + pos * 8;
-            const uint32_t b_lo = w_lo + tap * (N * 128 >> 4);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_ss_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, kDescHi, idesc, (tap | k) != 0);
-            if (w_rel) umma_commit(&bar_wfree[tap]);   // the next layer's tap may overwrite once these MMAs finish
-          };
+#define FEN_B2_ISSUE_TAP(tap)                                                                              \
+  {                                                                                                        \
+    const uint32_t off = ((tap) / 3) * kPitch + ((tap) % 3);                                               \
+    uint32_t pos = m + off;                                                                                \
+    if (pos >= uint32_t(kB2RingPx)) pos -= kB2RingPx;                                                      \
+    const uint32_t a_lo = ring_lo + pos * 8;                                                               \
+    const uint32_t b_lo = w_lo + (tap) * (N * 128 >> 4);                                                   \
+    _Pragma("unroll") for (int k = 0; k < 4; ++k)                                                          \
+        umma_bf16_ss_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, kDescHi, idesc, ((tap) | k) != 0);           \
+    if (w_rel) umma_commit(&bar_wfree[tap]); /* the next layer's tap may overwrite once these MMAs finish */ \
+  }
           if (!w_seen) {
+#pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(&bar_w[tap], L & 1);
               __syncwarp();
-              if (leader) issue_tap(tap);
+              if (leader) FEN_B2_ISSUE_TAP(tap)
               __syncwarp();
             }
-          } else {
-            if (leader) {
+          } else if (leader) {
 #pragma unroll
-              for (int tap = 0; tap < 9; ++tap) issue_tap(tap);
-            }
+            for (int tap = 0; tap < 9; ++tap) FEN_B2_ISSUE_TAP(tap)
           }
           w_seen = true;
           __syncwarp();
