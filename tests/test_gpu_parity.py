@@ -197,6 +197,33 @@ def test_forward_batch64_full_model_against_oracle(dev):
     assert fen_oracle.psnr(y1[0], y[31]) >= PSNR_BAR
 
 
+@pytest.mark.parametrize("B", [1, 2, 7, 10, 16, 24, 88, 140])
+def test_body_kernel_batch_geometries(B, dev):
+    """The persistent body kernel splits the batch into two interleaved image sets (even B) and gives
+    every CTA a fixed run of tiles: 1 tile per CTA (B <= 8), odd / even tile counts, runs that straddle
+    two images, one issuer warp without tiles ...  Every geometry must agree with the oracle (bf16 noise
+    only) on a model whose conv_last is LARGE enough to expose the body (sigma 3e-2, not the T1 1e-3)."""
+    cfg = dict(num_groups=1, blocks_per_group=2)
+    sd = weights.make_state_dict(3, "T1", **cfg)
+    g = torch.Generator().manual_seed(77)
+    sd["conv_last.weight"] = torch.randn(sd["conv_last.weight"].shape, generator=g) * 3e-2
+    x = torch.rand(B, 3, 64, 64, generator=torch.Generator().manual_seed(B))
+    m = _model(cfg, sd, dev, train=True)
+    with torch.no_grad():
+        y = m(x.to(dev)).cpu()
+    idx = sorted(set([0, B // 2, B - 1]))
+    taps = {}
+    ref = fen_oracle.fen_forward(sd, x[idx], training=True, taps=taps)
+    err = (y[idx] - ref).abs().max().item()
+    scale = (ref - F.interpolate(x[idx], scale_factor=4, mode="bicubic", align_corners=False)).abs().max().item()
+    assert not torch.isnan(y).any()
+    assert scale > 0.05, scale                    # the body really contributes
+    assert err <= 0.03 * scale + 1e-3, (err, scale)
+    maps = m.eval().get_attention_maps(x.to(dev))
+    got = torch.stack([maps["group0_rcab0"], maps["group0_rcab1"]], 1).cpu()[idx]
+    assert (got - taps["se"]).abs().max().item() <= 1e-2
+
+
 def test_attention_maps_match_reference(dev):
     name = "small_T1"
     _, cfg, tier, seed, _ = [c for c in cases.FEN_CASES if c[0] == name][0]
