@@ -349,6 +349,50 @@ __global__ void __launch_bounds__(256) lr_from_hr_kernel(const uint8_t* __restri
   }
 }
 
+// Float bicubic /4 (trainer.py:416-421, scripts/test_model.py:139-156): out = sum_i w_i (sum_j w_j in[4y+i][4x+j]),
+// w = [-3, 19, 19, -3] / 32 (cubic convolution, A = -0.75, t = 0.5; exact in fp32), rows first like ATen.
+// One thread per output pixel and channel; the 4 x 4 source block is four 16-byte loads.
+__global__ void __launch_bounds__(256) lr_from_hr_f32_kernel(const float* __restrict__ hr, float* __restrict__ lr_f32,
+                                                             uint8_t* __restrict__ lr_u8, int B, int C, int H, int W,
+                                                             int bgr) {
+  const int w = W >> 2, h = H >> 2;
+  const size_t total = size_t(B) * C * h * w;
+  const float w0 = -0.09375f, w1 = 0.59375f;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int x = int(i % w);
+    const int y = int((i / w) % h);
+    const int c = int((i / (size_t(w) * h)) % C);
+    const int n = int(i / (size_t(w) * h * C));
+    const float* src = hr + ((size_t(n) * C + c) * H + 4 * y) * W + 4 * x;
+    float r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + size_t(k) * W));
+      r[k] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v.x, w0), __fmul_rn(v.y, w1)), __fmul_rn(v.z, w1)), __fmul_rn(v.w, w0));
+    }
+    const float o = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r[0], w0), __fmul_rn(r[1], w1)), __fmul_rn(r[2], w1)), __fmul_rn(r[3], w0));
+    if (lr_f32) lr_f32[i] = o;
+    if (lr_u8) {
+      const float q = fminf(fmaxf(__fmul_rn(o, 255.0f), 0.f), 255.f);
+      const int cc = bgr ? C - 1 - c : c;
+      lr_u8[((size_t(n) * h + y) * w + x) * C + cc] = uint8_t(int(q));   // truncation, as numpy astype(uint8)
+    }
+  }
+}
+
+// to_numpy of the scripts (test_model.py:176-190): fp32 NCHW -> uint8 HWC, trunc(clip(v * 255, 0, 255)).
+__global__ void __launch_bounds__(256) sr_to_u8_kernel(const float* __restrict__ sr, uint8_t* __restrict__ out, int B, int C,
+                                                       int H, int W, int bgr) {
+  const size_t hw = size_t(H) * W, total = size_t(B) * hw;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const size_t n = i / hw, pix = i - n * hw;
+    for (int c = 0; c < C; ++c) {
+      const float q = fminf(fmaxf(__fmul_rn(__ldg(sr + (n * C + c) * hw + pix), 255.0f), 0.f), 255.f);
+      out[i * C + (bgr ? C - 1 - c : c)] = uint8_t(int(q));
+    }
+  }
+}
+
 // ===================================================================== parameter / blob layout
 struct Layout {
   int C, G, Bk, R, n_rcab;
@@ -843,6 +887,43 @@ int64_t fen_forward_tap(const fen_config* cfg, const void* workspace, int B, int
       return act;
     default: return fail(FEN_EINVAL, "fen_forward_tap: unknown tap");
   }
+}
+
+int fen_lr_from_hr_f32(const float* hr, float* lr_f32, uint8_t* lr_u8, int B, int C, int H, int W, int bgr,
+                       void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  g_launches = 0;
+  if (B == 0) return FEN_OK;
+  if (!hr || (!lr_u8 && !lr_f32)) return fail(FEN_EINVAL, "fen_lr_from_hr_f32: null pointer");
+  if (B < 0 || C < 1 || H < 4 || W < 4 || (H & 3) || (W & 3))
+    return fail(FEN_EINVAL, "fen_lr_from_hr_f32: H and W must be multiples of 4");
+  if (reinterpret_cast<uintptr_t>(hr) & 15) return fail(FEN_EINVAL, "fen_lr_from_hr_f32: hr must be 16-byte aligned");
+  const size_t total = size_t(B) * C * (H / 4) * (W / 4);
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = size_t(num_sms()) * 32;
+  if (blocks > cap) blocks = cap;
+  lr_from_hr_f32_kernel<<<unsigned(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(hr, lr_f32, lr_u8, B, C, H, W, bgr);
+  FEN_CUDA(cudaGetLastError());
+  ++g_launches;
+  return FEN_OK;
+}
+
+int fen_sr_to_u8(const float* sr, uint8_t* out, int B, int C, int H, int W, int bgr, void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  g_launches = 0;
+  if (B == 0) return FEN_OK;
+  if (!sr || !out) return fail(FEN_EINVAL, "fen_sr_to_u8: null pointer");
+  if (B < 0 || C < 1 || H < 1 || W < 1) return fail(FEN_EINVAL, "fen_sr_to_u8: bad shape");
+  const size_t total = size_t(B) * H * W;
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = size_t(num_sms()) * 32;
+  if (blocks > cap) blocks = cap;
+  sr_to_u8_kernel<<<unsigned(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(sr, out, B, C, H, W, bgr);
+  FEN_CUDA(cudaGetLastError());
+  ++g_launches;
+  return FEN_OK;
 }
 
 int fen_lr_from_hr_u8(const uint8_t* hr, uint8_t* lr_u8, float* lr_f32, int B, int H, int W, int C,

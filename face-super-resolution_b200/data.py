@@ -38,6 +38,50 @@ def lr_from_hr(hr: torch.Tensor, want_u8: bool = True, want_f32: bool = True
     return u8, f32
 
 
+def lr_from_hr_float(hr: torch.Tensor, want_f32: bool = True, want_u8: bool = False, bgr: bool = False
+                     ) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """The trainer's / the scripts' float LR generator on the GPU:
+    F.interpolate(hr, scale_factor=0.25, mode='bicubic', align_corners=False) (trainer.py:416-421) and,
+    with want_u8, generate_lr of scripts/test_model.py:139-156 (np.clip(lr * 255, 0, 255).astype(uint8), HWC,
+    BGR when bgr).  hr: float32 CUDA tensor [B,C,H,W] in [0,1].  Returns (lr_f32 [B,C,H/4,W/4], lr_u8 [B,H/4,W/4,C])."""
+    if hr.dtype != torch.float32 or hr.dim() != 4:
+        raise TypeError("hr must be a float32 tensor [B,C,H,W]")
+    if not hr.is_cuda:
+        raise RuntimeError("lr_from_hr_float needs a CUDA tensor: there is no CPU fallback")
+    if not (want_u8 or want_f32):
+        raise ValueError("nothing requested")
+    hr = hr.contiguous()
+    B, Cn, H, W = hr.shape
+    if H % 4 or W % 4:
+        raise ValueError("H and W must be multiples of 4")
+    lib = _lib.load()
+    with torch.cuda.device(hr.device):
+        f32 = torch.empty((B, Cn, H // 4, W // 4), dtype=torch.float32, device=hr.device) if want_f32 else None
+        u8 = torch.empty((B, H // 4, W // 4, Cn), dtype=torch.uint8, device=hr.device) if want_u8 else None
+        rc = lib.fen_lr_from_hr_f32(hr.data_ptr(), f32.data_ptr() if want_f32 else None,
+                                    u8.data_ptr() if want_u8 else None, B, Cn, H, W, int(bgr),
+                                    torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "fen_lr_from_hr_f32")
+    return f32, u8
+
+
+def sr_to_uint8(sr: torch.Tensor, bgr: bool = False) -> torch.Tensor:
+    """to_numpy of the evaluation scripts (scripts/test_model.py:176-190) on the GPU: float32 [B,C,H,W] ->
+    uint8 [B,H,W,C], np.clip(x * 255, 0, 255).astype(uint8) (truncation), BGR channel order when bgr."""
+    if sr.dtype != torch.float32 or sr.dim() != 4:
+        raise TypeError("sr must be a float32 tensor [B,C,H,W]")
+    if not sr.is_cuda:
+        raise RuntimeError("sr_to_uint8 needs a CUDA tensor: there is no CPU fallback")
+    sr = sr.contiguous()
+    B, Cn, H, W = sr.shape
+    lib = _lib.load()
+    with torch.cuda.device(sr.device):
+        out = torch.empty((B, H, W, Cn), dtype=torch.uint8, device=sr.device)
+        rc = lib.fen_sr_to_u8(sr.data_ptr(), out.data_ptr(), B, Cn, H, W, int(bgr), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "fen_sr_to_u8")
+    return out
+
+
 def create_lr_image(hr_image: np.ndarray, lr_size: int = 64, method: str = "bicubic") -> np.ndarray:
     """Same signature as the reference's create_lr_image (prepare_data.py:23-59): HWC uint8 numpy in,
     HWC uint8 numpy out, computed by the CUDA kernel.  Only the path's method ('bicubic') at the exact

@@ -20,10 +20,10 @@ from .blocks import (  # noqa: E402,F401
     PixelShuffleUpsample,
     UpsampleModule,
 )
-from .data import create_lr_image, lr_from_hr, to_tensor  # noqa: E402,F401
+from .data import create_lr_image, lr_from_hr, lr_from_hr_float, sr_to_uint8, to_tensor  # noqa: E402,F401
 
 __all__ = [
     "FaceEnhanceNet", "FaceEnhanceNetConfig", "FaceEnhanceNetLite", "create_face_enhance_net",
     "ChannelAttention", "RCAB", "ResidualGroup", "PixelShuffleUpsample", "UpsampleModule",
-    "create_lr_image", "lr_from_hr", "to_tensor",
+    "create_lr_image", "lr_from_hr", "lr_from_hr_float", "sr_to_uint8", "to_tensor",
 ]

@@ -89,6 +89,24 @@ int64_t fen_forward_tap(const fen_config* cfg, const void* workspace, int B, int
 int fen_lr_from_hr_u8(const uint8_t* hr, uint8_t* lr_u8, float* lr_f32, int B, int H, int W, int C,
                       void* stream);
 
+/* Replaces the float LR generation of the trainer and of the evaluation scripts:
+ * F.interpolate(hr, scale_factor=0.25, mode='bicubic', align_corners=False) (reference
+ * src/training/trainer.py:416-421, also :568-573, :798-803) and generate_lr of scripts/test_model.py:139-156
+ * (the same taps, then clip(v * 255, 0, 255) truncated to uint8).  At the exact /4 ratio the 16 taps are
+ * w_i w_j, w = [-3, 19, 19, -3] / 32, on pixels 4y .. 4y+3 x 4x .. 4x+3; fp32, no rounding, no clamp.
+ *   hr      [B,C,H,W] fp32 NCHW, H and W multiples of 4
+ *   lr_f32  optional [B,C,H/4,W/4] fp32 NCHW (the trainer's tensor; tolerance vs PyTorch 2.4e-7)
+ *   lr_u8   optional [B,H/4,W/4,C] uint8 HWC, trunc(clip(v * 255, 0, 255)); channel order reversed
+ *           (RGB -> BGR, cv2 convention of the scripts) when bgr != 0 */
+int fen_lr_from_hr_f32(const float* hr, float* lr_f32, uint8_t* lr_u8, int B, int C, int H, int W, int bgr,
+                       void* stream);
+
+/* Replaces to_numpy of the evaluation scripts (reference scripts/test_model.py:176-190,
+ * scripts/compare_two_models.py:150-179, app/demo.py:180-222): network output fp32 NCHW in [0,1] ->
+ * uint8 HWC, trunc(clip(v * 255, 0, 255)), channel order reversed when bgr != 0.
+ *   sr   [B,C,H,W] fp32      out  [B,H,W,C] uint8 */
+int fen_sr_to_u8(const float* sr, uint8_t* out, int B, int C, int H, int W, int bgr, void* stream);
+
 /* One 3x3 / pad-1 convolution with 64 input and 64 output channels on NHWC bf16 tensors
  * (the RCAB building block, reference src/models/blocks.py:122-130): out = epilogue(conv(x) + bias).
  *   w_packed [9][64][64] bf16 (tap, cout, cin), as produced by fen_pack_conv3x3

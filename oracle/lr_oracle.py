@@ -69,3 +69,33 @@ def lr_from_hr_u8_loops(hr: np.ndarray) -> np.ndarray:
 def to_tensor_chw(lr_u8: np.ndarray) -> np.ndarray:
     """``to_tensor`` of src/data/transforms.py:260-279: HWC uint8 -> CHW float32 divided by 255."""
     return (np.moveaxis(lr_u8, -1, -3).astype(np.float32) / np.float32(255.0)).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Float LR generator of the trainer and of the evaluation scripts (SURVEY.md 8 a-14, f-2).
+# The reference code IS a single PyTorch call, so the oracle executes exactly that call on the CPU:
+#   src/training/trainer.py:416-421  lr = F.interpolate(hr, scale_factor=0.25, mode='bicubic', align_corners=False)
+#   scripts/test_model.py:139-156    generate_lr: same taps, then np.clip(lr * 255, 0, 255).astype(np.uint8)
+#   scripts/test_model.py:176-190    to_numpy: np.clip(sr * 255, 0, 255).astype(np.uint8), CHW -> HWC, RGB -> BGR
+# lr_from_hr_float_taps restates the algorithm (16 taps w_i w_j, w = [-3, 19, 19, -3] / 32) and
+# tests/test_oracle_lr.py pins it against the PyTorch call to 2.4e-7 (fp32 summation order).
+def lr_from_hr_float(hr):
+    """hr: float32 torch tensor [B,C,H,W] -> [B,C,H/4,W/4], the trainer's exact call."""
+    import torch.nn.functional as F
+    return F.interpolate(hr.detach().float().cpu(), scale_factor=0.25, mode="bicubic", align_corners=False)
+
+
+def lr_from_hr_float_taps(hr: np.ndarray) -> np.ndarray:
+    """The same operation as explicit taps (numpy, float32): rows first, then columns."""
+    w = np.array([-0.09375, 0.59375, 0.59375, -0.09375], dtype=np.float32)
+    hr = np.asarray(hr, dtype=np.float32)
+    rows = [sum(hr[..., i::4, j::4] * w[j] for j in range(4)).astype(np.float32) for i in range(4)]
+    return sum(rows[i] * w[i] for i in range(4)).astype(np.float32)
+
+
+def quantize_u8_hwc(x_chw: np.ndarray, bgr: bool = False) -> np.ndarray:
+    """np.clip(x * 255, 0, 255).astype(np.uint8) on [..., C, H, W] float32 -> [..., H, W, C] (scripts' to_numpy /
+    generate_lr; astype truncates), channel order reversed when bgr (cv2.COLOR_RGB2BGR)."""
+    q = np.clip(np.asarray(x_chw, dtype=np.float32) * np.float32(255), 0, 255).astype(np.uint8)
+    q = np.moveaxis(q, -3, -1)
+    return q[..., ::-1].copy() if bgr else q

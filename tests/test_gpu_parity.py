@@ -71,6 +71,39 @@ def test_create_lr_image_numpy_boundary(dev):
     assert out.dtype == np.uint8 and np.array_equal(out, LR_GOLD["random_256"])
 
 
+def test_float_lr_generator_matches_trainer_call(dev):
+    """F.interpolate(hr, 0.25, bicubic) in fp32 (tolerance 2.4e-7: summation order) and
+    the scripts' uint8 variant (truncation: a 1-LSB difference only where v * 255 sits on an integer)."""
+    g = torch.Generator().manual_seed(21)
+    hr8 = torch.randint(0, 256, (5, 3, 256, 256), generator=g, dtype=torch.uint8)
+    hr = hr8.float() / 255.0                                   # scripts: uint8 image / 255
+    ref = lr_oracle.lr_from_hr_float(hr)
+    f32, u8 = fsr_b200.lr_from_hr_float(hr.to(dev), want_f32=True, want_u8=True, bgr=True)
+    assert f32.shape == (5, 3, 64, 64) and u8.shape == (5, 64, 64, 3)
+    assert (f32.cpu() - ref).abs().max().item() <= 2.4e-7
+    assert f32.min() < 0 and f32.max() > 1                     # neither rounded nor clamped
+    q_ref = lr_oracle.quantize_u8_hwc(ref.numpy(), bgr=True)
+    diff = np.abs(u8.cpu().numpy().astype(np.int32) - q_ref.astype(np.int32))
+    assert diff.max() <= 1 and (diff != 0).mean() <= 1e-3
+    # trainer input (continuous values), other shapes, error behaviour
+    x = torch.rand(2, 1, 8, 12, generator=g)
+    f32, _ = fsr_b200.lr_from_hr_float(x.to(dev))
+    assert (f32.cpu() - lr_oracle.lr_from_hr_float(x)).abs().max().item() <= 2.4e-7
+    with pytest.raises(ValueError):
+        fsr_b200.lr_from_hr_float(torch.rand(1, 3, 6, 8, device=dev))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fsr_b200.lr_from_hr_float(torch.rand(1, 3, 8, 8))
+
+
+def test_sr_to_uint8_matches_scripts_to_numpy(dev):
+    g = torch.Generator().manual_seed(22)
+    sr = torch.rand(3, 3, 40, 56, generator=g) * 1.4 - 0.2     # values outside [0, 1] get clipped
+    sr[0, 0, 0, :4] = torch.tensor([0.0, 1.0, 127.0 / 255.0, 254.999 / 255.0])
+    for bgr in (False, True):
+        got = fsr_b200.sr_to_uint8(sr.to(dev), bgr=bgr).cpu().numpy()
+        assert np.array_equal(got, lr_oracle.quantize_u8_hwc(sr.numpy(), bgr=bgr))
+
+
 # ------------------------------------------------------------------ single convolution (C ABI)
 def _conv_call(dev, x, w, bias, slope, res, epi):
     lib = _lib.load()

@@ -96,3 +96,26 @@ def test_live_cv2_if_available():
         hr = rng.integers(0, 256, (256, 256, 3), dtype=np.uint8)
         ref = cv2.resize(hr, (64, 64), interpolation=cv2.INTER_CUBIC)
         assert np.array_equal(lr_oracle.lr_from_hr_u8(hr), ref)
+
+
+def test_float_lr_taps_restate_the_trainer_call():
+    """trainer.py:416-421 is F.interpolate(scale_factor=0.25, bicubic): 16 fixed taps at the /4 ratio."""
+    import torch
+    g = torch.Generator().manual_seed(3)
+    hr = torch.rand(2, 3, 64, 96, generator=g)
+    ref = lr_oracle.lr_from_hr_float(hr).numpy()
+    taps = lr_oracle.lr_from_hr_float_taps(hr.numpy())
+    assert ref.shape == (2, 3, 16, 24)
+    assert np.abs(ref - taps).max() <= 2.4e-7
+    # no rounding, no clamp: a checkerboard of 0 / 1 leaves [0, 1]
+    cb = torch.zeros(1, 1, 8, 8)
+    cb[..., 1:3, 1:3] = 1.0
+    out = lr_oracle.lr_from_hr_float(cb)
+    assert out.max() > 1.0 and lr_oracle.lr_from_hr_float(1 - cb).min() < 0.0
+
+
+def test_quantize_u8_truncates_and_reorders():
+    x = np.array([[[0.9999, -0.2]], [[0.5, 1.2]], [[1.0 / 255 * 7.9, 0.0]]], dtype=np.float32)   # [C=3, H=1, W=2]
+    q = lr_oracle.quantize_u8_hwc(x)
+    assert q.shape == (1, 2, 3) and q.tolist() == [[[254, 127, 7], [0, 255, 0]]]
+    assert lr_oracle.quantize_u8_hwc(x, bgr=True).tolist() == [[[7, 127, 254], [0, 255, 0]]]
