@@ -1,0 +1,27 @@
+"""Developer script: repeat the full forward many times and check that every run reproduces the first one
+up to the SE-pool summation order (fp32 atomics), which bf16 re-rounding amplifies to the parity-noise level
+(a few % of the body's contribution with this stress conv_last); a race (a tile computed from stale data)
+shows up as an O(1) relative deviation."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, fsr_b200
+from oracle import weights
+dev = torch.device("cuda:0")
+cfg = dict(num_groups=6, blocks_per_group=10)
+sd = weights.make_state_dict(0, "T1", **cfg)
+g = torch.Generator().manual_seed(7)
+sd["conv_last.weight"] = torch.randn(sd["conv_last.weight"].shape, generator=g) * 1e-2   # expose the body
+m = fsr_b200.FaceEnhanceNet(**cfg); m.load_state_dict(sd); m = m.to(dev).train()
+worst = 0.0
+for B in [int(a) for a in sys.argv[2:]] or [64]:
+    x = torch.rand(B, 3, 64, 64, device=dev)
+    with torch.no_grad():
+        ref = m(x).clone()
+        scale = (ref - torch.nn.functional.interpolate(x, scale_factor=4, mode="bicubic", align_corners=False)).abs().max().item()
+        for it in range(int(sys.argv[1]) if len(sys.argv) > 1 else 50):
+            y = m(x)
+            d = (y - ref).abs().max().item() / scale      # relative to the body's contribution
+            worst = max(worst, d)
+            if d > 0.15 or torch.isnan(y).any():
+                print(f"B={B} iteration {it}: max deviation {d:.3e} - RACE?"); sys.exit(1)
+    print(f"B={B}: {sys.argv[1] if len(sys.argv) > 1 else 50} forwards, max deviation from the first {worst:.3e}")
