@@ -1,6 +1,7 @@
 // C-ABI implementation (include/fen_b200.h) of the B200-native FaceEnhanceNet forward path.
 // Host orchestration + the small CUDA-core kernels; the tensor-core convolution lives in
 // conv3x3_umma.cuh.  Build: see face-super-resolution_b200/build.py (nvcc, sm_100a only).
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -390,6 +391,72 @@ __global__ void __launch_bounds__(256) sr_to_u8_kernel(const float* __restrict__
       const float q = fminf(fmaxf(__fmul_rn(__ldg(sr + (n * C + c) * hw + pix), 255.0f), 0.f), 255.f);
       out[i * C + (bgr ? C - 1 - c : c)] = uint8_t(int(q));
     }
+  }
+}
+
+// ===================================================================== loss / optimiser kernels (Stage-1 step)
+constexpr int kRedBlocks = 1024;   // partial sums of the two-stage reductions (fixed -> deterministic)
+
+__device__ __forceinline__ float block_sum_256(float v, float* sh) {
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = (threadIdx.x < 8) ? sh[threadIdx.x] : 0.f;
+  if (threadIdx.x < 32) {
+#pragma unroll
+    for (int d = 4; d >= 1; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+  }
+  return t;   // valid in thread 0
+}
+// mode 0: sum |a - b| (and dsr = sign(a - b) * inv_n); mode 1: sum a^2
+__global__ void __launch_bounds__(256) reduce_partial_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                            float* __restrict__ dsr, int64_t n, float inv_n, int mode,
+                                                            float* __restrict__ partial) {
+  __shared__ float sh[8];
+  float acc = 0.f;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    if (mode == 0) {
+      const float d = a[i] - b[i];
+      acc += fabsf(d);
+      if (dsr) dsr[i] = (d > 0.f) ? inv_n : (d < 0.f ? -inv_n : 0.f);
+    } else {
+      acc = fmaf(a[i], a[i], acc);
+    }
+  }
+  const float t = block_sum_256(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+// out[0] = scale * sum(partial)  (or sqrt of it), accumulated in double by one block
+__global__ void __launch_bounds__(256) reduce_final_kernel(const float* __restrict__ partial, int count, float scale,
+                                                          int take_sqrt, float* __restrict__ out) {
+  __shared__ double sh[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < count; i += 256) acc += double(partial[i]);
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int d = 128; d >= 1; d >>= 1) {
+    if (threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = take_sqrt ? float(sqrt(sh[0])) : float(sh[0] * double(scale));
+}
+// clip_grad_norm_ + AdamW (torch.optim.AdamW single-tensor formulas, trainer.py:217-221,490-503)
+__global__ void __launch_bounds__(256) clip_adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                        float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                        const float* __restrict__ total_norm, float max_norm, float lr,
+                                                        float beta1, float beta2, float eps, float wd, float step_size,
+                                                        float bc2_sqrt) {
+  float coef = 1.f;
+  if (max_norm > 0.f) coef = fminf(max_norm / (__ldg(total_norm) + 1e-6f), 1.f);
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * coef;
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = m[i] + (gi - m[i]) * (1.f - beta1);          // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = v[i] * beta2 + (1.f - beta2) * gi * gi;      // mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= step_size * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
   }
 }
 
@@ -887,6 +954,69 @@ int64_t fen_forward_tap(const fen_config* cfg, const void* workspace, int B, int
       return act;
     default: return fail(FEN_EINVAL, "fen_forward_tap: unknown tap");
   }
+}
+
+int64_t fen_train_workspace_bytes(int64_t n) {
+  (void)n;
+  return int64_t(kRedBlocks) * 4;
+}
+
+static int reduce_launch(const float* a, const float* b, float* dsr, int64_t n, float inv_n, int mode, float scale,
+                         int take_sqrt, float* out, void* workspace, int64_t ws_bytes, cudaStream_t st) {
+  if (ws_bytes < int64_t(kRedBlocks) * 4) return fail(FEN_ENOMEM, "training workspace too small");
+  float* partial = static_cast<float*>(workspace);
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > kRedBlocks) blocks = kRedBlocks;
+  if (blocks < 1) blocks = 1;
+  reduce_partial_kernel<<<unsigned(blocks), 256, 0, st>>>(a, b, dsr, n, inv_n, mode, partial);
+  FEN_CUDA(cudaGetLastError());
+  reduce_final_kernel<<<1, 256, 0, st>>>(partial, int(blocks), scale, take_sqrt, out);
+  FEN_CUDA(cudaGetLastError());
+  g_launches += 2;
+  return FEN_OK;
+}
+
+int fen_l1_loss(const float* sr, const float* hr, int64_t n, float* loss, float* dsr, void* workspace,
+                int64_t workspace_bytes, void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  g_launches = 0;
+  if (!sr || !hr || !loss || !workspace) return fail(FEN_EINVAL, "fen_l1_loss: null pointer");
+  if (n < 1) return fail(FEN_EINVAL, "fen_l1_loss: empty input");
+  return reduce_launch(sr, hr, dsr, n, 1.f / float(n), 0, 1.f / float(n), 0, loss, workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int fen_grad_norm(const float* grads, int64_t n, float* norm_out, void* workspace, int64_t workspace_bytes,
+                  void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  g_launches = 0;
+  if (!grads || !norm_out || !workspace) return fail(FEN_EINVAL, "fen_grad_norm: null pointer");
+  if (n < 1) return fail(FEN_EINVAL, "fen_grad_norm: empty input");
+  return reduce_launch(grads, nullptr, nullptr, n, 0.f, 1, 1.f, 1, norm_out, workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int fen_clip_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        const float* total_norm, float max_norm, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, int step, void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  g_launches = 0;
+  if (!params || !grads || !exp_avg || !exp_avg_sq) return fail(FEN_EINVAL, "fen_clip_adamw_step: null pointer");
+  if (max_norm > 0.f && !total_norm) return fail(FEN_EINVAL, "fen_clip_adamw_step: total_norm required for clipping");
+  if (n < 1 || step < 1) return fail(FEN_EINVAL, "fen_clip_adamw_step: n and step must be >= 1");
+  const double bc1 = 1.0 - pow(double(beta1), double(step)), bc2 = 1.0 - pow(double(beta2), double(step));
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = int64_t(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  clip_adamw_kernel<<<unsigned(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      params, grads, exp_avg, exp_avg_sq, n, total_norm, max_norm, lr, beta1, beta2, eps, weight_decay,
+      float(double(lr) / bc1), float(sqrt(bc2)));
+  FEN_CUDA(cudaGetLastError());
+  ++g_launches;
+  return FEN_OK;
 }
 
 int fen_lr_from_hr_f32(const float* hr, float* lr_f32, uint8_t* lr_u8, int B, int C, int H, int W, int bgr,

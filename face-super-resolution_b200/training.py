@@ -1,0 +1,88 @@
+"""Loss / optimiser side of the reference's Stage-1 training step on the GPU:
+nn.L1Loss (src/losses/combined.py:38-47), clip_grad_norm_ and AdamW (src/training/trainer.py:217-221,
+490-503), plus the data-parallel gradient exchange.  The network's backward pass is not
+built yet; these functions operate on flat fp32 tensors so that it can be dropped in between them."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def _workspace(device: torch.device, n: int) -> torch.Tensor:
+    lib = _lib.load()
+    return torch.empty(int(lib.fen_train_workspace_bytes(n)), dtype=torch.uint8, device=device)
+
+
+def _check_cuda_f32(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t.dtype != torch.float32:
+            raise TypeError("float32 tensors expected")
+        if not t.is_cuda:
+            raise RuntimeError("the training kernels need CUDA tensors: there is no CPU fallback")
+        if not t.is_contiguous():
+            raise ValueError("contiguous tensors expected")
+
+
+def l1_loss(sr: torch.Tensor, hr: torch.Tensor, want_grad: bool = True
+            ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """nn.L1Loss(reduction='mean')(sr, hr) and d loss / d sr = sign(sr - hr) / numel.  Returns (loss [1], dsr)."""
+    _check_cuda_f32(sr, hr)
+    if sr.shape != hr.shape:
+        raise ValueError("sr and hr must have the same shape")
+    lib = _lib.load()
+    with torch.cuda.device(sr.device):
+        loss = torch.empty(1, dtype=torch.float32, device=sr.device)
+        dsr = torch.empty_like(sr) if want_grad else None
+        ws = _workspace(sr.device, sr.numel())
+        rc = lib.fen_l1_loss(sr.data_ptr(), hr.data_ptr(), sr.numel(), loss.data_ptr(),
+                             dsr.data_ptr() if want_grad else None, ws.data_ptr(), ws.numel(),
+                             torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "fen_l1_loss")
+    return loss, dsr
+
+
+def allreduce_mean_(flat_grad: torch.Tensor) -> torch.Tensor:
+    """Data-parallel gradient exchange: one all-reduce (sum) of the flat gradient, then / world_size, in place.
+    NCCL over NVLink on GPUs; identity when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+        flat_grad.div_(dist.get_world_size())
+    return flat_grad
+
+
+class ClipAdamW:
+    """clip_grad_norm_(params, max_norm) + torch.optim.AdamW.step() on ONE flat fp32 parameter vector
+    (trainer.py:217-221: AdamW(lr, weight_decay), default betas (0.9, 0.999), eps 1e-8; :490-496 clip 0.5)."""
+
+    def __init__(self, flat_params: torch.Tensor, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.0, max_norm: float = 0.5):
+        _check_cuda_f32(flat_params)
+        self.params = flat_params
+        self.exp_avg = torch.zeros_like(flat_params)
+        self.exp_avg_sq = torch.zeros_like(flat_params)
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, betas, eps, weight_decay, max_norm
+        self.step_count = 0
+        self.total_norm = torch.zeros(1, dtype=torch.float32, device=flat_params.device)
+        self._ws = _workspace(flat_params.device, flat_params.numel())
+
+    def step(self, flat_grad: torch.Tensor) -> torch.Tensor:
+        """One optimiser step; returns the (device) total gradient norm before clipping."""
+        _check_cuda_f32(flat_grad)
+        if flat_grad.numel() != self.params.numel():
+            raise ValueError("gradient size mismatch")
+        lib = _lib.load()
+        self.step_count += 1
+        with torch.cuda.device(self.params.device):
+            st = torch.cuda.current_stream().cuda_stream
+            n = self.params.numel()
+            _lib.check(lib.fen_grad_norm(flat_grad.data_ptr(), n, self.total_norm.data_ptr(), self._ws.data_ptr(),
+                                         self._ws.numel(), st), "fen_grad_norm")
+            _lib.check(lib.fen_clip_adamw_step(self.params.data_ptr(), flat_grad.data_ptr(), self.exp_avg.data_ptr(),
+                                               self.exp_avg_sq.data_ptr(), n, self.total_norm.data_ptr(),
+                                               self.max_norm, self.lr, self.betas[0], self.betas[1], self.eps,
+                                               self.weight_decay, self.step_count, st), "fen_clip_adamw_step")
+        return self.total_norm

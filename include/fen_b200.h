@@ -107,6 +107,32 @@ int fen_lr_from_hr_f32(const float* hr, float* lr_f32, uint8_t* lr_u8, int B, in
  *   sr   [B,C,H,W] fp32      out  [B,H,W,C] uint8 */
 int fen_sr_to_u8(const float* sr, uint8_t* out, int B, int C, int H, int W, int bgr, void* stream);
 
+/* ---- Stage-1 training step, loss / optimiser side.  The backward pass of the network is
+ * not built yet; these are the pieces of Trainer._train_epoch that follow it.
+ *
+ * Scratch for the deterministic two-stage reductions below. */
+int64_t fen_train_workspace_bytes(int64_t n);
+
+/* Replaces nn.L1Loss(reduction='mean') (reference src/losses/combined.py:38-47, summed into total_loss at
+ * :148-177 with weight 1) and its backward: loss[0] = mean |sr - hr| over n elements (device scalar),
+ * dsr[i] = sign(sr[i] - hr[i]) / n (optional; what loss.backward() hands to the network output). */
+int fen_l1_loss(const float* sr, const float* hr, int64_t n, float* loss, float* dsr, void* workspace,
+                int64_t workspace_bytes, void* stream);
+
+/* Global L2 norm of the flat gradient (what clip_grad_norm_ computes, reference src/training/trainer.py:490-496);
+ * norm_out is a device scalar.  After a data-parallel all-reduce every rank holds the same gradient, so the norm
+ * needs no second collective. */
+int fen_grad_norm(const float* grads, int64_t n, float* norm_out, void* workspace, int64_t workspace_bytes,
+                  void* stream);
+
+/* Replaces torch.nn.utils.clip_grad_norm_(params, max_norm) followed by torch.optim.AdamW.step()
+ * (reference src/training/trainer.py:217-221, 490-503): g *= min(1, max_norm / (total_norm + 1e-6)) (no
+ * clipping when max_norm <= 0), then the decoupled-weight-decay Adam update with bias correction for
+ * `step` (1-based).  total_norm is the device scalar of fen_grad_norm; one fused pass over the 4 arrays. */
+int fen_clip_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                        const float* total_norm, float max_norm, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, int step, void* stream);
+
 /* One 3x3 / pad-1 convolution with 64 input and 64 output channels on NHWC bf16 tensors
  * (the RCAB building block, reference src/models/blocks.py:122-130): out = epilogue(conv(x) + bias).
  *   w_packed [9][64][64] bf16 (tap, cout, cin), as produced by fen_pack_conv3x3

@@ -104,6 +104,49 @@ def test_sr_to_uint8_matches_scripts_to_numpy(dev):
         assert np.array_equal(got, lr_oracle.quantize_u8_hwc(sr.numpy(), bgr=bgr))
 
 
+# ------------------------------------------------------------------ Stage-1 step: loss / optimiser side
+def test_l1_loss_and_gradient_match_torch(dev):
+    """nn.L1Loss(mean) (combined.py:38-47) and what loss.backward() hands to the network output."""
+    g = torch.Generator().manual_seed(31)
+    sr = (torch.rand(2, 3, 256, 256, generator=g) * 1.3 - 0.15).requires_grad_(True)
+    hr = torch.rand(2, 3, 256, 256, generator=g)
+    hr.view(-1)[:100] = sr.detach().view(-1)[:100]                  # exact zeros: sign(0) = 0 as in torch
+    ref = torch.nn.L1Loss(reduction="mean")(sr, hr)
+    ref.backward()
+    loss, dsr = fsr_b200.l1_loss(sr.detach().to(dev), hr.to(dev))
+    assert abs(loss.item() - ref.item()) <= 1e-6 * abs(ref.item()) + 1e-9
+    assert torch.equal(dsr.cpu(), sr.grad)
+    loss2, none = fsr_b200.l1_loss(sr.detach().to(dev), hr.to(dev), want_grad=False)
+    assert none is None and loss2.item() == loss.item()             # deterministic two-stage reduction
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fsr_b200.l1_loss(sr.detach(), hr)
+
+
+@pytest.mark.parametrize("max_norm,wd", [(0.5, 0.0), (0.5, 1e-2), (0.0, 0.0), (1e3, 0.0)])
+def test_clip_adamw_matches_torch(max_norm, wd, dev):
+    """clip_grad_norm_(0.5) + AdamW(lr 1e-4) of the trainer (trainer.py:217-221, 490-503), 5 steps on a flat
+    vector of the model's size class, against torch.optim.AdamW on the CPU."""
+    g = torch.Generator().manual_seed(41)
+    n = 200_003
+    p0 = torch.randn(n, generator=g) * 0.05
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt_ref = torch.optim.AdamW([ref_p], lr=1e-4, weight_decay=wd, foreach=False)
+    p_dev = p0.clone().to(dev)
+    opt = fsr_b200.ClipAdamW(p_dev, lr=1e-4, weight_decay=wd, max_norm=max_norm)
+    for step in range(5):
+        grad = torch.randn(n, generator=g) * (10.0 if step % 2 == 0 else 1e-4)   # clipped and unclipped steps
+        ref_p.grad = grad.clone()
+        ref_norm = torch.nn.utils.clip_grad_norm_([ref_p], max_norm) if max_norm > 0 else grad.norm()
+        opt_ref.step()
+        norm = opt.step(grad.to(dev))
+        assert abs(norm.item() - ref_norm.item()) <= 2e-6 * ref_norm.item()
+        assert (p_dev.cpu() - ref_p.detach()).abs().max().item() <= 2e-7   # lr 1e-4: updates are ~1e-4
+    m_ref = opt_ref.state[ref_p]["exp_avg"]
+    assert (opt.exp_avg.cpu() - m_ref).abs().max().item() <= 5e-6 * m_ref.abs().max().item() + 1e-9
+    rel = (opt.exp_avg_sq.cpu() - opt_ref.state[ref_p]["exp_avg_sq"]).abs().max() / opt_ref.state[ref_p]["exp_avg_sq"].abs().max()
+    assert rel.item() <= 5e-5      # (clip coefficient from a norm that differs by ~2e-6 relative, squared, 5 steps)
+
+
 # ------------------------------------------------------------------ single convolution (C ABI)
 def _conv_call(dev, x, w, bias, slope, res, epi):
     lib = _lib.load()

@@ -37,7 +37,11 @@ def _worker(rank, world, port, q):
         sharding.barrier()
         t = sharding.max_over_ranks(10.0 + rank, torch.device("cpu"))
         n = sharding.sum_over_ranks(float(e - b), torch.device("cpu"))
-        q.put((rank, b, e, t, n))
+        # data-parallel gradient exchange of the training step: sum, then / world
+        from fsr_b200 import training
+        g = torch.full((5,), float(rank + 1)) * torch.arange(1, 6)
+        training.allreduce_mean_(g)
+        q.put((rank, b, e, t, n, g.tolist()))
     finally:
         dist.destroy_process_group()
 
@@ -58,3 +62,10 @@ def test_two_rank_timing_protocol_gloo():
     assert [(r[1], r[2]) for r in res] == [(0, 32768), (32768, 65536)]
     assert all(r[3] == 11.0 for r in res)      # max over ranks of the per-rank time
     assert all(r[4] == 65536.0 for r in res)   # every image processed exactly once
+    assert all(r[5] == [1.5, 3.0, 4.5, 6.0, 7.5] for r in res)   # mean of the two ranks' gradients, on both
+
+
+def test_allreduce_mean_is_identity_without_process_group():
+    from fsr_b200 import training
+    g = torch.arange(4, dtype=torch.float32)
+    assert torch.equal(training.allreduce_mean_(g.clone()), g)
