@@ -10,6 +10,7 @@
 
 #include "../../include/fen_b200.h"
 #include "conv3x3_umma.cuh"
+#include "conv3x3_umma2.cuh"
 #include "body_umma.cuh"
 #include "body2_umma.cuh"
 
@@ -163,7 +164,23 @@ static int launch_conv_n(const ConvArgs& a, cudaStream_t st) {
   p.tiles_per_cta = (p.total_tiles + ctas_x - 1) / ctas_x;
   ctas_x = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
   dim3 grid(ctas_x, ctas_y);
-  conv3x3_umma_kernel<N><<<grid, ConvCfg<N>::kThreads, ConvCfg<N>::kDynBytes, st>>>(tm_in, tm_w, p);
+  // second-generation (table-driven) kernel when a CTA's run fits its tables; FEN_CONV_KERNEL=1 forces the first
+  static int conv_version = -1;
+  if (conv_version < 0) { const char* e = getenv("FEN_CONV_KERNEL"); conv_version = (e && e[0] == '1') ? 1 : (e && e[0] == '3') ? 3 : 2; }
+  const int boxes_bound = p.tiles_per_cta * kTileM / kBoxPx + 3 * ((p.tiles_per_cta + p.tiles_per_seg - 1) / p.tiles_per_seg + 1);
+  // (measured at batch 64: conv_last 220 vs 240 us with the second generation, the 64-wide upsample convs
+  // 320 vs 285 us - their 3-slot ring starves either way - so only N = 16 takes it by default)
+  if ((conv_version == 2 && N == 16 || conv_version == 3) && p.tiles_per_cta <= kC2MaxTiles && boxes_bound <= kC2MaxBoxes) {
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      FEN_CUDA(cudaFuncSetAttribute(conv3x3_umma2_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    ConvCfg<N>::kDynBytes));
+      attr2_set = true;
+    }
+    conv3x3_umma2_kernel<N><<<grid, ConvCfg<N>::kThreads, ConvCfg<N>::kDynBytes, st>>>(tm_in, tm_w, p);
+  } else {
+    conv3x3_umma_kernel<N><<<grid, ConvCfg<N>::kThreads, ConvCfg<N>::kDynBytes, st>>>(tm_in, tm_w, p);
+  }
   FEN_CUDA(cudaGetLastError());
   ++g_launches;
   return FEN_OK;
