@@ -113,10 +113,12 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
   __shared__ uint64_t bar_acc_full[kB2AccBufs], bar_acc_empty[kB2AccBufs];
   __shared__ uint64_t bar_done, bar_s_ready, bar_s_free, bar_se_full, bar_se_empty, bar_scale[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ B2Tile tile_tab[kB2MaxTiles];
-  __shared__ B2Box box_tab[kB2MaxBoxes];
-  __shared__ B2Unit unit_tab[kBodyMaxUnits];
-  __shared__ int s_meta[4];                            // tiles, boxes, units, odd-use slot mask
+  // per-pass tables, one set of them per image set (the two sets give a CTA runs of different length)
+  __shared__ B2Tile tile_tab2[2][kB2MaxTiles];
+  __shared__ B2Box box_tab2[2][kB2MaxBoxes];
+  __shared__ B2Unit unit_tab2[2][kBodyMaxUnits];
+  __shared__ int s_meta[2][4];                         // per set: tiles, boxes, units, -
+  __shared__ int s_peer[2][2];                         // per set: first / last CTA sharing an image with this one
   __shared__ __align__(16) float s_scale[2][kBodyMaxUnits][kC];   // res_scale * s, per set and unit
   __shared__ __align__(16) float s_mean[kBodyMaxUnits][kC], s_hid[kBodyMaxUnits][kC];
   __shared__ __align__(16) float s_raw[2 * kBodyMaxUnits][kC];     // raw SE accumulator rows (hi / lo per unit)
@@ -125,45 +127,60 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr uint32_t kTmemCols = 512;
 
-  const int g_begin = blockIdx.x * p.tiles_per_cta;
-  const int g_end = min(p.total_tiles, g_begin + p.tiles_per_cta);
-  // peers: CTAs owning tiles of the images this CTA touches (same for both sets)
-  const int img0 = g_begin / p.tiles_per_seg, img1 = (g_end - 1) / p.tiles_per_seg;
-  const int peer0 = (img0 * p.tiles_per_seg) / p.tiles_per_cta;
-  const int peer1 = min(int(gridDim.x) - 1, ((img1 + 1) * p.tiles_per_seg - 1) / p.tiles_per_cta);
+  // Tile runs.  The T tiles of a set are dealt to the C CTAs as evenly as possible (q or q + 1 tiles); set 0
+  // gives the extra tile to the FIRST T % C CTAs, set 1 to the LAST ones, so that over a layer a CTA handles at
+  // most ceil(2T / C) tiles instead of 2 ceil(T / C) (batch 64: 15 instead of 16, on 148 CTAs instead of 132).
+  const int T = p.total_tiles, Cn = int(gridDim.x);
+  const int rq = T / Cn, rr = T % Cn;
+  auto run_begin = [&](int c, int s) { return (s == 0) ? c * rq + min(c, rr) : c * rq + max(0, c - (Cn - rr)); };
+  auto cta_of = [&](int g, int s) {
+    if (s == 0) return (g < rr * (rq + 1)) ? g / (rq + 1) : rr + (g - rr * (rq + 1)) / rq;
+    const int h0 = Cn - rr;
+    return (g < h0 * rq) ? g / rq : h0 + (g - h0 * rq) / (rq + 1);
+  };
 
   if (warp == kB2FirstMmaWarp) tmem_alloc(&tmem_slot, kTmemCols);
   if (tid == 0) {
-    // ---- per-pass tables (identical for every layer and both sets)
-    int first_box[kB2MaxTiles + 2];
-    int b_cum = 0, i = 0, u = 0;
-    for (int g = g_begin; g < g_end; ++u) {
-      const BUnit bu = body_unit(p, g, g_end);
-      unit_tab[u].img = bu.n; unit_tab[u].t0 = bu.t0; unit_tab[u].t1 = bu.t1; unit_tab[u].pad = 0;
-      for (int j = 0; j < bu.nboxes; ++j) {
-        B2Box e;
-        e.img = int16_t(bu.n); e.y0 = int8_t(bu.ra - 1 + j * kBBoxRows);
-        e.mirror = uint8_t(j > 0);   // continues the previous box of its unit: mirrored when it lands in slot 0
-        box_tab[b_cum + j] = e;
+    int max_tiles = 0;
+    for (int s = 0; s < p.nset; ++s) {
+      const int g_begin = run_begin(blockIdx.x, s), g_end = run_begin(blockIdx.x + 1, s);
+      B2Tile* tile_tab = tile_tab2[s]; B2Box* box_tab = box_tab2[s]; B2Unit* unit_tab = unit_tab2[s];
+      // ---- per-pass tables (identical for every layer)
+      int first_box[kB2MaxTiles + 2];
+      int b_cum = 0, i = 0, u = 0;
+      for (int g = g_begin; g < g_end; ++u) {
+        const BUnit bu = body_unit(p, g, g_end);
+        unit_tab[u].img = bu.n; unit_tab[u].t0 = bu.t0; unit_tab[u].t1 = bu.t1; unit_tab[u].pad = 0;
+        for (int j = 0; j < bu.nboxes; ++j) {
+          B2Box e;
+          e.img = int16_t(bu.n); e.y0 = int8_t(bu.ra - 1 + j * kBBoxRows);
+          e.mirror = uint8_t(j > 0);   // continues the previous box of its unit: mirrored when it lands in slot 0
+          box_tab[b_cum + j] = e;
+        }
+        for (int t = bu.t0; t < bu.t1; ++t, ++i) {
+          const int base = kTileM * t - kPitch * bu.ra;
+          first_box[i] = b_cum + base / kBBoxPx;
+          B2Tile e;
+          e.m = uint16_t(b_cum * kBBoxPx + base);   // pixel position of the tile's view, relative to the pass's first box
+          e.wait_upto = uint8_t(b_cum + min((base + kTileM + kMaxShift - 1) / kBBoxPx, bu.nboxes - 1) + 1);
+          e.rel_upto = 0; e.unit = uint8_t(u); e.t = uint8_t(t); e.pad = 0;
+          tile_tab[i] = e;
+        }
+        b_cum += bu.nboxes;
+        g += bu.t1 - bu.t0;
       }
-      for (int t = bu.t0; t < bu.t1; ++t, ++i) {
-        const int base = kTileM * t - kPitch * bu.ra;
-        first_box[i] = b_cum + base / kBBoxPx;
-        B2Tile e;
-        e.m = uint16_t(b_cum * kBBoxPx + base);   // pixel position of the tile's view, relative to the pass's first box
-        e.wait_upto = uint8_t(b_cum + min((base + kTileM + kMaxShift - 1) / kBBoxPx, bu.nboxes - 1) + 1);
-        e.rel_upto = 0; e.unit = uint8_t(u); e.t = uint8_t(t); e.pad = 0;
-        tile_tab[i] = e;
-      }
-      b_cum += bu.nboxes;
-      g += bu.t1 - bu.t0;
+      for (int k = 0; k < i; ++k) tile_tab[k].rel_upto = uint8_t((k + 2 < i) ? first_box[k + 2] : b_cum);
+      s_meta[s][0] = i; s_meta[s][1] = b_cum; s_meta[s][2] = u; s_meta[s][3] = 0;
+      max_tiles = max(max_tiles, i);
+      // peers: CTAs owning tiles of the images this CTA touches in this set (including itself)
+      const int img0 = g_begin / p.tiles_per_seg, img1 = (g_end - 1) / p.tiles_per_seg;
+      s_peer[s][0] = cta_of(img0 * p.tiles_per_seg, s);
+      s_peer[s][1] = cta_of(min(T, (img1 + 1) * p.tiles_per_seg) - 1, s);
     }
-    for (int k = 0; k < i; ++k) tile_tab[k].rel_upto = uint8_t((k + 2 < i) ? first_box[k + 2] : b_cum);
-    const int odd = 0;
-    s_meta[0] = i; s_meta[1] = b_cum; s_meta[2] = u; s_meta[3] = odd;
-    // ---- barriers.  A CTA with a single tile per pass has no odd tile: issuer warp 3 stays out of the
-    // ring / weight release protocol entirely (an issuer without MMAs could lap the other one).
-    const uint32_t n_issuers = (i >= 2) ? 2u : 1u;
+    // ---- barriers.  A CTA with a single tile per pass in every set has no odd tile: issuer warp 3 stays out
+    // of the ring / weight release protocol entirely.
+    const uint32_t n_issuers = (max_tiles >= 2) ? 2u : 1u;
+    s_meta[0][3] = int(n_issuers);
     for (int k = 0; k < 9; ++k) { mbar_init(&bar_w[k], 1); mbar_init(&bar_wfree[k], n_issuers); }
     for (int k = 0; k < kB2Slots; ++k) { mbar_init(&bar_full[k], 1); mbar_init(&bar_empty[k], n_issuers); }
     for (int k = 0; k < kB2AccBufs; ++k) { mbar_init(&bar_acc_full[k], 1); mbar_init(&bar_acc_empty[k], kB2EpiWarps); }
@@ -179,8 +196,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  const int n_tiles = s_meta[0], n_boxes = s_meta[1], n_units = s_meta[2];
-  if (n_tiles <= 0) return;   // never happens with the host's grid sizing
+  const int n_issuers = s_meta[0][3];
 
   if (warp == kB2TmaWarp) {
     // ============================================================ TMA issuer + peer-flag poller
@@ -196,7 +212,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
         B2W(1, 2, L, s, 0);
         if (L > 0) {
           const int* fl = p.flags + s * int(gridDim.x);
-          for (int k = peer0 + lane; k <= peer1; k += 32)
+          for (int k = s_peer[s][0] + lane; k <= s_peer[s][1]; k += 32)
             while (ld_acquire_gpu(fl + k) < L) { __nanosleep(20); }
           __syncwarp();
           fence_proxy_async_all();
@@ -205,7 +221,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
       auto issue_boxes = [&](int s, int b0, int b1) {     // lane 0 only
         const int img_base = s * p.set_B;
         for (int b = b0; b < b1; ++b) {
-          const B2Box e = box_tab[b];
+          const B2Box e = box_tab2[s][b];
           B2T2(P, 9, b);
           B2W(1, 3, L, s, b);
           mbar_wait(&bar_empty[slot], (use & 1u) ^ 1u);
@@ -220,7 +236,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           if (++slot == kB2Slots) { slot = 0; ++use; }
         }
       };
-      const int pre = min(kPre, n_boxes);
+      const int pre = min(kPre, s_meta[0][1]);
       wait_flags(0);
       if (lane == 0) {
         B2TRACE(P, 0);
@@ -238,7 +254,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           wait_flags(s);
           if (lane == 0) B2TRACE(P, 0);
         }
-        if (lane == 0) issue_boxes(s, s == 0 ? pre : 0, n_boxes);
+        if (lane == 0) issue_boxes(s, s == 0 ? pre : 0, s_meta[s][1]);
         __syncwarp();
       }
     }
@@ -252,14 +268,18 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
     const uint32_t s_lo = (smem_u32(s_buf) >> 4) | kLbo;
     const bool leader = elect_one();
     const int wi = warp - kB2FirstMmaWarp;
-    const int last_own = ((n_tiles - 1 - wi) >= 0) ? wi + 2 * ((n_tiles - 1 - wi) >> 1) : -1;
-    uint32_t P = 0, gbase = 0, se_n = 0;
-    for (int L = 0; L < (last_own >= 0 ? p.n_layers : 0); ++L) {
+    uint32_t P = 0, gbase = 0, gbox = 0, se_n = 0;
+    for (int L = 0; L < ((wi == 0 || n_issuers == 2) ? p.n_layers : 0); ++L) {
       const bool conv2 = body_layer(p, L).epi == kBEpiSeResidual;
       bool w_seen = false;
       int se_done = 0;
-      for (int s = 0; s < p.nset; ++s, ++P, gbase += n_tiles) {
-        const uint32_t gb0 = P * uint32_t(n_boxes);                 // running index of the pass's first box
+      for (int s = 0; s < p.nset; ++s, ++P) {
+        const B2Tile* tile_tab = tile_tab2[s];
+        const int n_tiles = s_meta[s][0], n_boxes = s_meta[s][1];
+        const int last_own = ((n_tiles - 1 - wi) >= 0) ? wi + 2 * ((n_tiles - 1 - wi) >> 1) : -1;
+        const uint32_t gb0 = gbox;                                  // running index of the pass's first box
+        const uint32_t gbase_pass = gbase;
+        gbox += uint32_t(n_boxes); gbase += uint32_t(n_tiles);
         const uint32_t start_px = (gb0 % kB2Slots) * kBBoxPx;
         const bool last_pass = (s == p.nset - 1);
         // SE batches of this layer still owed: the one of set s must run before this pass's epilogue can start,
@@ -302,9 +322,27 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           ++se_done;
           __syncwarp();
         };
+        if (last_own < 0) {
+          // no tile of this parity in this pass (a one-tile run): see every box of the pass arrive, then hand
+          // it back - and the weights, if this is the layer's last pass (the commit covers this warp's MMAs of
+          // the other set)
+          while (waited < uint32_t(n_boxes)) {
+            const uint32_t g = gb0 + waited;
+            mbar_wait(&bar_full[g % kB2Slots], (g / kB2Slots) & 1u);
+            ++waited;
+          }
+          __syncwarp();
+          if (leader) {
+            for (int b = 0; b < n_boxes; ++b) umma_commit(&bar_empty[(gb0 + b) % kB2Slots]);
+            if (last_pass)
+              for (int tap = 0; tap < 9; ++tap) umma_commit(&bar_wfree[tap]);
+          }
+          __syncwarp();
+          continue;
+        }
         for (int i = wi; i < n_tiles; i += 2) {
           const B2Tile e = tile_tab[i];
-          const uint32_t G = gbase + i, acc = G % kB2AccBufs, aph = (G / kB2AccBufs) & 1;
+          const uint32_t G = gbase_pass + i, acc = G % kB2AccBufs, aph = (G / kB2AccBufs) & 1;
           B2W(2 + wi, 1, L, s, i);
           if (se_layer && se_done <= s) {
             // The epilogue of this pass cannot free accumulators before the SE batch of this set has run: never
@@ -417,10 +455,12 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
         B2TS(L * p.nset + s, 0);
         {
           const int* fl = p.flags + s * int(gridDim.x);
-          for (int k = peer0 + lane; k <= peer1; k += 32)
+          for (int k = s_peer[s][0] + lane; k <= s_peer[s][1]; k += 32)
             while (ld_acquire_gpu(fl + k) < L) { __nanosleep(20); }
           __syncwarp();
         }
+        const B2Unit* unit_tab = unit_tab2[s];
+        const int n_units = s_meta[s][2];
         const int img_base = s * p.set_B;
         // 9 sums x 2 channels per lane and unit, all requested before the first use (one L2 round trip)
         float2 qv[kBodyMaxUnits][kHsCount];
@@ -586,6 +626,9 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
         }
       }
       for (int s = 0; s < p.nset; ++s, ++P) {
+        const B2Tile* tile_tab = tile_tab2[s];
+        const B2Unit* unit_tab = unit_tab2[s];
+        const int n_tiles = s_meta[s][0];
         const int img_base = s * p.set_B;
         if (ew == 0) B2W(4, 1, L, s, 0);
 #ifndef FEN_B2_X2

@@ -663,7 +663,7 @@ static bool body2_usable(const Layout& L, int B, int H, int W) {
   const int tps = (H * kPitch + kTileM - 1) / kTileM;
   if (tps > 255) return false;
   const int set_tiles = (B / body2_nset(B)) * tps;
-  const int tpc = (set_tiles + num_sms() - 1) / num_sms();
+  const int tpc = (set_tiles + num_sms() - 1) / num_sms();   // longest run of a CTA in one set
   if (tpc > kB2MaxTiles - 8) return false;
   return (tpc + tps - 2) / tps + 1 <= kBodyMaxUnits;
 }
@@ -684,8 +684,8 @@ static int launch_body2(const fen_config* cfg, const Layout& L, const Workspace&
   p.n_layers = L.G * (2 * L.Bk + 1) + 1;
   p.tiles_per_seg = (H * kPitch + kTileM - 1) / kTileM;
   p.total_tiles = p.set_B * p.tiles_per_seg;
-  p.tiles_per_cta = (p.total_tiles + num_sms() - 1) / num_sms();
-  const int ctas = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  p.tiles_per_cta = (p.total_tiles + num_sms() - 1) / num_sms();   // (upper bound; the kernel deals q or q + 1 tiles)
+  const int ctas = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   p.res_scale = cfg->res_scale; p.inv_hw = 1.f / float(H * W);
   const int nbuf = 5 + L.G;
   int64_t offs[kBodyMaxBufs];

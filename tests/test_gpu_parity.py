@@ -273,11 +273,12 @@ def test_forward_batch64_full_model_against_oracle(dev):
     assert fen_oracle.psnr(y1[0], y[31]) >= PSNR_BAR
 
 
-@pytest.mark.parametrize("B", [1, 2, 7, 10, 16, 24, 88, 140])
+@pytest.mark.parametrize("B", [1, 2, 5, 7, 9, 10, 12, 16, 24, 88, 140])
 def test_body_kernel_batch_geometries(B, dev):
     """The persistent body kernel splits the batch into two interleaved image sets (even B) and gives
     every CTA a fixed run of tiles: 1 tile per CTA (B <= 8), odd / even tile counts, runs that straddle
-    two images, one issuer warp without tiles ...  Every geometry must agree with the oracle (bf16 noise
+    two images, runs of different length in the two sets (one issuer warp without tiles in one of them) ...
+    Every geometry must agree with the oracle (bf16 noise
     only) on a model whose conv_last is LARGE enough to expose the body (sigma 3e-2, not the T1 1e-3)."""
     cfg = dict(num_groups=1, blocks_per_group=2)
     sd = weights.make_state_dict(3, "T1", **cfg)
