@@ -2,7 +2,7 @@
 // one cooperative launch (see body_umma.cuh for the layer chain and the references:
 // src/models/custom.py:167-175, src/models/blocks.py:75-92,135-153,185-189).
 //
-// What changed against body_umma.cuh, and why (B200 timelines in profiles/r01_body_trace.txt):
+// What changed against body_umma.cuh, and why (B200 timelines: profiles/r01_body2_trace.txt):
 //  * Table-driven issue loops.  Every layer has the same geometry, so the per-tile bookkeeping (ring
 //    position of the tile's view, boxes to wait for / to release, image of the tile) is computed ONCE
 //    into shared-memory tables.  The old issuer warps spent ~2500 cycles of scalar work per tile, in
@@ -18,6 +18,11 @@
 //    shared memory, and ONE extra batch of 36 tcgen05.mma against the conv2 weights that are in shared
 //    memory anyway produces the 64x576 mat-vec of up to 4 images.  The SE warp finishes with the two
 //    tiny FC layers + sigmoid.  The old 20k-cycle CUDA-core chain on the epilogue warps is gone.
+//  * One running activation ring over all passes, the first boxes of a layer requested before its weights;
+//    tile runs of q or q + 1 tiles with the extra tile on opposite ends for the two sets (all 148 SMs busy).
+//  * Rules every role follows (found with cuda-gdb): every mbarrier wait is executed by the
+//    whole warp and followed by __syncwarp() before any tcgen05 / TMA issue; elected-lane blocks contain
+//    straight-line code only; a ring slot is released only by a warp that has seen it arrive.
 #pragma once
 #include "body_umma.cuh"
 
