@@ -426,7 +426,7 @@ __device__ __forceinline__ float block_sum_256(float v, float* sh) {
   }
   return t;   // valid in thread 0
 }
-// mode 0: sum |a - b| (and dsr = sign(a - b) * inv_n); mode 1: sum a^2
+// mode 0: sum |a - b| (and dsr = sign(a - b) * inv_n); mode 1: sum a^2; mode 2: sum (a - b)^2
 __global__ void __launch_bounds__(256) reduce_partial_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                             float* __restrict__ dsr, int64_t n, float inv_n, int mode,
                                                             float* __restrict__ partial) {
@@ -437,8 +437,11 @@ __global__ void __launch_bounds__(256) reduce_partial_kernel(const float* __rest
       const float d = a[i] - b[i];
       acc += fabsf(d);
       if (dsr) dsr[i] = (d > 0.f) ? inv_n : (d < 0.f ? -inv_n : 0.f);
-    } else {
+    } else if (mode == 1) {
       acc = fmaf(a[i], a[i], acc);
+    } else {
+      const float d = a[i] - b[i];
+      acc = fmaf(d, d, acc);
     }
   }
   const float t = block_sum_256(acc, sh);
@@ -456,7 +459,11 @@ __global__ void __launch_bounds__(256) reduce_final_kernel(const float* __restri
     if (threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[0] = take_sqrt ? float(sqrt(sh[0])) : float(sh[0] * double(scale));
+  if (threadIdx.x == 0) {
+    if (take_sqrt == 1) out[0] = float(sqrt(sh[0]));
+    else if (take_sqrt == 2) out[0] = float(10.0 * log10(1.0 / (sh[0] * double(scale))));   // PSNR; mse == 0 -> +inf
+    else out[0] = float(sh[0] * double(scale));
+  }
 }
 // clip_grad_norm_ + AdamW (torch.optim.AdamW single-tensor formulas, trainer.py:217-221,490-503)
 __global__ void __launch_bounds__(256) clip_adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
@@ -1002,6 +1009,18 @@ int fen_l1_loss(const float* sr, const float* hr, int64_t n, float* loss, float*
   if (n < 1) return fail(FEN_EINVAL, "fen_l1_loss: empty input");
   return reduce_launch(sr, hr, dsr, n, 1.f / float(n), 0, 1.f / float(n), 0, loss, workspace, workspace_bytes,
                        static_cast<cudaStream_t>(stream));
+}
+
+int fen_psnr(const float* pred, const float* target, int64_t n, float data_range, float* psnr, void* workspace,
+             int64_t workspace_bytes, void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  g_launches = 0;
+  if (!pred || !target || !psnr || !workspace) return fail(FEN_EINVAL, "fen_psnr: null pointer");
+  if (n < 1 || !(data_range > 0.f)) return fail(FEN_EINVAL, "fen_psnr: n >= 1 and data_range > 0 required");
+  // scale = 1 / (n * range^2): the final kernel evaluates 10 log10(1 / (sum * scale))
+  return reduce_launch(pred, target, nullptr, n, 0.f, 2, float(1.0 / (double(n) * double(data_range) * double(data_range))),
+                       2, psnr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int fen_grad_norm(const float* grads, int64_t n, float* norm_out, void* workspace, int64_t workspace_bytes,

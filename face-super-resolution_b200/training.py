@@ -45,6 +45,22 @@ def l1_loss(sr: torch.Tensor, hr: torch.Tensor, want_grad: bool = True
     return loss, dsr
 
 
+def psnr(pred: torch.Tensor, target: torch.Tensor, data_range: float = 1.0) -> torch.Tensor:
+    """Trainer._compute_psnr (trainer.py:621-628) / metrics.psnr (metrics.py:17-34) on the GPU:
+    10 log10(data_range^2 / mean((pred - target)^2)) over the whole batch; returns a device scalar [1]."""
+    _check_cuda_f32(pred, target)
+    if pred.shape != target.shape:
+        raise ValueError("pred and target must have the same shape")
+    lib = _lib.load()
+    with torch.cuda.device(pred.device):
+        out = torch.empty(1, dtype=torch.float32, device=pred.device)
+        ws = _workspace(pred.device, pred.numel())
+        rc = lib.fen_psnr(pred.data_ptr(), target.data_ptr(), pred.numel(), float(data_range), out.data_ptr(),
+                          ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "fen_psnr")
+    return out
+
+
 def allreduce_mean_(flat_grad: torch.Tensor) -> torch.Tensor:
     """Data-parallel gradient exchange: one all-reduce (sum) of the flat gradient, then / world_size, in place.
     NCCL over NVLink on GPUs; identity when torch.distributed is not initialised."""

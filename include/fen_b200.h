@@ -119,6 +119,12 @@ int64_t fen_train_workspace_bytes(int64_t n);
 int fen_l1_loss(const float* sr, const float* hr, int64_t n, float* loss, float* dsr, void* workspace,
                 int64_t workspace_bytes, void* stream);
 
+/* Replaces the validation metric Trainer._compute_psnr (reference src/training/trainer.py:621-628) and
+ * psnr() of src/evaluation/metrics.py:17-34: psnr[0] = 10 log10(data_range^2 / mean((pred - target)^2)) over
+ * ALL n elements of the batch (+inf when the mean squared error is 0); device scalar, deterministic. */
+int fen_psnr(const float* pred, const float* target, int64_t n, float data_range, float* psnr, void* workspace,
+             int64_t workspace_bytes, void* stream);
+
 /* Global L2 norm of the flat gradient (what clip_grad_norm_ computes, reference src/training/trainer.py:490-496);
  * norm_out is a device scalar.  After a data-parallel all-reduce every rank holds the same gradient, so the norm
  * needs no second collective. */

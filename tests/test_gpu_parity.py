@@ -122,6 +122,18 @@ def test_l1_loss_and_gradient_match_torch(dev):
         fsr_b200.l1_loss(sr.detach(), hr)
 
 
+def test_psnr_matches_trainer_metric(dev):
+    """Trainer._compute_psnr (trainer.py:621-628): 10 log10(1 / mse) over the whole batch."""
+    g = torch.Generator().manual_seed(51)
+    hr = torch.rand(3, 3, 128, 96, generator=g)
+    sr = (hr + torch.randn(hr.shape, generator=g) * 0.03).clamp(0, 1)
+    ref = 10 * torch.log10(1.0 / torch.mean((sr - hr) ** 2))
+    got = fsr_b200.psnr(sr.to(dev), hr.to(dev))
+    assert abs(got.item() - ref.item()) <= 1e-4
+    assert abs(fsr_b200.psnr(sr.to(dev) * 255, hr.to(dev) * 255, data_range=255.0).item() - ref.item()) <= 1e-3
+    assert fsr_b200.psnr(hr.to(dev), hr.to(dev)).item() == float("inf")
+
+
 @pytest.mark.parametrize("max_norm,wd", [(0.5, 0.0), (0.5, 1e-2), (0.0, 0.0), (1e3, 0.0)])
 def test_clip_adamw_matches_torch(max_norm, wd, dev):
     """clip_grad_norm_(0.5) + AdamW(lr 1e-4) of the trainer (trainer.py:217-221, 490-503), 5 steps on a flat
