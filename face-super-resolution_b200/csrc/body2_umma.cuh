@@ -24,6 +24,7 @@
 //    whole warp and followed by __syncwarp() before any tcgen05 / TMA issue; elected-lane blocks contain
 //    straight-line code only; a ring slot is released only by a warp that has seen it arrive.
 #pragma once
+#include <type_traits>
 #include "body_umma.cuh"
 
 namespace fen {
@@ -639,11 +640,16 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
 #ifndef FEN_B2_X2
         if (ly.epi == kBEpiSeResidual) mbar_wait(&bar_scale[s], m_cnt & 1);
 #endif
+        // The tile loop is instantiated once per epilogue kind: in one loop with run-time branches every kind's
+        // loop-carried state (the 32 channel sums of conv1, the residual words of conv2 ...) stays live in all of
+        // them, and the epilogue is register bound (168).
+        auto run_tiles = [&](auto epi_tag) {
+        constexpr int EPI = decltype(epi_tag)::value;
         int cur_unit = -1, img = 0;
         float csum[CW], col0sum = 0.f, colLsum = 0.f;
         float* hs = nullptr;
         auto flush_unit = [&]() {
-          if (ly.epi != kBEpiPreluHsum || cur_unit < 0) return;
+          if (EPI != kBEpiPreluHsum || cur_unit < 0) return;
           // total: reduce-scatter butterfly over the warp, lane l ends with channel col0 + l
 #pragma unroll
           for (int d = 16, len = CW; d >= 1; d >>= 1, len >>= 1) {
@@ -668,8 +674,8 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
 #pragma unroll
             for (int c = 0; c < CW; ++c) csum[c] = 0.f;
             col0sum = 0.f; colLsum = 0.f;
-            if (ly.epi == kBEpiPreluHsum) hs = p.hsum + (size_t(ly.rcab) * p.B + img) * (kHsCount * kC);
-            if (ly.epi == kBEpiSeResidual) {             // `slope` doubles as the SE scale of this image
+            if (EPI == kBEpiPreluHsum) hs = p.hsum + (size_t(ly.rcab) * p.B + img) * (kHsCount * kC);
+            if (EPI == kBEpiSeResidual) {             // `slope` doubles as the SE scale of this image
 #pragma unroll
               for (int j = 0; j < CW / 4; ++j) {
                 const float4 s4 = *reinterpret_cast<const float4*>(&s_scale[s][cur_unit][col0 + 4 * j]);
@@ -687,7 +693,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
 #ifdef FEN_EXP_NORES
           if (false) {
 #else
-          if (valid && ly.epi != kBEpiPreluHsum) {
+          if (valid && EPI != kBEpiPreluHsum) {
 #endif
             const bf16* rsd = resp + opix * kC + col0;
             ld_cg_256_hint(rsd, kPolicyEvictFirst, *reinterpret_cast<uint32_t(*)[8]>(&rv[0]));
@@ -712,11 +718,11 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           float f[CW];
 #pragma unroll
           for (int c = 0; c < CW; ++c) f[c] = __uint_as_float(v[c]) + bias[c];
-          if (ly.epi == kBEpiPreluHsum) {
+          if (EPI == kBEpiPreluHsum) {
 #pragma unroll
             for (int c = 0; c < CW; ++c) f[c] = fmaxf(f[c], 0.f) + slope[c] * fminf(f[c], 0.f);
           } else {
-            if (ly.epi == kBEpiSeResidual) {
+            if (EPI == kBEpiSeResidual) {
 #pragma unroll
               for (int c = 0; c < CW; ++c) f[c] *= slope[c];
             }
@@ -770,7 +776,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           }
 #endif
           if (ew == 0 && lane == 0) B2T2(P, 3, i);
-          if (ly.epi == kBEpiPreluHsum) {
+          if (EPI == kBEpiPreluHsum) {
             // ---- the 9 channel sums of the bf16-ROUNDED h (what conv2 will read) that the SE pool needs
             if (valid) {
 #pragma unroll
@@ -839,6 +845,10 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           }
         }
         flush_unit();
+        };
+        if (ly.epi == kBEpiPreluHsum) run_tiles(std::integral_constant<int, kBEpiPreluHsum>{});
+        else if (ly.epi == kBEpiSeResidual) run_tiles(std::integral_constant<int, kBEpiSeResidual>{});
+        else run_tiles(std::integral_constant<int, kBEpiResidual>{});
         // ---- pass done for this warp: make its global writes visible, then publish the CTA's flag
         __threadfence();
         __syncwarp();
