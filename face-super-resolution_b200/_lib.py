@@ -44,6 +44,13 @@ SIGNATURES = {
     "fen_clip_adamw_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                       C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
                                       C.c_void_p]),
+    "fen_packed_bwd_bytes": (C.c_int64, [C.POINTER(FenConfig)]),
+    "fen_pack_weights_bwd": (C.c_int, [C.POINTER(FenConfig), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fen_step_workspace_bytes": (C.c_int64, [C.POINTER(FenConfig), C.c_int, C.c_int, C.c_int]),
+    "fen_forward_train": (C.c_int, [C.POINTER(FenConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                    C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "fen_backward": (C.c_int, [C.POINTER(FenConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "fen_conv3x3_c64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fen_pack_conv3x3": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

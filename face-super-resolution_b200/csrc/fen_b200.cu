@@ -13,6 +13,7 @@
 #include "conv3x3_umma2.cuh"
 #include "body_umma.cuh"
 #include "body2_umma.cuh"
+#include "fen_backward.cuh"
 
 namespace fen {
 
@@ -730,6 +731,8 @@ static int launch_body2(const fen_config* cfg, const Layout& L, const Workspace&
   return FEN_OK;
 }
 
+#include "fen_step_host.cuh"
+
 }  // namespace fen
 
 using namespace fen;
@@ -1115,6 +1118,96 @@ int fen_lr_from_hr_u8(const uint8_t* hr, uint8_t* lr_u8, float* lr_f32, int B, i
   FEN_CUDA(cudaGetLastError());
   ++g_launches;
   return FEN_OK;
+}
+
+// ===================================================================== Stage-1 step, network side
+int64_t fen_packed_bwd_bytes(const fen_config* cfg) {
+  Layout L;
+  if (make_layout(cfg, &L)) return FEN_EINVAL;
+  BwdLayout K;
+  make_bwd_layout(L, &K);
+  return K.total;
+}
+
+int fen_pack_weights_bwd(const fen_config* cfg, const float* params, void* packed_bwd, void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  Layout L;
+  if ((rc = make_layout(cfg, &L))) return rc;
+  if (!params || !packed_bwd) return fail(FEN_EINVAL, "fen_pack_weights_bwd: null pointer");
+  BwdLayout K;
+  make_bwd_layout(L, &K);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* kb = static_cast<uint8_t*>(packed_bwd);
+  auto packT = [&](const float* w, int groups, int64_t off) -> int {
+    const int total = groups * 9 * 64 * 64;
+    pack_conv_T_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, reinterpret_cast<bf16*>(kb + off), groups);
+    FEN_CUDA(cudaGetLastError());
+    return FEN_OK;
+  };
+  for (int g = 0; g < L.G; ++g) {
+    const float* pg = params + L.p_rcab0 + g * L.p_group_stride;
+    for (int b = 0; b < L.Bk; ++b) {
+      const float* pr = pg + b * L.p_rcab_stride;
+      const int64_t off = K.rcab0 + int64_t(g * L.Bk + b) * K.rcab_stride;
+      if ((rc = packT(pr, 1, off))) return rc;                               // conv1
+      if ((rc = packT(pr + kConvW + 64 + 64, 1, off + kConvWBytes))) return rc;   // conv2
+    }
+    if ((rc = packT(pg + L.p_gconv_w_in_group, 1, K.gconv0 + g * kConvWBytes))) return rc;
+  }
+  if ((rc = packT(params + L.p_after_w, 1, K.after))) return rc;
+  for (int s = 0; s < 2; ++s)
+    if ((rc = packT(params + L.p_up[s], 4, K.up[s]))) return rc;
+  pack_last_T_kernel<<<(27 * 64 + 255) / 256, 256, 0, st>>>(params + L.p_last_w, reinterpret_cast<float*>(kb + K.last));
+  FEN_CUDA(cudaGetLastError());
+  FEN_CUDA(cudaMemsetAsync(kb + K.zeros, 0, 256, st));
+  return FEN_OK;
+}
+
+int64_t fen_step_workspace_bytes(const fen_config* cfg, int B, int H, int W) {
+  Layout L;
+  if (make_layout(cfg, &L)) return FEN_EINVAL;
+  if (B < 1 || H < 1 || W < 1) { fail(FEN_EINVAL, "bad batch / size"); return FEN_EINVAL; }
+  StepWs ws;
+  make_step_ws(L, B, H, W, &ws);
+  return ws.total;
+}
+
+static int step_args(const fen_config* cfg, Layout* L, StepWs* ws, int B, int H, int W, int64_t bytes, const char* who) {
+  int rc = check_device();
+  if (rc) return rc;
+  g_launches = 0;
+  if ((rc = make_layout(cfg, L))) return rc;
+  if (B < 1 || H < 64 || W < 64 || H % 64 || W % 64)
+    return fail(FEN_EINVAL, std::string(who) + ": H and W must be positive multiples of 64 (no fallback path)");
+  make_step_ws(*L, B, H, W, ws);
+  if (bytes < ws->total) return fail(FEN_ENOMEM, std::string(who) + ": workspace too small");
+  return FEN_OK;
+}
+
+int fen_forward_train(const fen_config* cfg, const void* packed, const float* x, float* out, int B, int H, int W,
+                      void* step_workspace, int64_t step_workspace_bytes, void* stream) {
+  Layout L;
+  StepWs ws;
+  int rc = step_args(cfg, &L, &ws, B, H, W, step_workspace_bytes, "fen_forward_train");
+  if (rc) return rc;
+  if (!packed || !x || !out || !step_workspace) return fail(FEN_EINVAL, "fen_forward_train: null pointer");
+  return step_forward(cfg, L, static_cast<const uint8_t*>(packed), x, out, B, H, W,
+                      static_cast<uint8_t*>(step_workspace), ws, static_cast<cudaStream_t>(stream));
+}
+
+int fen_backward(const fen_config* cfg, const void* packed, const void* packed_bwd, const float* x, const float* dout,
+                 float* grads, int B, int H, int W, void* step_workspace, int64_t step_workspace_bytes, void* stream) {
+  Layout L;
+  StepWs ws;
+  int rc = step_args(cfg, &L, &ws, B, H, W, step_workspace_bytes, "fen_backward");
+  if (rc) return rc;
+  if (!packed || !packed_bwd || !x || !dout || !grads || !step_workspace)
+    return fail(FEN_EINVAL, "fen_backward: null pointer");
+  BwdLayout K;
+  make_bwd_layout(L, &K);
+  return step_backward(cfg, L, static_cast<const uint8_t*>(packed), static_cast<const uint8_t*>(packed_bwd), K, x, dout,
+                       grads, B, H, W, static_cast<uint8_t*>(step_workspace), ws, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,425 @@
+// Backward pass of FaceEnhanceNet (the network side of the reference's Stage-1 step: loss.backward() in
+// src/training/trainer.py:458-505 over src/models/custom.py:147-190 / blocks.py:75-263), first generation.
+//
+// Data gradients (dgrad) of every 64-channel convolution run on the SAME tcgen05 implicit-GEMM kernel as the
+// forward (conv3x3_umma.cuh) with transposed + tap-flipped weights; the kernels in this file are what the
+// forward kernel cannot do: weight gradients (a contraction over PIXELS, K = B*H*W, fp32 accumulate on the
+// CUDA cores in this first generation), the two 3-channel ends of the network, and the element-wise
+// backward of PReLU / PixelShuffle / squeeze-and-excitation.  Activations and data gradients are NHWC bf16,
+// parameter gradients fp32 (accumulated with atomics into the flat gradient vector, which the caller zeroes).
+#pragma once
+#include "conv3x3_umma.cuh"
+
+namespace fen {
+
+__device__ __forceinline__ void unpack4(uint2 v, float (&f)[4]) {
+  f[0] = bf16lo(v.x); f[1] = bf16hi(v.x); f[2] = bf16lo(v.y); f[3] = bf16hi(v.y);
+}
+__device__ __forceinline__ void unpack8(uint4 v, float (&f)[8]) {
+  f[0] = bf16lo(v.x); f[1] = bf16hi(v.x); f[2] = bf16lo(v.y); f[3] = bf16hi(v.y);
+  f[4] = bf16lo(v.z); f[5] = bf16hi(v.z); f[6] = bf16lo(v.w); f[7] = bf16hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 r;
+  r.x = pack_bf16(f[0], f[1]); r.y = pack_bf16(f[2], f[3]); r.z = pack_bf16(f[4], f[5]); r.w = pack_bf16(f[6], f[7]);
+  return r;
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// Weight gradient of a 64 -> 64 3x3 / pad-1 convolution:
+//   dW[co][ci][ky][kx] += sum_{b,y,x} dY[b,y,x,co] * X[b,y+ky-1,x+kx-1,ci]        db[co] += sum dY[b,y,x,co]
+// One CTA walks over "bands" (one image row of one 64-column strip): dY row (8 KB) and the three X rows with a
+// one-pixel halo (25 KB) are staged in shared memory; thread (cb, ib) owns the 4 x 4 x 9 block
+// co = 4 cb .. 4 cb + 3, ci = 4 ib .. 4 ib + 3, all taps (144 fp32 accumulators) for the whole kernel and
+// flushes it once with atomics.  Output rows are co * co_mul + co_off (the PixelShuffle convolutions are four
+// interleaved 64-row groups).
+constexpr int kWgPx = kStripW;
+__global__ void __launch_bounds__(256, 1)
+wgrad_c64_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, float* __restrict__ dW,
+                 float* __restrict__ dB, int B, int H, int W, int co_mul, int co_off) {
+  __shared__ __align__(16) bf16 sY[kWgPx * kC];
+  __shared__ __align__(16) bf16 sX[3 * (kWgPx + 2) * kC];
+  const int tid = threadIdx.x;
+  const int cb = tid >> 4, ib = tid & 15;
+  float acc[9][4][4];
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[t][a][c] = 0.f;
+  const int strips = W / kWgPx;
+  const int bands = B * H * strips;
+  for (int band = blockIdx.x; band < bands; band += gridDim.x) {
+    const int sidx = band % strips;
+    const int y = (band / strips) % H;
+    const int b = band / (strips * H);
+    const int x0 = sidx * kWgPx;
+    __syncthreads();   // previous band fully consumed
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(dY + ((size_t(b) * H + y) * W + x0) * kC);
+      uint4* dst = reinterpret_cast<uint4*>(sY);
+      dst[tid] = __ldg(src + tid);
+      dst[tid + 256] = __ldg(src + tid + 256);
+      uint4* dx = reinterpret_cast<uint4*>(sX);
+      for (int i = tid; i < 3 * (kWgPx + 2) * 8; i += 256) {
+        const int chunk = i & 7, col = (i >> 3) % (kWgPx + 2), r = i / (8 * (kWgPx + 2));
+        const int yy = y - 1 + r, xx = x0 - 1 + col;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+          v = __ldg(reinterpret_cast<const uint4*>(X + ((size_t(b) * H + yy) * W + xx) * kC) + chunk);
+        dx[i] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int px = 0; px < kWgPx; ++px) {
+      float d[4];
+      unpack4(*reinterpret_cast<const uint2*>(sY + px * kC + 4 * cb), d);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) bsum[a] += d[a];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          float xv[4];
+          unpack4(*reinterpret_cast<const uint2*>(sX + (r * (kWgPx + 2) + px + kx) * kC + 4 * ib), xv);
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r * 3 + kx][a][c] = fmaf(d[a], xv[c], acc[r * 3 + kx][a][c]);
+        }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int co = (4 * cb + a) * co_mul + co_off;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float* dst = dW + (size_t(co) * kC + 4 * ib + c) * 9;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) atomicAdd(dst + t, acc[t][a][c]);
+    }
+    if (ib == 0) atomicAdd(dB + co, bsum[a]);
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// Weight gradient of the two 3-channel convolutions (conv_first 3 -> 64 and conv_last 64 -> 3): a 64-channel
+// NHWC bf16 tensor F against a 3-channel fp32 NCHW image I, both of size H x W:
+//   a[c3][f][t] = sum_{b,y,x} F[b,y,x,f] * I[b,c3,y+ty-1,x+tx-1]
+// mode 0 (conv_first: F = d f0, I = network input):  dW[f][c3][t] += a, db[f] += sum F
+// mode 1 (conv_last:  F = u1,   I = d out):          dW[c3][f][8-t] += a, db[c3] += sum I
+// grid (ceil(H / rows_per_cta), B), 256 threads = 64 channels x 4 column quarters; dynamic smem 9 * (W + 2) floats.
+__global__ void __launch_bounds__(256)
+wgrad_c3_kernel(const bf16* __restrict__ F, const float* __restrict__ I, float* __restrict__ dW,
+                float* __restrict__ dB, int H, int W, int rows_per_cta, int mode) {
+  extern __shared__ float sI[];   // [c3][r][W + 2]
+  const int tid = threadIdx.x, f = tid & 63, xq = tid >> 6;
+  const int b = blockIdx.y;
+  const int Wp = W + 2;
+  float acc[3][9];
+  float bs = 0.f, is[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[c][t] = 0.f;
+  const int y_begin = blockIdx.x * rows_per_cta;
+  const int y_end = min(H, y_begin + rows_per_cta);
+  for (int y = y_begin; y < y_end; ++y) {
+    __syncthreads();
+    for (int i = tid; i < 9 * Wp; i += 256) {
+      const int col = i % Wp, r = (i / Wp) % 3, c3 = i / (3 * Wp);
+      const int yy = y - 1 + r, xx = col - 1;
+      sI[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(I + ((size_t(b) * 3 + c3) * H + yy) * W + xx) : 0.f;
+    }
+    __syncthreads();
+    const int xw = W / 4;
+    const bf16* frow = F + ((size_t(b) * H + y) * W) * kC + f;
+    for (int x = xq * xw; x < (xq + 1) * xw; ++x) {
+      const float v = __bfloat162float(frow[size_t(x) * kC]);
+      bs += v;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) acc[c][r * 3 + kx] = fmaf(v, sI[(c * 3 + r) * Wp + x + kx], acc[c][r * 3 + kx]);
+        if (f == 0) is[c] += sI[(c * 3 + 1) * Wp + x + 1];
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      if (mode == 0) atomicAdd(dW + (size_t(f) * 3 + c) * 9 + t, acc[c][t]);
+      else atomicAdd(dW + (size_t(c) * kC + f) * 9 + (8 - t), acc[c][t]);
+    }
+  if (mode == 0) atomicAdd(dB + f, bs);
+  else if (f == 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) atomicAdd(dB + c, is[c]);
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// conv_last data gradient fused with the backward of the last PReLU + PixelShuffle (blocks.py:223-227):
+//   dU[b,y,x,c]  = sum_{co<3,t} dOut[b,co,y+ty-1,x+tx-1] * wk[co*9+t][c]      (wk = tap-flipped conv_last weights)
+//   dPre         = dU * (u > 0 ? 1 : slope[c])          dslope[c] += dU * min(u, 0) / slope[c]
+//   dY[sub][b][y>>1][x>>1][c] = dPre,  sub = 2 (y&1) + (x&1)                  (the conv's sub-pixel planes)
+// u = prelu(pre) is the saved stage output; sign(u) = sign(pre) needs slope > 0 (checked by the host side).
+// grid (H, B), 256 threads: 64 columns x 4 channel quarters, like conv_first_kernel.
+__global__ void __launch_bounds__(256)
+last_dgrad_kernel(const float* __restrict__ dOut, const float* __restrict__ wk, const bf16* __restrict__ u,
+                  const float* __restrict__ slope, bf16* __restrict__ dY, float* __restrict__ dslope, int B, int H,
+                  int W) {
+  __shared__ float sw[27 * kC];
+  __shared__ float s_sl[kC], s_ds[kC];
+  for (int i = threadIdx.x; i < 27 * kC; i += blockDim.x) sw[i] = wk[i];
+  if (threadIdx.x < kC) { s_sl[threadIdx.x] = slope[threadIdx.x]; s_ds[threadIdx.x] = 0.f; }
+  __syncthreads();
+  const int n = blockIdx.y, y = blockIdx.x;
+  const int q = threadIdx.x >> 6;
+  float ds[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) ds[c] = 0.f;
+  for (int x0 = 0; x0 < W; x0 += 64) {
+    const int xx = x0 + (threadIdx.x & 63);
+    float in[27];
+#pragma unroll
+    for (int co = 0; co < 3; ++co)
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int yy = y + ky - 1, xc = xx + kx - 1;
+          in[co * 9 + ky * 3 + kx] =
+              (yy >= 0 && yy < H && xc >= 0 && xc < W) ? __ldg(dOut + ((size_t(n) * 3 + co) * H + yy) * W + xc) : 0.f;
+        }
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+      const float4* wp = reinterpret_cast<const float4*>(sw + k * kC + q * 16);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w4 = wp[j];
+        acc[4 * j + 0] = fmaf(in[k], w4.x, acc[4 * j + 0]);
+        acc[4 * j + 1] = fmaf(in[k], w4.y, acc[4 * j + 1]);
+        acc[4 * j + 2] = fmaf(in[k], w4.z, acc[4 * j + 2]);
+        acc[4 * j + 3] = fmaf(in[k], w4.w, acc[4 * j + 3]);
+      }
+    }
+    const uint4* up = reinterpret_cast<const uint4*>(u + ((size_t(n) * H + y) * W + xx) * kC + q * 16);
+    float uv[16];
+    {
+      float t8[8];
+      unpack8(__ldg(up), t8);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) uv[c] = t8[c];
+      unpack8(__ldg(up + 1), t8);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) uv[8 + c] = t8[c];
+    }
+    float o[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float sl = s_sl[q * 16 + c];
+      const bool pos = uv[c] > 0.f;
+      o[c] = pos ? acc[c] : acc[c] * sl;
+      ds[c] += pos ? 0.f : acc[c] * (uv[c] / sl);
+    }
+    const int sub = 2 * (y & 1) + (xx & 1);
+    uint4* dst = reinterpret_cast<uint4*>(
+        dY + (((size_t(sub) * B + n) * (H >> 1) + (y >> 1)) * (W >> 1) + (xx >> 1)) * kC + q * 16);
+    float t8[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) t8[c] = o[c];
+    dst[0] = pack8(t8);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) t8[c] = o[8 + c];
+    dst[1] = pack8(t8);
+  }
+#pragma unroll
+  for (int c = 0; c < 16; ++c) atomicAdd(&s_ds[q * 16 + c], ds[c]);
+  __syncthreads();
+  if (threadIdx.x < kC) atomicAdd(dslope + threadIdx.x, s_ds[threadIdx.x]);
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// PReLU backward on NHWC bf16 (RCAB conv1, blocks.py:139-141; upsample stage, blocks.py:227):
+//   out = g * (act > 0 ? 1 : slope[c])      dslope[c] += g * min(act, 0) / slope[c]
+// act = prelu(pre) is the saved activation.  unshuffle != 0: g / act are the PixelShuffle'd [B,H,W,64] tensors and
+// `out` is written as the four sub-pixel planes [4][B][H/2][W/2][64] of the producing convolution.
+__global__ void __launch_bounds__(256)
+prelu_bwd_kernel(const bf16* g, const bf16* __restrict__ act, const float* __restrict__ slope, bf16* out,
+                 float* __restrict__ dslope, int B, int H, int W, int unshuffle) {   // out may alias g (in place)
+  __shared__ float s_ds[kC];
+  if (threadIdx.x < kC) s_ds[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int cg = threadIdx.x & 7;
+  float sl[8], ds[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { sl[c] = __ldg(slope + cg * 8 + c); ds[c] = 0.f; }
+  const size_t total = size_t(B) * H * W * 8;
+  const uint4* gv = reinterpret_cast<const uint4*>(g);
+  const uint4* av = reinterpret_cast<const uint4*>(act);
+  uint4* ov = reinterpret_cast<uint4*>(out);
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    float gf[8], af[8], of[8];
+    unpack8(gv[i], gf);
+    unpack8(__ldg(av + i), af);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const bool pos = af[c] > 0.f;
+      of[c] = pos ? gf[c] : gf[c] * sl[c];
+      ds[c] += pos ? 0.f : gf[c] * (af[c] / sl[c]);
+    }
+    size_t o = i;
+    if (unshuffle) {
+      const size_t pix = i >> 3;
+      const int x = int(pix % W), y = int((pix / W) % H), n = int(pix / (size_t(W) * H));
+      const int sub = 2 * (y & 1) + (x & 1);
+      o = ((((size_t(sub) * B + n) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1)) << 3) + cg;
+    }
+    ov[o] = pack8(of);
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) atomicAdd(&s_ds[cg * 8 + c], ds[c]);
+  __syncthreads();
+  if (threadIdx.x < kC) atomicAdd(dslope + threadIdx.x, s_ds[threadIdx.x]);
+}
+
+// --------------------------------------------------------------------------------------------------------------
+// Squeeze-and-excitation backward (blocks.py:86-92,153), x' = x + rs * s * o, s = sigmoid(W2 relu(W0 mean(o))).
+// Pass 1: dsum[b][c] += sum_px dx'[b,px,c] * o[b,px,c].   grid (chunks, B).
+__global__ void __launch_bounds__(256)
+se_bwd_reduce_kernel(const bf16* __restrict__ dxo, const bf16* __restrict__ o, float* __restrict__ dsum, int hw) {
+  __shared__ float s_acc[kC];
+  if (threadIdx.x < kC) s_acc[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int n = blockIdx.y, cg = threadIdx.x & 7;
+  const size_t base = size_t(n) * hw * 8;
+  const int total = hw * 8;
+  const uint4* gv = reinterpret_cast<const uint4*>(dxo) + base;
+  const uint4* ov = reinterpret_cast<const uint4*>(o) + base;
+  float a[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) a[c] = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    float gf[8], of[8];
+    unpack8(__ldg(gv + i), gf);
+    unpack8(__ldg(ov + i), of);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[c] = fmaf(gf[c], of[c], a[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) atomicAdd(&s_acc[cg * 8 + c], a[c]);
+  __syncthreads();
+  if (threadIdx.x < kC) atomicAdd(dsum + size_t(n) * kC + threadIdx.x, s_acc[threadIdx.x]);
+}
+
+// Pass 2: the tiny FC chain backward per image (recomputed by every CTA of the image), parameter gradients of the
+// two Linear layers (CTA 0 of the image), and  dO = rs * s[c] * dx' + dy[c] / HW.
+//   y = sums / HW; z = relu(W0 y); t = W2 z; s = sigmoid(t)
+//   ds = rs * dsum; dt = ds s (1 - s); dW2 += dt z^T; dz = W2^T dt; dzr = dz [z > 0]; dW0 += dzr y^T; dy = W0^T dzr
+__global__ void __launch_bounds__(256)
+se_bwd_apply_kernel(const bf16* __restrict__ dxo, const float* __restrict__ sums, const float* __restrict__ dsum,
+                    const float* __restrict__ fc0, const float* __restrict__ fc2, int R, float inv_hw, float res_scale,
+                    bf16* __restrict__ dO, float* __restrict__ dfc0, float* __restrict__ dfc2, int hw) {
+  __shared__ float s_y[kC], s_z[kC], s_dt[kC], s_dzr[kC], s_mul[kC], s_add[kC];
+  const int n = blockIdx.y, tid = threadIdx.x;
+  if (tid < kC) s_y[tid] = sums[size_t(n) * kC + tid] * inv_hw;
+  __syncthreads();
+  if (tid < R) {
+    float a = 0.f;
+    for (int c = 0; c < kC; ++c) a = fmaf(fc0[tid * kC + c], s_y[c], a);
+    s_z[tid] = fmaxf(a, 0.f);
+  }
+  __syncthreads();
+  if (tid < kC) {
+    float a = 0.f;
+    for (int j = 0; j < R; ++j) a = fmaf(fc2[tid * R + j], s_z[j], a);
+    const float s = 1.f / (1.f + expf(-a));
+    s_mul[tid] = s * res_scale;
+    s_dt[tid] = res_scale * dsum[size_t(n) * kC + tid] * s * (1.f - s);
+  }
+  __syncthreads();
+  if (tid < R) {
+    float a = 0.f;
+    for (int c = 0; c < kC; ++c) a = fmaf(fc2[c * R + tid], s_dt[c], a);
+    s_dzr[tid] = s_z[tid] > 0.f ? a : 0.f;
+  }
+  __syncthreads();
+  if (tid < kC) {
+    float a = 0.f;
+    for (int j = 0; j < R; ++j) a = fmaf(fc0[j * kC + tid], s_dzr[j], a);
+    s_add[tid] = a * inv_hw;
+  }
+  if (blockIdx.x == 0) {
+    for (int i = tid; i < kC * R; i += blockDim.x) {
+      atomicAdd(dfc2 + i, s_dt[i / R] * s_z[i % R]);       // fc2 [64][R]
+      atomicAdd(dfc0 + i, s_dzr[i / kC] * s_y[i % kC]);    // fc0 [R][64]
+    }
+  }
+  __syncthreads();
+  const int cg = tid & 7;
+  float mul[8], add[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) { mul[c] = s_mul[cg * 8 + c]; add[c] = s_add[cg * 8 + c]; }
+  const size_t base = size_t(n) * hw * 8;
+  const int total = hw * 8;
+  const uint4* gv = reinterpret_cast<const uint4*>(dxo) + base;
+  uint4* ov = reinterpret_cast<uint4*>(dO) + base;
+  for (int i = blockIdx.x * blockDim.x + tid; i < total; i += gridDim.x * blockDim.x) {
+    float gf[8], of[8];
+    unpack8(__ldg(gv + i), gf);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) of[c] = fmaf(gf[c], mul[c], add[c]);
+    ov[i] = pack8(of);
+  }
+}
+
+// out = a + b (skip connections meeting in the backward pass), NHWC bf16, n8 = number of 8-element groups.
+__global__ void __launch_bounds__(256)
+add_bf16_kernel(const bf16* a, const bf16* b, bf16* out, size_t n8) {   // out may alias a or b
+  const uint4* av = reinterpret_cast<const uint4*>(a);
+  const uint4* bv = reinterpret_cast<const uint4*>(b);
+  uint4* ov = reinterpret_cast<uint4*>(out);
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += size_t(gridDim.x) * blockDim.x) {
+    float x[8], y[8];
+    unpack8(av[i], x);
+    unpack8(bv[i], y);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) x[c] += y[c];
+    ov[i] = pack8(x);
+  }
+}
+
+// Transposed + tap-flipped weights for the data-gradient convolutions:
+//   dst[grp][t][r = ci][col = c] = W[co = (groups == 4 ? 4 c + grp : c)][ci][8 - t]        (fp32 OIHW -> bf16)
+// so that conv(dY_grp, dst_grp) = dX.  For the PixelShuffle convolutions the four sub-pixel planes are four
+// 64 -> 64 convolutions whose results add up.
+__global__ void pack_conv_T_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int groups) {
+  const int total = groups * 9 * kC * kC;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % kC;
+    const int ci = (i / kC) % kC;
+    const int t = (i / (kC * kC)) % 9;
+    const int grp = i / (kC * kC * 9);
+    const int co = groups == 4 ? 4 * c + grp : c;
+    dst[i] = __float2bfloat16(w[(size_t(co) * kC + ci) * 9 + (8 - t)]);
+  }
+}
+// conv_last weights OIHW [3][64][3][3] -> wk[co*9 + t][ci] = W[co][ci][8 - t] (fp32) for last_dgrad_kernel
+__global__ void pack_last_T_kernel(const float* __restrict__ w, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 27 * kC) return;
+  const int ci = i % kC, k = i / kC, co = k / 9, t = k % 9;
+  dst[i] = w[(size_t(co) * kC + ci) * 9 + (8 - t)];
+}
+
+}  // namespace fen

@@ -1,0 +1,282 @@
+// Host orchestration of the Stage-1 training step, network side: a forward pass that KEEPS what the backward
+// needs (per-layer launches of the tcgen05 convolution kernel) and the backward pass itself.
+// Included by fen_b200.cu inside namespace fen (uses its Layout / ConvArgs / launch_conv helpers).
+#pragma once
+
+// ---------------------------------------------------------------- transposed weights for the dgrad convolutions
+struct BwdLayout {
+  int64_t rcab0, rcab_stride;   // per RCAB: [w1T][w2T]
+  int64_t gconv0;               // per group: [wT]
+  int64_t after, up[2], last, zeros, total;
+};
+static void make_bwd_layout(const Layout& L, BwdLayout* K) {
+  int64_t o = 0;
+  K->rcab0 = o; K->rcab_stride = 2 * kConvWBytes; o += int64_t(L.n_rcab) * K->rcab_stride;
+  K->gconv0 = o; o += int64_t(L.G) * kConvWBytes;
+  K->after = o; o += kConvWBytes;
+  for (int s = 0; s < 2; ++s) { K->up[s] = o; o += 4 * kConvWBytes; }
+  K->last = o; o += align256(27 * 64 * 4);
+  K->zeros = o; o += 256;
+  K->total = o;
+}
+
+// ---------------------------------------------------------------- saved activations + gradient buffers
+struct StepWs {
+  int64_t act;                      // bytes of one [B][H][W][64] bf16 tensor
+  int64_t f0, body, xs0, h0, o0, gout0, u0, u1, sums;     // forward (xs/h/o: one per RCAB, gout: one per group)
+  int64_t dy1, du0, dy0, g[6], dsum;                      // backward
+  int64_t total;
+};
+static void make_step_ws(const Layout& L, int B, int H, int W, StepWs* w) {
+  const int64_t act = align256(int64_t(B) * H * W * 64 * 2);
+  w->act = act;
+  int64_t o = 0;
+  w->f0 = o; o += act;
+  w->body = o; o += act;
+  w->xs0 = o; o += act * L.n_rcab;
+  w->h0 = o; o += act * L.n_rcab;
+  w->o0 = o; o += act * L.n_rcab;
+  w->gout0 = o; o += act * L.G;
+  w->u0 = o; o += 4 * act;
+  w->u1 = o; o += 16 * act;
+  w->sums = o; o += align256(int64_t(L.n_rcab) * B * 64 * 4);
+  w->dy1 = o; o += 16 * act;
+  w->du0 = o; o += 4 * act;
+  w->dy0 = o; o += 4 * act;
+  for (int i = 0; i < 6; ++i) { w->g[i] = o; o += act; }
+  w->dsum = o; o += align256(int64_t(B) * 64 * 4);
+  w->total = o;
+}
+
+static int conv64(const bf16* in, const void* w, const float* bias, const float* slope, const bf16* res, float* sm,
+                  bf16* out, int epi, int B, int h, int w_, cudaStream_t st) {
+  ConvArgs a{};
+  a.x = in; a.w = w; a.n = 64; a.groups = (epi == kEpiShuffle) ? 4 : 1;
+  a.p.B = B; a.p.H = h; a.p.W = w_; a.p.epi = epi; a.p.bias = bias; a.p.slope = slope; a.p.residual = res;
+  a.p.out = out; a.p.sums = sm;
+  return launch_conv(a, st);
+}
+
+static int ew_blocks(size_t items) {
+  size_t b = (items + 255) / 256;
+  const size_t cap = size_t(num_sms()) * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return int(b);
+}
+
+// Forward in train() mode (no clamp, custom.py:187) that keeps every RCAB's x / h / o, the group outputs and both
+// upsample stages for the backward pass.
+static int step_forward(const fen_config* cfg, const Layout& L, const uint8_t* k, const float* x, float* out, int B,
+                        int H, int W, uint8_t* wsb, const StepWs& ws, cudaStream_t st) {
+  int rc;
+  const RcabRec rr = rcab_rec(L.R);
+  auto act = [&](int64_t off) { return reinterpret_cast<bf16*>(wsb + off); };
+  float* sums = reinterpret_cast<float*>(wsb + ws.sums);
+  FEN_CUDA(cudaMemsetAsync(sums, 0, size_t(L.n_rcab) * B * 64 * 4, st));
+  conv_first_kernel<<<dim3(H, B), 256, 0, st>>>(x, reinterpret_cast<const float*>(k + L.k_first_w),
+                                                reinterpret_cast<const float*>(k + L.k_first_b), act(ws.f0), H, W);
+  FEN_CUDA(cudaGetLastError());
+  ++g_launches;
+  const int hw = H * W;
+  const bf16* cur = act(ws.f0);
+  for (int g = 0; g < L.G; ++g) {
+    const bf16* gin = cur;
+    for (int b = 0; b < L.Bk; ++b) {
+      const int r = g * L.Bk + b;
+      const uint8_t* kr = k + L.k_rcab0 + int64_t(r) * L.k_rcab_stride;
+      float* sm = sums + size_t(r) * B * 64;
+      bf16* h = act(ws.h0 + r * ws.act);
+      bf16* o = act(ws.o0 + r * ws.act);
+      bf16* nxt = act(ws.xs0 + r * ws.act);
+      if ((rc = conv64(cur, kr + rr.w1, reinterpret_cast<const float*>(kr + rr.b1),
+                       reinterpret_cast<const float*>(kr + rr.slope), nullptr, nullptr, h, kEpiPrelu, B, H, W, st)))
+        return rc;
+      if ((rc = conv64(h, kr + rr.w2, reinterpret_cast<const float*>(kr + rr.b2), nullptr, nullptr, sm, o, kEpiSum, B,
+                       H, W, st)))
+        return rc;
+      se_residual_kernel<<<dim3(32, B), 256, 0, st>>>(cur, o, sm, reinterpret_cast<const float*>(kr + rr.fc0),
+                                                      reinterpret_cast<const float*>(kr + rr.fc2), L.R,
+                                                      1.f / float(hw), cfg->res_scale, nxt, nullptr, 0, hw);
+      FEN_CUDA(cudaGetLastError());
+      ++g_launches;
+      cur = nxt;
+    }
+    const uint8_t* kg = k + L.k_gconv0 + g * L.k_gconv_stride;
+    bf16* gout = act(ws.gout0 + g * ws.act);
+    if ((rc = conv64(cur, kg, reinterpret_cast<const float*>(kg + kConvWBytes), nullptr, gin, nullptr, gout,
+                     kEpiResidual, B, H, W, st)))
+      return rc;
+    cur = gout;
+  }
+  if ((rc = conv64(cur, k + L.k_after, reinterpret_cast<const float*>(k + L.k_after + kConvWBytes), nullptr,
+                   act(ws.f0), nullptr, act(ws.body), kEpiResidual, B, H, W, st)))
+    return rc;
+  const uint8_t* ku = k + L.k_up[0];
+  if ((rc = conv64(act(ws.body), ku, reinterpret_cast<const float*>(ku + 4 * kConvWBytes),
+                   reinterpret_cast<const float*>(ku + 4 * kConvWBytes + 1024), nullptr, nullptr, act(ws.u0),
+                   kEpiShuffle, B, H, W, st)))
+    return rc;
+  ku = k + L.k_up[1];
+  if ((rc = conv64(act(ws.u0), ku, reinterpret_cast<const float*>(ku + 4 * kConvWBytes),
+                   reinterpret_cast<const float*>(ku + 4 * kConvWBytes + 1024), nullptr, nullptr, act(ws.u1),
+                   kEpiShuffle, B, 2 * H, 2 * W, st)))
+    return rc;
+  ConvArgs a{};
+  a.x = act(ws.u1); a.w = k + L.k_last; a.n = 16; a.groups = 1;
+  a.p.B = B; a.p.H = 4 * H; a.p.W = 4 * W; a.p.epi = kEpiLast; a.p.training = 1;
+  a.p.bias = reinterpret_cast<const float*>(k + L.k_last + 9 * 16 * 64 * 2);
+  a.p.lr = x; a.p.out_f32 = out;
+  return launch_conv(a, st);
+}
+
+static int wgrad64(const bf16* dY, const bf16* X, float* dW, float* dB, int B, int H, int W, int co_mul, int co_off,
+                   cudaStream_t st) {
+  const int bands = B * H * (W / kStripW);
+  const int grid = bands < num_sms() ? bands : num_sms();
+  wgrad_c64_kernel<<<grid, 256, 0, st>>>(dY, X, dW, dB, B, H, W, co_mul, co_off);
+  FEN_CUDA(cudaGetLastError());
+  ++g_launches;
+  return FEN_OK;
+}
+
+// Backward of step_forward: dout [B,3,4H,4W] fp32 (d loss / d network output) -> grads (flat fp32, the layout of
+// the flat parameter vector, zeroed here).
+static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* k, const uint8_t* kb,
+                         const BwdLayout& K, const float* x, const float* dout, float* grads, int B, int H, int W,
+                         uint8_t* wsb, const StepWs& ws, cudaStream_t st) {
+  int rc;
+  const RcabRec rr = rcab_rec(L.R);
+  auto act = [&](int64_t off) { return reinterpret_cast<bf16*>(wsb + off); };
+  const float* zeros = reinterpret_cast<const float*>(kb + K.zeros);
+  const float* sums = reinterpret_cast<const float*>(wsb + ws.sums);
+  float* dsum = reinterpret_cast<float*>(wsb + ws.dsum);
+  const int Ho = 4 * H, Wo = 4 * W;
+  const size_t n8 = size_t(B) * H * W * 8;   // 8-element groups of one body-resolution tensor
+  FEN_CUDA(cudaMemsetAsync(grads, 0, size_t(L.p_total) * 4, st));
+
+  // ---- conv_last: weight / bias gradient, then data gradient fused with PReLU + PixelShuffle backward of stage 1
+  {
+    const int rows = 8;
+    wgrad_c3_kernel<<<dim3((Ho + rows - 1) / rows, B), 256, 9 * (Wo + 2) * sizeof(float), st>>>(
+        act(ws.u1), dout, grads + L.p_last_w, grads + L.p_last_b, Ho, Wo, rows, 1);
+    FEN_CUDA(cudaGetLastError());
+    ++g_launches;
+    const float* slope1 = reinterpret_cast<const float*>(k + L.k_up[1] + 4 * kConvWBytes + 1024);
+    last_dgrad_kernel<<<dim3(Ho, B), 256, 0, st>>>(dout, reinterpret_cast<const float*>(kb + K.last), act(ws.u1),
+                                                   slope1, act(ws.dy1), grads + L.p_up[1] + 4 * kConvW + 256, B, Ho,
+                                                   Wo);
+    FEN_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
+  // ---- upsample stage 1 (conv 64 -> 256 on 2H x 2W, input u0): 4 sub-pixel planes
+  {
+    const int h2 = 2 * H, w2 = 2 * W;
+    const int64_t plane = 4 * ws.act;   // one [B][2H][2W][64] plane of dy1
+    bf16* acc[2] = {act(ws.du0), act(ws.dy0)};   // ping-pong; dy0 is free until the unshuffle below
+    for (int sub = 0; sub < 4; ++sub) {
+      const bf16* dy = act(ws.dy1 + sub * plane);
+      if ((rc = wgrad64(dy, act(ws.u0), grads + L.p_up[1], grads + L.p_up[1] + 4 * kConvW, B, h2, w2, 4, sub, st)))
+        return rc;
+      if ((rc = conv64(dy, kb + K.up[1] + sub * kConvWBytes, zeros, nullptr, sub ? acc[(sub - 1) & 1] : nullptr,
+                       nullptr, acc[sub & 1], sub ? kEpiResidual : kEpiBias, B, h2, w2, st)))
+        return rc;
+    }
+    // result in acc[1] = dy0 region -> PReLU + PixelShuffle backward of stage 0 writes the planes into du0 region
+    const float* slope0 = reinterpret_cast<const float*>(k + L.k_up[0] + 4 * kConvWBytes + 1024);
+    prelu_bwd_kernel<<<ew_blocks(size_t(B) * h2 * w2 * 8), 256, 0, st>>>(
+        acc[1], act(ws.u0), slope0, acc[0], grads + L.p_up[0] + 4 * kConvW + 256, B, h2, w2, 1);
+    FEN_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
+  // ---- upsample stage 0 (conv 64 -> 256 on H x W, input body): planes in du0 region, result -> g[0] (= d body)
+  bf16* dBody = act(ws.g[0]);
+  {
+    bf16* acc[2] = {act(ws.g[1]), act(ws.g[0])};
+    for (int sub = 0; sub < 4; ++sub) {
+      const bf16* dy = act(ws.du0 + sub * ws.act);
+      if ((rc = wgrad64(dy, act(ws.body), grads + L.p_up[0], grads + L.p_up[0] + 4 * kConvW, B, H, W, 4, sub, st)))
+        return rc;
+      if ((rc = conv64(dy, kb + K.up[0] + sub * kConvWBytes, zeros, nullptr, sub ? acc[(sub - 1) & 1] : nullptr,
+                       nullptr, acc[sub & 1], sub ? kEpiResidual : kEpiBias, B, H, W, st)))
+        return rc;
+    }
+  }
+  // ---- conv_after_body + long skip: body = conv(gout[G-1]) + f0
+  bf16* dCur = act(ws.g[1]);
+  {
+    const bf16* feat = act(ws.gout0 + (L.G - 1) * ws.act);
+    if ((rc = wgrad64(dBody, feat, grads + L.p_after_w, grads + L.p_after_b, B, H, W, 1, 0, st))) return rc;
+    if ((rc = conv64(dBody, kb + K.after, zeros, nullptr, nullptr, nullptr, dCur, kEpiBias, B, H, W, st))) return rc;
+  }
+  // ---- residual groups, last to first.  dCur = d gout[g]
+  bf16* dX = act(ws.g[2]);
+  bf16* dXn = act(ws.g[3]);
+  bf16* dO = act(ws.g[4]);
+  bf16* dH = act(ws.g[5]);
+  const int hw = H * W;
+  for (int g = L.G - 1; g >= 0; --g) {
+    float* pg = grads + L.p_rcab0 + g * L.p_group_stride;
+    const bf16* gin = g ? act(ws.gout0 + (g - 1) * ws.act) : act(ws.f0);
+    const bf16* blocks_out = act(ws.xs0 + (g * L.Bk + L.Bk - 1) * ws.act);
+    if ((rc = wgrad64(dCur, blocks_out, pg + L.p_gconv_w_in_group, pg + L.p_gconv_w_in_group + kConvW, B, H, W, 1, 0,
+                      st)))
+      return rc;
+    if ((rc = conv64(dCur, kb + K.gconv0 + g * kConvWBytes, zeros, nullptr, nullptr, nullptr, dX, kEpiBias, B, H, W,
+                     st)))
+      return rc;
+    for (int b = L.Bk - 1; b >= 0; --b) {
+      const int r = g * L.Bk + b;
+      const uint8_t* kr = k + L.k_rcab0 + int64_t(r) * L.k_rcab_stride;
+      float* pr = pg + b * L.p_rcab_stride;
+      float* d_c1w = pr; float* d_c1b = d_c1w + kConvW; float* d_sl = d_c1b + 64;
+      float* d_c2w = d_sl + 64; float* d_c2b = d_c2w + kConvW; float* d_fc0 = d_c2b + 64;
+      float* d_fc2 = d_fc0 + L.R * 64;
+      const bf16* xin = b ? act(ws.xs0 + (r - 1) * ws.act) : gin;
+      const bf16* h = act(ws.h0 + r * ws.act);
+      const bf16* o = act(ws.o0 + r * ws.act);
+      // squeeze-and-excitation + scaled residual
+      FEN_CUDA(cudaMemsetAsync(dsum, 0, size_t(B) * 64 * 4, st));
+      se_bwd_reduce_kernel<<<dim3(32, B), 256, 0, st>>>(dX, o, dsum, hw);
+      FEN_CUDA(cudaGetLastError());
+      se_bwd_apply_kernel<<<dim3(32, B), 256, 0, st>>>(dX, sums + size_t(r) * B * 64, dsum,
+                                                       reinterpret_cast<const float*>(kr + rr.fc0),
+                                                       reinterpret_cast<const float*>(kr + rr.fc2), L.R,
+                                                       1.f / float(hw), cfg->res_scale, dO, d_fc0, d_fc2, hw);
+      FEN_CUDA(cudaGetLastError());
+      g_launches += 2;
+      // conv2
+      if ((rc = wgrad64(dO, h, d_c2w, d_c2b, B, H, W, 1, 0, st))) return rc;
+      if ((rc = conv64(dO, kb + K.rcab0 + r * K.rcab_stride + kConvWBytes, zeros, nullptr, nullptr, nullptr, dH,
+                       kEpiBias, B, H, W, st)))
+        return rc;
+      // PReLU (in place: dH becomes dA)
+      prelu_bwd_kernel<<<ew_blocks(n8), 256, 0, st>>>(dH, h, reinterpret_cast<const float*>(kr + rr.slope), dH, d_sl,
+                                                      B, H, W, 0);
+      FEN_CUDA(cudaGetLastError());
+      ++g_launches;
+      // conv1 + the identity path of the RCAB
+      if ((rc = wgrad64(dH, xin, d_c1w, d_c1b, B, H, W, 1, 0, st))) return rc;
+      if ((rc = conv64(dH, kb + K.rcab0 + r * K.rcab_stride, zeros, nullptr, dX, nullptr, dXn, kEpiResidual, B, H, W,
+                       st)))
+        return rc;
+      bf16* t = dX; dX = dXn; dXn = t;
+    }
+    // group skip: d gin = dX + dCur
+    add_bf16_kernel<<<ew_blocks(n8), 256, 0, st>>>(dX, dCur, dCur, n8);
+    FEN_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
+  // ---- long skip + conv_first
+  add_bf16_kernel<<<ew_blocks(n8), 256, 0, st>>>(dCur, dBody, dCur, n8);
+  FEN_CUDA(cudaGetLastError());
+  ++g_launches;
+  {
+    const int rows = 2;
+    wgrad_c3_kernel<<<dim3((H + rows - 1) / rows, B), 256, 9 * (W + 2) * sizeof(float), st>>>(
+        dCur, x, grads + L.p_first_w, grads + L.p_first_b, H, W, rows, 0);
+    FEN_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
+  return FEN_OK;
+}

@@ -7,8 +7,9 @@ with the reference).  forward(x: [B,3,H,W] fp32 CUDA in [0,1]) -> [B,3,4H,4W] fp
 [0,1] iff not self.training (custom.py:187-188).
 
 There is no CPU path and no cuDNN dispatch: CPU tensors, non-64-channel configs or a missing CUDA
-library raise.  Backward is not implemented in this build (forward returns a tensor without a grad
-graph; calling it in train mode with grad enabled raises).
+library raise.  In train() mode with grad enabled, forward runs fen_forward_train (activations kept) and
+returns a tensor whose grad_fn calls fen_backward: `loss.backward()` fills `.grad` of every parameter as
+in the reference's Trainer._train_epoch (src/training/trainer.py:458-505).  The input gets no gradient.
 """
 from __future__ import annotations
 
@@ -37,6 +38,29 @@ class FaceEnhanceNetConfig:
     out_channels: int = 3
     init_scale: float = 0.1
     num_rcab_blocks: int = 8
+
+
+class _FenTrainFunction(torch.autograd.Function):
+    """sr = model(lr) in train() mode; backward = fen_backward (the network side of loss.backward())."""
+
+    @staticmethod
+    def forward(ctx, model, x, *params):
+        out, step_ws = model._forward_train(x)
+        ctx.model, ctx.x, ctx.step_ws = model, x, step_ws
+        ctx.shapes = [p.shape for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        flat = ctx.model._backward(ctx.x, dout, ctx.step_ws)
+        grads, off = [], 0
+        for shp in ctx.shapes:
+            n = 1
+            for d in shp:
+                n *= d
+            grads.append(flat[off:off + n].view(shp))
+            off += n
+        return (None, None, *grads)
 
 
 class FaceEnhanceNet(nn.Module):
@@ -101,20 +125,85 @@ class FaceEnhanceNet(nn.Module):
         _lib.check(lib.fen_pack_weights(C.byref(cfg), flat.data_ptr(), packed.data_ptr(), stream_ptr),
                    "fen_pack_weights")
         self._packed, self._packed_key = packed, key
+        self._flat = flat
         return packed
 
-    def _run(self, x: torch.Tensor, want_se: bool):
+    def mark_parameters_updated(self) -> None:
+        """Tell the module that its parameters were updated in place through raw pointers (the fused optimiser
+        kernel of training.Stage1Step does not bump torch's version counters): the packed copies are rebuilt."""
+        self._packed_key = None
+
+    def _ensure_packed_bwd(self, device: torch.device, stream_ptr: int) -> torch.Tensor:
+        """Transposed / tap-flipped weights for the data-gradient convolutions (fen_pack_weights_bwd)."""
+        self._ensure_packed(device, stream_ptr)
+        if getattr(self, "_packed_bwd", None) is not None and self._packed_bwd_key == self._packed_key:
+            return self._packed_bwd
+        lib, cfg = _lib.load(), self._c_config()
+        nbytes = lib.fen_packed_bwd_bytes(C.byref(cfg))
+        _lib.check(nbytes, "fen_packed_bwd_bytes")
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _lib.check(lib.fen_pack_weights_bwd(C.byref(cfg), self._flat.data_ptr(), packed.data_ptr(), stream_ptr),
+                   "fen_pack_weights_bwd")
+        slopes = torch.cat([m.weight.detach().reshape(-1) for m in self.modules() if isinstance(m, nn.PReLU)])
+        if bool((slopes <= 0).any()):
+            raise RuntimeError("the B200 backward keeps post-PReLU activations and needs PReLU slopes > 0")
+        self._packed_bwd, self._packed_bwd_key = packed, self._packed_key
+        return packed
+
+    def _check_input(self, x: torch.Tensor) -> None:
         if not isinstance(x, torch.Tensor) or x.dim() != 4 or x.shape[1] != 3:
             raise RuntimeError(f"expected input [B,3,H,W], got {tuple(getattr(x, 'shape', ()))}")
         if not x.is_cuda:
             raise RuntimeError("FaceEnhanceNet (B200 path) needs a CUDA tensor: there is no CPU fallback")
         if next(self.parameters()).device != x.device:
             raise RuntimeError("input and parameters are on different devices")
-        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise RuntimeError("backward is not implemented in this build of the B200 path; "
-                               "call forward under torch.no_grad() or in eval() mode")
+
+    def _forward_train(self, x: torch.Tensor):
+        """fen_forward_train: unclamped output + the step workspace holding the saved activations."""
+        lib, cfg = _lib.load(), self._c_config()
+        B, _, H, W = x.shape
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            packed = self._ensure_packed(x.device, stream)
+            skey = (str(x.device), B, H, W)
+            if getattr(self, "_step_ws_key", None) != skey:
+                nbytes = lib.fen_step_workspace_bytes(C.byref(cfg), B, H, W)
+                _lib.check(nbytes, "fen_step_workspace_bytes")
+                self._step_ws = None
+                self._step_ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+                self._step_ws_key = skey
+            ws = self._step_ws
+            s = self.scale_factor
+            out = torch.empty((B, 3, H * s, W * s), dtype=torch.float32, device=x.device)
+            _lib.check(lib.fen_forward_train(C.byref(cfg), packed.data_ptr(), x.data_ptr(), out.data_ptr(), B, H, W,
+                                             ws.data_ptr(), ws.numel(), stream), "fen_forward_train")
+        return out, ws
+
+    def _backward(self, x: torch.Tensor, dout: torch.Tensor, ws: torch.Tensor) -> torch.Tensor:
+        """fen_backward: flat fp32 gradient in parameter order for the last _forward_train on `ws`."""
+        lib, cfg = _lib.load(), self._c_config()
+        if ws is not getattr(self, "_step_ws", None):
+            raise RuntimeError("the step workspace of this forward was replaced by a later forward with another shape")
+        B, _, H, W = x.shape
+        dout = dout.detach().to(torch.float32).contiguous()
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            packed = self._ensure_packed(x.device, stream)
+            packed_bwd = self._ensure_packed_bwd(x.device, stream)
+            grads = torch.empty(self._flat.numel(), dtype=torch.float32, device=x.device)
+            _lib.check(lib.fen_backward(C.byref(cfg), packed.data_ptr(), packed_bwd.data_ptr(), x.data_ptr(),
+                                        dout.data_ptr(), grads.data_ptr(), B, H, W, ws.data_ptr(), ws.numel(), stream),
+                       "fen_backward")
+        return grads
+
+    def _run(self, x: torch.Tensor, want_se: bool):
+        self._check_input(x)
         lib, cfg = _lib.load(), self._c_config()
         x = x.detach().to(torch.float32).contiguous()
+        if (not want_se and self.training and torch.is_grad_enabled()
+                and any(p.requires_grad for p in self.parameters())):
+            self._c_config()
+            return _FenTrainFunction.apply(self, x, *self.parameters()), None
         B, _, H, W = x.shape
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream().cuda_stream

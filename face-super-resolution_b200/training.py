@@ -1,7 +1,8 @@
-"""Loss / optimiser side of the reference's Stage-1 training step on the GPU:
-nn.L1Loss (src/losses/combined.py:38-47), clip_grad_norm_ and AdamW (src/training/trainer.py:217-221,
-490-503), plus the data-parallel gradient exchange.  The network's backward pass is not
-built yet; these functions operate on flat fp32 tensors so that it can be dropped in between them."""
+"""The reference's Stage-1 training step on the GPU (BASELINE config 5): nn.L1Loss
+(src/losses/combined.py:38-47), clip_grad_norm_ and AdamW (src/training/trainer.py:217-221, 490-503), the
+data-parallel gradient exchange, and `Stage1Step`, which strings them together with the float LR
+generator and the network's forward / backward kernels (FaceEnhanceNet._forward_train / _backward) into one
+iteration of Trainer._train_epoch (trainer.py:410-505).  Everything operates on flat fp32 tensors."""
 from __future__ import annotations
 
 from typing import Optional, Tuple
@@ -102,3 +103,50 @@ class ClipAdamW:
                                                self.max_norm, self.lr, self.betas[0], self.betas[1], self.eps,
                                                self.weight_decay, self.step_count, st), "fen_clip_adamw_step")
         return self.total_norm
+
+
+class Stage1Step:
+    """One iteration of Trainer._train_epoch for Stage 1 (trainer.py:410-505; L1 only, fp32 master weights,
+    `mixed_precision: false` in configs/stage1_psnr_config.yaml:78):
+
+        lr = F.interpolate(hr, scale_factor=0.25, mode='bicubic')      -> fen_lr_from_hr_f32
+        sr = model(lr)                       (train mode, unclamped)    -> fen_forward_train
+        loss = L1(sr, hr); loss.backward()                              -> fen_l1_loss, fen_backward
+        [data parallel: all-reduce(mean) of the flat gradient, NCCL]    -> allreduce_mean_
+        clip_grad_norm_(0.5); AdamW.step()                              -> fen_grad_norm, fen_clip_adamw_step
+
+    The model's parameters are re-pointed at views of ONE flat fp32 vector (registration order = the order of the
+    C ABI), so the optimiser updates them in place and `model.state_dict()` stays the reference's schema."""
+
+    def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                 max_norm: float = 0.5):
+        params = list(model.parameters())
+        if not params or not params[0].is_cuda:
+            raise RuntimeError("Stage1Step needs the model on a CUDA device: there is no CPU fallback")
+        flat = torch.cat([p.detach().reshape(-1).to(torch.float32) for p in params]).contiguous()
+        off = 0
+        for p in params:
+            n = p.numel()
+            p.data = flat[off:off + n].view(p.shape)
+            off += n
+        self.model, self.flat = model, flat
+        self.opt = ClipAdamW(flat, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_norm=max_norm)
+        self.last_grad: Optional[torch.Tensor] = None
+
+    def step(self, hr: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """hr: [B,3,4H,4W] fp32 CUDA in [0,1].  Returns (loss [1], total gradient norm before clipping [1]),
+        both device scalars: nothing in the step synchronises with the host."""
+        from .data import lr_from_hr_float
+        _check_cuda_f32(hr)
+        model = self.model
+        model.train()
+        lr_img, _ = lr_from_hr_float(hr)
+        model._check_input(lr_img)
+        sr, ws = model._forward_train(lr_img)
+        loss, dsr = l1_loss(sr, hr)
+        grads = model._backward(lr_img, dsr, ws)
+        allreduce_mean_(grads)
+        norm = self.opt.step(grads)
+        model.mark_parameters_updated()
+        self.last_grad = grads
+        return loss, norm

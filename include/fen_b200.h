@@ -107,8 +107,8 @@ int fen_lr_from_hr_f32(const float* hr, float* lr_f32, uint8_t* lr_u8, int B, in
  *   sr   [B,C,H,W] fp32      out  [B,H,W,C] uint8 */
 int fen_sr_to_u8(const float* sr, uint8_t* out, int B, int C, int H, int W, int bgr, void* stream);
 
-/* ---- Stage-1 training step, loss / optimiser side.  The backward pass of the network is
- * not built yet; these are the pieces of Trainer._train_epoch that follow it.
+/* ---- Stage-1 training step, loss / optimiser side.  The backward pass of the network
+ * is fen_forward_train / fen_backward below; these are the pieces of Trainer._train_epoch that follow it.
  *
  * Scratch for the deterministic two-stage reductions below. */
 int64_t fen_train_workspace_bytes(int64_t n);
@@ -138,6 +138,34 @@ int fen_grad_norm(const float* grads, int64_t n, float* norm_out, void* workspac
 int fen_clip_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                         const float* total_norm, float max_norm, float lr, float beta1, float beta2, float eps,
                         float weight_decay, int step, void* stream);
+
+/* ---- Stage-1 training step, network side (BASELINE config 5): what sr = model(lr) in train()
+ * mode and loss.backward() do in Trainer._train_epoch (reference src/training/trainer.py:458-505) over
+ * FaceEnhanceNet.forward (src/models/custom.py:147-190) and its blocks (src/models/blocks.py:75-263).
+ *
+ * Bytes of the transposed / tap-flipped weight blob the data-gradient convolutions read. */
+int64_t fen_packed_bwd_bytes(const fen_config* cfg);
+
+/* fp32 state_dict tensors (flat vector, see fen_param_count) -> bf16 [tap][Cin][Cout] weights with the taps
+ * flipped (every 64-channel convolution; the PixelShuffle convolutions as four sub-pixel groups) and the fp32
+ * conv_last weights in the layout of its data-gradient kernel.  Call after every parameter update. */
+int fen_pack_weights_bwd(const fen_config* cfg, const float* params, void* packed_bwd, void* stream);
+
+/* Bytes of the step workspace for a batch of B LR images of H x W: the activations fen_forward_train keeps
+ * (per RCAB its input, h and o, the group outputs, both upsample stages) plus the gradient buffers. */
+int64_t fen_step_workspace_bytes(const fen_config* cfg, int B, int H, int W);
+
+/* FaceEnhanceNet.forward in train() mode (no clamp, custom.py:187-188) that keeps what fen_backward needs in
+ * `step_workspace`.  Same arguments as fen_forward otherwise; runs one tcgen05 convolution launch per layer. */
+int fen_forward_train(const fen_config* cfg, const void* packed, const float* x, float* out, int B, int H, int W,
+                      void* step_workspace, int64_t step_workspace_bytes, void* stream);
+
+/* loss.backward() through the network: dout [B,3,4H,4W] fp32 = d loss / d output of the LAST fen_forward_train on
+ * this workspace (same x, B, H, W) -> grads, fp32, flat, in the order of fen_param_count (what .grad of every
+ * state_dict tensor holds after backward(); overwritten, not accumulated).  PReLU slopes must be > 0 (the saved
+ * activations are post-PReLU).  Data gradients and saved activations are bf16, parameter gradients fp32. */
+int fen_backward(const fen_config* cfg, const void* packed, const void* packed_bwd, const float* x, const float* dout,
+                 float* grads, int B, int H, int W, void* step_workspace, int64_t step_workspace_bytes, void* stream);
 
 /* One 3x3 / pad-1 convolution with 64 input and 64 output channels on NHWC bf16 tensors
  * (the RCAB building block, reference src/models/blocks.py:122-130): out = epilogue(conv(x) + bias).

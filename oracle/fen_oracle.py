@@ -64,6 +64,10 @@ def fen_forward(
     tensors: 'conv_first', 'group{g}', 'body', 'up{s}', 'se' ([B, n_rcab, C] attention scales)."""
     sd = {k: v.detach().to(torch.float32).cpu() for k, v in sd.items()}
     x = x.detach().to(torch.float32).cpu()
+    return _forward(sd, x, training, res_scale, scale_factor, taps)
+
+
+def _forward(sd, x, training, res_scale, scale_factor, taps):
     n_groups, n_blocks = count_groups_blocks(sd)
     bicubic = F.interpolate(x, scale_factor=scale_factor, mode="bicubic", align_corners=False)
     feat = _conv(sd, "conv_first", x)
@@ -98,6 +102,23 @@ def fen_forward(
     if not training:
         out = torch.clamp(out, 0.0, 1.0)
     return out
+
+
+def fen_backward(sd: Dict[str, torch.Tensor], x: torch.Tensor, dout: torch.Tensor, res_scale: float = 0.2,
+                 scale_factor: int = 4):
+    """What `sr = model(lr); sr.backward(dout)` leaves in .grad of every state_dict tensor in train() mode
+    (the network side of loss.backward() in src/training/trainer.py:462-488): fp32 autograd over the
+    restatement above.  Returns (sr, {key: grad})."""
+    leaves = {k: v.detach().to(torch.float32).cpu().clone().requires_grad_(True) for k, v in sd.items()}
+    with torch.enable_grad():
+        sr = _forward(leaves, x.detach().to(torch.float32).cpu(), True, res_scale, scale_factor, None)
+        sr.backward(dout.detach().to(torch.float32).cpu())
+    return sr.detach(), {k: v.grad for k, v in leaves.items()}
+
+
+def l1_grad(sr: torch.Tensor, hr: torch.Tensor) -> torch.Tensor:
+    """d mean|sr - hr| / d sr (nn.L1Loss, src/losses/combined.py:38-47)."""
+    return torch.sign(sr - hr) / sr.numel()
 
 
 def bicubic_x4_weights():

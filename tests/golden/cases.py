@@ -52,3 +52,17 @@ def fen_input(name: str) -> np.ndarray:
     batch = FEN_CASES[idx][4]
     rng = np.random.default_rng(2000 + idx)
     return rng.random((batch, 3, 64, 64), dtype=np.float32)
+
+
+GRAD_CASES = ["small_T1"]   # FEN_CASES entries that also have a gradient golden (fen_grad_golden.npz)
+
+
+def grad_dout(name: str) -> np.ndarray:
+    """d loss / d sr handed to the network in the gradient cases: the structure nn.L1Loss gives it
+    (+-1 / numel, src/losses/combined.py:38-47) with a fixed random sign pattern."""
+    idx = [c[0] for c in FEN_CASES].index(name)
+    batch = FEN_CASES[idx][4]
+    rng = np.random.default_rng(3000 + idx)
+    shape = (batch, 3, 256, 256)
+    sign = rng.integers(0, 2, shape).astype(np.float32) * 2.0 - 1.0
+    return (sign / float(np.prod(shape))).astype(np.float32)

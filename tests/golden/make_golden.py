@@ -8,6 +8,9 @@
                   from /root/reference) with weights from oracle/weights.py loaded by
                   load_state_dict(strict=True) in train() mode (unclamped; the eval() output is exactly its clamp to
                   [0,1], asserted at generation time), plus its get_attention_maps.
+  fen_grad_golden.npz  .grad of every parameter of the same unmodified module after
+                  `m.train(); m(x).backward(dout)` for cases.GRAD_CASES (dout = cases.grad_dout): what
+                  loss.backward() leaves behind in Trainer._train_epoch (src/training/trainer.py:462-488).
 Nothing at test time reads /root/reference."""
 import os
 import sys
@@ -58,8 +61,29 @@ def make_fen():
     np.savez_compressed(os.path.join(HERE, "fen_golden.npz"), **out)
 
 
+def make_fen_grad():
+    sys.path.insert(0, "/root/reference")
+    from src.models import FaceEnhanceNet
+    torch.set_num_threads(8)
+    out = {"torch_version": np.array(torch.__version__)}
+    for name in cases.GRAD_CASES:
+        _, cfg, tier, seed, _ = [c for c in cases.FEN_CASES if c[0] == name][0]
+        m = FaceEnhanceNet(num_channels=64, scale_factor=4, **cfg)
+        m.load_state_dict(weights.make_state_dict(seed, tier, **cfg), strict=True)
+        m.train()
+        m(torch.from_numpy(cases.fen_input(name))).backward(torch.from_numpy(cases.grad_dout(name)))
+        for k, p in m.named_parameters():
+            out[name + "/" + k] = p.grad.numpy().astype(np.float32)
+        print(name, "grad norm", float(torch.sqrt(sum((p.grad.double() ** 2).sum() for p in m.parameters()))))
+    np.savez_compressed(os.path.join(HERE, "fen_grad_golden.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--grad-only" in sys.argv:
+        make_fen_grad()
+        sys.exit(0)
     make_lr()
     make_fen()
-    for f in ("lr_golden.npz", "fen_golden.npz"):
+    make_fen_grad()
+    for f in ("lr_golden.npz", "fen_golden.npz", "fen_grad_golden.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

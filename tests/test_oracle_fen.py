@@ -30,6 +30,25 @@ def test_oracle_matches_reference_golden(name):
     assert (taps["se"] - torch.from_numpy(GOLD[name + "/se"])).abs().max().item() <= 1e-5
 
 
+@pytest.mark.parametrize("name", cases.GRAD_CASES)
+def test_oracle_backward_matches_reference_golden(name):
+    # the gradient oracle (autograd over the restatement) against .grad of the unmodified reference module
+    gold = np.load(os.path.join(HERE, "golden", "fen_grad_golden.npz"))
+    _, cfg, tier, seed, _ = [c for c in cases.FEN_CASES if c[0] == name][0]
+    sd = weights.make_state_dict(seed, tier, **cfg)
+    sr, grads = fen_oracle.fen_backward(sd, torch.from_numpy(cases.fen_input(name)),
+                                        torch.from_numpy(cases.grad_dout(name)))
+    assert (sr - torch.from_numpy(GOLD[name + "/train"])).abs().max().item() <= TOL
+    assert set(grads) == set(sd)
+    for k, g in grads.items():
+        ref = torch.from_numpy(gold[name + "/" + k])
+        assert g.shape == ref.shape
+        assert (g - ref).norm().item() <= 1e-4 * ref.norm().item() + 1e-12, k
+    # nn.L1Loss gradient helper
+    a, b = torch.tensor([[0.2, 0.9]]), torch.tensor([[0.5, 0.1]])
+    assert torch.equal(fen_oracle.l1_grad(a, b), torch.tensor([[-0.5, 0.5]]))
+
+
 def test_literal_init_is_vacuous_without_the_weight_recipe():
     # trap 1 of SURVEY.md: conv_last == 0  =>  forward == clamp(bicubic_up(x))
     cfg = dict(num_groups=1, blocks_per_group=1)
