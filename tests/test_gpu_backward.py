@@ -6,7 +6,7 @@ Tolerance (floating point; BASELINE.json states none for gradients, so it is sta
 gradients are bf16 on the GPU, parameter gradients are accumulated in fp32.  Two regimes:
 
 * COHERENT output gradient (one sign, smooth magnitude): every sum in the backward adds up coherently, so the
-  error is the bf16 rounding of the operands: per parameter tensor relative L2 error <= 3e-2.
+  error is the bf16 rounding of the operands: per parameter tensor relative L2 error <= 2e-2 (measured <= 0.85 %).
 * SIGN-PATTERN output gradient (what nn.L1Loss produces, +-1/numel): every parameter gradient is a sqrt(N)-sized
   random-sign sum, and the ~0.4 % of PReLU inputs whose sign differs between the bf16 and the fp32 FORWARD each
   change one term by (1 - slope): that alone is sqrt(0.004) ~ 4 % per PReLU layer crossed, added in quadrature
@@ -24,7 +24,7 @@ from oracle import fen_oracle, weights
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
-REL_COHERENT, REL_SIGN, COS_BAR, NORM_BAR = 3e-2, 0.2, 0.999, 2e-2
+REL_COHERENT, REL_SIGN, COS_BAR, NORM_BAR = 2e-2, 0.2, 0.999, 2e-2
 
 
 @pytest.fixture(scope="module")
@@ -136,6 +136,33 @@ def test_train_mode_semantics(dev):
         m.upsample.stages[0].prelu.weight[3] = -0.1
     with pytest.raises(RuntimeError):
         m(x).sum().backward()
+
+
+def test_stage1_step_is_the_trainers_iteration(dev):
+    # Trainer._train_epoch (trainer.py:410-505): float LR -> forward -> L1 -> backward -> clip 0.5 -> AdamW(1e-4)
+    cfg = dict(num_groups=1, blocks_per_group=2)
+    sd = weights.make_state_dict(4, "T1", **cfg)
+    m = _model(cfg, sd, dev)
+    step = fsr_b200.Stage1Step(m, lr=1e-4, max_norm=0.5)
+    assert all(p.data_ptr() >= step.flat.data_ptr() for p in m.parameters())      # parameters are views of `flat`
+    hr = torch.rand(2, 3, 256, 256, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+    before = step.flat.clone()
+    loss, norm = step.step(hr)
+    g = step.last_grad
+    # the same step with torch: oracle forward for the loss, torch AdamW on the gradient the kernels produced
+    lr_img = torch.nn.functional.interpolate(hr.cpu(), scale_factor=0.25, mode="bicubic", align_corners=False)
+    sr_ref = fen_oracle.fen_forward(sd, lr_img, training=True)
+    assert abs(loss.item() - (sr_ref - hr.cpu()).abs().mean().item()) <= 1e-4
+    assert abs(norm.item() - g.norm().item()) <= 1e-4 * g.norm().item()
+    p = before.clone().requires_grad_(True)
+    p.grad = g * min(1.0, 0.5 / (g.norm().item() + 1e-6))
+    torch.optim.AdamW([p], lr=1e-4, weight_decay=0.0).step()
+    assert torch.allclose(step.flat, p.detach(), rtol=0, atol=2e-7)
+    assert (step.flat - before).abs().max().item() > 5e-5          # first AdamW step moves every weight by ~lr
+    # next forward uses the updated weights (packed copies rebuilt), state_dict keeps the reference schema
+    l2, _ = step.step(hr)
+    assert torch.isfinite(l2).all() and l2.item() < loss.item()
+    assert list(m.state_dict().keys()) == list(sd.keys())
 
 
 def test_backward_rejects_bad_arguments(dev, built_lib):
