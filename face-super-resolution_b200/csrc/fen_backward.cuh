@@ -106,6 +106,145 @@ wgrad_c64_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, float*
 }
 
 // --------------------------------------------------------------------------------------------------------------
+// Second generation of the same weight gradient on the warp-level tensor-core path (mma.sync m16n8k16, bf16 in,
+// fp32 accumulate): per band D_tap[co][ci] += dY^T[co][px] * X_tap[px][ci], K = the 64 pixels of the band.  Both
+// operands sit pixel-major in shared memory (the contraction index is the slow one), so both fragments come from
+// ldmatrix.trans; rows are padded to 144 B to keep the 8 row addresses of an 8x8 matrix on distinct banks.
+// Warp (mb, nb) owns co 16 mb .. +16, ci 32 nb .. +32 for all 9 taps: 36 m16n8 accumulator tiles = 144 registers.
+constexpr int kWgPitch = kC + 8;   // elements per padded shared-memory row
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// Loads are double-buffered with cp.async (zero-fill outside the image); the accumulators leave through shared
+// memory, 16 output rows at a time, as coalesced 128-bit reductions (red.global.add.v4.f32): a quarter of the
+// instructions and an eighth of the L2 sectors of one scalar atomic per element.
+constexpr int kWgStageElems = (kWgPx + 3 * (kWgPx + 2)) * kWgPitch;        // one buffer: dY row + 3 X rows
+constexpr int kWgDynBytes = 2 * kWgStageElems * 2;                         // 75 456 B
+constexpr int kWgOutPitch = kC * 9 + 4;                                    // floats per staged output row (padded)
+static_assert(16 * kWgOutPitch * 4 <= kWgDynBytes, "output staging must fit the operand buffers");
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* dst, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__global__ void __launch_bounds__(256, 1)
+wgrad_c64_mma_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, float* __restrict__ dW,
+                     float* __restrict__ dB, int B, int H, int W, int co_mul, int co_off) {
+  extern __shared__ __align__(16) uint8_t wg_smem[];
+  const uint32_t smem_u32 = uint32_t(__cvta_generic_to_shared(wg_smem));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int mb = warp >> 1, nb = warp & 1;
+  float acc[9][4][4];   // [tap][n8 tile][c fragment]
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[t][j][c] = 0.f;
+  float bsum = 0.f;
+  // per-lane ldmatrix row offsets (bytes, relative to the k-step / tap origin)
+  const uint32_t a_off = uint32_t((((lane & 7) + ((lane >> 4) << 3)) * kWgPitch + 16 * mb + ((lane >> 3) & 1) * 8) * 2);
+  const uint32_t b_off = uint32_t((((lane & 7) + ((lane >> 3) & 1) * 8) * kWgPitch + 32 * nb + (lane >> 4) * 8) * 2);
+  const int strips = W / kWgPx;
+  const int bands = B * H * strips;
+  auto prefetch = [&](int band, int buf) {
+    const int sidx = band % strips;
+    const int y = (band / strips) % H;
+    const int b = band / (strips * H);
+    const int x0 = sidx * kWgPx;
+    const uint32_t sYb = smem_u32 + uint32_t(buf * kWgStageElems * 2);
+    const uint32_t sXb = sYb + uint32_t(kWgPx * kWgPitch * 2);
+    const bf16* src = dY + ((size_t(b) * H + y) * W + x0) * kC;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = tid + 256 * k;
+      cp_async_16(sYb + uint32_t(((i >> 3) * kWgPitch + (i & 7) * 8) * 2), src + i * 8, 16);
+    }
+    for (int i = tid; i < 3 * (kWgPx + 2) * 8; i += 256) {
+      const int chunk = i & 7, col = (i >> 3) % (kWgPx + 2), r = i / (8 * (kWgPx + 2));
+      const int yy = y - 1 + r, xx = x0 - 1 + col;
+      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      const bf16* sx = ok ? X + ((size_t(b) * H + yy) * W + xx) * kC + chunk * 8 : X;
+      cp_async_16(sXb + uint32_t(((r * (kWgPx + 2) + col) * kWgPitch + chunk * 8) * 2), sx, ok ? 16 : 0);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int buf = 0;
+  if (int(blockIdx.x) < bands) prefetch(blockIdx.x, 0);
+  for (int band = blockIdx.x; band < bands; band += gridDim.x, buf ^= 1) {
+    const int next = band + gridDim.x;
+    if (next < bands) {
+      prefetch(next, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t sY_u32 = smem_u32 + uint32_t(buf * kWgStageElems * 2);
+    const uint32_t sX_u32 = sY_u32 + uint32_t(kWgPx * kWgPitch * 2);
+    if (tid < kC) {
+      const bf16* sY = reinterpret_cast<const bf16*>(wg_smem) + buf * kWgStageElems;
+      float s = 0.f;
+#pragma unroll 8
+      for (int px = 0; px < kWgPx; ++px) s += __bfloat162float(sY[px * kWgPitch + tid]);
+      bsum += s;
+    }
+#pragma unroll 1
+    for (int ks = 0; ks < kWgPx / 16; ++ks) {
+      uint32_t a[4];
+      ldmatrix_x4_trans(sY_u32 + uint32_t(ks * 16 * kWgPitch * 2) + a_off, a);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const uint32_t base = sX_u32 + uint32_t(((r * (kWgPx + 2) + ks * 16 + kx) * kWgPitch) * 2) + b_off;
+          uint32_t b0[4], b1[4];
+          ldmatrix_x4_trans(base, b0);        // ci tiles 0, 1 of this warp's 32
+          ldmatrix_x4_trans(base + 32, b1);   // ci tiles 2, 3
+          mma_bf16_16816(acc[r * 3 + kx][0], a, b0[0], b0[1]);
+          mma_bf16_16816(acc[r * 3 + kx][1], a, b0[2], b0[3]);
+          mma_bf16_16816(acc[r * 3 + kx][2], a, b1[0], b1[1]);
+          mma_bf16_16816(acc[r * 3 + kx][3], a, b1[2], b1[3]);
+        }
+    }
+    __syncthreads();   // this buffer is refilled by the prefetch of the next iteration
+  }
+  // ---- flush: 4 passes of 16 output rows (co) through shared memory, then 128-bit reductions
+  float* stage = reinterpret_cast<float*>(wg_smem);
+  const int g = lane >> 2, t4 = lane & 3;
+  for (int pass = 0; pass < 4; ++pass) {
+    if (mb == pass) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float* dst = stage + (g + (c >> 1) * 8) * kWgOutPitch + (32 * nb + 8 * j + 2 * t4 + (c & 1)) * 9;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) dst[t] = acc[t][j][c];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 16 * (kC * 9 / 4); i += 256) {
+      const int row = i / (kC * 9 / 4), q = i % (kC * 9 / 4);
+      const float4 v = *reinterpret_cast<const float4*>(stage + row * kWgOutPitch + 4 * q);
+      const int co = (16 * pass + row) * co_mul + co_off;
+      red_add_v4(dW + size_t(co) * (kC * 9) + 4 * q, v);
+    }
+    __syncthreads();
+  }
+  if (tid < kC) atomicAdd(dB + tid * co_mul + co_off, bsum);
+}
+
+// --------------------------------------------------------------------------------------------------------------
 // Weight gradient of the two 3-channel convolutions (conv_first 3 -> 64 and conv_last 64 -> 3): a 64-channel
 // NHWC bf16 tensor F against a 3-channel fp32 NCHW image I, both of size H x W:
 //   a[c3][f][t] = sum_{b,y,x} F[b,y,x,f] * I[b,c3,y+ty-1,x+tx-1]
@@ -243,8 +382,16 @@ last_dgrad_kernel(const float* __restrict__ dOut, const float* __restrict__ wk, 
     for (int c = 0; c < 8; ++c) t8[c] = o[8 + c];
     dst[1] = pack8(t8);
   }
+  // a warp shares its channel quarter: reduce over the 32 pixels of the warp first
 #pragma unroll
-  for (int c = 0; c < 16; ++c) atomicAdd(&s_ds[q * 16 + c], ds[c]);
+  for (int c = 0; c < 16; ++c) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) ds[c] += __shfl_xor_sync(0xffffffffu, ds[c], d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) atomicAdd(&s_ds[q * 16 + c], ds[c]);
+  }
   __syncthreads();
   if (threadIdx.x < kC) atomicAdd(dslope + threadIdx.x, s_ds[threadIdx.x]);
 }

@@ -134,7 +134,18 @@ static int wgrad64(const bf16* dY, const bf16* X, float* dW, float* dB, int B, i
                    cudaStream_t st) {
   const int bands = B * H * (W / kStripW);
   const int grid = bands < num_sms() ? bands : num_sms();
-  wgrad_c64_kernel<<<grid, 256, 0, st>>>(dY, X, dW, dB, B, H, W, co_mul, co_off);
+  // FEN_WGRAD=0: first generation (fp32 FMA on the CUDA cores); default: warp-level tensor-core kernel
+  static int version = -1;
+  if (version < 0) version = env_int("FEN_WGRAD", 1);
+  if (version == 0) wgrad_c64_kernel<<<grid, 256, 0, st>>>(dY, X, dW, dB, B, H, W, co_mul, co_off);
+  else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      FEN_CUDA(cudaFuncSetAttribute(wgrad_c64_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgDynBytes));
+      attr_set = true;
+    }
+    wgrad_c64_mma_kernel<<<grid, 256, kWgDynBytes, st>>>(dY, X, dW, dB, B, H, W, co_mul, co_off);
+  }
   FEN_CUDA(cudaGetLastError());
   ++g_launches;
   return FEN_OK;
