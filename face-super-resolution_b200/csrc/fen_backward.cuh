@@ -110,7 +110,9 @@ wgrad_c64_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, float*
 // fp32 accumulate): per band D_tap[co][ci] += dY^T[co][px] * X_tap[px][ci], K = the 64 pixels of the band.  Both
 // operands sit pixel-major in shared memory (the contraction index is the slow one), so both fragments come from
 // ldmatrix.trans; rows are padded to 144 B to keep the 8 row addresses of an 8x8 matrix on distinct banks.
-// Warp (mb, nb) owns co 16 mb .. +16, ci 32 nb .. +32 for all 9 taps: 36 m16n8 accumulator tiles = 144 registers.
+// Warp (mb, nb) owns co 32 mb .. +32, ci 16 nb .. +16 for all 9 taps: 36 m16n8 accumulator tiles = 144 registers.
+// The dY fragments (2 ldmatrix.x4) are shared by the 9 taps, each tap needs ONE ldmatrix.x4 of X: 11 shared-memory
+// fragment loads per 36 MMAs (a 16 x 32 warp tile needs 19).
 constexpr int kWgPitch = kC + 8;   // elements per padded shared-memory row
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -142,8 +144,8 @@ wgrad_c64_mma_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, fl
   extern __shared__ __align__(16) uint8_t wg_smem[];
   const uint32_t smem_u32 = uint32_t(__cvta_generic_to_shared(wg_smem));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int mb = warp >> 1, nb = warp & 1;
-  float acc[9][4][4];   // [tap][n8 tile][c fragment]
+  const int mb = warp >> 2, nb = warp & 3;
+  float acc[9][4][4];   // [tap][2 * m16 tile + n8 tile][c fragment]
 #pragma unroll
   for (int t = 0; t < 9; ++t)
 #pragma unroll
@@ -152,10 +154,26 @@ wgrad_c64_mma_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, fl
       for (int c = 0; c < 4; ++c) acc[t][j][c] = 0.f;
   float bsum = 0.f;
   // per-lane ldmatrix row offsets (bytes, relative to the k-step / tap origin)
-  const uint32_t a_off = uint32_t((((lane & 7) + ((lane >> 4) << 3)) * kWgPitch + 16 * mb + ((lane >> 3) & 1) * 8) * 2);
-  const uint32_t b_off = uint32_t((((lane & 7) + ((lane >> 3) & 1) * 8) * kWgPitch + 32 * nb + (lane >> 4) * 8) * 2);
+  const uint32_t a_off = uint32_t((((lane & 7) + ((lane >> 4) << 3)) * kWgPitch + 32 * mb + ((lane >> 3) & 1) * 8) * 2);
+  const uint32_t b_off = uint32_t((((lane & 7) + ((lane >> 3) & 1) * 8) * kWgPitch + 16 * nb + (lane >> 4) * 8) * 2);
   const int strips = W / kWgPx;
   const int bands = B * H * strips;
+  // band-independent half of the halo-load addressing (the same 16-byte chunks every band): shared-memory
+  // destination, source offset relative to the band origin and which image borders the chunk depends on.  The loads
+  // are issued by the warps that issue the MMAs, so every instruction spent here is taken from them.
+  constexpr int kXChunks = 3 * (kWgPx + 2) * 8, kXIter = (kXChunks + 255) / 256;
+  int x_rel[kXIter];
+  uint32_t x_dst[kXIter], x_border = 0;
+#pragma unroll
+  for (int k = 0; k < kXIter; ++k) {
+    const int i = tid + 256 * k;
+    const int chunk = i & 7, col = (i >> 3) % (kWgPx + 2), r = i / (8 * (kWgPx + 2));
+    x_rel[k] = ((r - 1) * W + (col - 1)) * kC + chunk * 8;
+    x_dst[k] = uint32_t(((r * (kWgPx + 2) + col) * kWgPitch + chunk * 8) * 2);
+    x_border |= (uint32_t(r == 0) | uint32_t(r == 2) << 1 | uint32_t(col == 0) << 2 | uint32_t(col == kWgPx + 1) << 3)
+                << (4 * k);
+  }
+  const uint32_t y_dst0 = uint32_t(((tid >> 3) * kWgPitch + (tid & 7) * 8) * 2);
   auto prefetch = [&](int band, int buf) {
     const int sidx = band % strips;
     const int y = (band / strips) % H;
@@ -163,21 +181,26 @@ wgrad_c64_mma_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, fl
     const int x0 = sidx * kWgPx;
     const uint32_t sYb = smem_u32 + uint32_t(buf * kWgStageElems * 2);
     const uint32_t sXb = sYb + uint32_t(kWgPx * kWgPitch * 2);
-    const bf16* src = dY + ((size_t(b) * H + y) * W + x0) * kC;
+    const size_t origin = ((size_t(b) * H + y) * W + x0) * kC;
+    const bf16* src = dY + origin + tid * 8;
+    cp_async_16(sYb + y_dst0, src, 16);
+    cp_async_16(sYb + y_dst0 + uint32_t(32 * kWgPitch * 2), src + 256 * 8, 16);
+    const uint32_t missing = (uint32_t(y == 0) | uint32_t(y == H - 1) << 1 | uint32_t(x0 == 0) << 2 |
+                              uint32_t(x0 + kWgPx == W) << 3) * 0x11111111u;
+    const uint32_t bad = x_border & missing;
+    const bf16* xo = X + origin;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int i = tid + 256 * k;
-      cp_async_16(sYb + uint32_t(((i >> 3) * kWgPitch + (i & 7) * 8) * 2), src + i * 8, 16);
-    }
-    for (int i = tid; i < 3 * (kWgPx + 2) * 8; i += 256) {
-      const int chunk = i & 7, col = (i >> 3) % (kWgPx + 2), r = i / (8 * (kWgPx + 2));
-      const int yy = y - 1 + r, xx = x0 - 1 + col;
-      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
-      const bf16* sx = ok ? X + ((size_t(b) * H + yy) * W + xx) * kC + chunk * 8 : X;
-      cp_async_16(sXb + uint32_t(((r * (kWgPx + 2) + col) * kWgPitch + chunk * 8) * 2), sx, ok ? 16 : 0);
+    for (int k = 0; k < kXIter; ++k) {
+      if (k < kXIter - 1 || tid + 256 * k < kXChunks) {
+        const bool ok = ((bad >> (4 * k)) & 0xFu) == 0u;
+        cp_async_16(sXb + x_dst[k], ok ? xo + x_rel[k] : X, ok ? 16 : 0);
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+#ifdef FEN_EXP_WG_NOLOAD    // developer experiment: compute on whatever shared memory holds
+#define prefetch(a, b) ((void)0)
+#endif
   int buf = 0;
   if (int(blockIdx.x) < bands) prefetch(blockIdx.x, 0);
   for (int band = blockIdx.x; band < bands; band += gridDim.x, buf ^= 1) {
@@ -200,36 +223,39 @@ wgrad_c64_mma_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, fl
     }
 #pragma unroll 1
     for (int ks = 0; ks < kWgPx / 16; ++ks) {
-      uint32_t a[4];
-      ldmatrix_x4_trans(sY_u32 + uint32_t(ks * 16 * kWgPitch * 2) + a_off, a);
+      uint32_t a0[4], a1[4];
+      ldmatrix_x4_trans(sY_u32 + uint32_t(ks * 16 * kWgPitch * 2) + a_off, a0);        // co rows 0..15 of the warp's 32
+      ldmatrix_x4_trans(sY_u32 + uint32_t(ks * 16 * kWgPitch * 2) + a_off + 32, a1);   // co rows 16..31
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
-          const uint32_t base = sX_u32 + uint32_t(((r * (kWgPx + 2) + ks * 16 + kx) * kWgPitch) * 2) + b_off;
-          uint32_t b0[4], b1[4];
-          ldmatrix_x4_trans(base, b0);        // ci tiles 0, 1 of this warp's 32
-          ldmatrix_x4_trans(base + 32, b1);   // ci tiles 2, 3
-          mma_bf16_16816(acc[r * 3 + kx][0], a, b0[0], b0[1]);
-          mma_bf16_16816(acc[r * 3 + kx][1], a, b0[2], b0[3]);
-          mma_bf16_16816(acc[r * 3 + kx][2], a, b1[0], b1[1]);
-          mma_bf16_16816(acc[r * 3 + kx][3], a, b1[2], b1[3]);
+          uint32_t bq[4];
+          ldmatrix_x4_trans(sX_u32 + uint32_t(((r * (kWgPx + 2) + ks * 16 + kx) * kWgPitch) * 2) + b_off, bq);
+          mma_bf16_16816(acc[r * 3 + kx][0], a0, bq[0], bq[1]);
+          mma_bf16_16816(acc[r * 3 + kx][1], a0, bq[2], bq[3]);
+          mma_bf16_16816(acc[r * 3 + kx][2], a1, bq[0], bq[1]);
+          mma_bf16_16816(acc[r * 3 + kx][3], a1, bq[2], bq[3]);
         }
     }
     __syncthreads();   // this buffer is refilled by the prefetch of the next iteration
   }
+#ifdef FEN_EXP_WG_NOFLUSH   // developer experiment: time the kernel without its output phase
+  if (bands >= 0) { if (acc[0][0][0] == 123.456f) dW[0] = bsum; return; }
+#endif
   // ---- flush: 4 passes of 16 output rows (co) through shared memory, then 128-bit reductions
   float* stage = reinterpret_cast<float*>(wg_smem);
   const int g = lane >> 2, t4 = lane & 3;
-  for (int pass = 0; pass < 4; ++pass) {
-    if (mb == pass) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+  for (int pass = 0; pass < 4; ++pass) {   // output rows co = 16 pass .. 16 pass + 15: m16 tile (pass & 1) of warps mb = pass >> 1
+    if (mb == (pass >> 1)) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float* dst = stage + (g + (c >> 1) * 8) * kWgOutPitch + (32 * nb + 8 * j + 2 * t4 + (c & 1)) * 9;
+          float* dst = stage + (g + (c >> 1) * 8) * kWgOutPitch + (16 * nb + 8 * j + 2 * t4 + (c & 1)) * 9;
 #pragma unroll
-          for (int t = 0; t < 9; ++t) dst[t] = acc[t][j][c];
+          for (int t = 0; t < 9; ++t) dst[t] = acc[t][2 * (pass & 1) + j][c];
         }
     }
     __syncthreads();
@@ -250,14 +276,16 @@ wgrad_c64_mma_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, fl
 //   a[c3][f][t] = sum_{b,y,x} F[b,y,x,f] * I[b,c3,y+ty-1,x+tx-1]
 // mode 0 (conv_first: F = d f0, I = network input):  dW[f][c3][t] += a, db[f] += sum F
 // mode 1 (conv_last:  F = u1,   I = d out):          dW[c3][f][8-t] += a, db[c3] += sum I
-// grid (ceil(H / rows_per_cta), B), 256 threads = 64 channels x 4 column quarters; dynamic smem 9 * (W + 2) floats.
+// grid (ceil(H / rows_per_cta), B), 256 threads = 64 channels x 4 column quarters; dynamic smem 9 * (W + 4) floats.
+// A thread takes 4 pixels at a time: the 3 x 6 image window of each channel comes in as one 128-bit + one 64-bit
+// shared-memory load per row (18 loads for 108 FMAs; one load per FMA made the kernel LSU bound).
 __global__ void __launch_bounds__(256)
 wgrad_c3_kernel(const bf16* __restrict__ F, const float* __restrict__ I, float* __restrict__ dW,
                 float* __restrict__ dB, int H, int W, int rows_per_cta, int mode) {
-  extern __shared__ float sI[];   // [c3][r][W + 2]
+  extern __shared__ __align__(16) float sI[];   // [c3][r][W + 4], column j = image column j - 1
   const int tid = threadIdx.x, f = tid & 63, xq = tid >> 6;
   const int b = blockIdx.y;
-  const int Wp = W + 2;
+  const int Wp = W + 4;
   float acc[3][9];
   float bs = 0.f, is[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -276,16 +304,25 @@ wgrad_c3_kernel(const bf16* __restrict__ F, const float* __restrict__ I, float* 
     __syncthreads();
     const int xw = W / 4;
     const bf16* frow = F + ((size_t(b) * H + y) * W) * kC + f;
-    for (int x = xq * xw; x < (xq + 1) * xw; ++x) {
-      const float v = __bfloat162float(frow[size_t(x) * kC]);
-      bs += v;
+    for (int x = xq * xw; x < (xq + 1) * xw; x += 4) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = __bfloat162float(frow[size_t(x + j) * kC]);
+      bs += (v[0] + v[1]) + (v[2] + v[3]);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+        for (int r = 0; r < 3; ++r) {
+          const float* p = sI + (c * 3 + r) * Wp + x;
+          const float4 lo = *reinterpret_cast<const float4*>(p);
+          const float2 hi = *reinterpret_cast<const float2*>(p + 4);
+          const float w[6] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y};
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) acc[c][r * 3 + kx] = fmaf(v, sI[(c * 3 + r) * Wp + x + kx], acc[c][r * 3 + kx]);
-        if (f == 0) is[c] += sI[(c * 3 + 1) * Wp + x + 1];
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) acc[c][r * 3 + kx] = fmaf(v[j], w[j + kx], acc[c][r * 3 + kx]);
+          if (r == 1 && f == 0) is[c] += (w[1] + w[2]) + (w[3] + w[4]);
+        }
       }
     }
   }

@@ -169,7 +169,7 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
   // ---- conv_last: weight / bias gradient, then data gradient fused with PReLU + PixelShuffle backward of stage 1
   {
     const int rows = 8;
-    wgrad_c3_kernel<<<dim3((Ho + rows - 1) / rows, B), 256, 9 * (Wo + 2) * sizeof(float), st>>>(
+    wgrad_c3_kernel<<<dim3((Ho + rows - 1) / rows, B), 256, 9 * (Wo + 4) * sizeof(float), st>>>(
         act(ws.u1), dout, grads + L.p_last_w, grads + L.p_last_b, Ho, Wo, rows, 1);
     FEN_CUDA(cudaGetLastError());
     ++g_launches;
@@ -284,7 +284,7 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
   ++g_launches;
   {
     const int rows = 2;
-    wgrad_c3_kernel<<<dim3((H + rows - 1) / rows, B), 256, 9 * (W + 2) * sizeof(float), st>>>(
+    wgrad_c3_kernel<<<dim3((H + rows - 1) / rows, B), 256, 9 * (W + 4) * sizeof(float), st>>>(
         dCur, x, grads + L.p_first_w, grads + L.p_first_b, H, W, rows, 0);
     FEN_CUDA(cudaGetLastError());
     ++g_launches;
