@@ -348,7 +348,26 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
               opix = (size_t(u.n) * p.H + y) * p.W + x;
             }
             bf16* dst = p.out + opix * kC + col0;
-            if (p.epi == kEpiResidual) {
+            if (p.epi == kEpiGate) {
+              const bf16* ap = p.residual + opix * kC + col0;
+#pragma unroll
+              for (int j = 0; j < CW / 16; ++j) {
+                uint32_t r[8];
+                ld_global_nc_256(ap + 16 * j, r);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+#pragma unroll
+                  for (int hlf = 0; hlf < 2; ++hlf) {
+                    const int c = 16 * j + 2 * e + hlf;
+                    const float a = hlf ? bf16hi(r[e]) : bf16lo(r[e]);
+                    const float sl = s_slope[col0 + c];
+                    csum[c] += a > 0.f ? 0.f : f[c] * (a / sl);
+                    f[c] = a > 0.f ? f[c] : f[c] * sl;
+                  }
+                }
+              }
+            }
+            if (p.epi == kEpiResidual || (p.epi == kEpiDot && p.residual != nullptr)) {
               const bf16* rsd = p.residual + opix * kC + col0;
 #pragma unroll
               for (int j = 0; j < CW / 16; ++j) {
@@ -358,6 +377,19 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
                 for (int e = 0; e < 8; ++e) {
                   f[16 * j + 2 * e] += bf16lo(r[e]);
                   f[16 * j + 2 * e + 1] += bf16hi(r[e]);
+                }
+              }
+            }
+            if (p.epi == kEpiDot) {
+              const bf16* xp = p.aux + opix * kC + col0;
+#pragma unroll
+              for (int j = 0; j < CW / 16; ++j) {
+                uint32_t r[8];
+                ld_global_nc_256(xp + 16 * j, r);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  csum[16 * j + 2 * e] = fmaf(f[16 * j + 2 * e], bf16lo(r[e]), csum[16 * j + 2 * e]);
+                  csum[16 * j + 2 * e + 1] = fmaf(f[16 * j + 2 * e + 1], bf16hi(r[e]), csum[16 * j + 2 * e + 1]);
                 }
               }
             }
@@ -373,8 +405,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
       }
       long long dbg_t2 = p.dbg ? clock64() : 0;
       if constexpr (N == kC) {
-        if (p.epi == kEpiSum) {
-          // Per-image channel sums for the squeeze-and-excitation pool.  Reduce-scatter butterfly
+        if (p.epi == kEpiSum || p.epi == kEpiGate || p.epi == kEpiDot) {
+          // Per-image channel sums for the squeeze-and-excitation pool (kEpiGate: one vector for the whole batch).  Reduce-scatter butterfly
           // over the warp: 16+8+4+2+1 shuffles leave lane l with the total of channel col0 + l
           // (the lane bits 16,8,4,2,1 select the upper/lower half kept at each level).
 #pragma unroll
@@ -387,7 +419,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
               csum[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
             }
           }
-          atomicAdd(p.sums + size_t(u.n) * kC + col0 + lane, csum[0]);
+          atomicAdd(p.sums + (p.epi == kEpiGate ? size_t(0) : size_t(u.n) * kC) + col0 + lane, csum[0]);
         }
       }
       if (p.dbg) dbg_etail += clock64() - dbg_t2;

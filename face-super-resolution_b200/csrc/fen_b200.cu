@@ -171,7 +171,7 @@ static int launch_conv_n(const ConvArgs& a, cudaStream_t st) {
   const int boxes_bound = p.tiles_per_cta * kTileM / kBoxPx + 3 * ((p.tiles_per_cta + p.tiles_per_seg - 1) / p.tiles_per_seg + 1);
   // (measured at batch 64: conv_last 220 vs 240 us with the second generation, the 64-wide upsample convs
   // 320 vs 285 us - their 3-slot ring starves either way - so only N = 16 takes it by default)
-  if ((conv_version == 2 && N == 16 || conv_version == 3) && p.tiles_per_cta <= kC2MaxTiles && boxes_bound <= kC2MaxBoxes) {
+  if ((conv_version == 2 && N == 16 || conv_version == 3) && p.epi < kEpiGate && p.tiles_per_cta <= kC2MaxTiles && boxes_bound <= kC2MaxBoxes) {
     static bool attr2_set = false;
     if (!attr2_set) {
       FEN_CUDA(cudaFuncSetAttribute(conv3x3_umma2_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,

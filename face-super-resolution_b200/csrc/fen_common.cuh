@@ -28,6 +28,10 @@ enum EpilogueKind : int {
   kEpiShuffle = 3,   // out[2y+i,2x+j,c] = prelu(acc + bias), sub-pixel = blockIdx.y (upsample conv)
   kEpiLast = 4,      // out_f32 NCHW = [clamp](acc + bias + bicubic_x4(lr))   (conv_last)
   kEpiBias = 5,      // out = acc + bias
+  // backward pass (fen_step_host.cuh): data-gradient convolutions with the element-wise backward that follows fused in
+  kEpiGate = 6,      // PReLU backward: out = acc * (a > 0 ? 1 : slope), sums[c] += acc * min(a, 0) / slope
+                     //   (a = `residual` = the saved post-PReLU activation; sums = the [64] slope gradient)
+  kEpiDot = 7,       // out = acc (+ residual if given); sums[n][c] += out * aux   (SE backward: sum dx' * o per image)
 };
 
 struct ConvParams {
@@ -40,9 +44,10 @@ struct ConvParams {
   int training;           // kEpiLast: no clamp when non-zero
   const float* bias;      // [gridDim.y][N]
   const float* slope;     // [64] PReLU slopes or nullptr
-  const bf16* residual;   // NHWC, same shape as out (kEpiResidual)
+  const bf16* residual;   // NHWC, same shape as out (kEpiResidual; kEpiGate: saved activation; kEpiDot: optional)
+  const bf16* aux;        // NHWC, same shape as out (kEpiDot)
   bf16* out;              // NHWC bf16 output
-  float* sums;            // [B][64] fp32, accumulated with atomics (kEpiSum)
+  float* sums;            // [B][64] fp32, accumulated with atomics (kEpiSum, kEpiDot); [64] for kEpiGate
   const float* lr;        // [B][3][H/4][W/4] fp32 network input (kEpiLast)
   float* out_f32;         // [B][3][H][W] fp32 (kEpiLast)
   long long* dbg;         // optional [gridDim.x][8] cycle counters (developer builds), else nullptr

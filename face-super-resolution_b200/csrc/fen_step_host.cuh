@@ -44,16 +44,16 @@ static void make_step_ws(const Layout& L, int B, int H, int W, StepWs* w) {
   w->du0 = o; o += 4 * act;
   w->dy0 = o; o += 4 * act;
   for (int i = 0; i < 6; ++i) { w->g[i] = o; o += act; }
-  w->dsum = o; o += align256(int64_t(B) * 64 * 4);
+  w->dsum = o; o += align256(int64_t(L.n_rcab) * B * 64 * 4);   // sum_px dx' * o per RCAB, image, channel
   w->total = o;
 }
 
 static int conv64(const bf16* in, const void* w, const float* bias, const float* slope, const bf16* res, float* sm,
-                  bf16* out, int epi, int B, int h, int w_, cudaStream_t st) {
+                  bf16* out, int epi, int B, int h, int w_, cudaStream_t st, const bf16* aux = nullptr) {
   ConvArgs a{};
   a.x = in; a.w = w; a.n = 64; a.groups = (epi == kEpiShuffle) ? 4 : 1;
   a.p.B = B; a.p.H = h; a.p.W = w_; a.p.epi = epi; a.p.bias = bias; a.p.slope = slope; a.p.residual = res;
-  a.p.out = out; a.p.sums = sm;
+  a.p.out = out; a.p.sums = sm; a.p.aux = aux;
   return launch_conv(a, st);
 }
 
@@ -165,6 +165,7 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
   const int Ho = 4 * H, Wo = 4 * W;
   const size_t n8 = size_t(B) * H * W * 8;   // 8-element groups of one body-resolution tensor
   FEN_CUDA(cudaMemsetAsync(grads, 0, size_t(L.p_total) * 4, st));
+  FEN_CUDA(cudaMemsetAsync(dsum, 0, size_t(L.n_rcab) * B * 64 * 4, st));
 
   // ---- conv_last: weight / bias gradient, then data gradient fused with PReLU + PixelShuffle backward of stage 1
   {
@@ -233,8 +234,10 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
     if ((rc = wgrad64(dCur, blocks_out, pg + L.p_gconv_w_in_group, pg + L.p_gconv_w_in_group + kConvW, B, H, W, 1, 0,
                       st)))
       return rc;
-    if ((rc = conv64(dCur, kb + K.gconv0 + g * kConvWBytes, zeros, nullptr, nullptr, nullptr, dX, kEpiBias, B, H, W,
-                     st)))
+    // d blocks_out, and with it sum_px dx' * o of the group's last RCAB (kEpiDot)
+    if ((rc = conv64(dCur, kb + K.gconv0 + g * kConvWBytes, zeros, nullptr, nullptr,
+                     dsum + size_t(g * L.Bk + L.Bk - 1) * B * 64, dX, kEpiDot, B, H, W, st,
+                     act(ws.o0 + (g * L.Bk + L.Bk - 1) * ws.act))))
       return rc;
     for (int b = L.Bk - 1; b >= 0; --b) {
       const int r = g * L.Bk + b;
@@ -245,32 +248,29 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
       float* d_fc2 = d_fc0 + L.R * 64;
       const bf16* xin = b ? act(ws.xs0 + (r - 1) * ws.act) : gin;
       const bf16* h = act(ws.h0 + r * ws.act);
-      const bf16* o = act(ws.o0 + r * ws.act);
-      // squeeze-and-excitation + scaled residual
-      FEN_CUDA(cudaMemsetAsync(dsum, 0, size_t(B) * 64 * 4, st));
-      se_bwd_reduce_kernel<<<dim3(32, B), 256, 0, st>>>(dX, o, dsum, hw);
-      FEN_CUDA(cudaGetLastError());
-      se_bwd_apply_kernel<<<dim3(32, B), 256, 0, st>>>(dX, sums + size_t(r) * B * 64, dsum,
+      // squeeze-and-excitation + scaled residual (the per-image sums of dx' * o came with dX)
+      se_bwd_apply_kernel<<<dim3(32, B), 256, 0, st>>>(dX, sums + size_t(r) * B * 64, dsum + size_t(r) * B * 64,
                                                        reinterpret_cast<const float*>(kr + rr.fc0),
                                                        reinterpret_cast<const float*>(kr + rr.fc2), L.R,
                                                        1.f / float(hw), cfg->res_scale, dO, d_fc0, d_fc2, hw);
       FEN_CUDA(cudaGetLastError());
-      g_launches += 2;
-      // conv2
-      if ((rc = wgrad64(dO, h, d_c2w, d_c2b, B, H, W, 1, 0, st))) return rc;
-      if ((rc = conv64(dO, kb + K.rcab0 + r * K.rcab_stride + kConvWBytes, zeros, nullptr, nullptr, nullptr, dH,
-                       kEpiBias, B, H, W, st)))
-        return rc;
-      // PReLU (in place: dH becomes dA)
-      prelu_bwd_kernel<<<ew_blocks(n8), 256, 0, st>>>(dH, h, reinterpret_cast<const float*>(kr + rr.slope), dH, d_sl,
-                                                      B, H, W, 0);
-      FEN_CUDA(cudaGetLastError());
       ++g_launches;
-      // conv1 + the identity path of the RCAB
-      if ((rc = wgrad64(dH, xin, d_c1w, d_c1b, B, H, W, 1, 0, st))) return rc;
-      if ((rc = conv64(dH, kb + K.rcab0 + r * K.rcab_stride, zeros, nullptr, dX, nullptr, dXn, kEpiResidual, B, H, W,
-                       st)))
+      // conv2: weight gradient, then data gradient with the PReLU backward in its epilogue (dH holds dA)
+      if ((rc = wgrad64(dO, h, d_c2w, d_c2b, B, H, W, 1, 0, st))) return rc;
+      if ((rc = conv64(dO, kb + K.rcab0 + r * K.rcab_stride + kConvWBytes, zeros,
+                       reinterpret_cast<const float*>(kr + rr.slope), h, d_sl, dH, kEpiGate, B, H, W, st)))
         return rc;
+      // conv1 + the identity path of the RCAB; the result is dx' of the previous RCAB of the group
+      if ((rc = wgrad64(dH, xin, d_c1w, d_c1b, B, H, W, 1, 0, st))) return rc;
+      if (b > 0) {
+        if ((rc = conv64(dH, kb + K.rcab0 + r * K.rcab_stride, zeros, nullptr, dX, dsum + size_t(r - 1) * B * 64, dXn,
+                         kEpiDot, B, H, W, st, act(ws.o0 + (r - 1) * ws.act))))
+          return rc;
+      } else {
+        if ((rc = conv64(dH, kb + K.rcab0 + r * K.rcab_stride, zeros, nullptr, dX, nullptr, dXn, kEpiResidual, B, H,
+                         W, st)))
+          return rc;
+      }
       bf16* t = dX; dX = dXn; dXn = t;
     }
     // group skip: d gin = dX + dCur

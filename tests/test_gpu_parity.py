@@ -352,9 +352,10 @@ def test_forward_error_behaviour(dev):
         m(torch.rand(1, 3, 48, 64, device=dev))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.rand(1, 3, 64, 64))
-    m.train()
-    with pytest.raises(RuntimeError, match="backward is not implemented"):
-        m(torch.rand(1, 3, 64, 64, device=dev))
+    m.train()                      # train mode with grad: the per-layer path with a grad_fn (tests/test_gpu_backward.py)
+    assert m(torch.rand(1, 3, 64, 64, device=dev)).grad_fn is not None
+    with pytest.raises(ValueError, match="multiples of 64"):
+        m(torch.rand(1, 3, 64, 96, device=dev))
     lite = fsr_b200.FaceEnhanceNetLite().to(dev).eval()
     with pytest.raises(ValueError, match="num_channels must be 64"):
         lite(torch.rand(1, 3, 64, 64, device=dev))
