@@ -566,6 +566,53 @@ static int pack_vec(const float* src, int count, int n_grp, int groups, int perm
   return FEN_OK;
 }
 
+// Batched packing (one launch for all RCABs, one for all plain convolutions): a training step repacks every weight
+// after the optimiser update, and one launch per tensor (~750 of them for the 6 x 10 model) cost more than the
+// forward pass itself.  blockIdx.y selects the record; element order as pack_conv_kernel (perm = 0).
+__device__ __forceinline__ void pack_conv64_dev(const float* __restrict__ w, bf16* __restrict__ dst, bool transposed) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 9 * kC * kC; i += gridDim.x * blockDim.x) {
+    const int c = i % kC, r = (i / kC) % kC, t = i / (kC * kC);
+    // forward: dst[t][co = r][ci = c] = W[r][c][t];   transposed (dgrad): dst[t][ci = r][co = c] = W[c][r][8 - t]
+    const float v = transposed ? w[(size_t(c) * kC + r) * 9 + (8 - t)] : w[(size_t(r) * kC + c) * 9 + t];
+    dst[i] = __float2bfloat16(v);
+  }
+}
+__global__ void pack_rcab_all_kernel(const float* __restrict__ params, uint8_t* __restrict__ k, Layout L, RcabRec rr) {
+  const int r = blockIdx.y, g = r / L.Bk, b = r % L.Bk;
+  const float* pr = params + L.p_rcab0 + g * L.p_group_stride + b * L.p_rcab_stride;
+  uint8_t* kr = k + L.k_rcab0 + int64_t(r) * L.k_rcab_stride;
+  const float* c1w = pr; const float* c1b = c1w + kConvW; const float* sl = c1b + 64;
+  const float* c2w = sl + 64; const float* c2b = c2w + kConvW; const float* fc0 = c2b + 64;
+  const float* fc2 = fc0 + L.R * 64;
+  pack_conv64_dev(c1w, reinterpret_cast<bf16*>(kr + rr.w1), false);
+  pack_conv64_dev(c2w, reinterpret_cast<bf16*>(kr + rr.w2), false);
+  if (blockIdx.x == 0) {
+    float* cv = reinterpret_cast<float*>(k + L.k_cvec) + L.cv_rcab0 + r * 192;
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+      reinterpret_cast<float*>(kr + rr.b1)[i] = c1b[i]; cv[i] = c1b[i];
+      reinterpret_cast<float*>(kr + rr.slope)[i] = sl[i]; cv[64 + i] = sl[i];
+      reinterpret_cast<float*>(kr + rr.b2)[i] = c2b[i]; cv[128 + i] = c2b[i];
+    }
+    for (int i = threadIdx.x; i < L.R * 64; i += blockDim.x) {
+      reinterpret_cast<float*>(kr + rr.fc0)[i] = fc0[i];
+      reinterpret_cast<float*>(kr + rr.fc2)[i] = fc2[i];
+    }
+  }
+}
+// records 0 .. G-1: the group convolutions, record G: conv_after_body
+__global__ void pack_plain_all_kernel(const float* __restrict__ params, uint8_t* __restrict__ k, Layout L) {
+  const int g = blockIdx.y;
+  const float* w = g < L.G ? params + L.p_rcab0 + g * L.p_group_stride + L.p_gconv_w_in_group : params + L.p_after_w;
+  uint8_t* kg = g < L.G ? k + L.k_gconv0 + g * L.k_gconv_stride : k + L.k_after;
+  pack_conv64_dev(w, reinterpret_cast<bf16*>(kg), false);
+  if (blockIdx.x == 0) {
+    float* cv = reinterpret_cast<float*>(k + L.k_cvec) + (g < L.G ? L.cv_gconv0 + g * 64 : L.cv_after);
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+      reinterpret_cast<float*>(kg + kConvWBytes)[i] = w[kConvW + i]; cv[i] = w[kConvW + i];
+    }
+  }
+}
+
 // ===================================================================== workspace
 struct Workspace {
   int64_t f0, x[2], h, o, grp0, grp_stride, u0, u1, sums, hsum, flags, total;
@@ -784,37 +831,10 @@ int fen_pack_weights(const fen_config* cfg, const float* params, void* packed, v
   pack_first_kernel<<<(27 * 64 + 255) / 256, 256, 0, st>>>(params + L.p_first_w, reinterpret_cast<float*>(k + L.k_first_w));
   FEN_CUDA(cudaGetLastError());
   if ((rc = pack_vec(params + L.p_first_b, 64, 64, 1, 0, k + L.k_first_b, st))) return rc;
-  for (int g = 0; g < L.G; ++g) {
-    const float* pg = params + L.p_rcab0 + g * L.p_group_stride;
-    for (int b = 0; b < L.Bk; ++b) {
-      const float* pr = pg + b * L.p_rcab_stride;
-      uint8_t* kr = k + L.k_rcab0 + int64_t(g * L.Bk + b) * L.k_rcab_stride;
-      const float* c1w = pr; const float* c1b = c1w + kConvW; const float* sl = c1b + 64;
-      const float* c2w = sl + 64; const float* c2b = c2w + kConvW; const float* fc0 = c2b + 64;
-      const float* fc2 = fc0 + L.R * 64;
-      if ((rc = pack_conv(c1w, 64, 64, 1, 0, kr + rr.w1, st))) return rc;
-      if ((rc = pack_conv(c2w, 64, 64, 1, 0, kr + rr.w2, st))) return rc;
-      if ((rc = pack_vec(c1b, 64, 64, 1, 0, kr + rr.b1, st))) return rc;
-      if ((rc = pack_vec(sl, 64, 64, 1, 0, kr + rr.slope, st))) return rc;
-      if ((rc = pack_vec(c2b, 64, 64, 1, 0, kr + rr.b2, st))) return rc;
-      if ((rc = pack_vec(fc0, L.R * 64, L.R * 64, 1, 0, kr + rr.fc0, st))) return rc;
-      if ((rc = pack_vec(fc2, L.R * 64, L.R * 64, 1, 0, kr + rr.fc2, st))) return rc;
-      float* cv = reinterpret_cast<float*>(k + L.k_cvec) + L.cv_rcab0 + (g * L.Bk + b) * 192;
-      if ((rc = pack_vec(c1b, 64, 64, 1, 0, cv, st))) return rc;
-      if ((rc = pack_vec(sl, 64, 64, 1, 0, cv + 64, st))) return rc;
-      if ((rc = pack_vec(c2b, 64, 64, 1, 0, cv + 128, st))) return rc;
-    }
-    uint8_t* kg = k + L.k_gconv0 + g * L.k_gconv_stride;
-    if ((rc = pack_conv(pg + L.p_gconv_w_in_group, 64, 64, 1, 0, kg, st))) return rc;
-    if ((rc = pack_vec(pg + L.p_gconv_w_in_group + kConvW, 64, 64, 1, 0, kg + kConvWBytes, st))) return rc;
-    if ((rc = pack_vec(pg + L.p_gconv_w_in_group + kConvW, 64, 64, 1, 0,
-                       reinterpret_cast<float*>(k + L.k_cvec) + L.cv_gconv0 + g * 64, st)))
-      return rc;
-  }
-  if ((rc = pack_conv(params + L.p_after_w, 64, 64, 1, 0, k + L.k_after, st))) return rc;
-  if ((rc = pack_vec(params + L.p_after_b, 64, 64, 1, 0, k + L.k_after + kConvWBytes, st))) return rc;
-  if ((rc = pack_vec(params + L.p_after_b, 64, 64, 1, 0, reinterpret_cast<float*>(k + L.k_cvec) + L.cv_after, st)))
-    return rc;
+  pack_rcab_all_kernel<<<dim3(36, L.n_rcab), 256, 0, st>>>(params, k, L, rr);
+  FEN_CUDA(cudaGetLastError());
+  pack_plain_all_kernel<<<dim3(36, L.G + 1), 256, 0, st>>>(params, k, L);
+  FEN_CUDA(cudaGetLastError());
   for (int s = 0; s < 2; ++s) {
     const float* pu = params + L.p_up[s];
     uint8_t* ku = k + L.k_up[s];
@@ -1145,17 +1165,8 @@ int fen_pack_weights_bwd(const fen_config* cfg, const float* params, void* packe
     FEN_CUDA(cudaGetLastError());
     return FEN_OK;
   };
-  for (int g = 0; g < L.G; ++g) {
-    const float* pg = params + L.p_rcab0 + g * L.p_group_stride;
-    for (int b = 0; b < L.Bk; ++b) {
-      const float* pr = pg + b * L.p_rcab_stride;
-      const int64_t off = K.rcab0 + int64_t(g * L.Bk + b) * K.rcab_stride;
-      if ((rc = packT(pr, 1, off))) return rc;                               // conv1
-      if ((rc = packT(pr + kConvW + 64 + 64, 1, off + kConvWBytes))) return rc;   // conv2
-    }
-    if ((rc = packT(pg + L.p_gconv_w_in_group, 1, K.gconv0 + g * kConvWBytes))) return rc;
-  }
-  if ((rc = packT(params + L.p_after_w, 1, K.after))) return rc;
+  pack_T_all_kernel<<<dim3(36, 2 * L.n_rcab + L.G + 1), 256, 0, st>>>(params, kb, L, K);
+  FEN_CUDA(cudaGetLastError());
   for (int s = 0; s < 2; ++s)
     if ((rc = packT(params + L.p_up[s], 4, K.up[s]))) return rc;
   pack_last_T_kernel<<<(27 * 64 + 255) / 256, 256, 0, st>>>(params + L.p_last_w, reinterpret_cast<float*>(kb + K.last));

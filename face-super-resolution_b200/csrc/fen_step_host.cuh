@@ -20,6 +20,26 @@ static void make_bwd_layout(const Layout& L, BwdLayout* K) {
   K->total = o;
 }
 
+// records 0 .. 2 n_rcab - 1: conv1 / conv2 of every RCAB, then the G group convolutions, then conv_after_body
+__global__ void pack_T_all_kernel(const float* __restrict__ params, uint8_t* __restrict__ kb, Layout L, BwdLayout K) {
+  const int i = blockIdx.y;
+  const float* w;
+  uint8_t* dst;
+  if (i < 2 * L.n_rcab) {
+    const int r = i >> 1, g = r / L.Bk, b = r % L.Bk;
+    w = params + L.p_rcab0 + g * L.p_group_stride + b * L.p_rcab_stride + ((i & 1) ? kConvW + 64 + 64 : 0);
+    dst = kb + K.rcab0 + int64_t(r) * K.rcab_stride + ((i & 1) ? kConvWBytes : 0);
+  } else if (i < 2 * L.n_rcab + L.G) {
+    const int g = i - 2 * L.n_rcab;
+    w = params + L.p_rcab0 + g * L.p_group_stride + L.p_gconv_w_in_group;
+    dst = kb + K.gconv0 + g * kConvWBytes;
+  } else {
+    w = params + L.p_after_w;
+    dst = kb + K.after;
+  }
+  pack_conv64_dev(w, reinterpret_cast<bf16*>(dst), true);
+}
+
 // ---------------------------------------------------------------- saved activations + gradient buffers
 struct StepWs {
   int64_t act;                      // bytes of one [B][H][W][64] bf16 tensor

@@ -117,7 +117,9 @@ class FaceEnhanceNet(nn.Module):
         lib, cfg = _lib.load(), self._c_config()
         nbytes = lib.fen_packed_bytes(C.byref(cfg))
         _lib.check(nbytes, "fen_packed_bytes")
-        flat = torch.cat([p.detach().reshape(-1).to(torch.float32) for p in self.parameters()])
+        flat = getattr(self, "_flat_master", None)       # training.Stage1Step: the parameters are views of this vector
+        if flat is None or flat.device != device:
+            flat = torch.cat([p.detach().reshape(-1).to(torch.float32) for p in self.parameters()])
         n_expected = lib.fen_param_count(C.byref(cfg))
         if flat.numel() != n_expected:
             raise RuntimeError(f"parameter count {flat.numel()} != kernel layout {n_expected}")

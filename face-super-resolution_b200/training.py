@@ -130,6 +130,7 @@ class Stage1Step:
             p.data = flat[off:off + n].view(p.shape)
             off += n
         self.model, self.flat = model, flat
+        model._flat_master = flat      # fen_pack_weights reads it directly (no torch.cat per step)
         self.opt = ClipAdamW(flat, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_norm=max_norm)
         self.last_grad: Optional[torch.Tensor] = None
 

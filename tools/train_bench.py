@@ -35,10 +35,11 @@ ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev) / steps
 from fsr_b200 import data, training
 marks = [ev() for _ in range(6)]
 hr = hrs[0]
-marks[0].record(); lr_img, _ = data.lr_from_hr_float(hr)
-sr, ws = m._forward_train(lr_img); marks[1].record()
+import time
+marks[0].record(); h0 = time.perf_counter(); lr_img, _ = data.lr_from_hr_float(hr)
+sr, ws = m._forward_train(lr_img); h1 = time.perf_counter(); marks[1].record()
 loss2, dsr = training.l1_loss(sr, hr); marks[2].record()
-grads = m._backward(lr_img, dsr, ws); marks[3].record()
+h2 = time.perf_counter(); grads = m._backward(lr_img, dsr, ws); h3 = time.perf_counter(); marks[3].record()
 training.allreduce_mean_(grads); marks[4].record()
 st.opt.step(grads); m.mark_parameters_updated(); marks[5].record()
 torch.cuda.synchronize()
@@ -48,5 +49,7 @@ if rank == 0:
           f"loss {losses[0].item():.5f} -> {losses[-1].item():.5f}, grad norm {norm.item():.4f}")
     for n, a, b in zip(names, marks[:-1], marks[1:]):
         print(f"   {n:42s} {a.elapsed_time(b):8.2f} ms")
+    print(f"   host time to ISSUE the forward {1e3 * (h1 - h0):.2f} ms, the backward {1e3 * (h3 - h2):.2f} ms "
+          f"(the GPU queue is empty when the forward starts: its device time above includes that)")
 if world > 1:
     torch.distributed.destroy_process_group()
