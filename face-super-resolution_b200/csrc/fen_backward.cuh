@@ -276,22 +276,25 @@ wgrad_c64_mma_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, fl
 //   a[c3][f][t] = sum_{b,y,x} F[b,y,x,f] * I[b,c3,y+ty-1,x+tx-1]
 // mode 0 (conv_first: F = d f0, I = network input):  dW[f][c3][t] += a, db[f] += sum F
 // mode 1 (conv_last:  F = u1,   I = d out):          dW[c3][f][8-t] += a, db[c3] += sum I
-// grid (ceil(H / rows_per_cta), B), 256 threads = 64 channels x 4 column quarters; dynamic smem 9 * (W + 4) floats.
-// A thread takes 4 pixels at a time: the 3 x 6 image window of each channel comes in as one 128-bit + one 64-bit
-// shared-memory load per row (18 loads for 108 FMAs; one load per FMA made the kernel LSU bound).
+// grid (ceil(H / rows_per_cta), B), 256 threads = 32 channel PAIRS x 8 column eighths; dynamic smem 9 * (W + 4) floats.
+// A thread takes 4 pixels of 2 channels at a time: one 32-bit load per pixel (a warp reads whole 128-byte lines),
+// and the 3 x 6 image window of each image channel comes in as one 128-bit + one 64-bit shared-memory load per row
+// (18 loads for 216 FMAs; one load per FMA made the first version LSU bound).
 __global__ void __launch_bounds__(256)
 wgrad_c3_kernel(const bf16* __restrict__ F, const float* __restrict__ I, float* __restrict__ dW,
                 float* __restrict__ dB, int H, int W, int rows_per_cta, int mode) {
   extern __shared__ __align__(16) float sI[];   // [c3][r][W + 4], column j = image column j - 1
-  const int tid = threadIdx.x, f = tid & 63, xq = tid >> 6;
+  const int tid = threadIdx.x, f2 = tid & 31, xq = tid >> 5;
   const int b = blockIdx.y;
   const int Wp = W + 4;
-  float acc[3][9];
-  float bs = 0.f, is[3] = {0.f, 0.f, 0.f};
+  float acc[2][3][9];
+  float bs[2] = {0.f, 0.f}, is[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-  for (int c = 0; c < 3; ++c)
+  for (int h = 0; h < 2; ++h)
 #pragma unroll
-    for (int t = 0; t < 9; ++t) acc[c][t] = 0.f;
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[h][c][t] = 0.f;
   const int y_begin = blockIdx.x * rows_per_cta;
   const int y_end = min(H, y_begin + rows_per_cta);
   for (int y = y_begin; y < y_end; ++y) {
@@ -302,13 +305,17 @@ wgrad_c3_kernel(const bf16* __restrict__ F, const float* __restrict__ I, float* 
       sI[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(I + ((size_t(b) * 3 + c3) * H + yy) * W + xx) : 0.f;
     }
     __syncthreads();
-    const int xw = W / 4;
-    const bf16* frow = F + ((size_t(b) * H + y) * W) * kC + f;
+    const int xw = W / 8;
+    const uint32_t* frow = reinterpret_cast<const uint32_t*>(F + ((size_t(b) * H + y) * W) * kC) + f2;
     for (int x = xq * xw; x < (xq + 1) * xw; x += 4) {
-      float v[4];
+      float v[2][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = __bfloat162float(frow[size_t(x + j) * kC]);
-      bs += (v[0] + v[1]) + (v[2] + v[3]);
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t pr = __ldg(frow + size_t(x + j) * (kC / 2));
+        v[0][j] = bf16lo(pr); v[1][j] = bf16hi(pr);
+      }
+      bs[0] += (v[0][0] + v[0][1]) + (v[0][2] + v[0][3]);
+      bs[1] += (v[1][0] + v[1][1]) + (v[1][2] + v[1][3]);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
 #pragma unroll
@@ -318,23 +325,37 @@ wgrad_c3_kernel(const bf16* __restrict__ F, const float* __restrict__ I, float* 
           const float2 hi = *reinterpret_cast<const float2*>(p + 4);
           const float w[6] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y};
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
+          for (int h = 0; h < 2; ++h)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) acc[c][r * 3 + kx] = fmaf(v[j], w[j + kx], acc[c][r * 3 + kx]);
-          if (r == 1 && f == 0) is[c] += (w[1] + w[2]) + (w[3] + w[4]);
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) acc[h][c][r * 3 + kx] = fmaf(v[h][j], w[j + kx], acc[h][c][r * 3 + kx]);
+          if (r == 1 && f2 == 0) is[c] += (w[1] + w[2]) + (w[3] + w[4]);
         }
       }
     }
   }
+  // the 8 column eighths of a channel meet in shared memory first: one global atomic per output and CTA
+  __shared__ float s_red[3 * 9 * kC + kC];
+  for (int i = tid; i < 3 * 9 * kC + kC; i += 256) s_red[i] = 0.f;
+  __syncthreads();
 #pragma unroll
-  for (int c = 0; c < 3; ++c)
+  for (int h = 0; h < 2; ++h) {
+    const int f = 2 * f2 + h;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      if (mode == 0) atomicAdd(dW + (size_t(f) * 3 + c) * 9 + t, acc[c][t]);
-      else atomicAdd(dW + (size_t(c) * kC + f) * 9 + (8 - t), acc[c][t]);
-    }
-  if (mode == 0) atomicAdd(dB + f, bs);
-  else if (f == 0) {
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) atomicAdd(&s_red[(c * 9 + t) * kC + f], acc[h][c][t]);
+    atomicAdd(&s_red[27 * kC + f], bs[h]);
+  }
+  __syncthreads();
+  for (int i = tid; i < 27 * kC; i += 256) {
+    const int f = i % kC, t = (i / kC) % 9, c = i / (9 * kC);
+    if (mode == 0) atomicAdd(dW + (size_t(f) * 3 + c) * 9 + t, s_red[i]);
+    else atomicAdd(dW + (size_t(c) * kC + f) * 9 + (8 - t), s_red[i]);
+  }
+  if (mode == 0 && tid < kC) atomicAdd(dB + tid, s_red[27 * kC + tid]);
+  if (mode != 0 && f2 == 0) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) atomicAdd(dB + c, is[c]);
   }
