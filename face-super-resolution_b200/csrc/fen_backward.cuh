@@ -1,12 +1,13 @@
 // Backward pass of FaceEnhanceNet (the network side of the reference's Stage-1 step: loss.backward() in
-// src/training/trainer.py:458-505 over src/models/custom.py:147-190 / blocks.py:75-263), first generation.
+// src/training/trainer.py:458-505 over src/models/custom.py:147-190 / blocks.py:75-263).
 //
 // Data gradients (dgrad) of every 64-channel convolution run on the SAME tcgen05 implicit-GEMM kernel as the
-// forward (conv3x3_umma.cuh) with transposed + tap-flipped weights; the kernels in this file are what the
-// forward kernel cannot do: weight gradients (a contraction over PIXELS, K = B*H*W, fp32 accumulate on the
-// CUDA cores in this first generation), the two 3-channel ends of the network, and the element-wise
-// backward of PReLU / PixelShuffle / squeeze-and-excitation.  Activations and data gradients are NHWC bf16,
-// parameter gradients fp32 (accumulated with atomics into the flat gradient vector, which the caller zeroes).
+// forward (conv3x3_umma.cuh) with transposed + tap-flipped weights, with the PReLU backward (kEpiGate) and the
+// squeeze-and-excitation dot product (kEpiDot) fused into its epilogue.  The kernels in this file are what that
+// kernel cannot do: weight gradients (a contraction over PIXELS, K = B*H*W: wgrad_c64_mma_kernel on the warp-level
+// tensor cores, wgrad_c64_kernel = the first, fp32 FMA generation kept for A/B runs), the two 3-channel ends of the
+// network, the PixelShuffle stages and the squeeze-and-excitation chain.  Activations and data gradients are NHWC
+// bf16, parameter gradients fp32 (accumulated with atomics into the flat gradient vector, which the caller zeroes).
 #pragma once
 #include "conv3x3_umma.cuh"
 
