@@ -114,6 +114,10 @@ wgrad_c64_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, float*
 // Warp (mb, nb) owns co 32 mb .. +32, ci 16 nb .. +16 for all 9 taps: 36 m16n8 accumulator tiles = 144 registers.
 // The dY fragments (2 ldmatrix.x4) are shared by the 9 taps, each tap needs ONE ldmatrix.x4 of X: 11 shared-memory
 // fragment loads per 36 MMAs (a 16 x 32 warp tile needs 19).
+#ifndef FEN_WG_UNROLL
+#define FEN_WG_UNROLL 4
+#endif
+constexpr int kWgUnroll = FEN_WG_UNROLL;   // k-steps of a band unrolled together (developer knob)
 constexpr int kWgPitch = kC + 8;   // elements per padded shared-memory row
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -222,7 +226,7 @@ wgrad_c64_mma_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, fl
       for (int px = 0; px < kWgPx; ++px) s += __bfloat162float(sY[px * kWgPitch + tid]);
       bsum += s;
     }
-#pragma unroll 1
+#pragma unroll kWgUnroll
     for (int ks = 0; ks < kWgPx / 16; ++ks) {
       uint32_t a0[4], a1[4];
       ldmatrix_x4_trans(sY_u32 + uint32_t(ks * 16 * kWgPitch * 2) + a_off, a0);        // co rows 0..15 of the warp's 32
