@@ -372,17 +372,24 @@ wgrad_c3_kernel(const bf16* __restrict__ F, const float* __restrict__ I, float* 
 //   dPre         = dU * (u > 0 ? 1 : slope[c])          dslope[c] += dU * min(u, 0) / slope[c]
 //   dY[sub][b][y>>1][x>>1][c] = dPre,  sub = 2 (y&1) + (x&1)                  (the conv's sub-pixel planes)
 // u = prelu(pre) is the saved stage output; sign(u) = sign(pre) needs slope > 0 (checked by the host side).
-// grid (H, B), 256 threads: 64 columns x 4 channel quarters, like conv_first_kernel.
+// grid (H, B), 256 threads: 64 columns x 4 channel quarters, like conv_first_kernel; dynamic smem 9 * (W + 2) floats.
 __global__ void __launch_bounds__(256)
 last_dgrad_kernel(const float* __restrict__ dOut, const float* __restrict__ wk, const bf16* __restrict__ u,
                   const float* __restrict__ slope, bf16* __restrict__ dY, float* __restrict__ dslope, int B, int H,
                   int W) {
+  extern __shared__ float s_in[];   // [co 3][row 3][W + 2]: the three dOut rows of this output row, zero padded
   __shared__ float sw[27 * kC];
   __shared__ float s_sl[kC], s_ds[kC];
+  const int n = blockIdx.y, y = blockIdx.x;
+  const int Wp = W + 2;
   for (int i = threadIdx.x; i < 27 * kC; i += blockDim.x) sw[i] = wk[i];
   if (threadIdx.x < kC) { s_sl[threadIdx.x] = slope[threadIdx.x]; s_ds[threadIdx.x] = 0.f; }
+  for (int i = threadIdx.x; i < 9 * Wp; i += blockDim.x) {
+    const int col = i % Wp, r = (i / Wp) % 3, co = i / (3 * Wp);
+    const int yy = y - 1 + r, xc = col - 1;
+    s_in[i] = (yy >= 0 && yy < H && xc >= 0 && xc < W) ? __ldg(dOut + ((size_t(n) * 3 + co) * H + yy) * W + xc) : 0.f;
+  }
   __syncthreads();
-  const int n = blockIdx.y, y = blockIdx.x;
   const int q = threadIdx.x >> 6;
   float ds[16];
 #pragma unroll
@@ -395,11 +402,7 @@ last_dgrad_kernel(const float* __restrict__ dOut, const float* __restrict__ wk, 
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int yy = y + ky - 1, xc = xx + kx - 1;
-          in[co * 9 + ky * 3 + kx] =
-              (yy >= 0 && yy < H && xc >= 0 && xc < W) ? __ldg(dOut + ((size_t(n) * 3 + co) * H + yy) * W + xc) : 0.f;
-        }
+        for (int kx = 0; kx < 3; ++kx) in[co * 9 + ky * 3 + kx] = s_in[(co * 3 + ky) * Wp + xx + kx];
     float acc[16];
 #pragma unroll
     for (int c = 0; c < 16; ++c) acc[c] = 0.f;

@@ -195,7 +195,7 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
     FEN_CUDA(cudaGetLastError());
     ++g_launches;
     const float* slope1 = reinterpret_cast<const float*>(k + L.k_up[1] + 4 * kConvWBytes + 1024);
-    last_dgrad_kernel<<<dim3(Ho, B), 256, 0, st>>>(dout, reinterpret_cast<const float*>(kb + K.last), act(ws.u1),
+    last_dgrad_kernel<<<dim3(Ho, B), 256, 9 * (Wo + 2) * sizeof(float), st>>>(dout, reinterpret_cast<const float*>(kb + K.last), act(ws.u1),
                                                    slope1, act(ws.dy1), grads + L.p_up[1] + 4 * kConvW + 256, B, Ho,
                                                    Wo);
     FEN_CUDA(cudaGetLastError());

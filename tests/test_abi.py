@@ -61,5 +61,11 @@ def test_compute_entry_points_fail_loudly_without_gpu(built_lib):
     assert rc == _lib.FEN_ENODEV
     assert b"no CPU fallback" in built_lib.fen_last_error()
     assert built_lib.fen_lr_from_hr_u8(buf, buf, None, 1, 4, 4, 1, None) == _lib.FEN_ENODEV
+    # the training-step entry points have no CPU path either
+    assert built_lib.fen_forward_train(C.byref(cfg), buf, buf, buf, 1, 64, 64, buf, 1 << 40, None) == _lib.FEN_ENODEV
+    assert built_lib.fen_backward(C.byref(cfg), buf, buf, buf, buf, buf, 1, 64, 64, buf, 1 << 40, None) == _lib.FEN_ENODEV
+    assert built_lib.fen_pack_weights_bwd(C.byref(cfg), buf, buf, None) == _lib.FEN_ENODEV
+    assert built_lib.fen_packed_bwd_bytes(C.byref(cfg)) > 2 * 9 * 64 * 64 * 2      # layout queries still answer
+    assert built_lib.fen_step_workspace_bytes(C.byref(cfg), 1, 64, 64) > 0
     with pytest.raises(RuntimeError):
         _lib.check(rc, "fen_forward")

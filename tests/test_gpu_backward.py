@@ -75,13 +75,15 @@ def test_backward_matches_reference_golden(name, dev):
     _compare([(k, p.grad) for k, p in m.named_parameters()], ref, REL_SIGN)
 
 
-@pytest.mark.parametrize("cfg,batch", [(dict(num_groups=1, blocks_per_group=2), 2),
-                                       (dict(num_groups=2, blocks_per_group=1), 1)])
-def test_backward_coherent_gradient_against_oracle(cfg, batch, dev):
+@pytest.mark.parametrize("cfg,batch,hw", [(dict(num_groups=1, blocks_per_group=2), 2, (64, 64)),
+                                          (dict(num_groups=2, blocks_per_group=1), 1, (64, 64)),
+                                          (dict(num_groups=1, blocks_per_group=1), 1, (64, 128)),    # two strips per row
+                                          (dict(num_groups=1, blocks_per_group=1), 5, (128, 64))])   # odd batch, tall
+def test_backward_coherent_gradient_against_oracle(cfg, batch, hw, dev):
     sd = weights.make_state_dict(9, "T1", **cfg)
     rng = np.random.default_rng(123)
-    x = torch.from_numpy(rng.random((batch, 3, 64, 64), dtype=np.float32))
-    yy, xx = np.mgrid[0:256, 0:256].astype(np.float32)
+    x = torch.from_numpy(rng.random((batch, 3, hw[0], hw[1]), dtype=np.float32))
+    yy, xx = np.mgrid[0:4 * hw[0], 0:4 * hw[1]].astype(np.float32)
     dout = (1.0 + 0.5 * np.sin(yy / 17.0)[None, None] * np.cos(xx / 23.0)[None, None]) * np.ones((batch, 3, 1, 1))
     dout = torch.from_numpy((dout / dout.size).astype(np.float32))
     m = _model(cfg, sd, dev)
