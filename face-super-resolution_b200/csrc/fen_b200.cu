@@ -14,6 +14,7 @@
 #include "body_umma.cuh"
 #include "body2_umma.cuh"
 #include "fen_backward.cuh"
+#include "wgrad_umma.cuh"
 
 namespace fen {
 
@@ -77,12 +78,13 @@ static EncodeTiledFn get_encode() {
 }
 
 // NHWC bf16 activation [B][H][W][64]: box = 64 ch x 66 px x 4 rows, 128B swizzle, OOB -> zeros.
-static int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int box_rows = kBoxRows) {
+static int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int box_rows = kBoxRows,
+                        int box_px = kPitch) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(FEN_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[4] = {cuuint64_t(kC), cuuint64_t(W), cuuint64_t(H), cuuint64_t(B)};
   cuuint64_t strides[3] = {cuuint64_t(kC) * 2, cuuint64_t(W) * kC * 2, cuuint64_t(H) * W * kC * 2};
-  cuuint32_t box[4] = {cuuint32_t(kC), cuuint32_t(kPitch), cuuint32_t(box_rows), 1};
+  cuuint32_t box[4] = {cuuint32_t(kC), cuuint32_t(box_px), cuuint32_t(box_rows), 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

@@ -150,21 +150,34 @@ static int step_forward(const fen_config* cfg, const Layout& L, const uint8_t* k
   return launch_conv(a, st);
 }
 
+constexpr int kWgradDefault = 2;
 static int wgrad64(const bf16* dY, const bf16* X, float* dW, float* dB, int B, int H, int W, int co_mul, int co_off,
                    cudaStream_t st) {
   const int bands = B * H * (W / kStripW);
   const int grid = bands < num_sms() ? bands : num_sms();
-  // FEN_WGRAD=0: first generation (fp32 FMA on the CUDA cores); default: warp-level tensor-core kernel
-  static int version = -1;
-  if (version < 0) version = env_int("FEN_WGRAD", 1);
-  if (version == 0) wgrad_c64_kernel<<<grid, 256, 0, st>>>(dY, X, dW, dB, B, H, W, co_mul, co_off);
-  else {
+  // FEN_WGRAD=0: first generation (fp32 FMA on the CUDA cores), 1: warp-level tensor cores (mma.sync),
+  // 2: tcgen05 with MN-major operands (wgrad_umma.cuh).  Read on every call so that tests can compare them.
+  const int version = env_int("FEN_WGRAD", kWgradDefault);
+  if (version == 0) {
+    wgrad_c64_kernel<<<grid, 256, 0, st>>>(dY, X, dW, dB, B, H, W, co_mul, co_off);
+  } else if (version == 1) {
     static bool attr_set = false;
     if (!attr_set) {
       FEN_CUDA(cudaFuncSetAttribute(wgrad_c64_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgDynBytes));
       attr_set = true;
     }
     wgrad_c64_mma_kernel<<<grid, 256, kWgDynBytes, st>>>(dY, X, dW, dB, B, H, W, co_mul, co_off);
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      FEN_CUDA(cudaFuncSetAttribute(wgrad_c64_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWuDynBytes));
+      attr_set = true;
+    }
+    CUtensorMap tm_y, tm_x;
+    int rc = make_act_map(&tm_y, dY, B, H, W, 1, kStripW);
+    if (rc) return rc;
+    if ((rc = make_act_map(&tm_x, X, B, H, W, 3, kPitch))) return rc;
+    wgrad_c64_umma_kernel<<<grid, kWuThreads, kWuDynBytes, st>>>(tm_y, tm_x, dW, dB, B, H, W, co_mul, co_off);
   }
   FEN_CUDA(cudaGetLastError());
   ++g_launches;
