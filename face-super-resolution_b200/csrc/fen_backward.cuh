@@ -4,8 +4,9 @@
 // Data gradients (dgrad) of every 64-channel convolution run on the SAME tcgen05 implicit-GEMM kernel as the
 // forward (conv3x3_umma.cuh) with transposed + tap-flipped weights, with the PReLU backward (kEpiGate) and the
 // squeeze-and-excitation dot product (kEpiDot) fused into its epilogue.  The kernels in this file are what that
-// kernel cannot do: weight gradients (a contraction over PIXELS, K = B*H*W: wgrad_c64_mma_kernel on the warp-level
-// tensor cores, wgrad_c64_kernel = the first, fp32 FMA generation kept for A/B runs), the two 3-channel ends of the
+// kernel cannot do: weight gradients (a contraction over PIXELS, K = B*H*W; the product kernel is the tcgen05 one in
+// wgrad_umma.cuh - here are its two predecessors, kept for A/B runs: wgrad_c64_mma_kernel on the warp-level tensor
+// cores and wgrad_c64_kernel with fp32 FMAs), the two 3-channel ends of the
 // network, the PixelShuffle stages and the squeeze-and-excitation chain.  Activations and data gradients are NHWC
 // bf16, parameter gradients fp32 (accumulated with atomics into the flat gradient vector, which the caller zeroes).
 #pragma once

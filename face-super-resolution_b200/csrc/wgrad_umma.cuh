@@ -21,7 +21,7 @@ namespace fen {
 constexpr int kWuStages = 5;
 constexpr int kWuYBytes = kStripW * kC * 2;                       // 8 192: dY row
 constexpr int kWuXBytes = 3 * kPitch * kC * 2;                    // 25 344: 3 rows of X with halo columns
-constexpr int kWuXPad = (kWuXBytes + 1023) / 1024 * 1024 + 1024;  // 26 624 + 1 024 (tap 8's unused partner reads past the box)
+constexpr int kWuXPad = (kWuXBytes + 1023) / 1024 * 1024 + 1024;  // 26 624: the next stage starts on a swizzle-atom boundary
 constexpr int kWuStageBytes = kWuYBytes + kWuXPad;                // multiple of 1 024
 constexpr int kWuOnesBytes = 2048;                                // [16 px][64 ch] of 1.0
 constexpr int kWuDynBytes = kWuStages * kWuStageBytes + kWuOnesBytes + 1024;
@@ -50,10 +50,6 @@ wgrad_c64_umma_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_con
     tma_prefetch_desc(&tm_x);
   }
   for (int i = tid; i < kWuOnesBytes / 4; i += kWuThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
-  // the halo padding behind every X box is read (never used) by tap 8's partner block: keep it finite
-  for (int s = 0; s < kWuStages; ++s)
-    for (int i = tid; i < (kWuXPad - kWuXBytes) / 4; i += kWuThreads)
-      reinterpret_cast<uint32_t*>(smem + s * kWuStageBytes + kWuYBytes + kWuXBytes)[i] = 0u;
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
