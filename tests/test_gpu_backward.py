@@ -111,6 +111,25 @@ def test_backward_two_groups_against_oracle_with_l1_loss(dev):
     _compare([(k, p.grad) for k, p in m.named_parameters()], ref, REL_SIGN)
 
 
+def test_weight_gradient_kernel_generations_agree(dev, monkeypatch):
+    # tcgen05 (MN-major operands, the product kernel) against the mma.sync and the fp32-FMA generations of the same
+    # weight gradient: only the fp32 summation order differs
+    cfg = dict(num_groups=1, blocks_per_group=1)
+    m = _model(cfg, weights.make_state_dict(6, "T1", **cfg), dev)
+    for shape in [(3, 3, 64, 64), (1, 3, 64, 128)]:
+        x = torch.rand(*shape, device=dev)
+        dout = torch.rand(shape[0], 3, 4 * shape[2], 4 * shape[3], device=dev) / 1e5
+        grads = {}
+        for v in ("2", "1", "0"):
+            monkeypatch.setenv("FEN_WGRAD", v)
+            m.zero_grad()
+            m(x).backward(dout)
+            grads[v] = [p.grad.clone() for p in m.parameters()]
+        for v in ("1", "0"):
+            for (k, _), a, b in zip(m.named_parameters(), grads["2"], grads[v]):
+                assert (a - b).norm().item() <= 1e-3 * b.norm().item() + 1e-30, (shape, v, k)
+
+
 def test_train_mode_semantics(dev):
     cfg = dict(num_groups=1, blocks_per_group=1)
     sd = weights.make_state_dict(2, "T1", **cfg)
