@@ -509,33 +509,8 @@ prelu_bwd_kernel(const bf16* g, const bf16* __restrict__ act, const float* __res
 
 // --------------------------------------------------------------------------------------------------------------
 // Squeeze-and-excitation backward (blocks.py:86-92,153), x' = x + rs * s * o, s = sigmoid(W2 relu(W0 mean(o))).
-// Pass 1: dsum[b][c] += sum_px dx'[b,px,c] * o[b,px,c].   grid (chunks, B).
-__global__ void __launch_bounds__(256)
-se_bwd_reduce_kernel(const bf16* __restrict__ dxo, const bf16* __restrict__ o, float* __restrict__ dsum, int hw) {
-  __shared__ float s_acc[kC];
-  if (threadIdx.x < kC) s_acc[threadIdx.x] = 0.f;
-  __syncthreads();
-  const int n = blockIdx.y, cg = threadIdx.x & 7;
-  const size_t base = size_t(n) * hw * 8;
-  const int total = hw * 8;
-  const uint4* gv = reinterpret_cast<const uint4*>(dxo) + base;
-  const uint4* ov = reinterpret_cast<const uint4*>(o) + base;
-  float a[8];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) a[c] = 0.f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    float gf[8], of[8];
-    unpack8(__ldg(gv + i), gf);
-    unpack8(__ldg(ov + i), of);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) a[c] = fmaf(gf[c], of[c], a[c]);
-  }
-#pragma unroll
-  for (int c = 0; c < 8; ++c) atomicAdd(&s_acc[cg * 8 + c], a[c]);
-  __syncthreads();
-  if (threadIdx.x < kC) atomicAdd(dsum + size_t(n) * kC + threadIdx.x, s_acc[threadIdx.x]);
-}
-
+// Pass 1, dsum[b][c] = sum_px dx'[b,px,c] * o[b,px,c], is done by the epilogue of the data-gradient convolution that
+// produces dx' (kEpiDot in conv3x3_umma.cuh).
 // Pass 2: the tiny FC chain backward per image (recomputed by every CTA of the image), parameter gradients of the
 // two Linear layers (CTA 0 of the image), and  dO = rs * s[c] * dx' + dy[c] / HW.
 //   y = sums / HW; z = relu(W0 y); t = W2 z; s = sigmoid(t)
