@@ -75,6 +75,19 @@ def test_no_cpu_fallback_anywhere():
         fsr_b200.lr_from_hr(torch.zeros(1, 8, 8, 3, dtype=torch.uint8))
 
 
+def test_training_path_has_no_cpu_fallback_either():
+    # train() mode with grad enabled takes the fen_forward_train / fen_backward path: CUDA only, like the rest
+    m = fsr_b200.FaceEnhanceNet(num_groups=1, blocks_per_group=1).train()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.rand(1, 3, 64, 64))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fsr_b200.Stage1Step(m)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fsr_b200.l1_loss(torch.rand(2, 2), torch.rand(2, 2))
+    m.mark_parameters_updated()          # harmless without a packed copy
+    assert m._packed is None
+
+
 def test_model_info_keys():
     info = fsr_b200.FaceEnhanceNet(num_groups=6, blocks_per_group=10).get_model_info()
     assert info["total_params"] == 5_115_651 and info["total_rcab_blocks"] == 60
