@@ -1,6 +1,7 @@
 """Measures the BASELINE.json configurations that bench.py does not print (they are parity-test cases for the
 driver): C3 = one residual group (10 RCAB + group conv, the fused conv + SE + residual chain)
 at batch 256; C4 = the sharded pipeline uint8 HR 256x256 -> integer LR kernel -> forward, images/s per GPU.
+(C5, the Stage-1 training step, is `python bench.py --workload train` / tools/train_bench.py.)
     python tools/configs_bench.py [n_images_c4]          (one process per GPU under torchrun for N > 1)"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
