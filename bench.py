@@ -1,28 +1,33 @@
 #!/usr/bin/env python
-"""Benchmark of the B200-native FaceEnhanceNet forward path (BASELINE.json metric:
-SR images/sec, 64x64 -> 256x256, bf16 tensor-core math).
+"""Benchmark of the B200-native FaceEnhanceNet forward path (BASELINE.json metric: SR images/sec, 64x64 -> 256x256).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch 64]
-    python bench.py --workload train [--gpus N] ...      (BASELINE config 5, not the headline: see run_train)
+    python bench.py --workload train [--gpus N] ...      (BASELINE config 5 alone, as its own bench line)
 
 One "step" = one forward of a batch of 64 synthetic 64x64 images (BASELINE.json config 2) per GPU.
 N > 1 (torchrun, one rank per GPU, NCCL): every rank runs the same per-GPU batch on its own shard -
 weak scaling, no data-path collective; the step time is the max over ranks.
 
-Prints ONE JSON line (rank 0):
+Both arms print ONE JSON line (rank 0) with the SAME metric / unit / direction / workload:
   value     images/s with inputs resident in HBM (inputs rotate through a pool larger than L2)
-  e2e       images/s through the public API with pinned HOST buffers: H2D of the LR batch, forward,
-            D2H of the SR batch, every step inside the timed region
+  e2e       images/s through the public API (model(x), fp32 NCHW out as the reference returns it) with pinned HOST
+            buffers: H2D of the LR batch, forward, D2H of the SR batch, every step inside the timed region
+  e2e_u8    the same with the evaluation scripts' uint8 HWC output (scripts/test_model.py:176-190) produced on
+            the GPU by model.forward_u8: 4x fewer D2H bytes
   roofline  the dominant kernel (body2_umma_kernel: the 127 64->64 3x3 convolutions of the body in one
             persistent launch): algorithmic FLOPs per launch / its average launch time (CUDA events on
-            the launch stream), against the measured sustained bf16 peak
-  cpu_baseline  the fp32 CPU oracle (a port of the reference's forward) on this box's host cores
---impl reference: times that CPU path alone (the reference is pure Python/PyTorch and is not installed
-on the GPU box; oracle/fen_oracle.py restates its forward with the same ATen ops).
+            the launch stream, over >= 2 s of back-to-back forwards), against the measured sustained bf16 peak
+            (`frac`) and the burst peak (`frac_burst`), with the SM clock median of that window
+  train     BASELINE config 5 (Stage-1 L1 step, batch 32 per GPU, NCCL gradient all-reduce) at the same N
+  cpu_baseline / gpu_eager_baseline (N = 1): the reference's forward on the host cores, and the same PyTorch
+            module run eagerly on the B200 (cuDNN; fp32 and bf16 channels_last) - the "kernel to beat"
+--impl reference: the reference's own CPU forward (the unmodified module from baseline/_ref when it is there,
+else the oracle port) on the box's host cores, batch 64 per step like the repo arm.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -34,19 +39,38 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+METRIC = "SR images/sec (64->256)"
+UNIT = "images/s"
 FLOP_PER_IMAGE = 44.633e9          # 22 316 703 744 MAC x 2, forward, 64x64 -> 256x256
 CONV64_FLOP_PER_IMAGE = 2.0 * 4096 * 64 * 64 * 9   # one 64->64 3x3 conv on a 64x64 map
 MODEL_CFG = dict(num_groups=6, blocks_per_group=10)
-WORKLOAD = "FaceEnhanceNet 6x10x64 bf16 inference, batch 64/GPU, synthetic 64x64 -> 256x256 (BASELINE config 2)"
+WORKLOAD = "FaceEnhanceNet 6x10x64 inference, batch 64/GPU, synthetic 64x64 -> 256x256 (BASELINE config 2)"
+TRAIN_WORKLOAD = ("Stage-1 L1 training step (float LR generation, forward, L1, backward, NCCL gradient all-reduce, "
+                  "clip 0.5 + AdamW), FaceEnhanceNet 6x10x64, batch 32/GPU, random-init T1 weights (BASELINE config 5)")
+
+
+def source_hash() -> str:
+    """Hash of the CUDA sources: profile-derived numbers (roofline.traffic) are only valid for the build they were
+    captured on."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "face-super-resolution_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            with open(os.path.join(d, f), "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 def ncu_traffic(batch: int):
-    """DRAM bytes per launch of the body kernel from the committed `ncu --set full` capture (profiles/)."""
+    """DRAM bytes per launch of the body kernel from the committed `ncu --set full` capture (profiles/).  The capture
+    is stamped with the source hash of the build it was taken on; a stale stamp gives null, not a stale number."""
     path = os.path.join(ROOT, "profiles", "body_kernel_traffic.json")
     try:
         with open(path) as f:
             d = json.load(f)
-        return float(d["dram_bytes_per_launch"]) if int(d.get("batch", -1)) == batch else None
+        if int(d.get("batch", -1)) != batch or d.get("src_hash") != source_hash():
+            return None
+        return float(d["dram_bytes_per_launch"])
     except (OSError, ValueError, KeyError):
         return None
 
@@ -108,70 +132,152 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_forward_rate(batch: int, budget_s: float, min_iters: int = 2):
-    """images/s of the fp32 CPU oracle (port of the reference forward) with all host threads."""
+# ===================================================================== the reference's CPU forward
+def reference_forward_fn():
+    """(callable(x) -> sr, kind, description).  The unmodified reference module when baseline/_ref holds it (the
+    driver-visible copy __graft_entry__.build() makes where /root/reference exists), else the oracle port - the same
+    ATen ops driven by a state_dict.  T1 weights either way (the literal init makes forward == clamp(bicubic))."""
     import torch
     from oracle import fen_oracle, weights
+    sd = weights.make_state_dict(0, "T1", **MODEL_CFG)
+    for base in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.isdir(os.path.join(base, "src", "models")):
+            try:
+                sys.path.insert(0, base)
+                from src.models.custom import FaceEnhanceNet as RefNet   # noqa: E402
+                m = RefNet(num_channels=64, scale_factor=4, **MODEL_CFG)
+                m.load_state_dict(sd, strict=True)
+                m.eval()
+                return (lambda x: m(x)), "reference", f"unmodified reference module from {base}"
+            except Exception:      # missing dependency of the reference package: fall through to the port
+                sys.path.remove(base)
+    return (lambda x: fen_oracle.fen_forward(sd, x)), "port", "oracle/fen_oracle.py (port of the reference forward)"
+
+
+def cpu_forward_rate(batch: int, budget_s: float, min_iters: int = 1):
+    """images/s of the reference's fp32 CPU forward with all host threads, batch `batch` per call."""
+    import torch
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    sd = weights.make_state_dict(0, "T1", **MODEL_CFG)
+    fwd, kind, desc = reference_forward_fn()
     x = torch.rand(batch, 3, 64, 64, generator=torch.Generator().manual_seed(0))
     with torch.no_grad():
-        fen_oracle.fen_forward(sd, x)  # warm-up
+        fwd(x[: min(batch, 8)])  # warm-up
         t0, n = time.perf_counter(), 0
         while n < min_iters or (time.perf_counter() - t0 < budget_s and n < 100):
-            fen_oracle.fen_forward(sd, x)
+            fwd(x)
             n += 1
         dt = time.perf_counter() - t0
-    return batch * n / dt, threads, n, dt
+    return batch * n / dt, threads, n, dt, kind, desc
 
 
 def run_reference(args, rank: int):
-    """--impl reference: the reference's CPU forward (oracle port) on the host cores, rank 0 only."""
+    """--impl reference: the reference's CPU forward on the host cores, rank 0 only, batch 64 per step."""
     if rank != 0:
         return
     import torch
-    from oracle import fen_oracle, weights
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    sample_batch = 8
-    sd = weights.make_state_dict(0, "T1", **MODEL_CFG)
-    x = torch.rand(sample_batch, 3, 64, 64, generator=torch.Generator().manual_seed(0))
+    fwd, kind, desc = reference_forward_fn()
+    B = args.batch
+    x = torch.rand(B, 3, 64, 64, generator=torch.Generator().manual_seed(0))
     with torch.no_grad():
-        for _ in range(max(1, args.warmup)):
-            fen_oracle.fen_forward(sd, x)
+        for _ in range(max(1, min(args.warmup, 3))):
+            fwd(x)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            fen_oracle.fen_forward(sd, x)
+            fwd(x)
         dt = time.perf_counter() - t0
-    value = sample_batch * args.steps / dt
-    sample = f"{sample_batch} images per step (bounded sample of the batch-64 workload), fp32, torch {torch.__version__}"
+    value = B * args.steps / dt
+    sample = f"{args.steps} fp32 forwards of batch {B} on {threads} host threads, torch {torch.__version__}; {desc}"
     line = {
-        "impl": "reference", "metric": "SR images/sec (64->256)", "value": value, "unit": "images/s",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": WORKLOAD, "global_batch": B, "parallelism": "host CPU (rank 0 only)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-TRAIN_WORKLOAD = ("Stage-1 L1 training step (float LR generation, forward, L1, backward, NCCL gradient all-reduce, "
-                  "clip 0.5 + AdamW), FaceEnhanceNet 6x10x64, batch 32/GPU, random-init T1 weights (BASELINE config 5)")
+# ===================================================================== BASELINE config 5: the Stage-1 step
+def train_record(args, rank: int, local_rank: int, world: int, dev, steps: int, warmup: int, B: int = 32):
+    """Times training.Stage1Step.step (float LR generation, forward, L1, backward, NCCL all-reduce, clip + AdamW) on
+    `B` synthetic 256x256 HR images per GPU.  Returns the record on rank 0 (None elsewhere).  Collective: called by
+    every rank."""
+    import torch
+    import fsr_b200
+    from fsr_b200 import _lib, sharding
+    from oracle import weights
+    lib = _lib.load()
+    model = fsr_b200.FaceEnhanceNet(**MODEL_CFG)
+    model.load_state_dict(weights.make_state_dict(0, "T1", **MODEL_CFG), strict=True)
+    model = model.to(dev).train()
+    stepper = fsr_b200.Stage1Step(model)
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+    pool = [torch.rand(B, 3, 256, 256, device=dev, generator=gen) for _ in range(8)]   # 8 x 25 MB > 126 MB L2
+    for i in range(warmup):
+        stepper.step(pool[i % 8])
+    n_launch = stepper.last_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(n, exchange):
+        stepper.exchange = exchange
+        torch.cuda.synchronize(); sharding.barrier()
+        e0.record()
+        for i in range(n):
+            loss, _ = stepper.step(pool[(warmup + i) % 8])
+        e1.record(); torch.cuda.synchronize(); sharding.barrier()
+        return sharding.max_over_ranks(e0.elapsed_time(e1), dev), loss
+
+    ms_total, loss = timed(steps, True)
+    ms_nocomm = timed(steps, False)[0] if world > 1 else ms_total
+    stepper.exchange = True
+    # e2e: pinned host HR batch -> H2D -> step -> loss read back on the host, every step
+    host = [torch.rand(B, 3, 256, 256).pin_memory() for _ in range(2)]
+    for i in range(2):
+        stepper.step(host[i & 1].to(dev, non_blocking=True))[0].item()
+    torch.cuda.synchronize(); sharding.barrier()
+    e0.record()
+    for i in range(steps):
+        loss_host = stepper.step(host[i & 1].to(dev, non_blocking=True))[0].item()
+    e1.record(); torch.cuda.synchronize(); sharding.barrier()
+    ms_e2e = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+    del stepper, model, pool
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    peaks = measured_peaks()
+    value = world * B * steps / (ms_total * 1e-3)
+    step_tflops = value / world * 3 * FLOP_PER_IMAGE / 1e12
+    return {
+        "workload": TRAIN_WORKLOAD, "value": value, "unit": UNIT, "ms_per_step": ms_total / steps,
+        "steps": steps, "warmup": warmup, "batch_per_gpu": B, "n_gpus": world,
+        "allreduce_exposed_us": max(0.0, (ms_total - ms_nocomm) / steps * 1e3),
+        "allreduce": stepper_exchange_description(world),
+        "gpu_launches_per_step": n_launch,
+        "e2e": {"value": world * B * steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 3 * 256 * 256 * 4,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / steps, "last_loss": loss_host},
+        "step_tflops": step_tflops, "step_frac": step_tflops / peaks["bf16_sustained"],
+        "step_frac_burst": step_tflops / peaks["bf16_burst"],
+    }
+
+
+def stepper_exchange_description(world: int) -> str:
+    if world == 1:
+        return "none (1 GPU)"
+    from fsr_b200 import training
+    return training.EXCHANGE_DESCRIPTION
 
 
 def run_train(args, rank: int, local_rank: int, world: int):
-    """--workload train: BASELINE config 5.  One step = training.Stage1Step.step on a batch of 32 synthetic
-    256x256 HR images per GPU; data parallel under torchrun (one NCCL all-reduce of the flat gradient per step)."""
+    """--workload train: BASELINE config 5 as its own bench line."""
     import torch
     import torch.distributed as dist
     import __graft_entry__ as entry
     entry.build()
-    import fsr_b200
-    from fsr_b200 import _lib, data, sharding, training
-    from oracle import fen_oracle, weights
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -179,79 +285,74 @@ def run_train(args, rank: int, local_rank: int, world: int):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    warmup, B, lib = max(3, args.warmup), (32 if args.batch == 64 else args.batch), _lib.load()
-    model = fsr_b200.FaceEnhanceNet(**MODEL_CFG)
-    model.load_state_dict(weights.make_state_dict(0, "T1", **MODEL_CFG), strict=True)
-    model = model.to(dev).train()
-    stepper = fsr_b200.Stage1Step(model)
-    gen = torch.Generator(device=dev).manual_seed(99 + rank)
-    pool = [torch.rand(B, 3, 256, 256, device=dev, generator=gen) for _ in range(8)]   # 8 x 25 MB > 126 MB L2
-    # kernels per step, counted once by hand through the same calls Stage1Step.step makes
-    lr_img, _ = data.lr_from_hr_float(pool[0]); n_launch = lib.fen_last_launch_count()
-    sr, ws = model._forward_train(lr_img); n_launch += lib.fen_last_launch_count()
-    _, dsr = training.l1_loss(sr, pool[0]); n_launch += 2
-    model._backward(lr_img, dsr, ws); n_launch += lib.fen_last_launch_count() + 3
-    for i in range(warmup):
-        stepper.step(pool[i % 8])
-    torch.cuda.synchronize(); sharding.barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        loss, _ = stepper.step(pool[(warmup + i) % 8])
-    e1.record(); torch.cuda.synchronize(); sharding.barrier()
-    ms_total = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+    rec = train_record(args, rank, local_rank, world, dev, args.steps, max(3, args.warmup),
+                       32 if args.batch == 64 else args.batch)
     clocks = sampler.stop() if rank == 0 else None
-    value = world * B * args.steps / (ms_total * 1e-3)
-    # e2e: pinned host HR batch -> H2D -> step -> loss read back on the host, every step
-    host = [torch.rand(B, 3, 256, 256).pin_memory() for _ in range(2)]
-    for i in range(warmup):
-        stepper.step(host[i & 1].to(dev, non_blocking=True))[0].item()
-    torch.cuda.synchronize(); sharding.barrier()
-    e0.record()
-    for i in range(args.steps):
-        loss_host = stepper.step(host[i & 1].to(dev, non_blocking=True))[0].item()
-    e1.record(); torch.cuda.synchronize(); sharding.barrier()
-    ms_e2e = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
         return
     peaks = measured_peaks()
-    step_tflops = value / world * 3 * FLOP_PER_IMAGE / 1e12
     line = {
-        "metric": "Stage-1 training images/sec (L1, 64->256, bf16 activations, fp32 master weights)", "value": value,
-        "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": TRAIN_WORKLOAD, "global_batch": world * B,
-                   "parallelism": f"data parallel x{world}, one NCCL all-reduce of the 20.5 MB fp32 gradient per step",
-                   "l2": "HR batches rotate through a 201 MB pool (> 126 MB L2); the step keeps 3.8 GB of activations"},
-        "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "images/s",
-                "h2d_bytes_per_step": B * 3 * 256 * 256 * 4, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
-                "last_loss": loss_host},
-        "gpu_launches": n_launch * args.steps,
+        "metric": "Stage-1 training images/sec (L1, 64->256, bf16 activations, fp32 master weights)",
+        "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": rec["warmup"],
+        "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": TRAIN_WORKLOAD, "global_batch": world * rec["batch_per_gpu"],
+                   "parallelism": f"data parallel x{world}: {rec['allreduce']}",
+                   "l2": "HR batches rotate through a 201 MB pool (> 126 MB L2); the step keeps ~4 GB of activations"},
+        "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches_per_step"] * args.steps,
+        "allreduce_exposed_us": rec["allreduce_exposed_us"],
         "roofline": {"bound": "tensor", "kernel": "whole step (forward + backward = 3 x 44.633 GFLOP per image)",
-                     "achieved": step_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": step_tflops / peaks["bf16_sustained"], "traffic": None,
+                     "achieved": rec["step_tflops"], "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                     "frac": rec["step_frac"], "frac_burst": rec["step_frac_burst"], "traffic": None,
                      "peak_source": peaks["source"] + " bf16_tflops_sustained"},
         "clocks": clocks,
     }
-    if not args.no_cpu_baseline and world == 1:
-        threads = os.cpu_count() or 1
-        torch.set_num_threads(threads)
-        sd = weights.make_state_dict(0, "T1", **MODEL_CFG)
-        x = torch.rand(2, 3, 64, 64)
-        dout = torch.full((2, 3, 256, 256), 1.0 / (2 * 3 * 256 * 256))
-        fen_oracle.fen_backward(sd, x, dout)
-        t0, n = time.perf_counter(), 0
-        while n < 2 or (time.perf_counter() - t0 < 10.0 and n < 50):
-            fen_oracle.fen_backward(sd, x, dout); n += 1
-        dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": 2 * n / dt, "unit": "images/s", "cores": threads, "kind": "port",
-                                "sample": f"{n} fp32 forward + backward passes of batch 2 in {dt:.1f} s (autograd oracle)"}
     print(json.dumps(line), flush=True)
+
+
+# ===================================================================== the reference module, eager, on the GPU
+def gpu_eager_baseline(dev, B: int):
+    """SURVEY 2.1's "kernel to beat": the reference's PyTorch module run eagerly on the same B200 (cuDNN convolutions,
+    ~700 launches per forward).  fp32 with TF32 off (the reference's numerics) and bf16 channels_last (the fastest
+    stock setting).  Never on the product path; timed after the product's numbers."""
+    import torch
+    import torch.nn.functional as F
+    from oracle import fen_oracle, weights
+    sd = weights.make_state_dict(0, "T1", **MODEL_CFG)
+    out = {}
+    x = torch.rand(B, 3, 64, 64, device=dev)
+    for name, dtype, cl in (("fp32", torch.float32, False), ("bf16_channels_last", torch.bfloat16, True)):
+        try:
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+            sdd = {k: v.to(dev, dtype) for k, v in sd.items()}
+            if cl:
+                sdd = {k: (v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v) for k, v in sdd.items()}
+            xx = x.to(dtype)
+            if cl:
+                xx = xx.contiguous(memory_format=torch.channels_last)
+            with torch.no_grad():
+                for _ in range(2):
+                    fen_oracle._forward(sdd, xx, False, 0.2, 4, None)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n = 5
+                e0.record()
+                for _ in range(n):
+                    fen_oracle._forward(sdd, xx, False, 0.2, 4, None)
+                e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n
+            out[name] = {"value": B / ms * 1e3, "unit": UNIT, "ms_per_step": ms}
+        except Exception as exc:   # a baseline that fails must not take the bench line with it
+            out[name] = {"error": str(exc)[:200]}
+    out["what"] = ("the reference forward (same ATen ops as src/models/custom.py:147-190) eager on this GPU through "
+                   "cuDNN, batch %d, resident inputs; not the product path" % B)
+    return out
 
 
 def main():
@@ -262,6 +363,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the config-5 sub-record")
+    ap.add_argument("--no-eager", action="store_true", help="skip the eager-PyTorch-on-GPU baseline")
     ap.add_argument("--workload", default="infer", choices=["infer", "train"],
                     help="infer = the headline (BASELINE config 2); train = the Stage-1 step (config 5)")
     args = ap.parse_args()
@@ -328,78 +431,83 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms_total * 1e-3)
 
-    # ---- e2e: pinned host LR batch -> H2D -> forward -> D2H of the SR batch, every step, through the
-    # public API (model(x)).  The D2H of step i runs on a copy stream and overlaps the forward of step
-    # i+1 (two pinned output buffers); every byte of every step is still moved inside the timed region.
+    # ---- e2e: pinned host LR batch -> H2D -> forward -> D2H of the SR batch, every step, through the public API.
+    # The D2H of step i runs on a copy stream and overlaps the forward of step i+1 (two pinned output buffers); every
+    # byte of every step is still moved inside the timed region.  `u8`: model.forward_u8 (uint8 HWC out).
     host_in = [torch.rand(B, 3, 64, 64).pin_memory() for _ in range(4)]
-    host_out = [torch.empty(B, 3, 256, 256).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
-    done = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_step(i):
-        with torch.no_grad():
-            x = host_in[i % 4].to(dev, non_blocking=True)
-            y = model(x)
-            ready = torch.cuda.Event()
-            ready.record()
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(ready)
-                done[i & 1].synchronize() if i >= 2 else None   # pinned buffer i&1 is free again
-                host_out[i & 1].copy_(y, non_blocking=True)
-                y.record_stream(copy_stream)
-                done[i & 1].record(copy_stream)
+    def e2e_leg(u8: bool):
+        host_out = [(torch.empty(B, 256, 256, 3, dtype=torch.uint8) if u8 else torch.empty(B, 3, 256, 256)).pin_memory()
+                    for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
 
-    for i in range(warmup):
-        e2e_step(i)
-    torch.cuda.synchronize()
-    sharding.barrier()
-    e0.record()
-    for i in range(args.steps):
-        e2e_step(i)
-    torch.cuda.current_stream().wait_stream(copy_stream)
-    e1.record()
-    torch.cuda.synchronize()
-    sharding.barrier()
-    ms_e2e = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
-    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+        def e2e_step(i):
+            with torch.no_grad():
+                x = host_in[i % 4].to(dev, non_blocking=True)
+                y = model.forward_u8(x) if u8 else model(x)
+                ready = torch.cuda.Event()
+                ready.record()
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(ready)
+                    done[i & 1].synchronize() if i >= 2 else None   # pinned buffer i&1 is free again
+                    host_out[i & 1].copy_(y, non_blocking=True)
+                    y.record_stream(copy_stream)
+                    done[i & 1].record(copy_stream)
 
-    # ---- roofline of the dominant kernel: body2_umma_kernel (all 127 64->64 3x3 convs of the body in one
-    # persistent launch, 86 % of the FLOPs).  Its launches are timed with CUDA events recorded on the
-    # launch stream by the library itself (fen_profile_body) during extra forwards of the same workload.
-    n_body_convs = MODEL_CFG["num_groups"] * (2 * MODEL_CFG["blocks_per_group"] + 1) + 1
-    lib.fen_profile_body(1)
-    body_ms = []
-    for i in range(max(5, min(args.steps, 20))):
-        step(i)
-        body_ms.append(lib.fen_last_body_ms())
-    lib.fen_profile_body(0)
-    body_ms = [m for m in body_ms if m > 0]
-    peaks = measured_peaks()
-    if body_ms:
-        k_ms = sum(body_ms) / len(body_ms)
-        k_name = "body2_umma_kernel (127 x 64->64 3x3 conv + SE + residuals in one persistent launch, batch %d)" % B
-        k_flop = CONV64_FLOP_PER_IMAGE * B * n_body_convs
-    else:  # configurations the persistent kernel does not cover fall back to per-layer launches
-        act = [torch.randn(B, 64, 64, 64, device=dev).mul_(0.3).to(torch.bfloat16) for _ in range(2)]
-        w = torch.randn(64, 64, 3, 3, device=dev) * 0.05
-        wp = torch.empty(9 * 64 * 64, dtype=torch.bfloat16, device=dev)
-        bias = torch.zeros(64, device=dev)
-        st = torch.cuda.current_stream().cuda_stream
-        _lib.check(lib.fen_pack_conv3x3(w.data_ptr(), 64, 64, wp.data_ptr(), st), "fen_pack_conv3x3")
-        for i in range(46):
-            if i == 6:
-                torch.cuda.synchronize()
-                e0.record()
-            _lib.check(lib.fen_conv3x3_c64(act[i & 1].data_ptr(), wp.data_ptr(), bias.data_ptr(), None, None, None,
-                                           act[(i + 1) & 1].data_ptr(), B, 64, 64, 5, st), "fen_conv3x3_c64")
+        for i in range(warmup):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        sharding.barrier()
+        e0.record()
+        for i in range(args.steps):
+            e2e_step(i)
+        torch.cuda.current_stream().wait_stream(copy_stream)
         e1.record()
         torch.cuda.synchronize()
-        k_ms = e0.elapsed_time(e1) / 40
-        k_name = "conv3x3_umma_kernel<64> (64->64 3x3 conv, batch %d)" % B
-        k_flop = CONV64_FLOP_PER_IMAGE * B
+        sharding.barrier()
+        ms = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
+        return {"value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 3 * 64 * 64 * 4,
+                "d2h_bytes_per_step": host_out[0].numel() * host_out[0].element_size(), "ms_per_step": ms / args.steps}
+
+    e2e = e2e_leg(False)
+    e2e_u8 = e2e_leg(True)
+
+    # ---- roofline of the dominant kernel: body2_umma_kernel (all 127 64->64 3x3 convs of the body in one persistent
+    # launch, 86 % of the FLOPs).  Its launches are timed with CUDA events recorded on the launch stream by the
+    # library itself (fen_profile_body) over >= 2 s of back-to-back forwards of the same workload, with the SM clock
+    # sampled over that window: the sustained-peak denominator is earned under the same kind of load.
+    n_body_convs = MODEL_CFG["num_groups"] * (2 * MODEL_CFG["blocks_per_group"] + 1) + 1
+    roof_sampler = ClockSampler(local_rank)
+    if rank == 0:
+        roof_sampler.start()
+    lib.fen_profile_body(1)
+    body_ms, t_begin, i = [], time.perf_counter(), 0
+    while (time.perf_counter() - t_begin < 2.0 or len(body_ms) < 20) and len(body_ms) < 5000:
+        step(i); i += 1
+        body_ms.append(lib.fen_last_body_ms())
+    lib.fen_profile_body(0)
+    window_s = round(time.perf_counter() - t_begin, 2)
+    roof_clocks = roof_sampler.stop() if rank == 0 else None
+    body_ms = [m for m in body_ms if m > 0]
+    peaks = measured_peaks()
+    k_ms = sum(body_ms) / len(body_ms)
+    k_name = "body2_umma_kernel (127 x 64->64 3x3 conv + SE + residuals in one persistent launch, batch %d)" % B
+    k_flop = CONV64_FLOP_PER_IMAGE * B * n_body_convs
     conv_tflops = k_flop / (k_ms * 1e-3) / 1e12
-    conv_ms = k_ms
     step_tflops = value / world * FLOP_PER_IMAGE / 1e12
+
+    # ---- BASELINE config 5 at the same N (driver-visible record of the NCCL path)
+    train = None
+    if not args.no_train:
+        del pool
+        model._workspaces.clear()
+        torch.cuda.empty_cache()
+        train = train_record(args, rank, local_rank, world, dev, steps=6, warmup=3)
+
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager:
+        eager = gpu_eager_baseline(dev, B)
 
     if world > 1:
         dist.destroy_process_group()
@@ -408,29 +516,37 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        rate, threads, n, dt = cpu_forward_rate(batch=1, budget_s=12.0)
-        cpu = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": f"{n} fp32 forwards of batch 1 in {dt:.1f} s (protocol of scripts/measure_inference_time.py:68-116)"}
+        rate, threads, n, dt, kind, desc = cpu_forward_rate(batch=B, budget_s=12.0)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"{n} fp32 forwards of batch {B} in {dt:.1f} s on {threads} host threads; {desc} "
+                         "(same call as --impl reference)"}
 
     line = {
-        "metric": "SR images/sec (64->256, bf16)", "value": value, "unit": "images/s", "n_gpus": world,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"batch-sharded x{world}, no collective",
                    "l2": f"inputs rotate through a {pool_n * B * 3 * 64 * 64 * 4 / 1e6:.0f} MB pool (> 126 MB L2); "
                          "per-step activation working set ~1 GB"},
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": B * 3 * 64 * 64 * 4,
-                "d2h_bytes_per_step": B * 3 * 256 * 256 * 4, "ms_per_step": ms_e2e / args.steps},
+        "e2e": e2e, "e2e_u8": e2e_u8,
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "tensor", "kernel": k_name,
                      "achieved": conv_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": conv_tflops / peaks["bf16_sustained"], "traffic": ncu_traffic(B) if body_ms else None,
-                     "peak_source": peaks["source"] + " bf16_tflops_sustained", "us_per_launch": conv_ms * 1e3,
-                     "step_achieved": step_tflops, "step_frac": step_tflops / peaks["bf16_sustained"]},
+                     "frac": conv_tflops / peaks["bf16_sustained"], "frac_burst": conv_tflops / peaks["bf16_burst"],
+                     "peak_burst": peaks["bf16_burst"], "traffic": ncu_traffic(B),
+                     "peak_source": peaks["source"] + " bf16_tflops_sustained (frac) / bf16_tflops (frac_burst)",
+                     "us_per_launch": k_ms * 1e3, "launches_timed": len(body_ms),
+                     "window_s": window_s, "clocks": roof_clocks,
+                     "step_achieved": step_tflops, "step_frac": step_tflops / peaks["bf16_sustained"],
+                     "step_frac_burst": step_tflops / peaks["bf16_burst"]},
         "clocks": clocks,
     }
+    if train is not None:
+        line["train"] = train
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if eager is not None:
+        line["gpu_eager_baseline"] = eager
     print(json.dumps(line), flush=True)
 
 

@@ -29,6 +29,8 @@ SIGNATURES = {
     "fen_forward_workspace_bytes": (C.c_int64, [C.POINTER(FenConfig), C.c_int, C.c_int, C.c_int]),
     "fen_forward": (C.c_int, [C.POINTER(FenConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                               C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "fen_forward_u8": (C.c_int, [C.POINTER(FenConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "fen_forward_tap": (C.c_int64, [C.POINTER(FenConfig), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.POINTER(C.c_void_p)]),
     "fen_lr_from_hr_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libfen_b200.so")
 SOURCES = ["fen_b200.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC",
+    "-shared", "-Xcompiler", "-fPIC", "-cudart", "shared", "-diag-suppress", "128",
 ]
 
 
@@ -61,5 +61,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def build_variant(name: str, defines, verbose: bool = False) -> str:
+    """Developer builds next to the product library (A/B runs, traces): variants/libfen_b200_<name>.so compiled with
+    the given -D flags.  Select one with FEN_B200_LIB=<path>; never loaded by default."""
+    out_dir = os.path.join(PKG_DIR, "variants")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, f"libfen_b200_{name}.so")
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+    if len(sys.argv) > 2 and sys.argv[1] == "variant":      # python build.py variant <name> [DEFINE ...]
+        print(build_variant(sys.argv[2], sys.argv[3:], verbose=True))
+    else:
+        print(build(force=True, verbose=True))

@@ -50,6 +50,9 @@ constexpr int kB2EpiWarps = 8;
 constexpr int kB2AccBufs = 7;                      // 7 x 64 TMEM columns for conv tiles ...
 constexpr uint32_t kB2SeCol = kB2AccBufs * kC;     // ... + 64 columns for the SE mat-vec
 constexpr int kB2SBytes = 9 * 1024;                // SE operand: one 8-row SWIZZLE_128B atom per tap
+#ifndef FEN_B2_TURN
+#define FEN_B2_TURN 0   // 1: the two MMA issuers alternate strictly (tile G is issued only after tile G - 1 has been enqueued)
+#endif
 #ifndef FEN_B2_STAGED_STORE
 #define FEN_B2_STAGED_STORE 0   // 1: outputs go through a shared-memory transpose to coalesced stores (measured slower)
 #endif
@@ -72,12 +75,12 @@ constexpr int kB2MaxBufs = 12;   // 5 + num_groups <= 12
 struct Body2Maps {
   CUtensorMap act[kB2MaxBufs];
   CUtensorMap w;
-  CUtensorMap st[kB2MaxBufs];
 };
 
 struct Body2Params : BodyParams {
   int nset;      // 1 or 2 interleaved image sets
   int set_B;     // images per set (B = nset * set_B)
+  const float* cvec;   // bias / slope table in the packed blob (BodyLayer::cv_bias / cv_slope index it), 512 B readable past any cv_bias
 };
 
 __device__ __forceinline__ float2 ld_cg_f32x2(const float* p) {
@@ -102,6 +105,13 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src_
                : "l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// plain (non-tensor) bulk copy global -> shared, completion on an mbarrier; 16-byte aligned, size a multiple of 16
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :
+               : "r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void st_shared_u32(uint32_t saddr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
@@ -118,6 +128,9 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
   __shared__ uint64_t bar_w[9], bar_wfree[9], bar_full[kB2Slots], bar_empty[kB2Slots];
   __shared__ uint64_t bar_acc_full[kB2AccBufs], bar_acc_empty[kB2AccBufs];
   __shared__ uint64_t bar_done, bar_s_ready, bar_s_free, bar_se_full, bar_se_empty, bar_scale[2];
+  __shared__ uint64_t bar_cv[2];                       // per-layer bias / slope vectors staged by the TMA warp (slot L & 1)
+  __shared__ __align__(16) float s_cv[2][128];
+  __shared__ uint64_t bar_turn;                        // FEN_B2_TURN: phase G completes when tile G (running index) is enqueued
   __shared__ uint32_t tmem_slot;
   // per-pass tables, one set of them per image set (the two sets give a CTA runs of different length)
   __shared__ B2Tile tile_tab2[2][kB2MaxTiles];
@@ -193,6 +206,8 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
     mbar_init(&bar_done, kB2EpiWarps);
     mbar_init(&bar_s_ready, 1); mbar_init(&bar_s_free, 1); mbar_init(&bar_se_full, 1); mbar_init(&bar_se_empty, 1);
     mbar_init(&bar_scale[0], 1); mbar_init(&bar_scale[1], 1);
+    mbar_init(&bar_turn, 1);
+    mbar_init(&bar_cv[0], 1); mbar_init(&bar_cv[1], 1);
     fence_mbar_init();
     tma_prefetch_desc(&maps.w);
   }
@@ -247,6 +262,10 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
       if (lane == 0) {
         B2TRACE(P, 0);
         issue_boxes(0, 0, pre);
+        // bias (+ slope) of this layer -> s_cv[L & 1].  The slot was last read by the epilogue of layer L - 2, which
+        // is complete: wait_flags saw this CTA's own flag reach L, i.e. its epilogue has finished layer L - 1.
+        mbar_expect_tx(&bar_cv[L & 1], 512);
+        bulk_load_1d(smem_u32(&s_cv[L & 1][0]), p.cvec + ly.cv_bias, 512, &bar_cv[L & 1]);
         for (int tap = 0; tap < 9; ++tap) {     // weights, tap by tap, as soon as the previous layer released the tap
           B2W(1, 1, L, 0, tap);
           if (L > 0) mbar_wait(&bar_wfree[tap], (L - 1) & 1);
@@ -382,6 +401,12 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           if (leader && i == wi) B2TRACE(P, 1 + wi);
           B2W(2 + wi, 4, L, s, i);
           if (leader) B2T2(P, 6, i);
+#if FEN_B2_TURN
+          // Strict alternation.  Left alone the two issuers fall into lock-step (they share the pipe at half rate,
+          // finish together and then do their per-tile barrier work together with the pipe idle); with the turn
+          // token one issuer's bookkeeping always runs under the other one's 36 MMAs.
+          if (n_issuers == 2 && G > 0) mbar_wait(&bar_turn, (G - 1) & 1);
+#endif
           __syncwarp();                            // converge after the spin-waits (see the commits below)
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * N;
@@ -413,6 +438,9 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
             for (int tap = 0; tap < 9; ++tap) FEN_B2_ISSUE_TAP(tap)
           }
           w_seen = true;
+#if FEN_B2_TURN
+          if (leader && n_issuers == 2) mbar_arrive(&bar_turn);
+#endif
           __syncwarp();
           if (leader) B2T2(P, 7, i);
           // A box may only be handed back after THIS warp has seen it arrive (the last boxes of a pass are
@@ -542,7 +570,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
               for (int k = 0; k < 16; ++k) {
                 const float4 hi = *reinterpret_cast<const float4*>(&s_raw[2 * u][4 * k]);
                 const float4 lo = *reinterpret_cast<const float4*>(&s_raw[2 * u + 1][4 * k]);
-                const float4 b4 = *reinterpret_cast<const float4*>(c_vec + ly.cv_bias + 4 * k);
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.cvec + ly.cv_bias) + k);
                 const float4 w1 = __ldg(reinterpret_cast<const float4*>(fc0 + (lane & 15) * kC) + k);   // L1 hit (prefetched)
                 acc = fmaf(w1.x, fmaf(hi.x + lo.x, p.inv_hw, b4.x), acc);
                 acc = fmaf(w1.y, fmaf(hi.y + lo.y, p.inv_hw, b4.y), acc);
@@ -576,7 +604,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
         } else {
           for (int idx = lane; idx < n_units * kC; idx += 32) {
             const int u = idx >> 6, c = idx & 63;
-            s_mean[u][c] = c_vec[ly.cv_bias + c] + (s_raw[2 * u][c] + s_raw[2 * u + 1][c]) * p.inv_hw;
+            s_mean[u][c] = __ldg(p.cvec + ly.cv_bias + c) + (s_raw[2 * u][c] + s_raw[2 * u + 1][c]) * p.inv_hw;
           }
           __syncwarp();
           for (int idx = lane; idx < n_units * p.R; idx += 32) {        // FC1 + ReLU
@@ -619,15 +647,16 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
       bf16* outp = p.buf[ly.out];
       const bf16* resp = ly.res >= 0 ? p.buf[ly.res] : nullptr;
       float bias[CW], slope[CW];
+      mbar_wait(&bar_cv[L & 1], (L >> 1) & 1);
 #pragma unroll
       for (int j = 0; j < CW / 4; ++j) {
-        const float4 b4 = *reinterpret_cast<const float4*>(c_vec + ly.cv_bias + col0 + 4 * j);
+        const float4 b4 = *reinterpret_cast<const float4*>(&s_cv[L & 1][col0 + 4 * j]);
         bias[4 * j] = b4.x; bias[4 * j + 1] = b4.y; bias[4 * j + 2] = b4.z; bias[4 * j + 3] = b4.w;
       }
       if (ly.epi == kBEpiPreluHsum) {
 #pragma unroll
         for (int j = 0; j < CW / 4; ++j) {
-          const float4 s4 = *reinterpret_cast<const float4*>(c_vec + ly.cv_slope + col0 + 4 * j);
+          const float4 s4 = *reinterpret_cast<const float4*>(&s_cv[L & 1][64 + col0 + 4 * j]);   // cv_slope = cv_bias + 64
           slope[4 * j] = s4.x; slope[4 * j + 1] = s4.y; slope[4 * j + 2] = s4.z; slope[4 * j + 3] = s4.w;
         }
       }

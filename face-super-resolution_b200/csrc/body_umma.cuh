@@ -60,9 +60,10 @@ constexpr int kBSlotBytes = kBBoxPx * kC * 2;         // 16896
 constexpr int kBSlots = 7;
 constexpr int kBRingBytes = (kBSlots + 1) * kBSlotBytes;
 constexpr int kBodyDynBytes = kBodyWBytes + kBRingBytes + 1024;
-constexpr int kConstVecFloats = 15872;   // 62 KB of __constant__ for biases + slopes
-
+#ifdef FEN_DEV
+constexpr int kConstVecFloats = 15872;   // 62 KB of __constant__ for biases + slopes (first-generation kernel only)
 __device__ __constant__ float c_vec[kConstVecFloats];
+#endif
 
 enum BodyBuf : int { kBufF0 = 0, kBufX0 = 1, kBufX1 = 2, kBufH = 3, kBufO = 4 /* unused */, kBufG0 = 5 };  // G0.. = group outputs
 enum BodyEpi : int { kBEpiPreluHsum = 0, kBEpiSeResidual = 1, kBEpiResidual = 2 };
@@ -200,6 +201,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+#ifdef FEN_DEV   // first-generation persistent kernel: developer builds only (A/B runs), not in the shipped library
 __global__ void __launch_bounds__(kBodyThreads, 1)
 body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
   constexpr int N = kC;
@@ -745,4 +747,5 @@ body_umma_kernel(const __grid_constant__ BodyMaps maps, const BodyParams p) {
   if (warp == kBodyFirstMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+#endif  // FEN_DEV
 }  // namespace fen

@@ -285,8 +285,8 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
 
         const int lin = kTileM * t + row_in_tile;       // strip-linear output pixel
         const int y = lin / kPitch, xs = lin - y * kPitch;
-        const bool valid = (xs < kStripW) && (y < p.H);
         const int x = u.strip * kStripW + xs;
+        const bool valid = (xs < kStripW) && (y < p.H) && (x < p.W);   // (the last strip of a ragged width is partial)
 
         if constexpr (N == 16) {
           // ---- conv_last: + bias + bicubic x4 skip (+ clamp), fp32 NCHW
@@ -311,11 +311,15 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
               }
               float o = __uint_as_float(v[c]) + s_bias[c] + accv;
               if (!p.training) o = fminf(fmaxf(o, 0.f), 1.f);
-              p.out_f32[((size_t(u.n) * 3 + c) * p.H + y) * p.W + x] = o;
+              if (p.out_f32) p.out_f32[((size_t(u.n) * 3 + c) * p.H + y) * p.W + x] = o;
+              if (p.out_u8)    // the scripts' to_numpy (test_model.py:176-190): trunc(clip(v * 255, 0, 255)), HWC, optional BGR
+                p.out_u8[((size_t(u.n) * p.H + y) * p.W + x) * 3 + (p.bgr ? 2 - c : c)] =
+                    uint8_t(int(fminf(fmaxf(__fmul_rn(o, 255.0f), 0.f), 255.f)));
             }
           }
         } else {
           float f[CW];
+          uint32_t mbits = 0;
 #pragma unroll
           for (int j = 0; j < CW / 4; ++j) {
             const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[col0 + 4 * j]);
@@ -330,6 +334,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
               for (int c = 0; c < CW; ++c) csum[c] += f[c];
             }
           } else if (p.epi == kEpiPrelu || p.epi == kEpiShuffle) {
+            if (p.mask_out) {                     // training forward: the sign bits of the pre-activation
+#pragma unroll
+              for (int c = 0; c < CW; ++c) mbits |= (f[c] > 0.f ? 1u : 0u) << c;
+            }
 #pragma unroll
             for (int j = 0; j < CW / 4; ++j) {
               const float4 s4 = *reinterpret_cast<const float4*>(&s_slope[col0 + 4 * j]);
@@ -348,7 +356,9 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
               opix = (size_t(u.n) * p.H + y) * p.W + x;
             }
             bf16* dst = p.out + opix * kC + col0;
+            if ((p.epi == kEpiPrelu || p.epi == kEpiShuffle) && p.mask_out) p.mask_out[opix * 2 + half] = mbits;
             if (p.epi == kEpiGate) {
+              const uint32_t pos_bits = __ldg(p.mask_in + opix * 2 + half);
               const bf16* ap = p.residual + opix * kC + col0;
 #pragma unroll
               for (int j = 0; j < CW / 16; ++j) {
@@ -361,8 +371,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
                     const int c = 16 * j + 2 * e + hlf;
                     const float a = hlf ? bf16hi(r[e]) : bf16lo(r[e]);
                     const float sl = s_slope[col0 + c];
-                    csum[c] += a > 0.f ? 0.f : f[c] * (a / sl);
-                    f[c] = a > 0.f ? f[c] : f[c] * sl;
+                    const bool pos = (pos_bits >> c) & 1u;
+                    // negative side: pre-activation z = a / slope (slope == 0 loses z: that term is dropped)
+                    csum[c] += (pos || sl == 0.f) ? 0.f : f[c] * (a / sl);
+                    f[c] = pos ? f[c] : f[c] * sl;
                   }
                 }
               }

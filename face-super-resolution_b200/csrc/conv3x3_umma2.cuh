@@ -223,8 +223,8 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
 
       const int lin = kTileM * t + row_in_tile;       // strip-linear output pixel
       const int y = lin / kPitch, xs = lin - y * kPitch;
-      const bool valid = (xs < kStripW) && (y < p.H);
       const int x = un_strip * kStripW + xs;
+      const bool valid = (xs < kStripW) && (y < p.H) && (x < p.W);   // (the last strip of a ragged width is partial)
 
       if constexpr (N == 16) {
         // ---- conv_last: + bias + bicubic x4 skip (+ clamp), fp32 NCHW
@@ -249,7 +249,10 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
             }
             float o = __uint_as_float(v[c]) + s_bias[c] + accv;
             if (!p.training) o = fminf(fmaxf(o, 0.f), 1.f);
-            p.out_f32[((size_t(un_n) * 3 + c) * p.H + y) * p.W + x] = o;
+            if (p.out_f32) p.out_f32[((size_t(un_n) * 3 + c) * p.H + y) * p.W + x] = o;
+            if (p.out_u8)    // the scripts' to_numpy (test_model.py:176-190): trunc(clip(v * 255, 0, 255)), HWC, optional BGR
+              p.out_u8[((size_t(un_n) * p.H + y) * p.W + x) * 3 + (p.bgr ? 2 - c : c)] =
+                  uint8_t(int(fminf(fmaxf(__fmul_rn(o, 255.0f), 0.f), 255.f)));
           }
         }
       } else {

@@ -5,7 +5,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/fen_b200.h"
@@ -23,7 +25,6 @@ static thread_local std::string g_err;
 static thread_local int g_launches = 0;
 static long long* g_dbg = nullptr;
 static int g_time_body = 0;           // fen_profile_body(1): CUDA events around the persistent body kernel
-static cudaEvent_t g_body_ev[2] = {nullptr, nullptr};  // developer hook: per-CTA cycle counters of fen_conv3x3_c64
 
 static int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -77,9 +78,41 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
+// ---- cache of encoded tensor maps.  Encoding costs ~1 us on the host and a forward needs ~25 of them (a training
+// step ~1 300): maps are keyed by everything that goes into them and live for the life of the process.
+struct MapKey {
+  const void* ptr; int kind, a, b, c, d, e;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && kind == o.kind && a == o.a && b == o.b && c == o.c && d == o.d && e == o.e;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    for (int v : {k.kind, k.a, k.b, k.c, k.d, k.e}) h = h * 1000003u ^ std::hash<int>()(v);
+    return h;
+  }
+};
+static std::mutex g_map_mutex;
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+static bool map_lookup(const MapKey& k, CUtensorMap* m) {
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  auto it = g_map_cache.find(k);
+  if (it == g_map_cache.end()) return false;
+  *m = it->second;
+  return true;
+}
+static void map_store(const MapKey& k, const CUtensorMap& m) {
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  if (g_map_cache.size() > 16384) g_map_cache.clear();   // bounded: workspaces that came and went
+  g_map_cache[k] = m;
+}
+
 // NHWC bf16 activation [B][H][W][64]: box = 64 ch x 66 px x 4 rows, 128B swizzle, OOB -> zeros.
 static int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int box_rows = kBoxRows,
                         int box_px = kPitch) {
+  const MapKey key{ptr, 0, B, H, W, box_rows, box_px};
+  if (map_lookup(key, m)) return FEN_OK;
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(FEN_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[4] = {cuuint64_t(kC), cuuint64_t(W), cuuint64_t(H), cuuint64_t(B)};
@@ -90,27 +123,13 @@ static int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, in
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(FEN_ECUDA, "cuTensorMapEncodeTiled(activation) failed: " + std::to_string(int(r)));
-  return FEN_OK;
-}
-// NHWC bf16 activation [B][H][W][64] as a TMA STORE target: box = 32 ch x 32 px x 1 row, 64B swizzle
-// (the epilogue warps of the body kernel stage 32 pixels x 32 channels each).
-static int make_act_store_map(CUtensorMap* m, const void* ptr, int B, int H, int W) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return fail(FEN_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
-  cuuint64_t dims[4] = {cuuint64_t(kC), cuuint64_t(W), cuuint64_t(H), cuuint64_t(B)};
-  cuuint64_t strides[3] = {cuuint64_t(kC) * 2, cuuint64_t(W) * kC * 2, cuuint64_t(H) * W * kC * 2};
-  cuuint32_t box[4] = {32, 32, 1, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  const char* e1 = getenv("FEN_ST_SWZ"); const char* e2 = getenv("FEN_ST_L2");
-  CUtensorMapSwizzle swz = (e1 && e1[0] == '0') ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_64B;
-  CUtensorMapL2promotion l2 = (e2 && e2[0] == '0') ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, l2, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(FEN_ECUDA, "cuTensorMapEncodeTiled(store) failed: " + std::to_string(int(r)));
+  map_store(key, *m);
   return FEN_OK;
 }
 // packed weights [rows][64] bf16, box = 64 x N rows.
 static int make_w_map(CUtensorMap* m, const void* ptr, int rows, int n) {
+  const MapKey key{ptr, 1, rows, n, 0, 0, 0};
+  if (map_lookup(key, m)) return FEN_OK;
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(FEN_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {cuuint64_t(kC), cuuint64_t(rows)};
@@ -121,18 +140,45 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int rows, int n) {
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(FEN_ECUDA, "cuTensorMapEncodeTiled(weights) failed: " + std::to_string(int(r)));
+  map_store(key, *m);
   return FEN_OK;
 }
 
+// ---- per-device state: SM count and the "max dynamic shared memory" function attributes are properties of a
+// device, not of the process (one process may drive several GPUs).
+constexpr int kMaxDevices = 64;
+enum KernelId : int { kKConv64 = 0, kKConv16, kKConv2_64, kKConv2_16, kKBody, kKBody2, kKWgMma, kKWgUmma, kKLastDgrad,
+                      kKWgradC3, kKernelIds };
+struct DevState {
+  int sms = 0;
+  bool attr[kKernelIds] = {};
+  cudaEvent_t body_ev[2] = {nullptr, nullptr};
+};
+static DevState g_dev[kMaxDevices];
+static DevState& dev_state() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) dev = 0;
+  return g_dev[dev];
+}
 static int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
+  DevState& d = dev_state();
+  if (!d.sms) {
+    int dev = 0, n = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    d.sms = n > 0 ? n : 148;
   }
-  return n;
+  return d.sms;
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize, once per device and kernel
+template <typename K>
+static cudaError_t ensure_smem_attr(KernelId id, K kernel, int bytes) {
+  DevState& d = dev_state();
+  if (d.attr[id]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) d.attr[id] = true;
+  return e;
 }
 
 // ===================================================================== conv launcher
@@ -146,19 +192,14 @@ struct ConvArgs {
 
 template <int N>
 static int launch_conv_n(const ConvArgs& a, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    FEN_CUDA(cudaFuncSetAttribute(conv3x3_umma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  ConvCfg<N>::kDynBytes));
-    attr_set = true;
-  }
+  FEN_CUDA(ensure_smem_attr(N == 64 ? kKConv64 : kKConv16, conv3x3_umma_kernel<N>, ConvCfg<N>::kDynBytes));
   CUtensorMap tm_in, tm_w;
   int rc = make_act_map(&tm_in, a.x, a.p.B, a.p.H, a.p.W);
   if (rc) return rc;
   rc = make_w_map(&tm_w, a.w, a.groups * 9 * N, N);
   if (rc) return rc;
   ConvParams p = a.p;
-  p.strips = p.W / kStripW;
+  p.strips = (p.W + kStripW - 1) / kStripW;
   p.tiles_per_seg = (p.H * kPitch + kTileM - 1) / kTileM;
   p.total_tiles = p.B * p.strips * p.tiles_per_seg;
   const int ctas_y = a.groups;
@@ -167,19 +208,15 @@ static int launch_conv_n(const ConvArgs& a, cudaStream_t st) {
   p.tiles_per_cta = (p.total_tiles + ctas_x - 1) / ctas_x;
   ctas_x = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
   dim3 grid(ctas_x, ctas_y);
-  // second-generation (table-driven) kernel when a CTA's run fits its tables; FEN_CONV_KERNEL=1 forces the first
-  static int conv_version = -1;
-  if (conv_version < 0) { const char* e = getenv("FEN_CONV_KERNEL"); conv_version = (e && e[0] == '1') ? 1 : (e && e[0] == '3') ? 3 : 2; }
+  // The table-driven second generation serves conv_last (N = 16: 220 vs 240 us at batch 64) when a CTA's run fits its
+  // tables; the 64-wide convolutions measured faster on the first generation (285 vs 320 us for the upsample stages).
+  int conv_version = (N == 16) ? 2 : 1;
+#ifdef FEN_DEV
+  { const char* e = getenv("FEN_CONV_KERNEL"); if (e && e[0] == '1') conv_version = 1; else if (e && e[0] == '3') conv_version = 3; }
+#endif
   const int boxes_bound = p.tiles_per_cta * kTileM / kBoxPx + 3 * ((p.tiles_per_cta + p.tiles_per_seg - 1) / p.tiles_per_seg + 1);
-  // (measured at batch 64: conv_last 220 vs 240 us with the second generation, the 64-wide upsample convs
-  // 320 vs 285 us - their 3-slot ring starves either way - so only N = 16 takes it by default)
-  if ((conv_version == 2 && N == 16 || conv_version == 3) && p.epi < kEpiGate && p.tiles_per_cta <= kC2MaxTiles && boxes_bound <= kC2MaxBoxes) {
-    static bool attr2_set = false;
-    if (!attr2_set) {
-      FEN_CUDA(cudaFuncSetAttribute(conv3x3_umma2_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    ConvCfg<N>::kDynBytes));
-      attr2_set = true;
-    }
+  if ((conv_version == 2 && N == 16 || conv_version == 3) && p.epi < kEpiGate && !p.mask_out && p.tiles_per_cta <= kC2MaxTiles && boxes_bound <= kC2MaxBoxes) {
+    FEN_CUDA(ensure_smem_attr(N == 64 ? kKConv2_64 : kKConv2_16, conv3x3_umma2_kernel<N>, ConvCfg<N>::kDynBytes));
     conv3x3_umma2_kernel<N><<<grid, ConvCfg<N>::kThreads, ConvCfg<N>::kDynBytes, st>>>(tm_in, tm_w, p);
   } else {
     conv3x3_umma_kernel<N><<<grid, ConvCfg<N>::kThreads, ConvCfg<N>::kDynBytes, st>>>(tm_in, tm_w, p);
@@ -190,7 +227,7 @@ static int launch_conv_n(const ConvArgs& a, cudaStream_t st) {
 }
 
 static int launch_conv(const ConvArgs& a, cudaStream_t st) {
-  if (a.p.W % kStripW || a.p.H <= 0 || a.p.B <= 0) return fail(FEN_EINVAL, "conv: W must be a positive multiple of 64");
+  if (a.p.W <= 0 || a.p.H <= 0 || a.p.B <= 0) return fail(FEN_EINVAL, "conv: empty tensor");
   if (a.n == 64) return launch_conv_n<64>(a, st);
   if (a.n == 16) return launch_conv_n<16>(a, st);
   return fail(FEN_EINVAL, "conv: unsupported N");
@@ -271,6 +308,7 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
         acc[4 * j + 3] = fmaf(in[k], w4.w, acc[4 * j + 3]);
       }
     }
+    if (xx >= W) continue;   // ragged width (no barrier inside this loop)
     uint4* dst = reinterpret_cast<uint4*>(out + ((size_t(n) * H + y) * W + xx) * kC + q * 16);
     uint4 o0, o1;
     o0.x = pack_bf16(acc[0], acc[1]);   o0.y = pack_bf16(acc[2], acc[3]);
@@ -366,6 +404,81 @@ __global__ void __launch_bounds__(256) lr_from_hr_kernel(const uint8_t* __restri
       qv = min(max(qv, 0), 255);
       if (lr_u8) lr_u8[i * C + c] = uint8_t(qv);
       if (lr_f32) lr_f32[((size_t(n) * C + c) * h + y) * w + x] = float(qv) / 255.0f;
+    }
+  }
+}
+
+// The RGB case the pipeline runs (C = 3, W a multiple of 16, 16-byte aligned rows): one thread makes FOUR output pixels
+// from 4 rows x 48 contiguous bytes (three 128-bit loads per row) and writes 12 bytes of u8 (three 32-bit stores) and
+// three float4 of the normalised NCHW tensor.  Same integer arithmetic as lr_from_hr_kernel, bit for bit; the point is
+// bytes in flight per thread and whole-sector stores: the kernel is HBM bound (208 896 B per image).
+__global__ void __launch_bounds__(256) lr_from_hr_rgb4_kernel(const uint8_t* __restrict__ hr, uint8_t* __restrict__ lr_u8,
+                                                              float* __restrict__ lr_f32, int B, int H, int W) {
+  const int w = W >> 2, h = H >> 2, wq = w >> 2;
+  const size_t total = size_t(B) * h * wq;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const int xq = int(i % wq);
+    const int y = int((i / wq) % h);
+    const int n = int(i / (size_t(wq) * h));
+    const uint8_t* src = hr + ((size_t(n) * H + 4 * y) * W + 16 * xq) * 3;
+    int u[4][3];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) u[p][c] = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int ar = (r == 0 || r == 3) ? -3 : 19;
+      const uint4* s128 = reinterpret_cast<const uint4*>(src + size_t(r) * W * 3);
+      uint32_t wds[12];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const uint4 v = __ldg(s128 + k);
+        wds[4 * k] = v.x; wds[4 * k + 1] = v.y; wds[4 * k + 2] = v.z; wds[4 * k + 3] = v.w;
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {           // output pixel p reads bytes 12 p .. 12 p + 11 = words 3 p .. 3 p + 2
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          int rowv = 0;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const int byte = 3 * t + c;       // within the 12 bytes of this output pixel
+            const int v = int((wds[3 * p + (byte >> 2)] >> (8 * (byte & 3))) & 0xffu);
+            rowv += ((t == 0 || t == 3) ? -3 : 19) * v;
+          }
+          u[p][c] += ar * rowv;
+        }
+      }
+    }
+    int q[4][3];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int qv = (u[p][c] + 511 + ((u[p][c] >> 10) & 1)) >> 10;
+        q[p][c] = min(max(qv, 0), 255);
+      }
+    if (lr_u8) {
+      uint32_t o[3] = {0u, 0u, 0u};
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int byte = 3 * p + c;
+          o[byte >> 2] |= uint32_t(q[p][c]) << (8 * (byte & 3));
+        }
+      uint32_t* dst = reinterpret_cast<uint32_t*>(lr_u8 + ((size_t(n) * h + y) * w + 4 * xq) * 3);
+      dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
+    }
+    if (lr_f32) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float4 f;
+        f.x = float(q[0][c]) / 255.0f; f.y = float(q[1][c]) / 255.0f;
+        f.z = float(q[2][c]) / 255.0f; f.w = float(q[3][c]) / 255.0f;
+        *reinterpret_cast<float4*>(lr_f32 + ((size_t(n) * 3 + c) * h + y) * w + 4 * xq) = f;
+      }
     }
   }
 }
@@ -551,7 +664,7 @@ static int make_layout(const fen_config* cfg, Layout* L) {
   L->k_last = k; k += kLastRec;
   L->cv_rcab0 = 0; L->cv_gconv0 = L->n_rcab * 192; L->cv_after = L->cv_gconv0 + L->G * 64;
   L->cv_total = L->cv_after + 64;
-  L->k_cvec = align256(k); k = L->k_cvec + int64_t(L->cv_total) * 4;
+  L->k_cvec = align256(k); k = L->k_cvec + int64_t(L->cv_total) * 4 + 512;   // (the body kernel stages 512 B from any cv_bias)
   L->k_total = align256(k);
   return FEN_OK;
 }
@@ -635,6 +748,7 @@ static void make_workspace(const Layout& L, int B, int H, int W, Workspace* ws) 
 }
 
 
+#ifdef FEN_DEV
 // ===================================================================== persistent body kernel launcher
 static bool body_kernel_usable(const Layout& L, int B, int H, int W) {
   static int disabled = -1;
@@ -651,11 +765,7 @@ static bool body_kernel_usable(const Layout& L, int B, int H, int W) {
 
 static int launch_body(const fen_config* cfg, const Layout& L, const Workspace& ws, uint8_t* wsb, const uint8_t* k,
                        int B, int H, int W, float* se_out, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    FEN_CUDA(cudaFuncSetAttribute(body_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBodyDynBytes));
-    attr_set = true;
-  }
+  FEN_CUDA(ensure_smem_attr(kKBody, body_umma_kernel, kBodyDynBytes));
   const RcabRec rr = rcab_rec(L.R);
   BodyMaps maps;
   BodyParams p{};
@@ -691,15 +801,17 @@ static int launch_body(const fen_config* cfg, const Layout& L, const Workspace& 
   FEN_CUDA(cudaMemcpyToSymbolAsync(c_vec, k + L.k_cvec, size_t(L.cv_total) * 4, 0, cudaMemcpyDeviceToDevice, st));
   void* args[] = {&maps, &p};
   if (g_time_body) {
-    if (!g_body_ev[0]) { FEN_CUDA(cudaEventCreate(&g_body_ev[0])); FEN_CUDA(cudaEventCreate(&g_body_ev[1])); }
-    FEN_CUDA(cudaEventRecord(g_body_ev[0], st));
+    if (!dev_state().body_ev[0]) { FEN_CUDA(cudaEventCreate(&dev_state().body_ev[0])); FEN_CUDA(cudaEventCreate(&dev_state().body_ev[1])); }
+    FEN_CUDA(cudaEventRecord(dev_state().body_ev[0], st));
   }
   FEN_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(body_umma_kernel), dim3(ctas), dim3(kBodyThreads), args,
                                        kBodyDynBytes, st));
-  if (g_time_body) FEN_CUDA(cudaEventRecord(g_body_ev[1], st));
+  if (g_time_body) FEN_CUDA(cudaEventRecord(dev_state().body_ev[1], st));
   ++g_launches;
   return FEN_OK;
 }
+
+#endif  // FEN_DEV
 
 // ===================================================================== second-generation body kernel launcher
 static int env_int(const char* name, int dflt) {
@@ -714,9 +826,11 @@ static int body2_nset(int B) {
   return 2;
 }
 static bool body2_usable(const Layout& L, int B, int H, int W) {
-  static int version = -1;
-  if (version < 0) version = env_int("FEN_BODY_KERNEL", 2);
-  if (version != 2 || W != kStripW || L.cv_total > kConstVecFloats || L.G > kB2MaxBufs - 5) return false;
+  int version = 2;
+#ifdef FEN_DEV
+  version = env_int("FEN_BODY_KERNEL", 2);
+#endif
+  if (version != 2 || W != kStripW || L.G > kB2MaxBufs - 5) return false;
   const int tps = (H * kPitch + kTileM - 1) / kTileM;
   if (tps > 255) return false;
   const int set_tiles = (B / body2_nset(B)) * tps;
@@ -727,11 +841,7 @@ static bool body2_usable(const Layout& L, int B, int H, int W) {
 
 static int launch_body2(const fen_config* cfg, const Layout& L, const Workspace& ws, uint8_t* wsb, const uint8_t* k,
                         int B, int H, int W, float* se_out, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    FEN_CUDA(cudaFuncSetAttribute(body2_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2DynBytes));
-    attr_set = true;
-  }
+  FEN_CUDA(ensure_smem_attr(kKBody2, body2_umma_kernel, kB2DynBytes));
   const RcabRec rr = rcab_rec(L.R);
   Body2Maps maps;
   Body2Params p{};
@@ -752,9 +862,8 @@ static int launch_body2(const fen_config* cfg, const Layout& L, const Workspace&
     p.buf[i] = reinterpret_cast<bf16*>(wsb + offs[i]);
     int rc = make_act_map(&maps.act[i], p.buf[i], B, H, W, kBBoxRows);
     if (rc) return rc;
-    if ((rc = make_act_store_map(&maps.st[i], p.buf[i], B, H, W))) return rc;
   }
-  for (int i = nbuf; i < kB2MaxBufs; ++i) { maps.act[i] = maps.act[0]; maps.st[i] = maps.st[0]; }
+  for (int i = nbuf; i < kB2MaxBufs; ++i) maps.act[i] = maps.act[0];
   int rc = make_w_map(&maps.w, k, int(L.k_total / 128), kC);
   if (rc) return rc;
   p.packed = k;
@@ -767,15 +876,15 @@ static int launch_body2(const fen_config* cfg, const Layout& L, const Workspace&
   p.dbg = g_dbg;
   FEN_CUDA(cudaMemsetAsync(p.flags, 0, 4096, st));
   FEN_CUDA(cudaMemsetAsync(p.hsum, 0, size_t(L.n_rcab) * B * 9 * 64 * 4, st));
-  FEN_CUDA(cudaMemcpyToSymbolAsync(c_vec, k + L.k_cvec, size_t(L.cv_total) * 4, 0, cudaMemcpyDeviceToDevice, st));
+  p.cvec = reinterpret_cast<const float*>(k + L.k_cvec);
   void* args[] = {&maps, &p};
   if (g_time_body) {
-    if (!g_body_ev[0]) { FEN_CUDA(cudaEventCreate(&g_body_ev[0])); FEN_CUDA(cudaEventCreate(&g_body_ev[1])); }
-    FEN_CUDA(cudaEventRecord(g_body_ev[0], st));
+    if (!dev_state().body_ev[0]) { FEN_CUDA(cudaEventCreate(&dev_state().body_ev[0])); FEN_CUDA(cudaEventCreate(&dev_state().body_ev[1])); }
+    FEN_CUDA(cudaEventRecord(dev_state().body_ev[0], st));
   }
   FEN_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(body2_umma_kernel), dim3(ctas), dim3(kB2Threads), args,
                                        kB2DynBytes, st));
-  if (g_time_body) FEN_CUDA(cudaEventRecord(g_body_ev[1], st));
+  if (g_time_body) FEN_CUDA(cudaEventRecord(dev_state().body_ev[1], st));
   ++g_launches;
   return FEN_OK;
 }
@@ -794,10 +903,10 @@ const char* fen_last_error(void) { return g_err.c_str(); }
 int fen_last_launch_count(void) { return g_launches; }
 int fen_profile_body(int enable) { g_time_body = enable ? 1 : 0; return FEN_OK; }
 float fen_last_body_ms(void) {
-  if (!g_body_ev[0] || !g_body_ev[1]) return -1.f;
-  if (cudaEventSynchronize(g_body_ev[1]) != cudaSuccess) { cudaGetLastError(); return -1.f; }
+  if (!dev_state().body_ev[0] || !dev_state().body_ev[1]) return -1.f;
+  if (cudaEventSynchronize(dev_state().body_ev[1]) != cudaSuccess) { cudaGetLastError(); return -1.f; }
   float ms = -1.f;
-  if (cudaEventElapsedTime(&ms, g_body_ev[0], g_body_ev[1]) != cudaSuccess) { cudaGetLastError(); return -1.f; }
+  if (cudaEventElapsedTime(&ms, dev_state().body_ev[0], dev_state().body_ev[1]) != cudaSuccess) { cudaGetLastError(); return -1.f; }
   return ms;
 }
 // developer hook (not in the public header): device buffer [ctas][8] of int64 cycle counters, or null
@@ -877,17 +986,17 @@ int fen_conv3x3_c64(const void* x, const void* w_packed, const float* bias, cons
   return launch_conv(a, static_cast<cudaStream_t>(stream));
 }
 
-int fen_forward(const fen_config* cfg, const void* packed, const float* x, float* out, int B, int H,
-                int W, int training, void* workspace, int64_t workspace_bytes, float* se_out,
-                void* stream) {
+static int forward_impl(const fen_config* cfg, const void* packed, const float* x, float* out, uint8_t* out_u8, int bgr,
+                        int B, int H, int W, int training, void* workspace, int64_t workspace_bytes, float* se_out,
+                        void* stream) {
   int rc = check_device();
   if (rc) return rc;
   g_launches = 0;
   Layout L;
   if ((rc = make_layout(cfg, &L))) return rc;
-  if (!packed || !x || !out || !workspace) return fail(FEN_EINVAL, "fen_forward: null pointer");
-  if (B < 1 || H < 64 || W < 64 || H % 64 || W % 64)
-    return fail(FEN_EINVAL, "fen_forward: H and W must be positive multiples of 64 (no fallback path)");
+  if (!packed || !x || (!out && !out_u8) || !workspace) return fail(FEN_EINVAL, "fen_forward: null pointer");
+  if (B < 1 || H < 1 || W < 1) return fail(FEN_EINVAL, "fen_forward: empty input");
+  if (H > 16384 || W > 16384) return fail(FEN_EINVAL, "fen_forward: H and W must be at most 16384");
   Workspace ws;
   make_workspace(L, B, H, W, &ws);
   if (workspace_bytes < ws.total) return fail(FEN_ENOMEM, "fen_forward: workspace too small");
@@ -917,9 +1026,11 @@ int fen_forward(const fen_config* cfg, const void* packed, const float* x, float
   if (body2_usable(L, B, H, W)) {
     if ((rc = launch_body2(cfg, L, ws, wsb, k, B, H, W, se_out, st))) return rc;
     if ((rc = stage_check("body kernel", st))) return rc;
+#ifdef FEN_DEV
   } else if (body_kernel_usable(L, B, H, W)) {
     if ((rc = launch_body(cfg, L, ws, wsb, k, B, H, W, se_out, st))) return rc;
     if ((rc = stage_check("body kernel", st))) return rc;
+#endif
   } else {
     const int hw = H * W;
     const int se_chunks = 32;
@@ -976,11 +1087,25 @@ int fen_forward(const fen_config* cfg, const void* packed, const float* x, float
     a.x = act(ws.u1); a.w = k + L.k_last; a.n = 16; a.groups = 1;
     a.p.B = B; a.p.H = 4 * H; a.p.W = 4 * W; a.p.epi = kEpiLast; a.p.training = training;
     a.p.bias = reinterpret_cast<const float*>(k + L.k_last + 9 * 16 * 64 * 2);
-    a.p.lr = x; a.p.out_f32 = out;
+    a.p.lr = x; a.p.out_f32 = out; a.p.out_u8 = out_u8; a.p.bgr = bgr;
     if ((rc = launch_conv(a, st))) return rc;
   }
   if ((rc = stage_check("conv_last", st))) return rc;
   return FEN_OK;
+}
+
+int fen_forward(const fen_config* cfg, const void* packed, const float* x, float* out, int B, int H,
+                int W, int training, void* workspace, int64_t workspace_bytes, float* se_out,
+                void* stream) {
+  if (!out) return fail(FEN_EINVAL, "fen_forward: null pointer");
+  return forward_impl(cfg, packed, x, out, nullptr, 0, B, H, W, training, workspace, workspace_bytes, se_out, stream);
+}
+
+int fen_forward_u8(const fen_config* cfg, const void* packed, const float* x, uint8_t* out_u8, int bgr, int B, int H,
+                   int W, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!out_u8) return fail(FEN_EINVAL, "fen_forward_u8: null pointer");
+  return forward_impl(cfg, packed, x, nullptr, out_u8, bgr ? 1 : 0, B, H, W, 0, workspace, workspace_bytes, nullptr,
+                      stream);
 }
 
 int64_t fen_forward_tap(const fen_config* cfg, const void* workspace, int B, int H, int W, int which,
@@ -1131,6 +1256,17 @@ int fen_lr_from_hr_u8(const uint8_t* hr, uint8_t* lr_u8, float* lr_f32, int B, i
   size_t blocks = (total + 255) / 256;
   const size_t cap = size_t(num_sms()) * 32;
   if (blocks > cap) blocks = cap;
+  const bool aligned = !(reinterpret_cast<uintptr_t>(hr) & 15) && !(reinterpret_cast<uintptr_t>(lr_u8) & 3) &&
+                       !(reinterpret_cast<uintptr_t>(lr_f32) & 15);
+  if (C == 3 && (W & 15) == 0 && aligned) {
+    const size_t quads = total / 4;
+    size_t qb = (quads + 255) / 256;
+    if (qb > cap) qb = cap;
+    lr_from_hr_rgb4_kernel<<<unsigned(qb), 256, 0, st>>>(hr, lr_u8, lr_f32, B, H, W);
+    FEN_CUDA(cudaGetLastError());
+    ++g_launches;
+    return FEN_OK;
+  }
   switch (C) {
     case 1: lr_from_hr_kernel<1><<<unsigned(blocks), 256, 0, st>>>(hr, lr_u8, lr_f32, B, H, W); break;
     case 2: lr_from_hr_kernel<2><<<unsigned(blocks), 256, 0, st>>>(hr, lr_u8, lr_f32, B, H, W); break;
@@ -1191,8 +1327,9 @@ static int step_args(const fen_config* cfg, Layout* L, StepWs* ws, int B, int H,
   if (rc) return rc;
   g_launches = 0;
   if ((rc = make_layout(cfg, L))) return rc;
-  if (B < 1 || H < 64 || W < 64 || H % 64 || W % 64)
-    return fail(FEN_EINVAL, std::string(who) + ": H and W must be positive multiples of 64 (no fallback path)");
+  if (B < 1 || H < 1 || W < 1) return fail(FEN_EINVAL, std::string(who) + ": empty input");
+  if (W > 336 || H > 4096)   // (the CUDA-core row kernels of the backward stage 4 W + 4 floats x 9 rows in 48 KB of shared memory)
+    return fail(FEN_EINVAL, std::string(who) + ": the training path takes LR inputs up to 336 columns x 4096 rows");
   make_step_ws(*L, B, H, W, ws);
   if (bytes < ws->total) return fail(FEN_ENOMEM, std::string(who) + ": workspace too small");
   return FEN_OK;

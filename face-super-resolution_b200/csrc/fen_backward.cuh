@@ -27,6 +27,13 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return r;
 }
 
+constexpr int kWgOutPitch = kC * 9 + 4;   // floats per staged output row of a weight-gradient flush (padded)
+__device__ __forceinline__ void red_add_v4(float* dst, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+#ifdef FEN_DEV   // the fp32-FMA and mma.sync generations of the 64 -> 64 weight gradient: developer builds only
 // --------------------------------------------------------------------------------------------------------------
 // Weight gradient of a 64 -> 64 3x3 / pad-1 convolution:
 //   dW[co][ci][ky][kx] += sum_{b,y,x} dY[b,y,x,co] * X[b,y+ky-1,x+kx-1,ci]        db[co] += sum dY[b,y,x,co]
@@ -135,14 +142,9 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 // instructions and an eighth of the L2 sectors of one scalar atomic per element.
 constexpr int kWgStageElems = (kWgPx + 3 * (kWgPx + 2)) * kWgPitch;        // one buffer: dY row + 3 X rows
 constexpr int kWgDynBytes = 2 * kWgStageElems * 2;                         // 75 456 B
-constexpr int kWgOutPitch = kC * 9 + 4;                                    // floats per staged output row (padded)
 static_assert(16 * kWgOutPitch * 4 <= kWgDynBytes, "output staging must fit the operand buffers");
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void red_add_v4(float* dst, float4 v) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-               : "memory");
 }
 __global__ void __launch_bounds__(256, 1)
 wgrad_c64_mma_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, float* __restrict__ dW,
@@ -276,13 +278,14 @@ wgrad_c64_mma_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, fl
   if (tid < kC) atomicAdd(dB + tid * co_mul + co_off, bsum);
 }
 
+#endif  // FEN_DEV
 // --------------------------------------------------------------------------------------------------------------
 // Weight gradient of the two 3-channel convolutions (conv_first 3 -> 64 and conv_last 64 -> 3): a 64-channel
 // NHWC bf16 tensor F against a 3-channel fp32 NCHW image I, both of size H x W:
 //   a[c3][f][t] = sum_{b,y,x} F[b,y,x,f] * I[b,c3,y+ty-1,x+tx-1]
 // mode 0 (conv_first: F = d f0, I = network input):  dW[f][c3][t] += a, db[f] += sum F
 // mode 1 (conv_last:  F = u1,   I = d out):          dW[c3][f][8-t] += a, db[c3] += sum I
-// grid (ceil(H / rows_per_cta), B), 256 threads = 32 channel PAIRS x 8 column eighths; dynamic smem 9 * (W + 4) floats.
+// grid (ceil(H / rows_per_cta), B), 256 threads = 32 channel PAIRS x 8 column eighths; dynamic smem 9 * (roundup(W, 32) + 4) floats.
 // A thread takes 4 pixels of 2 channels at a time: one 32-bit load per pixel (a warp reads whole 128-byte lines),
 // and the 3 x 6 image window of each image channel comes in as one 128-bit + one 64-bit shared-memory load per row
 // (18 loads for 216 FMAs; one load per FMA made the first version LSU bound).
@@ -292,7 +295,8 @@ wgrad_c3_kernel(const bf16* __restrict__ F, const float* __restrict__ I, float* 
   extern __shared__ __align__(16) float sI[];   // [c3][r][W + 4], column j = image column j - 1
   const int tid = threadIdx.x, f2 = tid & 31, xq = tid >> 5;
   const int b = blockIdx.y;
-  const int Wp = W + 4;
+  const int Wr = (W + 31) & ~31;          // columns are dealt to the 8 warps in quads: ragged widths are zero-extended
+  const int Wp = Wr + 4;
   float acc[2][3][9];
   float bs[2] = {0.f, 0.f}, is[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -311,13 +315,13 @@ wgrad_c3_kernel(const bf16* __restrict__ F, const float* __restrict__ I, float* 
       sI[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(I + ((size_t(b) * 3 + c3) * H + yy) * W + xx) : 0.f;
     }
     __syncthreads();
-    const int xw = W / 8;
+    const int xw = Wr / 8;
     const uint32_t* frow = reinterpret_cast<const uint32_t*>(F + ((size_t(b) * H + y) * W) * kC) + f2;
-    for (int x = xq * xw; x < (xq + 1) * xw; x += 4) {
+    for (int x = xq * xw; x < (xq + 1) * xw && x < W; x += 4) {
       float v[2][4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint32_t pr = __ldg(frow + size_t(x + j) * (kC / 2));
+        const uint32_t pr = (x + j < W) ? __ldg(frow + size_t(x + j) * (kC / 2)) : 0u;
         v[0][j] = bf16lo(pr); v[1][j] = bf16hi(pr);
       }
       bs[0] += (v[0][0] + v[0][1]) + (v[0][2] + v[0][3]);
@@ -372,12 +376,12 @@ wgrad_c3_kernel(const bf16* __restrict__ F, const float* __restrict__ I, float* 
 //   dU[b,y,x,c]  = sum_{co<3,t} dOut[b,co,y+ty-1,x+tx-1] * wk[co*9+t][c]      (wk = tap-flipped conv_last weights)
 //   dPre         = dU * (u > 0 ? 1 : slope[c])          dslope[c] += dU * min(u, 0) / slope[c]
 //   dY[sub][b][y>>1][x>>1][c] = dPre,  sub = 2 (y&1) + (x&1)                  (the conv's sub-pixel planes)
-// u = prelu(pre) is the saved stage output; sign(u) = sign(pre) needs slope > 0 (checked by the host side).
+// u = prelu(pre) is the saved stage output, `mask` the sign bits of pre saved by the forward (ConvParams::mask_out).
 // grid (H, B), 256 threads: 64 columns x 4 channel quarters, like conv_first_kernel; dynamic smem 9 * (W + 2) floats.
 __global__ void __launch_bounds__(256)
 last_dgrad_kernel(const float* __restrict__ dOut, const float* __restrict__ wk, const bf16* __restrict__ u,
-                  const float* __restrict__ slope, bf16* __restrict__ dY, float* __restrict__ dslope, int B, int H,
-                  int W) {
+                  const uint32_t* __restrict__ mask, const float* __restrict__ slope, bf16* __restrict__ dY,
+                  float* __restrict__ dslope, int B, int H, int W) {
   extern __shared__ float s_in[];   // [co 3][row 3][W + 2]: the three dOut rows of this output row, zero padded
   __shared__ float sw[27 * kC];
   __shared__ float s_sl[kC], s_ds[kC];
@@ -397,6 +401,7 @@ last_dgrad_kernel(const float* __restrict__ dOut, const float* __restrict__ wk, 
   for (int c = 0; c < 16; ++c) ds[c] = 0.f;
   for (int x0 = 0; x0 < W; x0 += 64) {
     const int xx = x0 + (threadIdx.x & 63);
+    if (xx >= W) continue;                      // ragged width (no barrier inside this loop)
     float in[27];
 #pragma unroll
     for (int co = 0; co < 3; ++co)
@@ -431,12 +436,13 @@ last_dgrad_kernel(const float* __restrict__ dOut, const float* __restrict__ wk, 
       for (int c = 0; c < 8; ++c) uv[8 + c] = t8[c];
     }
     float o[16];
+    const uint32_t pos_bits = __ldg(mask + ((size_t(n) * H + y) * W + xx) * 2 + (q >> 1)) >> ((q & 1) * 16);
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
       const float sl = s_sl[q * 16 + c];
-      const bool pos = uv[c] > 0.f;
+      const bool pos = (pos_bits >> c) & 1u;
       o[c] = pos ? acc[c] : acc[c] * sl;
-      ds[c] += pos ? 0.f : acc[c] * (uv[c] / sl);
+      ds[c] += (pos || sl == 0.f) ? 0.f : acc[c] * (uv[c] / sl);
     }
     const int sub = 2 * (y & 1) + (xx & 1);
     uint4* dst = reinterpret_cast<uint4*>(
@@ -465,12 +471,13 @@ last_dgrad_kernel(const float* __restrict__ dOut, const float* __restrict__ wk, 
 
 // --------------------------------------------------------------------------------------------------------------
 // PReLU backward on NHWC bf16 (RCAB conv1, blocks.py:139-141; upsample stage, blocks.py:227):
-//   out = g * (act > 0 ? 1 : slope[c])      dslope[c] += g * min(act, 0) / slope[c]
-// act = prelu(pre) is the saved activation.  unshuffle != 0: g / act are the PixelShuffle'd [B,H,W,64] tensors and
+//   out = g * (pre > 0 ? 1 : slope[c])      dslope[c] += g * min(pre, 0),  min(pre, 0) = act / slope[c] on that side
+// act = prelu(pre) is the saved activation, `mask` the sign bits of pre (ConvParams::mask_out of the forward).  unshuffle != 0: g / act are the PixelShuffle'd [B,H,W,64] tensors and
 // `out` is written as the four sub-pixel planes [4][B][H/2][W/2][64] of the producing convolution.
 __global__ void __launch_bounds__(256)
-prelu_bwd_kernel(const bf16* g, const bf16* __restrict__ act, const float* __restrict__ slope, bf16* out,
-                 float* __restrict__ dslope, int B, int H, int W, int unshuffle) {   // out may alias g (in place)
+prelu_bwd_kernel(const bf16* g, const bf16* __restrict__ act, const uint32_t* __restrict__ mask,
+                 const float* __restrict__ slope, bf16* out, float* __restrict__ dslope, int B, int H, int W,
+                 int unshuffle) {   // out may alias g (in place)
   __shared__ float s_ds[kC];
   if (threadIdx.x < kC) s_ds[threadIdx.x] = 0.f;
   __syncthreads();
@@ -486,11 +493,12 @@ prelu_bwd_kernel(const bf16* g, const bf16* __restrict__ act, const float* __res
     float gf[8], af[8], of[8];
     unpack8(gv[i], gf);
     unpack8(__ldg(av + i), af);
+    const uint32_t pos_bits = __ldg(mask + (i >> 3) * 2 + (cg >> 2)) >> ((cg & 3) * 8);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const bool pos = af[c] > 0.f;
+      const bool pos = (pos_bits >> c) & 1u;
       of[c] = pos ? gf[c] : gf[c] * sl[c];
-      ds[c] += pos ? 0.f : gf[c] * (af[c] / sl[c]);
+      ds[c] += (pos || sl[c] == 0.f) ? 0.f : gf[c] * (af[c] / sl[c]);
     }
     size_t o = i;
     if (unshuffle) {

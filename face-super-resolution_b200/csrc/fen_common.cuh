@@ -29,8 +29,9 @@ enum EpilogueKind : int {
   kEpiLast = 4,      // out_f32 NCHW = [clamp](acc + bias + bicubic_x4(lr))   (conv_last)
   kEpiBias = 5,      // out = acc + bias
   // backward pass (fen_step_host.cuh): data-gradient convolutions with the element-wise backward that follows fused in
-  kEpiGate = 6,      // PReLU backward: out = acc * (a > 0 ? 1 : slope), sums[c] += acc * min(a, 0) / slope
-                     //   (a = `residual` = the saved post-PReLU activation; sums = the [64] slope gradient)
+  kEpiGate = 6,      // PReLU backward: out = acc * (z > 0 ? 1 : slope), sums[c] += acc * min(z, 0)
+                     //   (z > 0 comes from `mask_in`, the sign bits saved by the forward; min(z, 0) = a / slope with
+                     //    a = `residual` = the saved post-PReLU activation; sums = the [64] slope gradient)
   kEpiDot = 7,       // out = acc (+ residual if given); sums[n][c] += out * aux   (SE backward: sum dx' * o per image)
 };
 
@@ -48,8 +49,13 @@ struct ConvParams {
   const bf16* aux;        // NHWC, same shape as out (kEpiDot)
   bf16* out;              // NHWC bf16 output
   float* sums;            // [B][64] fp32, accumulated with atomics (kEpiSum, kEpiDot); [64] for kEpiGate
+  uint32_t* mask_out;     // kEpiPrelu / kEpiShuffle, optional: bit c of word [2 * output pixel + column half] = (pre-activation
+                          //   of channel 32 * half + c > 0) - what the PReLU backward needs for slopes of any sign
+  const uint32_t* mask_in;  // kEpiGate: those words of the activation being differentiated
   const float* lr;        // [B][3][H/4][W/4] fp32 network input (kEpiLast)
-  float* out_f32;         // [B][3][H][W] fp32 (kEpiLast)
+  float* out_f32;         // [B][3][H][W] fp32 (kEpiLast), optional when out_u8 is given
+  uint8_t* out_u8;        // [B][H][W][3] uint8 = trunc(clip(out * 255, 0, 255)) (kEpiLast), optional
+  int bgr;                // out_u8 channel order B, G, R
   long long* dbg;         // optional [gridDim.x][8] cycle counters (developer builds), else nullptr
 };
 

@@ -44,6 +44,7 @@ __global__ void pack_T_all_kernel(const float* __restrict__ params, uint8_t* __r
 struct StepWs {
   int64_t act;                      // bytes of one [B][H][W][64] bf16 tensor
   int64_t f0, body, xs0, h0, o0, gout0, u0, u1, sums;     // forward (xs/h/o: one per RCAB, gout: one per group)
+  int64_t m_h0, m_stride, m_u0, m_u1;                     // PReLU sign masks (8 B per pixel): per RCAB conv1, the two stages
   int64_t dy1, du0, dy0, g[6], dsum;                      // backward
   int64_t total;
 };
@@ -60,6 +61,10 @@ static void make_step_ws(const Layout& L, int B, int H, int W, StepWs* w) {
   w->u0 = o; o += 4 * act;
   w->u1 = o; o += 16 * act;
   w->sums = o; o += align256(int64_t(L.n_rcab) * B * 64 * 4);
+  w->m_stride = align256(int64_t(B) * H * W * 8);
+  w->m_h0 = o; o += w->m_stride * L.n_rcab;
+  w->m_u0 = o; o += 4 * w->m_stride;
+  w->m_u1 = o; o += 16 * w->m_stride;
   w->dy1 = o; o += 16 * act;
   w->du0 = o; o += 4 * act;
   w->dy0 = o; o += 4 * act;
@@ -69,11 +74,13 @@ static void make_step_ws(const Layout& L, int B, int H, int W, StepWs* w) {
 }
 
 static int conv64(const bf16* in, const void* w, const float* bias, const float* slope, const bf16* res, float* sm,
-                  bf16* out, int epi, int B, int h, int w_, cudaStream_t st, const bf16* aux = nullptr) {
+                  bf16* out, int epi, int B, int h, int w_, cudaStream_t st, const bf16* aux = nullptr,
+                  uint32_t* mask = nullptr) {
   ConvArgs a{};
   a.x = in; a.w = w; a.n = 64; a.groups = (epi == kEpiShuffle) ? 4 : 1;
   a.p.B = B; a.p.H = h; a.p.W = w_; a.p.epi = epi; a.p.bias = bias; a.p.slope = slope; a.p.residual = res;
   a.p.out = out; a.p.sums = sm; a.p.aux = aux;
+  if (epi == kEpiGate) a.p.mask_in = mask; else a.p.mask_out = mask;
   return launch_conv(a, st);
 }
 
@@ -110,7 +117,8 @@ static int step_forward(const fen_config* cfg, const Layout& L, const uint8_t* k
       bf16* o = act(ws.o0 + r * ws.act);
       bf16* nxt = act(ws.xs0 + r * ws.act);
       if ((rc = conv64(cur, kr + rr.w1, reinterpret_cast<const float*>(kr + rr.b1),
-                       reinterpret_cast<const float*>(kr + rr.slope), nullptr, nullptr, h, kEpiPrelu, B, H, W, st)))
+                       reinterpret_cast<const float*>(kr + rr.slope), nullptr, nullptr, h, kEpiPrelu, B, H, W, st,
+                       nullptr, reinterpret_cast<uint32_t*>(wsb + ws.m_h0 + r * ws.m_stride))))
         return rc;
       if ((rc = conv64(h, kr + rr.w2, reinterpret_cast<const float*>(kr + rr.b2), nullptr, nullptr, sm, o, kEpiSum, B,
                        H, W, st)))
@@ -135,12 +143,12 @@ static int step_forward(const fen_config* cfg, const Layout& L, const uint8_t* k
   const uint8_t* ku = k + L.k_up[0];
   if ((rc = conv64(act(ws.body), ku, reinterpret_cast<const float*>(ku + 4 * kConvWBytes),
                    reinterpret_cast<const float*>(ku + 4 * kConvWBytes + 1024), nullptr, nullptr, act(ws.u0),
-                   kEpiShuffle, B, H, W, st)))
+                   kEpiShuffle, B, H, W, st, nullptr, reinterpret_cast<uint32_t*>(wsb + ws.m_u0))))
     return rc;
   ku = k + L.k_up[1];
   if ((rc = conv64(act(ws.u0), ku, reinterpret_cast<const float*>(ku + 4 * kConvWBytes),
                    reinterpret_cast<const float*>(ku + 4 * kConvWBytes + 1024), nullptr, nullptr, act(ws.u1),
-                   kEpiShuffle, B, 2 * H, 2 * W, st)))
+                   kEpiShuffle, B, 2 * H, 2 * W, st, nullptr, reinterpret_cast<uint32_t*>(wsb + ws.m_u1))))
     return rc;
   ConvArgs a{};
   a.x = act(ws.u1); a.w = k + L.k_last; a.n = 16; a.groups = 1;
@@ -150,29 +158,24 @@ static int step_forward(const fen_config* cfg, const Layout& L, const uint8_t* k
   return launch_conv(a, st);
 }
 
-constexpr int kWgradDefault = 2;
 static int wgrad64(const bf16* dY, const bf16* X, float* dW, float* dB, int B, int H, int W, int co_mul, int co_off,
                    cudaStream_t st) {
-  const int bands = B * H * (W / kStripW);
+  const int bands = B * H * ((W + kStripW - 1) / kStripW);
   const int grid = bands < num_sms() ? bands : num_sms();
-  // FEN_WGRAD=0: first generation (fp32 FMA on the CUDA cores), 1: warp-level tensor cores (mma.sync),
-  // 2: tcgen05 with MN-major operands (wgrad_umma.cuh).  Read on every call so that tests can compare them.
-  const int version = env_int("FEN_WGRAD", kWgradDefault);
+  // The product library carries the tcgen05 kernel (wgrad_umma.cuh).  Developer builds (-DFEN_DEV) also hold the
+  // two earlier generations for A/B runs: FEN_WGRAD=0 fp32 FMA on the CUDA cores, 1 warp-level mma.sync.
+  int version = 2;
+#ifdef FEN_DEV
+  version = env_int("FEN_WGRAD", 2);
   if (version == 0) {
     wgrad_c64_kernel<<<grid, 256, 0, st>>>(dY, X, dW, dB, B, H, W, co_mul, co_off);
   } else if (version == 1) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      FEN_CUDA(cudaFuncSetAttribute(wgrad_c64_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgDynBytes));
-      attr_set = true;
-    }
+    FEN_CUDA(ensure_smem_attr(kKWgMma, wgrad_c64_mma_kernel, kWgDynBytes));
     wgrad_c64_mma_kernel<<<grid, 256, kWgDynBytes, st>>>(dY, X, dW, dB, B, H, W, co_mul, co_off);
-  } else {
-    static bool attr_set = false;
-    if (!attr_set) {
-      FEN_CUDA(cudaFuncSetAttribute(wgrad_c64_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWuDynBytes));
-      attr_set = true;
-    }
+  }
+#endif
+  if (version == 2) {
+    FEN_CUDA(ensure_smem_attr(kKWgUmma, wgrad_c64_umma_kernel, kWuDynBytes));
     CUtensorMap tm_y, tm_x;
     int rc = make_act_map(&tm_y, dY, B, H, W, 1, kStripW);
     if (rc) return rc;
@@ -203,14 +206,14 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
   // ---- conv_last: weight / bias gradient, then data gradient fused with PReLU + PixelShuffle backward of stage 1
   {
     const int rows = 8;
-    wgrad_c3_kernel<<<dim3((Ho + rows - 1) / rows, B), 256, 9 * (Wo + 4) * sizeof(float), st>>>(
+    wgrad_c3_kernel<<<dim3((Ho + rows - 1) / rows, B), 256, 9 * (((Wo + 31) & ~31) + 4) * sizeof(float), st>>>(
         act(ws.u1), dout, grads + L.p_last_w, grads + L.p_last_b, Ho, Wo, rows, 1);
     FEN_CUDA(cudaGetLastError());
     ++g_launches;
     const float* slope1 = reinterpret_cast<const float*>(k + L.k_up[1] + 4 * kConvWBytes + 1024);
-    last_dgrad_kernel<<<dim3(Ho, B), 256, 9 * (Wo + 2) * sizeof(float), st>>>(dout, reinterpret_cast<const float*>(kb + K.last), act(ws.u1),
-                                                   slope1, act(ws.dy1), grads + L.p_up[1] + 4 * kConvW + 256, B, Ho,
-                                                   Wo);
+    last_dgrad_kernel<<<dim3(Ho, B), 256, 9 * (Wo + 2) * sizeof(float), st>>>(
+        dout, reinterpret_cast<const float*>(kb + K.last), act(ws.u1), reinterpret_cast<const uint32_t*>(wsb + ws.m_u1),
+        slope1, act(ws.dy1), grads + L.p_up[1] + 4 * kConvW + 256, B, Ho, Wo);
     FEN_CUDA(cudaGetLastError());
     ++g_launches;
   }
@@ -230,7 +233,8 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
     // result in acc[1] = dy0 region -> PReLU + PixelShuffle backward of stage 0 writes the planes into du0 region
     const float* slope0 = reinterpret_cast<const float*>(k + L.k_up[0] + 4 * kConvWBytes + 1024);
     prelu_bwd_kernel<<<ew_blocks(size_t(B) * h2 * w2 * 8), 256, 0, st>>>(
-        acc[1], act(ws.u0), slope0, acc[0], grads + L.p_up[0] + 4 * kConvW + 256, B, h2, w2, 1);
+        acc[1], act(ws.u0), reinterpret_cast<const uint32_t*>(wsb + ws.m_u0), slope0, acc[0],
+        grads + L.p_up[0] + 4 * kConvW + 256, B, h2, w2, 1);
     FEN_CUDA(cudaGetLastError());
     ++g_launches;
   }
@@ -291,7 +295,8 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
       // conv2: weight gradient, then data gradient with the PReLU backward in its epilogue (dH holds dA)
       if ((rc = wgrad64(dO, h, d_c2w, d_c2b, B, H, W, 1, 0, st))) return rc;
       if ((rc = conv64(dO, kb + K.rcab0 + r * K.rcab_stride + kConvWBytes, zeros,
-                       reinterpret_cast<const float*>(kr + rr.slope), h, d_sl, dH, kEpiGate, B, H, W, st)))
+                       reinterpret_cast<const float*>(kr + rr.slope), h, d_sl, dH, kEpiGate, B, H, W, st, nullptr,
+                       reinterpret_cast<uint32_t*>(wsb + ws.m_h0 + r * ws.m_stride))))
         return rc;
       // conv1 + the identity path of the RCAB; the result is dx' of the previous RCAB of the group
       if ((rc = wgrad64(dH, xin, d_c1w, d_c1b, B, H, W, 1, 0, st))) return rc;
@@ -317,7 +322,7 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
   ++g_launches;
   {
     const int rows = 2;
-    wgrad_c3_kernel<<<dim3((H + rows - 1) / rows, B), 256, 9 * (W + 4) * sizeof(float), st>>>(
+    wgrad_c3_kernel<<<dim3((H + rows - 1) / rows, B), 256, 9 * (((W + 31) & ~31) + 4) * sizeof(float), st>>>(
         dCur, x, grads + L.p_first_w, grads + L.p_first_b, H, W, rows, 0);
     FEN_CUDA(cudaGetLastError());
     ++g_launches;

@@ -38,7 +38,7 @@ wgrad_c64_umma_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_con
   __shared__ uint64_t bar_full[kWuStages], bar_empty[kWuStages], bar_done;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int strips = W / kStripW;
+  const int strips = (W + kStripW - 1) / kStripW;   // a ragged last strip is zero-filled by TMA
   const int bands = B * H * strips;
 
   if (warp == 1) tmem_alloc(&tmem_slot, kWuTmemCols);

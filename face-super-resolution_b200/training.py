@@ -62,6 +62,9 @@ def psnr(pred: torch.Tensor, target: torch.Tensor, data_range: float = 1.0) -> t
     return out
 
 
+EXCHANGE_DESCRIPTION = "one NCCL all-reduce (sum, then / world) of the flat 20.5 MB fp32 gradient after the backward"
+
+
 def allreduce_mean_(flat_grad: torch.Tensor) -> torch.Tensor:
     """Data-parallel gradient exchange: one all-reduce (sum) of the flat gradient, then / world_size, in place.
     NCCL over NVLink on GPUs; identity when torch.distributed is not initialised."""
@@ -133,6 +136,8 @@ class Stage1Step:
         model._flat_master = flat      # fen_pack_weights reads it directly (no torch.cat per step)
         self.opt = ClipAdamW(flat, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_norm=max_norm)
         self.last_grad: Optional[torch.Tensor] = None
+        self.exchange = True          # False: skip the gradient all-reduce (bench.py measures its exposed time that way)
+        self.last_launches = 0        # kernels launched by the last step (counted by the library)
 
     def step(self, hr: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """hr: [B,3,4H,4W] fp32 CUDA in [0,1].  Returns (loss [1], total gradient norm before clipping [1]),
@@ -141,13 +146,17 @@ class Stage1Step:
         _check_cuda_f32(hr)
         model = self.model
         model.train()
-        lr_img, _ = lr_from_hr_float(hr)
+        lib = _lib.load()
+        lr_img, _ = lr_from_hr_float(hr); n = lib.fen_last_launch_count()
         model._check_input(lr_img)
-        sr, ws = model._forward_train(lr_img)
-        loss, dsr = l1_loss(sr, hr)
-        grads = model._backward(lr_img, dsr, ws)
-        allreduce_mean_(grads)
-        norm = self.opt.step(grads)
+        sr, lease = model._forward_train(lr_img); n += lib.fen_last_launch_count()
+        loss, dsr = l1_loss(sr, hr); n += lib.fen_last_launch_count()
+        grads = model._backward(lr_img, dsr, lease); n += lib.fen_last_launch_count()
+        del lease                      # the saved activations go back to the model's pool
+        if self.exchange:
+            allreduce_mean_(grads)
+        norm = self.opt.step(grads); n += 3          # grad norm (2 kernels) + clip/AdamW
+        self.last_launches = n
         model.mark_parameters_updated()
         self.last_grad = grads
         return loss, norm

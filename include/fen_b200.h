@@ -68,10 +68,19 @@ int64_t fen_forward_workspace_bytes(const fen_config* cfg, int B, int H, int W);
  *   out      [B,3,4H,4W] fp32 NCHW; clamped to [0,1] unless `training` (custom.py:187-188)
  *   se_out   optional [B, num_groups*blocks_per_group, 64] fp32: the channel-attention scales of
  *            every RCAB (what get_attention_maps, custom.py:192-230, returns); may be NULL
- * H and W must be multiples of 64 (the benchmark uses 64 x 64). */
+ * Any H, W >= 1 (the network is fully convolutional; the demo feeds sizes up to 128 x 128, app/demo.py:247-251).
+ * 64-column inputs (the benchmark's 64 x 64) run the whole residual body in one persistent kernel; other widths
+ * take one convolution launch per layer. */
 int fen_forward(const fen_config* cfg, const void* packed, const float* x, float* out, int B, int H,
                 int W, int training, void* workspace, int64_t workspace_bytes, float* se_out,
                 void* stream);
+
+/* fen_forward in eval mode followed by the evaluation scripts' to_numpy (scripts/test_model.py:176-190,
+ * scripts/compare_two_models.py:150-179): out_u8 [B,4H,4W,3] uint8 HWC = trunc(clip(sr * 255, 0, 255)), channel order
+ * B,G,R when `bgr`.  The conversion runs in the epilogue of conv_last: the fp32 SR tensor is never written.
+ * Bit-identical to fen_sr_to_u8(fen_forward(x)). */
+int fen_forward_u8(const fen_config* cfg, const void* packed, const float* x, uint8_t* out_u8, int bgr, int B, int H,
+                   int W, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Debug / parity taps: copies of intermediate NHWC bf16 feature maps of the LAST fen_forward on this
  * workspace.  which: 0 = conv_first output, 1 = body output (after conv_after_body + long skip),

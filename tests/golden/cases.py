@@ -66,3 +66,48 @@ def grad_dout(name: str) -> np.ndarray:
     shape = (batch, 3, 256, 256)
     sign = rng.integers(0, 2, shape).astype(np.float32) * 2.0 - 1.0
     return (sign / float(np.prod(shape))).astype(np.float32)
+
+
+# ---- round 2: configurations beyond the 64-channel square benchmark, fen_golden2.npz
+FEN2_CASES = [
+    # name, reference constructor ("net" = FaceEnhanceNet(**cfg), "lite" = FaceEnhanceNetLite()), weight cfg, tier, seed, input shape
+    ("default_T1", "net", dict(num_groups=3, blocks_per_group=4), "T1", 11, (1, 3, 64, 64)),        # dataclass defaults (custom.py:28-29)
+    ("lite_T1", "lite", dict(num_groups=3, blocks_per_group=4, num_channels=32, reduction_ratio=2), "T1", 12, (1, 3, 64, 64)),
+    ("ragged_T1", "net", dict(num_groups=1, blocks_per_group=2), "T1", 13, (1, 3, 48, 80)),          # neither side a multiple of 64
+]
+
+
+def fen2_input(name: str) -> np.ndarray:
+    idx = [c[0] for c in FEN2_CASES].index(name)
+    rng = np.random.default_rng(4000 + idx)
+    return rng.random(FEN2_CASES[idx][5], dtype=np.float32)
+
+
+def negative_slopes(sd, seed: int = 0):
+    """The same state_dict with every PReLU slope redrawn from U(-0.4, 0.45): about half of them negative, which
+    nn.PReLU allows (blocks.py:127,146,216) and a trained checkpoint may contain."""
+    import torch
+    rng = np.random.default_rng(5000 + seed)
+    out = {k: v.clone() for k, v in sd.items()}
+    for k in out:
+        if k.endswith("prelu.weight"):
+            out[k] = torch.from_numpy(rng.uniform(-0.4, 0.45, tuple(out[k].shape)).astype(np.float32))
+    return out
+
+
+# gradient golden with negative slopes: 1 x 1 model, batch 1, dout = grad_dout-like sign pattern; only the tensors
+# named here are stored (every PReLU slope gradient, the SE matrices, biases, and conv_first.weight, which sees
+# every layer above it)
+NEG_GRAD_CFG = dict(num_groups=1, blocks_per_group=1)
+NEG_GRAD_SEED = 21
+
+
+def neg_grad_inputs():
+    rng = np.random.default_rng(6000)
+    x = rng.random((1, 3, 64, 64), dtype=np.float32)
+    sign = rng.integers(0, 2, (1, 3, 256, 256)).astype(np.float32) * 2.0 - 1.0
+    return x, (sign / float(sign.size)).astype(np.float32)
+
+
+def neg_grad_stored(key: str, numel: int) -> bool:
+    return numel <= 5000 or key == "conv_first.weight"

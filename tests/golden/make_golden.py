@@ -78,12 +78,50 @@ def make_fen_grad():
     np.savez_compressed(os.path.join(HERE, "fen_grad_golden.npz"), **out)
 
 
+def make_fen2():
+    """fen_golden2.npz: the unmodified reference on configurations beyond the benchmark's (default 3 x 4 config,
+    FaceEnhanceNetLite, a ragged input size) and its gradients with NEGATIVE PReLU slopes."""
+    sys.path.insert(0, "/root/reference")
+    from src.models.custom import FaceEnhanceNet, FaceEnhanceNetLite
+    torch.set_num_threads(8)
+    out = {"torch_version": np.array(torch.__version__)}
+    for name, ctor, cfg, tier, seed, shape in cases.FEN2_CASES:
+        sd = weights.make_state_dict(seed, tier, **cfg)
+        m = FaceEnhanceNetLite() if ctor == "lite" else FaceEnhanceNet(**cfg)
+        m.load_state_dict(sd, strict=True)
+        x = torch.from_numpy(cases.fen2_input(name))
+        with torch.no_grad():
+            m.train()
+            y = m(x)
+        out[name + "/train"] = y.numpy().astype(np.float32)
+        print(name, tuple(y.shape), float(y.min()), float(y.max()))
+    sd = cases.negative_slopes(weights.make_state_dict(cases.NEG_GRAD_SEED, "T1", **cases.NEG_GRAD_CFG), cases.NEG_GRAD_SEED)
+    m = FaceEnhanceNet(**cases.NEG_GRAD_CFG)
+    m.load_state_dict(sd, strict=True)
+    m.train()
+    x, dout = cases.neg_grad_inputs()
+    y = m(torch.from_numpy(x))
+    y.backward(torch.from_numpy(dout))
+    out["neg/train"] = y.detach().numpy().astype(np.float32)
+    for k, p in m.named_parameters():
+        if cases.neg_grad_stored(k, p.numel()):
+            out["neg/grad/" + k] = p.grad.numpy().astype(np.float32)
+    n_neg = sum(int((v < 0).sum()) for k, v in sd.items() if k.endswith("prelu.weight"))
+    print("negative-slope gradient case:", n_neg, "negative slopes")
+    np.savez_compressed(os.path.join(HERE, "fen_golden2.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--round2-only" in sys.argv:
+        make_fen2()
+        print("fen_golden2.npz", os.path.getsize(os.path.join(HERE, "fen_golden2.npz")) // 1024, "KiB")
+        sys.exit(0)
     if "--grad-only" in sys.argv:
         make_fen_grad()
         sys.exit(0)
     make_lr()
     make_fen()
     make_fen_grad()
-    for f in ("lr_golden.npz", "fen_golden.npz", "fen_grad_golden.npz"):
+    make_fen2()
+    for f in ("lr_golden.npz", "fen_golden.npz", "fen_grad_golden.npz", "fen_golden2.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -33,7 +33,7 @@ def dev(built_lib):
     return torch.device("cuda:0")
 
 
-def _compare(named_grads, ref_grads, rel_bar):
+def _compare(named_grads, ref_grads, rel_bar, whole=True, report_to=None):
     rows, bad = [], []
     num = den_a = den_b = 0.0
     for k, g in named_grads:
@@ -49,8 +49,15 @@ def _compare(named_grads, ref_grads, rel_bar):
     ratio = (den_a / max(den_b, 1e-300)) ** 0.5
     report = "\n".join(rows) + f"\ncosine {cos:.6f} norm ratio {ratio:.4f}"
     print(report)
-    assert not bad, "per-tensor relative error above the bar:\n" + "\n".join(bad) + "\n\nall:\n" + report
-    assert cos >= COS_BAR and abs(ratio - 1.0) <= NORM_BAR, report
+    if report_to:
+        os.makedirs(os.path.dirname(report_to), exist_ok=True)
+        with open(report_to, "w") as f:
+            f.write(report + "\n")
+    if rel_bar is not None:
+        assert not bad, "per-tensor relative error above the bar:\n" + "\n".join(bad) + "\n\nall:\n" + report
+    if whole:
+        assert cos >= COS_BAR and abs(ratio - 1.0) <= NORM_BAR, report
+    return cos, ratio
 
 
 def _model(cfg, sd, dev):
@@ -111,25 +118,6 @@ def test_backward_two_groups_against_oracle_with_l1_loss(dev):
     _compare([(k, p.grad) for k, p in m.named_parameters()], ref, REL_SIGN)
 
 
-def test_weight_gradient_kernel_generations_agree(dev, monkeypatch):
-    # tcgen05 (MN-major operands, the product kernel) against the mma.sync and the fp32-FMA generations of the same
-    # weight gradient: only the fp32 summation order differs
-    cfg = dict(num_groups=1, blocks_per_group=1)
-    m = _model(cfg, weights.make_state_dict(6, "T1", **cfg), dev)
-    for shape in [(3, 3, 64, 64), (1, 3, 64, 128)]:
-        x = torch.rand(*shape, device=dev)
-        dout = torch.rand(shape[0], 3, 4 * shape[2], 4 * shape[3], device=dev) / 1e5
-        grads = {}
-        for v in ("2", "1", "0"):
-            monkeypatch.setenv("FEN_WGRAD", v)
-            m.zero_grad()
-            m(x).backward(dout)
-            grads[v] = [p.grad.clone() for p in m.parameters()]
-        for v in ("1", "0"):
-            for (k, _), a, b in zip(m.named_parameters(), grads["2"], grads[v]):
-                assert (a - b).norm().item() <= 1e-3 * b.norm().item() + 1e-30, (shape, v, k)
-
-
 def test_train_mode_semantics(dev):
     cfg = dict(num_groups=1, blocks_per_group=1)
     sd = weights.make_state_dict(2, "T1", **cfg)
@@ -152,11 +140,37 @@ def test_train_mode_semantics(dev):
     m(x).sum().backward()
     for a, p in zip(g1, m.parameters()):
         assert torch.allclose(p.grad, 2 * a, rtol=1e-3, atol=1e-4 * float(a.abs().max()) + 1e-12)
-    # non-positive PReLU slopes are refused (post-activation tensors are what the backward keeps)
+    # two outstanding train-mode forwards (each owns its saved activations), as nn.Module allows
+    x2 = torch.rand(2, 3, 64, 64, device=dev)
+    m.zero_grad(); m(x).sum().backward(); ga = [p.grad.clone() for p in m.parameters()]
+    m.zero_grad(); m(x2).sum().backward(); gb = [p.grad.clone() for p in m.parameters()]
+    m.zero_grad()
+    y1, y2 = m(x), m(x2)
+    (y1.sum() + y2.sum()).backward()
+    for a, b, p in zip(ga, gb, m.parameters()):
+        assert torch.allclose(p.grad, a + b, rtol=1e-3, atol=1e-4 * float((a + b).abs().max()) + 1e-12)
+
+
+def test_backward_with_negative_prelu_slopes(dev):
+    """nn.PReLU allows slopes of any sign (blocks.py:127,146,216): the backward takes the sign of the PRE-activation
+    from the bit masks the forward saves.  Reference gradients: tests/golden/fen_golden2.npz (unmodified module)."""
+    gold = np.load(os.path.join(HERE, "golden", "fen_golden2.npz"))
+    sd = cases.negative_slopes(weights.make_state_dict(cases.NEG_GRAD_SEED, "T1", **cases.NEG_GRAD_CFG), cases.NEG_GRAD_SEED)
+    assert sum(int((v < 0).sum()) for k, v in sd.items() if k.endswith("prelu.weight")) > 50
+    x, dout = cases.neg_grad_inputs()
+    m = _model(cases.NEG_GRAD_CFG, sd, dev)
+    sr = m(torch.from_numpy(x).to(dev))
+    assert fen_oracle.psnr(sr.detach().cpu(), torch.from_numpy(gold["neg/train"])) >= 50.0
+    sr.backward(torch.from_numpy(dout).to(dev))
+    named = dict(m.named_parameters())
+    keys = [k[len("neg/grad/"):] for k in gold.files if k.startswith("neg/grad/")]
+    ref = {k: torch.from_numpy(gold["neg/grad/" + k]) for k in keys}
+    _compare([(k, named[k].grad) for k in keys], ref, REL_SIGN, whole=False)
+    # the eval-mode forward with negative slopes too (fused body kernel)
+    m.eval()
     with torch.no_grad():
-        m.upsample.stages[0].prelu.weight[3] = -0.1
-    with pytest.raises(RuntimeError):
-        m(x).sum().backward()
+        y = m(torch.from_numpy(x).to(dev)).cpu()
+    assert fen_oracle.psnr(y, torch.from_numpy(gold["neg/train"]).clamp(0, 1)) >= 50.0
 
 
 def test_stage1_step_is_the_trainers_iteration(dev):
@@ -186,6 +200,60 @@ def test_stage1_step_is_the_trainers_iteration(dev):
     assert list(m.state_dict().keys()) == list(sd.keys())
 
 
+def test_stage1_step_uses_fresh_weights_in_every_pass(dev):
+    """Steps 2 and 3 must differentiate the UPDATED weights in forward, data-gradient and weight-gradient kernels
+    alike (the transposed copies of the data-gradient convolutions are a separate cache).  A coherent (positive) d
+    loss / d sr keeps the comparison at bf16-rounding level; lr is large so that stale weights would be far off."""
+    cfg = dict(num_groups=1, blocks_per_group=2)
+    sd = weights.make_state_dict(8, "T1", **cfg)
+    m = _model(cfg, sd, dev)
+    step = fsr_b200.Stage1Step(m, lr=3e-3, max_norm=0.5)
+    hr = torch.rand(2, 3, 256, 256, device=dev, generator=torch.Generator(device=dev).manual_seed(11))
+    for _ in range(2):
+        step.step(hr)
+    # third pass by hand on the step's own (twice updated) weights, with a coherent output gradient
+    sd_now = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    assert max((sd_now[k] - sd[k]).abs().max().item() for k in sd) > 1e-3
+    x = torch.rand(2, 3, 64, 64, device=dev, generator=torch.Generator(device=dev).manual_seed(12))
+    yy, xx = np.mgrid[0:256, 0:256].astype(np.float32)
+    dout = torch.from_numpy(((1.0 + 0.5 * np.sin(yy / 17.0) * np.cos(xx / 23.0)) / (2 * 3 * 256 * 256)).astype(np.float32))
+    dout = dout.expand(2, 3, 256, 256).contiguous()
+    sr, lease = m._forward_train(x)
+    g = m._backward(x, dout.to(dev), lease)
+    _, ref = fen_oracle.fen_backward(sd_now, x.cpu(), dout)
+    named, off = [], 0
+    for k, p in m.named_parameters():
+        named.append((k, g[off:off + p.numel()].view(p.shape))); off += p.numel()
+    _compare(named, ref, REL_COHERENT)
+
+
+def test_backward_full_model_config5_against_oracle(dev):
+    """BASELINE config 5's network (6 groups x 10 RCAB) with nn.L1Loss, batch 2: whole-gradient cosine >= 0.999 and
+    norm within 2 % of the fp32 autograd oracle.  Per-tensor errors are printed and written to
+    gpurun_out/grad_parity_6x10.txt (committed under profiles/): with a sign-pattern d loss / d sr they grow with
+    the number of PReLU layers between the tensor and the output, so only the whole gradient has a bar here."""
+    cfg = dict(num_groups=6, blocks_per_group=10)
+    sd = weights.make_state_dict(0, "T1", **cfg)
+    rng = np.random.default_rng(2025)
+    x = torch.from_numpy(rng.random((2, 3, 64, 64), dtype=np.float32))
+    hr = torch.from_numpy(rng.random((2, 3, 256, 256), dtype=np.float32))
+    m = _model(cfg, sd, dev)
+    sr = m(x.to(dev))
+    loss = torch.nn.L1Loss()(sr, hr.to(dev))
+    loss.backward()
+    dout = fen_oracle.l1_grad(sr.detach().cpu(), hr)
+    sr_ref, ref = fen_oracle.fen_backward(sd, x, dout)
+    assert fen_oracle.psnr(sr.detach().cpu(), sr_ref) >= 50.0
+    assert abs(loss.item() - (sr_ref - hr).abs().mean().item()) <= 1e-4
+    out = os.path.join(os.path.dirname(HERE), "gpurun_out", "grad_parity_6x10.txt")
+    cos, ratio = _compare([(k, p.grad) for k, p in m.named_parameters()], ref, None, whole=True, report_to=out)
+    # early layers: how far is the worst tensor (informational bar, 60 PReLU layers deep)
+    worst = max(((p.grad.detach().double().cpu() - ref[k].double()).norm() / ref[k].double().norm().clamp_min(1e-30)).item()
+                for k, p in m.named_parameters())
+    print(f"6x10 config-5 gradient: cosine {cos:.6f}, norm ratio {ratio:.4f}, worst per-tensor relative error {worst:.3f}")
+    assert worst <= 0.6
+
+
 def test_backward_rejects_bad_arguments(dev, built_lib):
     import ctypes as C
     from fsr_b200 import _lib
@@ -193,7 +261,7 @@ def test_backward_rejects_bad_arguments(dev, built_lib):
     buf = torch.zeros(1024, dtype=torch.uint8, device=dev)
     p = buf.data_ptr()
     assert built_lib.fen_forward_train(C.byref(cfg), p, p, p, 1, 64, 64, p, 1024, None) == _lib.FEN_ENOMEM
-    assert built_lib.fen_backward(C.byref(cfg), p, p, p, p, p, 1, 60, 64, p, 1 << 40, None) == _lib.FEN_EINVAL
+    assert built_lib.fen_backward(C.byref(cfg), p, p, p, p, p, 1, 64, 400, p, 1 << 40, None) == _lib.FEN_EINVAL   # > 336 columns
     assert built_lib.fen_backward(C.byref(cfg), p, None, p, p, p, 1, 64, 64, p, 1 << 40, None) == _lib.FEN_EINVAL
     assert built_lib.fen_step_workspace_bytes(C.byref(cfg), 2, 64, 64) > built_lib.fen_forward_workspace_bytes(
         C.byref(cfg), 2, 64, 64)

@@ -106,3 +106,30 @@ def test_psnr_formula():
     a = torch.zeros(4, 4)
     assert fen_oracle.psnr(a, a) == float("inf")
     assert abs(fen_oracle.psnr(a, a + 0.1) - 20.0) < 1e-4
+
+
+# ---- round 2 goldens: default 3 x 4 config, FaceEnhanceNetLite (32 channels), a ragged input size, negative slopes
+GOLD2 = np.load(os.path.join(HERE, "golden", "fen_golden2.npz"))
+
+
+@pytest.mark.parametrize("name", [c[0] for c in cases.FEN2_CASES])
+def test_oracle_matches_reference_golden_round2(name):
+    _, _, cfg, tier, seed, shape = [c for c in cases.FEN2_CASES if c[0] == name][0]
+    sd = weights.make_state_dict(seed, tier, **cfg)
+    y = fen_oracle.fen_forward(sd, torch.from_numpy(cases.fen2_input(name)), training=True)
+    ref = torch.from_numpy(GOLD2[name + "/train"])
+    assert y.shape == ref.shape == (shape[0], 3, 4 * shape[2], 4 * shape[3])
+    assert (y - ref).abs().max().item() <= TOL
+
+
+def test_oracle_backward_with_negative_slopes_matches_reference_golden():
+    sd = cases.negative_slopes(weights.make_state_dict(cases.NEG_GRAD_SEED, "T1", **cases.NEG_GRAD_CFG), cases.NEG_GRAD_SEED)
+    x, dout = cases.neg_grad_inputs()
+    sr, grads = fen_oracle.fen_backward(sd, torch.from_numpy(x), torch.from_numpy(dout))
+    assert (sr - torch.from_numpy(GOLD2["neg/train"])).abs().max().item() <= TOL
+    stored = [k for k in GOLD2.files if k.startswith("neg/grad/")]
+    assert len(stored) >= 10
+    for key in stored:
+        ref = torch.from_numpy(GOLD2[key])
+        g = grads[key[len("neg/grad/"):]]
+        assert (g - ref).norm().item() <= 1e-4 * ref.norm().item() + 1e-12, key
