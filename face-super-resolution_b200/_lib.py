@@ -46,6 +46,9 @@ SIGNATURES = {
     "fen_clip_adamw_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                       C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
                                       C.c_void_p]),
+    "fen_ssim_workspace_bytes": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "fen_ssim": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int,
+                           C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "fen_packed_bwd_bytes": (C.c_int64, [C.POINTER(FenConfig)]),
     "fen_pack_weights_bwd": (C.c_int, [C.POINTER(FenConfig), C.c_void_p, C.c_void_p, C.c_void_p]),
     "fen_step_workspace_bytes": (C.c_int64, [C.POINTER(FenConfig), C.c_int, C.c_int, C.c_int]),

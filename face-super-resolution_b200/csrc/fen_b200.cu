@@ -17,6 +17,7 @@
 #include "body2_umma.cuh"
 #include "fen_backward.cuh"
 #include "wgrad_umma.cuh"
+#include "ssim.cuh"
 
 namespace fen {
 
@@ -1275,6 +1276,60 @@ int fen_lr_from_hr_u8(const uint8_t* hr, uint8_t* lr_u8, float* lr_f32, int B, i
   }
   FEN_CUDA(cudaGetLastError());
   ++g_launches;
+  return FEN_OK;
+}
+
+// ===================================================================== SSIM (validation metric, Stage-2 loss term)
+static int64_t ssim_ws(int B, int C, int H, int W, int want_grad, int64_t* partial_bytes) {
+  const int64_t tiles = int64_t((H + kSsimTile - 1) / kSsimTile) * ((W + kSsimTile - 1) / kSsimTile);
+  *partial_bytes = align256(int64_t(B) * C * tiles * 4);
+  return *partial_bytes + (want_grad ? 3 * align256(int64_t(B) * C * H * W * 4) : 0);
+}
+int64_t fen_ssim_workspace_bytes(int B, int C, int H, int W, int want_grad) {
+  if (B < 1 || C < 1 || H < 1 || W < 1) { fail(FEN_EINVAL, "fen_ssim_workspace_bytes: bad shape"); return FEN_EINVAL; }
+  int64_t pb;
+  return ssim_ws(B, C, H, W, want_grad, &pb);
+}
+
+int fen_ssim(const float* pred, const float* target, int B, int C, int H, int W, const float* window_1d, int window_size,
+             float c1, float c2, float* per_image, float* mean, float* grad_pred, void* workspace,
+             int64_t workspace_bytes, void* stream) {
+  int rc = check_device();
+  if (rc) return rc;
+  g_launches = 0;
+  if (!pred || !target || !window_1d || !workspace || (!per_image && !mean && !grad_pred))
+    return fail(FEN_EINVAL, "fen_ssim: null pointer");
+  if (B < 1 || C < 1 || H < 1 || W < 1 || int64_t(B) * C > 65535) return fail(FEN_EINVAL, "fen_ssim: bad shape");
+  if (window_size < 1 || window_size > kSsimMaxWin || !(window_size & 1))
+    return fail(FEN_EINVAL, "fen_ssim: window_size must be odd and at most 11");
+  int64_t pb;
+  if (workspace_bytes < ssim_ws(B, C, H, W, grad_pred != nullptr, &pb)) return fail(FEN_ENOMEM, "fen_ssim: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SsimParams P{};
+  P.B = B; P.C = C; P.H = H; P.W = W; P.ws = window_size; P.c1 = c1; P.c2 = c2;
+  for (int i = 0; i < window_size; ++i) P.g[i] = window_1d[i];
+  P.tiles_x = (W + kSsimTile - 1) / kSsimTile; P.tiles_y = (H + kSsimTile - 1) / kSsimTile;
+  const int tiles = P.tiles_x * P.tiles_y;
+  uint8_t* wsb = static_cast<uint8_t*>(workspace);
+  float* partial = reinterpret_cast<float*>(wsb);
+  const int64_t plane_bytes = align256(int64_t(B) * C * H * W * 4);
+  float* gmu = grad_pred ? reinterpret_cast<float*>(wsb + pb) : nullptr;
+  float* gpp = grad_pred ? reinterpret_cast<float*>(wsb + pb + plane_bytes) : nullptr;
+  float* gpt = grad_pred ? reinterpret_cast<float*>(wsb + pb + 2 * plane_bytes) : nullptr;
+  ssim_fwd_kernel<<<dim3(tiles, B * C), 256, 0, st>>>(pred, target, P, partial, gmu, gpp, gpt);
+  FEN_CUDA(cudaGetLastError());
+  ++g_launches;
+  if (per_image || mean) {
+    ssim_reduce_kernel<<<1, 256, 0, st>>>(partial, B, C, tiles, 1.0 / (double(C) * H * W), per_image, mean);
+    FEN_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
+  if (grad_pred) {
+    ssim_bwd_kernel<<<dim3(tiles, B * C), 256, 0, st>>>(pred, target, gmu, gpp, gpt, P,
+                                                        float(1.0 / (double(B) * C * H * W)), grad_pred);
+    FEN_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
   return FEN_OK;
 }
 

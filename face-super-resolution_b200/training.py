@@ -160,3 +160,82 @@ class Stage1Step:
         model.mark_parameters_updated()
         self.last_grad = grads
         return loss, norm
+
+
+# ===================================================================== SSIM (validation metric, Stage-2 loss term)
+def _gaussian_1d(window_size: int, sigma: float) -> torch.Tensor:
+    """The 1-D factor of create_gaussian_window (src/losses/ssim_loss.py:14-41), computed the same way in fp32."""
+    coords = torch.arange(window_size, dtype=torch.float32)
+    coords -= window_size // 2
+    g = torch.exp(-(coords ** 2) / (2 * sigma ** 2))
+    g /= g.sum()
+    return g
+
+
+def _ssim_call(pred, target, window_size, sigma, data_range, K, want_grad):
+    import ctypes as C
+    _check_cuda_f32(pred, target)
+    if pred.shape != target.shape or pred.dim() != 4:
+        raise ValueError("pred and target must be [B,C,H,W] tensors of the same shape")
+    if window_size % 2 == 0 or window_size > 11:
+        raise ValueError("window_size must be odd and at most 11 on the B200 path")
+    lib = _lib.load()
+    B, Cn, H, W = pred.shape
+    g = _gaussian_1d(window_size, sigma)
+    garr = (C.c_float * window_size)(*[float(v) for v in g])
+    with torch.cuda.device(pred.device):
+        per_image = torch.empty(B, dtype=torch.float32, device=pred.device)
+        mean = torch.empty(1, dtype=torch.float32, device=pred.device)
+        grad = torch.empty_like(pred) if want_grad else None
+        nbytes = lib.fen_ssim_workspace_bytes(B, Cn, H, W, int(want_grad))
+        _lib.check(nbytes, "fen_ssim_workspace_bytes")
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=pred.device)
+        rc = lib.fen_ssim(pred.data_ptr(), target.data_ptr(), B, Cn, H, W, garr, window_size,
+                          float((K[0] * data_range) ** 2), float((K[1] * data_range) ** 2), per_image.data_ptr(),
+                          mean.data_ptr(), grad.data_ptr() if want_grad else None, ws.data_ptr(), ws.numel(),
+                          torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "fen_ssim")
+    return per_image, mean, grad
+
+
+class _SsimFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, window_size, sigma, data_range, size_average, K):
+        want_grad = pred.requires_grad
+        per_image, mean, grad = _ssim_call(pred.detach().contiguous(), target.detach().contiguous(), window_size, sigma,
+                                           data_range, K, want_grad)
+        ctx.grad_mean, ctx.size_average, ctx.B = grad, size_average, pred.shape[0]
+        return mean[0] if size_average else per_image
+
+    @staticmethod
+    def backward(ctx, gout):
+        if ctx.grad_mean is None:
+            return (None,) * 7
+        if ctx.size_average:
+            g = ctx.grad_mean * gout
+        else:                      # d mean_b / d pred = B * d mean / d pred on the pixels of image b
+            g = ctx.grad_mean * (gout.view(-1, 1, 1, 1) * float(ctx.B))
+        return (g, None, None, None, None, None, None)
+
+
+def ssim(pred: torch.Tensor, target: torch.Tensor, window_size: int = 11, sigma: float = 1.5, data_range: float = 1.0,
+         size_average: bool = True, K=(0.01, 0.03)) -> torch.Tensor:
+    """src/losses/ssim_loss.py:44-98 on the GPU (same signature): the mean of the SSIM map (size_average) or its mean
+    per image.  Differentiable w.r.t. `pred` (the target gets no gradient: it is the ground truth in every caller)."""
+    return _SsimFunction.apply(pred, target, window_size, sigma, data_range, size_average, tuple(K))
+
+
+class SSIMLoss(torch.nn.Module):
+    """src/losses/ssim_loss.py:166-226: 1 - ssim(pred, target)."""
+
+    def __init__(self, window_size: int = 11, sigma: float = 1.5, data_range: float = 1.0, size_average: bool = True,
+                 channel: int = 3):
+        super().__init__()
+        self.window_size, self.sigma, self.data_range, self.size_average, self.channel = \
+            window_size, sigma, data_range, size_average, channel
+        self.register_buffer("window", (_gaussian_1d(window_size, sigma).unsqueeze(1) @ _gaussian_1d(window_size, sigma)
+                                        .unsqueeze(0)).expand(channel, 1, window_size, window_size).contiguous())
+
+    def forward(self, pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        return 1 - ssim(pred, target, window_size=self.window_size, sigma=self.sigma, data_range=self.data_range,
+                        size_average=self.size_average)

@@ -20,11 +20,11 @@ from .blocks import (  # noqa: E402,F401
     PixelShuffleUpsample,
     UpsampleModule,
 )
-from .training import ClipAdamW, Stage1Step, allreduce_mean_, l1_loss, psnr  # noqa: E402,F401
+from .training import ClipAdamW, SSIMLoss, Stage1Step, allreduce_mean_, l1_loss, psnr, ssim  # noqa: E402,F401
 from .data import create_lr_image, lr_from_hr, lr_from_hr_float, sr_to_uint8, to_tensor  # noqa: E402,F401
 
 __all__ = [
     "FaceEnhanceNet", "FaceEnhanceNetConfig", "FaceEnhanceNetLite", "create_face_enhance_net",
     "ChannelAttention", "RCAB", "ResidualGroup", "PixelShuffleUpsample", "UpsampleModule",
-    "ClipAdamW", "Stage1Step", "allreduce_mean_", "l1_loss", "psnr", "create_lr_image", "lr_from_hr", "lr_from_hr_float", "sr_to_uint8", "to_tensor",
+    "ClipAdamW", "SSIMLoss", "ssim", "Stage1Step", "allreduce_mean_", "l1_loss", "psnr", "create_lr_image", "lr_from_hr", "lr_from_hr_float", "sr_to_uint8", "to_tensor",
 ]

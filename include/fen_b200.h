@@ -148,6 +148,19 @@ int fen_clip_adamw_step(float* params, const float* grads, float* exp_avg, float
                         const float* total_norm, float max_norm, float lr, float beta1, float beta2, float eps,
                         float weight_decay, int step, void* stream);
 
+/* Replaces ssim() / SSIMLoss (reference src/losses/ssim_loss.py:44-98, 166-226; callers Trainer._compute_ssim,
+ * src/training/trainer.py:630-634, evaluation/metrics.py:77, CombinedLoss src/losses/combined.py:134-138): SSIM of
+ * pred vs target, both [B,C,H,W] fp32, Gaussian window g g^T (window_1d: the ws normalised 1-D weights, HOST pointer;
+ * ws odd, <= 11), zero padding ws / 2, C1 = (K1 range)^2, C2 = (K2 range)^2.
+ *   per_image  optional [B]: mean of the SSIM map per image (size_average = False)
+ *   mean       optional [1]: mean over everything            (size_average = True)
+ *   grad_pred  optional [B,C,H,W]: d mean / d pred (the loss 1 - ssim has the opposite sign; per-image means: times B)
+ * One pass over pred and target (the five filtered maps stay in shared memory), a second pass for the gradient. */
+int64_t fen_ssim_workspace_bytes(int B, int C, int H, int W, int want_grad);
+int fen_ssim(const float* pred, const float* target, int B, int C, int H, int W, const float* window_1d, int window_size,
+             float c1, float c2, float* per_image, float* mean, float* grad_pred, void* workspace,
+             int64_t workspace_bytes, void* stream);
+
 /* ---- Stage-1 training step, network side (BASELINE config 5): what sr = model(lr) in train()
  * mode and loss.backward() do in Trainer._train_epoch (reference src/training/trainer.py:458-505) over
  * FaceEnhanceNet.forward (src/models/custom.py:147-190) and its blocks (src/models/blocks.py:75-263).

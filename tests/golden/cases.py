@@ -111,3 +111,18 @@ def neg_grad_inputs():
 
 def neg_grad_stored(key: str, numel: int) -> bool:
     return numel <= 5000 or key == "conv_first.weight"
+
+
+# ---- SSIM (src/losses/ssim_loss.py): (name, shape, window_size, sigma); pred = target + noise, clipped to [0, 1]
+SSIM_CASES = [("ragged", (2, 3, 40, 52), 11, 1.5), ("sr_size", (2, 3, 256, 256), 11, 1.5), ("win7", (1, 1, 33, 64), 7, 1.0)]
+
+
+def ssim_inputs(name: str):
+    idx = [c[0] for c in SSIM_CASES].index(name)
+    shape = SSIM_CASES[idx][1]
+    rng = np.random.default_rng(7000 + idx)
+    yy, xx = np.mgrid[0:shape[2], 0:shape[3]].astype(np.float32)
+    base = 0.5 + 0.3 * np.sin(yy / 5.0)[None, None] * np.cos(xx / 7.0)[None, None]
+    target = np.clip(base + 0.15 * rng.standard_normal(shape), 0, 1).astype(np.float32)
+    pred = np.clip(target + 0.08 * rng.standard_normal(shape), 0, 1).astype(np.float32)
+    return pred, target

@@ -111,7 +111,28 @@ def make_fen2():
     np.savez_compressed(os.path.join(HERE, "fen_golden2.npz"), **out)
 
 
+def make_ssim():
+    """ssim_golden.npz: src.losses.ssim_loss.ssim of the unmodified reference (mean, per-image means) and the gradient
+    of SSIMLoss w.r.t. the prediction (small cases only)."""
+    sys.path.insert(0, "/root/reference")
+    from src.losses.ssim_loss import SSIMLoss, ssim
+    out = {}
+    for name, shape, ws, sigma in cases.SSIM_CASES:
+        pred, target = (torch.from_numpy(a) for a in cases.ssim_inputs(name))
+        out[name + "/mean"] = ssim(pred, target, window_size=ws, sigma=sigma).numpy()
+        out[name + "/per_image"] = ssim(pred, target, window_size=ws, sigma=sigma, size_average=False).numpy()
+        if pred.numel() < 50000:
+            p = pred.clone().requires_grad_(True)
+            SSIMLoss(window_size=ws, sigma=sigma, channel=shape[1])(p, target).backward()
+            out[name + "/loss_grad"] = p.grad.numpy()
+        print("ssim", name, float(out[name + "/mean"]))
+    np.savez_compressed(os.path.join(HERE, "ssim_golden.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--ssim-only" in sys.argv:
+        make_ssim()
+        sys.exit(0)
     if "--round2-only" in sys.argv:
         make_fen2()
         print("fen_golden2.npz", os.path.getsize(os.path.join(HERE, "fen_golden2.npz")) // 1024, "KiB")
@@ -123,5 +144,6 @@ if __name__ == "__main__":
     make_fen()
     make_fen_grad()
     make_fen2()
+    make_ssim()
     for f in ("lr_golden.npz", "fen_golden.npz", "fen_grad_golden.npz", "fen_golden2.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

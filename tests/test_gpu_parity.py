@@ -498,3 +498,33 @@ def test_lr_generator_feeds_the_model(dev):
     assert torch.equal(lr.cpu(), ref_lr)
     ref = fen_oracle.fen_forward(sd, ref_lr)
     assert fen_oracle.psnr(y, ref) >= PSNR_BAR and (y - ref).abs().max().item() <= MAXABS_BAR
+
+
+# ------------------------------------------------------------------ SSIM metric / loss
+@pytest.mark.parametrize("name", [c[0] for c in cases.SSIM_CASES])
+def test_ssim_matches_reference_golden(name, dev):
+    """src/losses/ssim_loss.py:44-98 (ssim) and :166-226 (SSIMLoss): value within 2e-6 of the unmodified reference
+    (fp32; separable evaluation of the same window), gradient within 1e-4 relative."""
+    gold = np.load(os.path.join(HERE, "golden", "ssim_golden.npz"))
+    _, shape, ws, sigma = [c for c in cases.SSIM_CASES if c[0] == name][0]
+    pred, target = (torch.from_numpy(a).to(dev) for a in cases.ssim_inputs(name))
+    m = fsr_b200.ssim(pred, target, window_size=ws, sigma=sigma)
+    per = fsr_b200.ssim(pred, target, window_size=ws, sigma=sigma, size_average=False)
+    assert m.shape == () and per.shape == (shape[0],)
+    assert abs(m.item() - float(gold[name + "/mean"])) <= 2e-6
+    assert np.abs(per.cpu().numpy() - gold[name + "/per_image"]).max() <= 2e-6
+    if name + "/loss_grad" in gold.files:
+        p = pred.clone().requires_grad_(True)
+        loss = fsr_b200.SSIMLoss(window_size=ws, sigma=sigma, channel=shape[1]).to(dev)(p, target)
+        assert abs(loss.item() - (1.0 - float(gold[name + "/mean"]))) <= 2e-6
+        loss.backward()
+        ref = torch.from_numpy(gold[name + "/loss_grad"])
+        assert ((p.grad.cpu() - ref).norm() / ref.norm()).item() <= 1e-4
+        # per-image means: the gradient of their sum is B times the gradient of the overall mean
+        p2 = pred.clone().requires_grad_(True)
+        fsr_b200.ssim(p2, target, window_size=ws, sigma=sigma, size_average=False).sum().backward()
+        assert torch.allclose(p2.grad, -p.grad * shape[0], rtol=1e-4, atol=1e-9)
+    with pytest.raises(ValueError):
+        fsr_b200.ssim(pred, target, window_size=12)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fsr_b200.ssim(pred.cpu(), target.cpu())
