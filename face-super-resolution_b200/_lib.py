@@ -56,6 +56,10 @@ SIGNATURES = {
                                     C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "fen_backward": (C.c_int, [C.POINTER(FenConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "fen_backward_num_stages": (C.c_int, [C.POINTER(FenConfig)]),
+    "fen_backward_stage_range": (C.c_int, [C.POINTER(FenConfig), C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "fen_backward_stages": (C.c_int, [C.POINTER(FenConfig), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "fen_conv3x3_c64": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fen_pack_conv3x3": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

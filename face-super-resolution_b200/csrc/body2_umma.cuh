@@ -71,17 +71,68 @@ struct B2Unit { int img, t0, t1, pad; };
 // BodyParams::B is the whole batch; total_tiles / tiles_per_cta count the tiles of ONE set.
 // Tensor maps (kernel parameters stay below 4 KB): per activation buffer one load map (box 64 ch x 66 px x
 // 2 rows, SWIZZLE_128B) and one store map (box 32 ch x 32 px, SWIZZLE_64B); the packed weights.
-constexpr int kB2MaxBufs = 12;   // 5 + num_groups <= 12
+// Tensor maps: ONE 5-D load map over all activation buffers of the workspace ([buffer][B][H][W][64] bf16, the buffers
+// lie at a constant stride; box 64 ch x 66 px x 2 rows, SWIZZLE_128B) - a layer's input is a coordinate, not a map, so
+// the training variant can address its ~190 saved tensors - and the packed weights.
 struct Body2Maps {
-  CUtensorMap act[kB2MaxBufs];
+  CUtensorMap act;
   CUtensorMap w;
 };
 
 struct Body2Params : BodyParams {
   int nset;      // 1 or 2 interleaved image sets
   int set_B;     // images per set (B = nset * set_B)
+  long long* hsum64;   // [n_rcab][B][9][64] fixed-point (2^-24) channel sums of the bf16-rounded h: integer atomics make the
+                       // SE pool - and with it the whole forward - independent of the order in which warps and CTAs arrive
+  bf16* act_base;      // buffer i = act_base + i * act_elems
+  int64_t act_elems;
+  // training variant (body2_umma_kernel<true>): what fen_backward needs besides the activations themselves
+  uint32_t* mask0;     // per RCAB [B][H][W][2] words: sign bits of conv1's pre-activation (ConvParams::mask_out layout)
+  int64_t mask_stride; //   words between RCABs
+  long long* pool_sums;  // [n_rcab][B][64] fixed point: sum over pixels of o = conv2(h) + b2 (the SE pool, as kEpiSum leaves it)
   const float* cvec;   // bias / slope table in the packed blob (BodyLayer::cv_bias / cv_slope index it), 512 B readable past any cv_bias
 };
+
+__device__ __forceinline__ float2 ld_cg_hs_x2(const long long* p) {     // two adjacent fixed-point sums -> float
+  long long a, b;
+  asm volatile("ld.global.cg.v2.s64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
+  return make_float2(__ll2float_rn(a) * (1.f / kHsScale), __ll2float_rn(b) * (1.f / kHsScale));
+}
+// Buffer indices.  Inference: the BodyBuf enum (F0, X0, X1, H, O, G0 ...: ping-pong buffers).  Training: every
+// tensor the backward needs is kept - [f0][body][x' of RCAB 0..n-1][h ...][o ...][group outputs ...] (StepWs order).
+struct B2Layer : BodyLayer { int out2; };       // out2: where conv2 also stores o (training), else -1
+template <bool kTrain>
+__device__ __forceinline__ B2Layer body2_layer(const Body2Params& p, int L) {
+  B2Layer l;
+  static_cast<BodyLayer&>(l) = body_layer(p, L);
+  l.out2 = -1;
+  if (!kTrain) return l;
+  const int n = p.G * p.Bk;
+  const int per_group = 2 * p.Bk + 1;
+  const int g = L / per_group, r = L - g * per_group;
+  auto xs = [&](int rc) { return 2 + rc; };
+  auto gout = [&](int gg) { return 2 + 3 * n + gg; };
+  l.last_use = 0;                                  // everything is read again by the backward
+  if (g == p.G) { l.in = gout(p.G - 1); l.res = 0; l.out = 1; return l; }
+  const int gin = (g == 0) ? 0 : gout(g - 1);
+  if (r == 2 * p.Bk) { l.in = xs(g * p.Bk + p.Bk - 1); l.res = gin; l.out = gout(g); return l; }
+  const int b = r >> 1, rc = g * p.Bk + b;
+  const int xb = (b == 0) ? gin : xs(rc - 1);
+  if ((r & 1) == 0) { l.in = xb; l.out = 2 + n + rc; }
+  else { l.in = 2 + n + rc; l.res = xb; l.out = xs(rc); l.out2 = 2 + 2 * n + rc; }
+  return l;
+}
+
+__device__ __forceinline__ void tma_load_5d_hint(const CUtensorMap* m, uint64_t* bar, uint32_t dst_smem, int c0, int c1,
+                                                 int c2, int c3, int c4, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+      :
+      : "r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+        "r"(c4), "l"(policy)
+      : "memory");
+}
 
 __device__ __forceinline__ float2 ld_cg_f32x2(const float* p) {
   float2 v;
@@ -116,6 +167,7 @@ __device__ __forceinline__ void st_shared_u32(uint32_t saddr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
 
+template <bool kTrain>
 __global__ void __launch_bounds__(kB2Threads, 1)
 body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
   constexpr int N = kC;
@@ -130,7 +182,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
   __shared__ uint64_t bar_done, bar_s_ready, bar_s_free, bar_se_full, bar_se_empty, bar_scale[2];
   __shared__ uint64_t bar_cv[2];                       // per-layer bias / slope vectors staged by the TMA warp (slot L & 1)
   __shared__ __align__(16) float s_cv[2][128];
-  __shared__ uint64_t bar_turn;                        // FEN_B2_TURN: phase G completes when tile G (running index) is enqueued
+  __shared__ volatile uint32_t s_turn;                 // FEN_B2_TURN: number of conv tiles enqueued so far (running index, all passes)
   __shared__ uint32_t tmem_slot;
   // per-pass tables, one set of them per image set (the two sets give a CTA runs of different length)
   __shared__ B2Tile tile_tab2[2][kB2MaxTiles];
@@ -206,7 +258,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
     mbar_init(&bar_done, kB2EpiWarps);
     mbar_init(&bar_s_ready, 1); mbar_init(&bar_s_free, 1); mbar_init(&bar_se_full, 1); mbar_init(&bar_se_empty, 1);
     mbar_init(&bar_scale[0], 1); mbar_init(&bar_scale[1], 1);
-    mbar_init(&bar_turn, 1);
+    s_turn = 0;
     mbar_init(&bar_cv[0], 1); mbar_init(&bar_cv[1], 1);
     fence_mbar_init();
     tma_prefetch_desc(&maps.w);
@@ -226,7 +278,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
     uint32_t P = 0, slot = 0, use = 0;
     constexpr int kPre = 4;                       // boxes of a new layer requested BEFORE its weights
     for (int L = 0; L < p.n_layers; ++L) {
-      const BodyLayer ly = body_layer(p, L);
+      const B2Layer ly = body2_layer<kTrain>(p, L);
       const uint64_t pol = ly.last_use ? kPolicyEvictFirst : 0x1000000000000000ull;
       auto wait_flags = [&](int s) {
         // every peer must have finished layer L-1 of this set: their outputs are my inputs / halos
@@ -248,11 +300,11 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           mbar_wait(&bar_empty[slot], (use & 1u) ^ 1u);
           const bool mirror = e.mirror && slot == 0;
           mbar_expect_tx(&bar_full[slot], mirror ? 2 * kBSlotBytes : kBSlotBytes);
-          tma_load_4d_hint(&maps.act[ly.in], &bar_full[slot], smem_u32(ring + slot * kBSlotBytes), 0, -1, e.y0,
-                           img_base + e.img, pol);
+          tma_load_5d_hint(&maps.act, &bar_full[slot], smem_u32(ring + slot * kBSlotBytes), 0, -1, e.y0,
+                           img_base + e.img, ly.in, pol);
           if (mirror)
-            tma_load_4d_hint(&maps.act[ly.in], &bar_full[slot], smem_u32(ring + kB2Slots * kBSlotBytes), 0, -1, e.y0,
-                             img_base + e.img, pol);
+            tma_load_5d_hint(&maps.act, &bar_full[slot], smem_u32(ring + kB2Slots * kBSlotBytes), 0, -1, e.y0,
+                             img_base + e.img, ly.in, pol);
           B2T2(P, 10, b);
           if (++slot == kB2Slots) { slot = 0; ++use; }
         }
@@ -295,7 +347,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
     const int wi = warp - kB2FirstMmaWarp;
     uint32_t P = 0, gbase = 0, gbox = 0, se_n = 0;
     for (int L = 0; L < ((wi == 0 || n_issuers == 2) ? p.n_layers : 0); ++L) {
-      const bool conv2 = body_layer(p, L).epi == kBEpiSeResidual;
+      const bool conv2 = body_layer(p, L).epi == kBEpiSeResidual;   // (the layer kinds do not depend on the variant)
       bool w_seen = false;
       int se_done = 0;
       for (int s = 0; s < p.nset; ++s, ++P) {
@@ -405,7 +457,16 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           // Strict alternation.  Left alone the two issuers fall into lock-step (they share the pipe at half rate,
           // finish together and then do their per-tile barrier work together with the pipe idle); with the turn
           // token one issuer's bookkeeping always runs under the other one's 36 MMAs.
-          if (n_issuers == 2 && G > 0) mbar_wait(&bar_turn, (G - 1) & 1);
+          // (A counter, not an mbarrier: a warp may fall several tiles behind, which a one-bit phase cannot express.
+          // Warp 2 keeps serving SE batches while it waits: the other issuer may be blocked on an accumulator that
+          // only frees once the epilogue has the SE scale, i.e. once this warp has issued that batch.)
+          if (n_issuers == 2) {
+            while (s_turn < G) {
+              if (se_layer && se_done < p.nset && w_seen &&
+                  __any_sync(0xffffffffu, mbar_test_wait(&bar_s_ready, se_n & 1)))
+                issue_se();
+            }
+          }
 #endif
           __syncwarp();                            // converge after the spin-waits (see the commits below)
           tc_fence_after();
@@ -439,7 +500,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           }
           w_seen = true;
 #if FEN_B2_TURN
-          if (leader && n_issuers == 2) mbar_arrive(&bar_turn);
+          if (leader && n_issuers == 2) s_turn = G + 1;
 #endif
           __syncwarp();
           if (leader) B2T2(P, 7, i);
@@ -475,7 +536,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
 #else
     for (int L = 0; L < p.n_layers; ++L) {
 #endif
-      const BodyLayer ly = body_layer(p, L);
+      const B2Layer ly = body2_layer<kTrain>(p, L);
       if (ly.epi != kBEpiSeResidual) continue;
       const uint8_t* rec = p.packed + p.k_rcab0 + int64_t(ly.rcab) * p.k_rcab_stride;
       const float* fc0 = reinterpret_cast<const float*>(rec + p.k_rcab_fc0);
@@ -501,9 +562,9 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
 #pragma unroll
         for (int u = 0; u < kBodyMaxUnits; ++u) {
           if (u < n_units) {
-            const float* hs = p.hsum + (size_t(ly.rcab) * p.B + img_base + unit_tab[u].img) * (kHsCount * kC) + 2 * lane;
+            const long long* hs = p.hsum64 + (size_t(ly.rcab) * p.B + img_base + unit_tab[u].img) * (kHsCount * kC) + 2 * lane;
 #pragma unroll
-            for (int k = 0; k < kHsCount; ++k) qv[u][k] = ld_cg_f32x2(hs + k * kC);
+            for (int k = 0; k < kHsCount; ++k) qv[u][k] = ld_cg_hs_x2(hs + k * kC);
           }
         }
         B2W(0, 2, L, s, se_n);
@@ -595,6 +656,12 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
             const float sv0 = 1.f / (1.f + expf(-a0)), sv1 = 1.f / (1.f + expf(-a1));
             s_scale[s][u][lane] = sv0 * p.res_scale;
             s_scale[s][u][lane + 32] = sv1 * p.res_scale;
+            if (kTrain && unit_tab[u].t0 == 0) {     // sum_px o = HW b2 + (hi + lo): what se_bwd_apply_kernel reads back
+              long long* ps = p.pool_sums + (size_t(ly.rcab) * p.B + img_base + unit_tab[u].img) * kC;
+              const float hw = 1.f / p.inv_hw;
+              ps[lane] = __float2ll_rn(kHsScale * fmaf(__ldg(p.cvec + ly.cv_bias + lane), hw, s_raw[2 * u][lane] + s_raw[2 * u + 1][lane]));
+              ps[lane + 32] = __float2ll_rn(kHsScale * fmaf(__ldg(p.cvec + ly.cv_bias + lane + 32), hw, s_raw[2 * u][lane + 32] + s_raw[2 * u + 1][lane + 32]));
+            }
             if (p.se_out && unit_tab[u].t0 == 0) {   // the CTA owning tile 0 of the image publishes the attention vector
               float* so = p.se_out + (size_t(img_base + unit_tab[u].img) * (p.G * p.Bk) + ly.rcab) * kC;
               so[lane] = sv0;
@@ -620,6 +687,8 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
             for (int j = 0; j < p.R; ++j) a = fmaf(__ldg(fc2 + c * p.R + j), s_hid[u][j], a);
             const float sv = 1.f / (1.f + expf(-a));
             s_scale[s][u][c] = sv * p.res_scale;
+            if (kTrain && unit_tab[u].t0 == 0)
+              p.pool_sums[(size_t(ly.rcab) * p.B + img_base + unit_tab[u].img) * kC + c] = __float2ll_rn(kHsScale * (s_mean[u][c] / p.inv_hw));
             if (p.se_out && unit_tab[u].t0 == 0)
               p.se_out[(size_t(img_base + unit_tab[u].img) * (p.G * p.Bk) + ly.rcab) * kC + c] = sv;
           }
@@ -643,9 +712,11 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
     const uint32_t pair_u32 = smem_u32(stage + q * 2 * kB2StageBytes);   // 4 KB per lane quarter
     uint32_t G = 0, P = 0, m_cnt = 0;
     for (int L = 0; L < p.n_layers; ++L) {
-      const BodyLayer ly = body_layer(p, L);
-      bf16* outp = p.buf[ly.out];
-      const bf16* resp = ly.res >= 0 ? p.buf[ly.res] : nullptr;
+      const B2Layer ly = body2_layer<kTrain>(p, L);
+      bf16* outp = p.act_base + size_t(ly.out) * p.act_elems;
+      const bf16* resp = ly.res >= 0 ? p.act_base + size_t(ly.res) * p.act_elems : nullptr;
+      bf16* out2p = (kTrain && ly.out2 >= 0) ? p.act_base + size_t(ly.out2) * p.act_elems : nullptr;
+      uint32_t* maskp = (kTrain && ly.epi == kBEpiPreluHsum) ? p.mask0 + size_t(ly.rcab) * p.mask_stride : nullptr;
       float bias[CW], slope[CW];
       mbar_wait(&bar_cv[L & 1], (L >> 1) & 1);
 #pragma unroll
@@ -676,7 +747,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
         constexpr int EPI = decltype(epi_tag)::value;
         int cur_unit = -1, img = 0;
         float csum[CW], col0sum = 0.f, colLsum = 0.f;
-        float* hs = nullptr;
+        long long* hs = nullptr;
         auto flush_unit = [&]() {
           if (EPI != kBEpiPreluHsum || cur_unit < 0) return;
           // total: reduce-scatter butterfly over the warp, lane l ends with channel col0 + l
@@ -690,9 +761,9 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
               csum[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
             }
           }
-          atomicAdd(hs + kHsTotal * kC + col0 + lane, csum[0]);
-          atomicAdd(hs + kHsCol0 * kC + col0 + lane, col0sum);
-          atomicAdd(hs + kHsColL * kC + col0 + lane, colLsum);
+          hs_add(hs + kHsTotal * kC + col0 + lane, csum[0]);
+          hs_add(hs + kHsCol0 * kC + col0 + lane, col0sum);
+          hs_add(hs + kHsColL * kC + col0 + lane, colLsum);
         };
         for (int i = 0; i < n_tiles; ++i, ++G) {
           const B2Tile e = tile_tab[i];
@@ -703,7 +774,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
 #pragma unroll
             for (int c = 0; c < CW; ++c) csum[c] = 0.f;
             col0sum = 0.f; colLsum = 0.f;
-            if (EPI == kBEpiPreluHsum) hs = p.hsum + (size_t(ly.rcab) * p.B + img) * (kHsCount * kC);
+            if (EPI == kBEpiPreluHsum) hs = p.hsum64 + (size_t(ly.rcab) * p.B + img) * (kHsCount * kC);
             if (EPI == kBEpiSeResidual) {             // `slope` doubles as the SE scale of this image
 #pragma unroll
               for (int j = 0; j < CW / 4; ++j) {
@@ -748,10 +819,25 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
 #pragma unroll
           for (int c = 0; c < CW; ++c) f[c] = __uint_as_float(v[c]) + bias[c];
           if (EPI == kBEpiPreluHsum) {
+            if (kTrain) {                           // sign bits of the pre-activation, for the PReLU backward
+              uint32_t mbits = 0;
+#pragma unroll
+              for (int c = 0; c < CW; ++c) mbits |= (f[c] > 0.f ? 1u : 0u) << c;
+              if (valid) maskp[opix * 2 + half] = mbits;
+            }
 #pragma unroll
             for (int c = 0; c < CW; ++c) f[c] = fmaxf(f[c], 0.f) + slope[c] * fminf(f[c], 0.f);
           } else {
             if (EPI == kBEpiSeResidual) {
+              if (kTrain) {                         // o = conv2(h) + b2 is kept: the SE backward needs sum dx' * o
+                uint32_t o2[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) o2[k] = pack_bf16(f[2 * k], f[2 * k + 1]);
+                if (valid) {
+                  st_global_256(out2p + opix * kC + col0, *reinterpret_cast<uint32_t(*)[8]>(&o2[0]));
+                  st_global_256(out2p + opix * kC + col0 + 16, *reinterpret_cast<uint32_t(*)[8]>(&o2[8]));
+                }
+              }
 #pragma unroll
               for (int c = 0; c < CW; ++c) f[c] *= slope[c];
             }
@@ -836,8 +922,8 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
                 const float val = (lane & 1) ? bf16hi(wv) : bf16lo(wv);
                 const int ys = __shfl_sync(0xffffffffu, y, src);
                 if (side) colLsum += val; else col0sum += val;
-                if (ys == 0) atomicAdd(hs + (side ? kHsC0L : kHsC00) * kC + col0 + lane, val);
-                if (ys == p.H - 1) atomicAdd(hs + (side ? kHsCL0 + 1 : kHsCL0) * kC + col0 + lane, val);
+                if (ys == 0) hs_add(hs + (side ? kHsC0L : kHsC00) * kC + col0 + lane, val);
+                if (ys == p.H - 1) hs_add(hs + (side ? kHsCL0 + 1 : kHsCL0) * kC + col0 + lane, val);
                 __syncwarp();
               }
             }
@@ -868,7 +954,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
                     f[k] = keep + __shfl_xor_sync(0xffffffffu, send, d);
                   }
                 }
-                atomicAdd(hs + (side ? kHsRowL : kHsRow0) * kC + col0 + lane, f[0]);
+                hs_add(hs + (side ? kHsRowL : kHsRow0) * kC + col0 + lane, f[0]);
               }
             }
           }

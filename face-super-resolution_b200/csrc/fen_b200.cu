@@ -148,7 +148,7 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int rows, int n) {
 // ---- per-device state: SM count and the "max dynamic shared memory" function attributes are properties of a
 // device, not of the process (one process may drive several GPUs).
 constexpr int kMaxDevices = 64;
-enum KernelId : int { kKConv64 = 0, kKConv16, kKConv2_64, kKConv2_16, kKBody, kKBody2, kKWgMma, kKWgUmma, kKLastDgrad,
+enum KernelId : int { kKConv64 = 0, kKConv16, kKConv2_64, kKConv2_16, kKBody, kKBody2, kKBody2Train, kKWgMma, kKWgUmma, kKLastDgrad,
                       kKWgradC3, kKernelIds };
 struct DevState {
   int sms = 0;
@@ -216,7 +216,7 @@ static int launch_conv_n(const ConvArgs& a, cudaStream_t st) {
   { const char* e = getenv("FEN_CONV_KERNEL"); if (e && e[0] == '1') conv_version = 1; else if (e && e[0] == '3') conv_version = 3; }
 #endif
   const int boxes_bound = p.tiles_per_cta * kTileM / kBoxPx + 3 * ((p.tiles_per_cta + p.tiles_per_seg - 1) / p.tiles_per_seg + 1);
-  if ((conv_version == 2 && N == 16 || conv_version == 3) && p.epi < kEpiGate && !p.mask_out && p.tiles_per_cta <= kC2MaxTiles && boxes_bound <= kC2MaxBoxes) {
+  if ((conv_version == 2 && N == 16 || conv_version == 3) && p.epi < kEpiGate && !p.mask_out && !p.sums64 && p.tiles_per_cta <= kC2MaxTiles && boxes_bound <= kC2MaxBoxes) {
     FEN_CUDA(ensure_smem_attr(N == 64 ? kKConv2_64 : kKConv2_16, conv3x3_umma2_kernel<N>, ConvCfg<N>::kDynBytes));
     conv3x3_umma2_kernel<N><<<grid, ConvCfg<N>::kThreads, ConvCfg<N>::kDynBytes, st>>>(tm_in, tm_w, p);
   } else {
@@ -325,13 +325,13 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
 //   s = sigmoid(W2 relu(W0 mean_hw(o)));  x' = o * s * res_scale + x
 // `sums` holds the per-image channel sums produced by the conv2 epilogue.  grid (chunks, B).
 __global__ void __launch_bounds__(256) se_residual_kernel(const bf16* __restrict__ x, const bf16* __restrict__ o,
-                                                          const float* __restrict__ sums,
+                                                          const long long* __restrict__ sums,
                                                           const float* __restrict__ fc0, const float* __restrict__ fc2,
                                                           int R, float inv_hw, float res_scale, bf16* __restrict__ xout,
                                                           float* __restrict__ se_out, int se_stride, int hw) {
   __shared__ float s_mean[kC], s_hid[kC], s_scale[kC];
   const int n = blockIdx.y, tid = threadIdx.x;
-  if (tid < kC) s_mean[tid] = sums[n * kC + tid] * inv_hw;
+  if (tid < kC) s_mean[tid] = hs_to_float(sums[n * kC + tid]) * inv_hw;
   __syncthreads();
   if (tid < R) {
     float a = 0.f;
@@ -742,8 +742,8 @@ static void make_workspace(const Layout& L, int B, int H, int W, Workspace* ws) 
   ws->grp0 = o; ws->grp_stride = act; o += act * L.G;
   ws->u0 = o; o += 4 * act;
   ws->u1 = o; o += 16 * act;
-  ws->sums = o; o += align256(int64_t(L.n_rcab) * B * 64 * 4);
-  ws->hsum = o; o += align256(int64_t(L.n_rcab) * B * 9 * 64 * 4);   // body kernel: 9 channel sums of h per RCAB, image
+  ws->sums = o; o += align256(int64_t(L.n_rcab) * B * 64 * 8);   // per-layer path: fixed-point SE pool sums
+  ws->hsum = o; o += align256(int64_t(L.n_rcab) * B * 9 * 64 * 8);   // body kernel: 9 channel sums of h per RCAB, image (int64 fixed point)
   ws->flags = o; o += 4096;   // one int per CTA of the persistent body kernel
   ws->total = o;
 }
@@ -831,7 +831,7 @@ static bool body2_usable(const Layout& L, int B, int H, int W) {
 #ifdef FEN_DEV
   version = env_int("FEN_BODY_KERNEL", 2);
 #endif
-  if (version != 2 || W != kStripW || L.G > kB2MaxBufs - 5) return false;
+  if (version != 2 || W != kStripW) return false;
   const int tps = (H * kPitch + kTileM - 1) / kTileM;
   if (tps > 255) return false;
   const int set_tiles = (B / body2_nset(B)) * tps;
@@ -840,9 +840,36 @@ static bool body2_usable(const Layout& L, int B, int H, int W) {
   return (tpc + tps - 2) / tps + 1 <= kBodyMaxUnits;
 }
 
-static int launch_body2(const fen_config* cfg, const Layout& L, const Workspace& ws, uint8_t* wsb, const uint8_t* k,
+// [nbuf][B][H][W][64] bf16 activation buffers at a constant stride: one 5-D map, box 64 ch x 66 px x 2 rows.
+static int make_act5_map(CUtensorMap* m, const void* base, int64_t buf_stride_bytes, int nbuf, int B, int H, int W) {
+  const MapKey key{base, 2, B, H, W, nbuf, int(buf_stride_bytes >> 8)};
+  if (map_lookup(key, m)) return FEN_OK;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(FEN_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[5] = {cuuint64_t(kC), cuuint64_t(W), cuuint64_t(H), cuuint64_t(B), cuuint64_t(nbuf)};
+  cuuint64_t strides[4] = {cuuint64_t(kC) * 2, cuuint64_t(W) * kC * 2, cuuint64_t(H) * W * kC * 2,
+                           cuuint64_t(buf_stride_bytes)};
+  cuuint32_t box[5] = {cuuint32_t(kC), cuuint32_t(kPitch), cuuint32_t(kBBoxRows), 1, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FEN_ECUDA, "cuTensorMapEncodeTiled(activation buffers) failed: " + std::to_string(int(r)));
+  map_store(key, *m);
+  return FEN_OK;
+}
+
+// Where the body kernel finds its buffers inside a workspace (inference: Workspace, training: StepWs).
+struct Body2Bufs {
+  uint8_t* act_base; int64_t act_stride; int nbuf;       // activation buffers (indices: body2_layer)
+  long long* hsum64; int* flags;
+  uint32_t* mask0; int64_t mask_stride_bytes; long long* pool_sums;   // training only
+};
+
+template <bool kTrain>
+static int launch_body2(const fen_config* cfg, const Layout& L, const Body2Bufs& bufs, const uint8_t* k,
                         int B, int H, int W, float* se_out, cudaStream_t st) {
-  FEN_CUDA(ensure_smem_attr(kKBody2, body2_umma_kernel, kB2DynBytes));
+  FEN_CUDA(ensure_smem_attr(kTrain ? kKBody2Train : kKBody2, body2_umma_kernel<kTrain>, kB2DynBytes));
   const RcabRec rr = rcab_rec(L.R);
   Body2Maps maps;
   Body2Params p{};
@@ -855,36 +882,30 @@ static int launch_body2(const fen_config* cfg, const Layout& L, const Workspace&
   p.tiles_per_cta = (p.total_tiles + num_sms() - 1) / num_sms();   // (upper bound; the kernel deals q or q + 1 tiles)
   const int ctas = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   p.res_scale = cfg->res_scale; p.inv_hw = 1.f / float(H * W);
-  const int nbuf = 5 + L.G;
-  int64_t offs[kBodyMaxBufs];
-  offs[kBufF0] = ws.f0; offs[kBufX0] = ws.x[0]; offs[kBufX1] = ws.x[1]; offs[kBufH] = ws.h; offs[kBufO] = ws.o;
-  for (int g = 0; g < L.G; ++g) offs[kBufG0 + g] = ws.grp0 + g * ws.grp_stride;
-  for (int i = 0; i < nbuf; ++i) {
-    p.buf[i] = reinterpret_cast<bf16*>(wsb + offs[i]);
-    int rc = make_act_map(&maps.act[i], p.buf[i], B, H, W, kBBoxRows);
-    if (rc) return rc;
-  }
-  for (int i = nbuf; i < kB2MaxBufs; ++i) maps.act[i] = maps.act[0];
-  int rc = make_w_map(&maps.w, k, int(L.k_total / 128), kC);
+  p.act_base = reinterpret_cast<bf16*>(bufs.act_base);
+  p.act_elems = bufs.act_stride / 2;
+  int rc = make_act5_map(&maps.act, bufs.act_base, bufs.act_stride, bufs.nbuf, B, H, W);
   if (rc) return rc;
+  if ((rc = make_w_map(&maps.w, k, int(L.k_total / 128), kC))) return rc;
   p.packed = k;
   p.k_rcab0 = L.k_rcab0; p.k_rcab_stride = L.k_rcab_stride; p.k_rcab_w2 = rr.w2; p.k_rcab_fc0 = rr.fc0; p.k_rcab_fc2 = rr.fc2;
   p.k_gconv0 = L.k_gconv0; p.k_gconv_stride = L.k_gconv_stride; p.k_after = L.k_after;
   p.cv_rcab0 = L.cv_rcab0; p.cv_gconv0 = L.cv_gconv0; p.cv_after = L.cv_after;
-  p.hsum = reinterpret_cast<float*>(wsb + ws.hsum);
+  p.hsum64 = bufs.hsum64;
   p.se_out = se_out;
-  p.flags = reinterpret_cast<int*>(wsb + ws.flags);
+  p.flags = bufs.flags;
+  p.mask0 = bufs.mask0; p.mask_stride = bufs.mask_stride_bytes / 4; p.pool_sums = bufs.pool_sums;
   p.dbg = g_dbg;
   FEN_CUDA(cudaMemsetAsync(p.flags, 0, 4096, st));
-  FEN_CUDA(cudaMemsetAsync(p.hsum, 0, size_t(L.n_rcab) * B * 9 * 64 * 4, st));
+  FEN_CUDA(cudaMemsetAsync(p.hsum64, 0, size_t(L.n_rcab) * B * 9 * 64 * 8, st));
   p.cvec = reinterpret_cast<const float*>(k + L.k_cvec);
   void* args[] = {&maps, &p};
   if (g_time_body) {
     if (!dev_state().body_ev[0]) { FEN_CUDA(cudaEventCreate(&dev_state().body_ev[0])); FEN_CUDA(cudaEventCreate(&dev_state().body_ev[1])); }
     FEN_CUDA(cudaEventRecord(dev_state().body_ev[0], st));
   }
-  FEN_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(body2_umma_kernel), dim3(ctas), dim3(kB2Threads), args,
-                                       kB2DynBytes, st));
+  FEN_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(body2_umma_kernel<kTrain>), dim3(ctas), dim3(kB2Threads),
+                                       args, kB2DynBytes, st));
   if (g_time_body) FEN_CUDA(cudaEventRecord(dev_state().body_ev[1], st));
   ++g_launches;
   return FEN_OK;
@@ -1006,8 +1027,7 @@ static int forward_impl(const fen_config* cfg, const void* packed, const float* 
   const uint8_t* k = static_cast<const uint8_t*>(packed);
   const RcabRec rr = rcab_rec(L.R);
   auto act = [&](int64_t off) { return reinterpret_cast<bf16*>(wsb + off); };
-  float* sums = reinterpret_cast<float*>(wsb + ws.sums);
-  FEN_CUDA(cudaMemsetAsync(sums, 0, size_t(L.n_rcab) * B * 64 * 4, st));
+  long long* sums = reinterpret_cast<long long*>(wsb + ws.sums);
 
   conv_first_kernel<<<dim3(H, B), 256, 0, st>>>(x, reinterpret_cast<const float*>(k + L.k_first_w),
                                                 reinterpret_cast<const float*>(k + L.k_first_b), act(ws.f0), H, W);
@@ -1015,17 +1035,20 @@ static int forward_impl(const fen_config* cfg, const void* packed, const float* 
   ++g_launches;
 
   auto conv = [&](const bf16* in, const uint8_t* w, const float* bias, const float* slope, const bf16* res,
-                  float* sm, bf16* o, int epi, int h, int w_) -> int {
+                  long long* sm, bf16* o, int epi, int h, int w_) -> int {
     ConvArgs a{};
     a.x = in; a.w = w; a.n = 64; a.groups = (epi == kEpiShuffle) ? 4 : 1;
     a.p.B = B; a.p.H = h; a.p.W = w_; a.p.epi = epi; a.p.bias = bias; a.p.slope = slope; a.p.residual = res;
-    a.p.out = o; a.p.sums = sm;
+    a.p.out = o; a.p.sums64 = sm;
     return launch_conv(a, st);
   };
 
   if ((rc = stage_check("conv_first", st))) return rc;
   if (body2_usable(L, B, H, W)) {
-    if ((rc = launch_body2(cfg, L, ws, wsb, k, B, H, W, se_out, st))) return rc;
+    Body2Bufs bufs{};
+    bufs.act_base = wsb + ws.f0; bufs.act_stride = ws.grp_stride; bufs.nbuf = 5 + L.G;   // f0 x0 x1 h o g0.. (BodyBuf order)
+    bufs.hsum64 = reinterpret_cast<long long*>(wsb + ws.hsum); bufs.flags = reinterpret_cast<int*>(wsb + ws.flags);
+    if ((rc = launch_body2<false>(cfg, L, bufs, k, B, H, W, se_out, st))) return rc;
     if ((rc = stage_check("body kernel", st))) return rc;
 #ifdef FEN_DEV
   } else if (body_kernel_usable(L, B, H, W)) {
@@ -1033,6 +1056,7 @@ static int forward_impl(const fen_config* cfg, const void* packed, const float* 
     if ((rc = stage_check("body kernel", st))) return rc;
 #endif
   } else {
+    FEN_CUDA(cudaMemsetAsync(sums, 0, size_t(L.n_rcab) * B * 64 * 8, st));
     const int hw = H * W;
     const int se_chunks = 32;
     const bf16* cur = act(ws.f0);
@@ -1041,7 +1065,7 @@ static int forward_impl(const fen_config* cfg, const void* packed, const float* 
       for (int b = 0; b < L.Bk; ++b) {
         const int r = g * L.Bk + b;
         const uint8_t* kr = k + L.k_rcab0 + int64_t(r) * L.k_rcab_stride;
-        float* sm = sums + size_t(r) * B * 64;
+        long long* sm = sums + size_t(r) * B * 64;
         if ((rc = conv(cur, kr + rr.w1, reinterpret_cast<const float*>(kr + rr.b1),
                        reinterpret_cast<const float*>(kr + rr.slope), nullptr, nullptr, act(ws.h), kEpiPrelu, H, W)))
           return rc;
@@ -1401,18 +1425,44 @@ int fen_forward_train(const fen_config* cfg, const void* packed, const float* x,
                       static_cast<uint8_t*>(step_workspace), ws, static_cast<cudaStream_t>(stream));
 }
 
-int fen_backward(const fen_config* cfg, const void* packed, const void* packed_bwd, const float* x, const float* dout,
-                 float* grads, int B, int H, int W, void* step_workspace, int64_t step_workspace_bytes, void* stream) {
+int fen_backward_stages(const fen_config* cfg, const void* packed, const void* packed_bwd, const float* x,
+                        const float* dout, float* grads, int B, int H, int W, void* step_workspace,
+                        int64_t step_workspace_bytes, int stage_begin, int stage_end, void* stream) {
   Layout L;
   StepWs ws;
   int rc = step_args(cfg, &L, &ws, B, H, W, step_workspace_bytes, "fen_backward");
   if (rc) return rc;
   if (!packed || !packed_bwd || !x || !dout || !grads || !step_workspace)
     return fail(FEN_EINVAL, "fen_backward: null pointer");
+  if (stage_begin < 0 || stage_end > bwd_num_stages(L) || stage_begin >= stage_end)
+    return fail(FEN_EINVAL, "fen_backward_stages: bad stage range");
   BwdLayout K;
   make_bwd_layout(L, &K);
   return step_backward(cfg, L, static_cast<const uint8_t*>(packed), static_cast<const uint8_t*>(packed_bwd), K, x, dout,
-                       grads, B, H, W, static_cast<uint8_t*>(step_workspace), ws, static_cast<cudaStream_t>(stream));
+                       grads, B, H, W, static_cast<uint8_t*>(step_workspace), ws, static_cast<cudaStream_t>(stream),
+                       stage_begin, stage_end);
+}
+
+int fen_backward(const fen_config* cfg, const void* packed, const void* packed_bwd, const float* x, const float* dout,
+                 float* grads, int B, int H, int W, void* step_workspace, int64_t step_workspace_bytes, void* stream) {
+  Layout L;
+  if (make_layout(cfg, &L)) return FEN_EINVAL;
+  return fen_backward_stages(cfg, packed, packed_bwd, x, dout, grads, B, H, W, step_workspace, step_workspace_bytes, 0,
+                             bwd_num_stages(L), stream);
+}
+
+int fen_backward_num_stages(const fen_config* cfg) {
+  Layout L;
+  if (make_layout(cfg, &L)) return FEN_EINVAL;
+  return bwd_num_stages(L);
+}
+
+int fen_backward_stage_range(const fen_config* cfg, int stage, int64_t* begin, int64_t* count) {
+  Layout L;
+  if (make_layout(cfg, &L)) return FEN_EINVAL;
+  if (!begin || !count || stage < 0 || stage >= bwd_num_stages(L)) return fail(FEN_EINVAL, "fen_backward_stage_range: bad arguments");
+  bwd_stage_range(L, stage, begin, count);
+  return FEN_OK;
 }
 
 }  // extern "C"

@@ -524,12 +524,12 @@ prelu_bwd_kernel(const bf16* g, const bf16* __restrict__ act, const uint32_t* __
 //   y = sums / HW; z = relu(W0 y); t = W2 z; s = sigmoid(t)
 //   ds = rs * dsum; dt = ds s (1 - s); dW2 += dt z^T; dz = W2^T dt; dzr = dz [z > 0]; dW0 += dzr y^T; dy = W0^T dzr
 __global__ void __launch_bounds__(256)
-se_bwd_apply_kernel(const bf16* __restrict__ dxo, const float* __restrict__ sums, const float* __restrict__ dsum,
+se_bwd_apply_kernel(const bf16* __restrict__ dxo, const long long* __restrict__ sums, const float* __restrict__ dsum,
                     const float* __restrict__ fc0, const float* __restrict__ fc2, int R, float inv_hw, float res_scale,
                     bf16* __restrict__ dO, float* __restrict__ dfc0, float* __restrict__ dfc2, int hw) {
   __shared__ float s_y[kC], s_z[kC], s_dt[kC], s_dzr[kC], s_mul[kC], s_add[kC];
   const int n = blockIdx.y, tid = threadIdx.x;
-  if (tid < kC) s_y[tid] = sums[size_t(n) * kC + tid] * inv_hw;
+  if (tid < kC) s_y[tid] = hs_to_float(sums[size_t(n) * kC + tid]) * inv_hw;
   __syncthreads();
   if (tid < R) {
     float a = 0.f;

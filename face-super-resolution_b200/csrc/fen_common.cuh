@@ -21,6 +21,15 @@ constexpr int kRingSlots = 3;                        // + 1 mirror slot after th
 constexpr int kRingBytes = (kRingSlots + 1) * kSlotBytes;
 constexpr int kMaxShift = 2 * kPitch + 2;            // largest tap offset in the strip-linear space
 
+// Fixed-point accumulation of the squeeze-and-excitation pool sums: 64-bit integer atomics are associative, so the sums
+// (and with them every output of the forward pass) do not depend on the order in which warps and CTAs arrive.
+// Scale 2^24: |sum| < 2^39 fits, resolution 6e-8 (sums of bf16 activations over <= 2^24 pixels).
+constexpr float kHsScale = 16777216.f;
+__device__ __forceinline__ void hs_add(long long* p, float v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(__float2ll_rn(v * kHsScale)));
+}
+__device__ __forceinline__ float hs_to_float(long long v) { return __ll2float_rn(v) * (1.f / kHsScale); }
+
 enum EpilogueKind : int {
   kEpiPrelu = 0,     // out = prelu(acc + bias)                       (RCAB conv1)
   kEpiSum = 1,       // out = acc + bias ; per-image channel sums     (RCAB conv2 -> SE pool)
@@ -49,6 +58,7 @@ struct ConvParams {
   const bf16* aux;        // NHWC, same shape as out (kEpiDot)
   bf16* out;              // NHWC bf16 output
   float* sums;            // [B][64] fp32, accumulated with atomics (kEpiSum, kEpiDot); [64] for kEpiGate
+  long long* sums64;      // kEpiSum, optional: accumulate there in fixed point (hs_add) instead of `sums`: deterministic
   uint32_t* mask_out;     // kEpiPrelu / kEpiShuffle, optional: bit c of word [2 * output pixel + column half] = (pre-activation
                           //   of channel 32 * half + c > 0) - what the PReLU backward needs for slopes of any sign
   const uint32_t* mask_in;  // kEpiGate: those words of the activation being differentiated

@@ -45,6 +45,7 @@ struct StepWs {
   int64_t act;                      // bytes of one [B][H][W][64] bf16 tensor
   int64_t f0, body, xs0, h0, o0, gout0, u0, u1, sums;     // forward (xs/h/o: one per RCAB, gout: one per group)
   int64_t m_h0, m_stride, m_u0, m_u1;                     // PReLU sign masks (8 B per pixel): per RCAB conv1, the two stages
+  int64_t hsum, flags;                                    // fused forward (body2_umma_kernel<true>)
   int64_t dy1, du0, dy0, g[6], dsum;                      // backward
   int64_t total;
 };
@@ -60,11 +61,13 @@ static void make_step_ws(const Layout& L, int B, int H, int W, StepWs* w) {
   w->gout0 = o; o += act * L.G;
   w->u0 = o; o += 4 * act;
   w->u1 = o; o += 16 * act;
-  w->sums = o; o += align256(int64_t(L.n_rcab) * B * 64 * 4);
+  w->sums = o; o += align256(int64_t(L.n_rcab) * B * 64 * 8);   // fixed-point SE pool sums (hs_add)
   w->m_stride = align256(int64_t(B) * H * W * 8);
   w->m_h0 = o; o += w->m_stride * L.n_rcab;
   w->m_u0 = o; o += 4 * w->m_stride;
   w->m_u1 = o; o += 16 * w->m_stride;
+  w->hsum = o; o += align256(int64_t(L.n_rcab) * B * 9 * 64 * 8);
+  w->flags = o; o += 4096;
   w->dy1 = o; o += 16 * act;
   w->du0 = o; o += 4 * act;
   w->dy0 = o; o += 4 * act;
@@ -75,11 +78,11 @@ static void make_step_ws(const Layout& L, int B, int H, int W, StepWs* w) {
 
 static int conv64(const bf16* in, const void* w, const float* bias, const float* slope, const bf16* res, float* sm,
                   bf16* out, int epi, int B, int h, int w_, cudaStream_t st, const bf16* aux = nullptr,
-                  uint32_t* mask = nullptr) {
+                  uint32_t* mask = nullptr, long long* sm64 = nullptr) {
   ConvArgs a{};
   a.x = in; a.w = w; a.n = 64; a.groups = (epi == kEpiShuffle) ? 4 : 1;
   a.p.B = B; a.p.H = h; a.p.W = w_; a.p.epi = epi; a.p.bias = bias; a.p.slope = slope; a.p.residual = res;
-  a.p.out = out; a.p.sums = sm; a.p.aux = aux;
+  a.p.out = out; a.p.sums = sm; a.p.sums64 = sm64; a.p.aux = aux;
   if (epi == kEpiGate) a.p.mask_in = mask; else a.p.mask_out = mask;
   return launch_conv(a, st);
 }
@@ -99,20 +102,31 @@ static int step_forward(const fen_config* cfg, const Layout& L, const uint8_t* k
   int rc;
   const RcabRec rr = rcab_rec(L.R);
   auto act = [&](int64_t off) { return reinterpret_cast<bf16*>(wsb + off); };
-  float* sums = reinterpret_cast<float*>(wsb + ws.sums);
-  FEN_CUDA(cudaMemsetAsync(sums, 0, size_t(L.n_rcab) * B * 64 * 4, st));
+  long long* sums = reinterpret_cast<long long*>(wsb + ws.sums);
   conv_first_kernel<<<dim3(H, B), 256, 0, st>>>(x, reinterpret_cast<const float*>(k + L.k_first_w),
                                                 reinterpret_cast<const float*>(k + L.k_first_b), act(ws.f0), H, W);
   FEN_CUDA(cudaGetLastError());
   ++g_launches;
   const int hw = H * W;
   const bf16* cur = act(ws.f0);
-  for (int g = 0; g < L.G; ++g) {
+  const bool fused = body2_usable(L, B, H, W);
+  if (fused) {
+    // the whole residual body in ONE persistent launch that also keeps what the backward needs: every RCAB's x', h
+    // and o, the PReLU sign masks, the SE pool sums (body2_umma_kernel<true>; StepWs buffer order = body2_layer's)
+    Body2Bufs bufs{};
+    bufs.act_base = wsb + ws.f0; bufs.act_stride = ws.act; bufs.nbuf = 2 + 3 * L.n_rcab + L.G;
+    bufs.hsum64 = reinterpret_cast<long long*>(wsb + ws.hsum); bufs.flags = reinterpret_cast<int*>(wsb + ws.flags);
+    bufs.mask0 = reinterpret_cast<uint32_t*>(wsb + ws.m_h0); bufs.mask_stride_bytes = ws.m_stride;
+    bufs.pool_sums = sums;
+    if ((rc = launch_body2<true>(cfg, L, bufs, k, B, H, W, nullptr, st))) return rc;
+  }
+  if (!fused) FEN_CUDA(cudaMemsetAsync(sums, 0, size_t(L.n_rcab) * B * 64 * 8, st));
+  for (int g = 0; g < (fused ? 0 : L.G); ++g) {
     const bf16* gin = cur;
     for (int b = 0; b < L.Bk; ++b) {
       const int r = g * L.Bk + b;
       const uint8_t* kr = k + L.k_rcab0 + int64_t(r) * L.k_rcab_stride;
-      float* sm = sums + size_t(r) * B * 64;
+      long long* sm = sums + size_t(r) * B * 64;
       bf16* h = act(ws.h0 + r * ws.act);
       bf16* o = act(ws.o0 + r * ws.act);
       bf16* nxt = act(ws.xs0 + r * ws.act);
@@ -120,8 +134,8 @@ static int step_forward(const fen_config* cfg, const Layout& L, const uint8_t* k
                        reinterpret_cast<const float*>(kr + rr.slope), nullptr, nullptr, h, kEpiPrelu, B, H, W, st,
                        nullptr, reinterpret_cast<uint32_t*>(wsb + ws.m_h0 + r * ws.m_stride))))
         return rc;
-      if ((rc = conv64(h, kr + rr.w2, reinterpret_cast<const float*>(kr + rr.b2), nullptr, nullptr, sm, o, kEpiSum, B,
-                       H, W, st)))
+      if ((rc = conv64(h, kr + rr.w2, reinterpret_cast<const float*>(kr + rr.b2), nullptr, nullptr, nullptr, o, kEpiSum, B,
+                       H, W, st, nullptr, nullptr, sm)))
         return rc;
       se_residual_kernel<<<dim3(32, B), 256, 0, st>>>(cur, o, sm, reinterpret_cast<const float*>(kr + rr.fc0),
                                                       reinterpret_cast<const float*>(kr + rr.fc2), L.R,
@@ -137,7 +151,8 @@ static int step_forward(const fen_config* cfg, const Layout& L, const uint8_t* k
       return rc;
     cur = gout;
   }
-  if ((rc = conv64(cur, k + L.k_after, reinterpret_cast<const float*>(k + L.k_after + kConvWBytes), nullptr,
+  if (!fused &&
+      (rc = conv64(cur, k + L.k_after, reinterpret_cast<const float*>(k + L.k_after + kConvWBytes), nullptr,
                    act(ws.f0), nullptr, act(ws.body), kEpiResidual, B, H, W, st)))
     return rc;
   const uint8_t* ku = k + L.k_up[0];
@@ -188,18 +203,33 @@ static int wgrad64(const bf16* dY, const bf16* X, float* dW, float* dB, int B, i
 }
 
 // Backward of step_forward: dout [B,3,4H,4W] fp32 (d loss / d network output) -> grads (flat fp32, the layout of
-// the flat parameter vector, zeroed here).
+// the flat parameter vector, zeroed by stage 0).  The pass is cut into G + 2 STAGES that each complete a contiguous
+// slice of the flat gradient, in the order the backward produces them - so that a data-parallel trainer can start the
+// all-reduce of a slice while the next stage still computes:
+//   stage 0        conv_last, both upsample stages, conv_after_body    -> grads[p_after_w, p_total)
+//   stage 1 + k    residual group G - 1 - k                            -> grads[that group's slice)
+//   stage G + 1    long skip + conv_first                              -> grads[0, p_rcab0)
+// All state between stages lives in the step workspace.  [stage_begin, stage_end) runs a sub-range.
+static int bwd_num_stages(const Layout& L) { return L.G + 2; }
+static void bwd_stage_range(const Layout& L, int stage, int64_t* begin, int64_t* count) {
+  if (stage == 0) { *begin = L.p_after_w; *count = L.p_total - L.p_after_w; }
+  else if (stage <= L.G) { *begin = L.p_rcab0 + int64_t(L.G - stage) * L.p_group_stride; *count = L.p_group_stride; }
+  else { *begin = 0; *count = L.p_rcab0; }
+}
 static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* k, const uint8_t* kb,
                          const BwdLayout& K, const float* x, const float* dout, float* grads, int B, int H, int W,
-                         uint8_t* wsb, const StepWs& ws, cudaStream_t st) {
+                         uint8_t* wsb, const StepWs& ws, cudaStream_t st, int stage_begin, int stage_end) {
   int rc;
   const RcabRec rr = rcab_rec(L.R);
   auto act = [&](int64_t off) { return reinterpret_cast<bf16*>(wsb + off); };
   const float* zeros = reinterpret_cast<const float*>(kb + K.zeros);
-  const float* sums = reinterpret_cast<const float*>(wsb + ws.sums);
+  const long long* sums = reinterpret_cast<const long long*>(wsb + ws.sums);
   float* dsum = reinterpret_cast<float*>(wsb + ws.dsum);
   const int Ho = 4 * H, Wo = 4 * W;
   const size_t n8 = size_t(B) * H * W * 8;   // 8-element groups of one body-resolution tensor
+  bf16* dBody = act(ws.g[0]);
+  bf16* dCur = act(ws.g[1]);
+  if (stage_begin <= 0 && stage_end > 0) {
   FEN_CUDA(cudaMemsetAsync(grads, 0, size_t(L.p_total) * 4, st));
   FEN_CUDA(cudaMemsetAsync(dsum, 0, size_t(L.n_rcab) * B * 64 * 4, st));
 
@@ -239,7 +269,6 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
     ++g_launches;
   }
   // ---- upsample stage 0 (conv 64 -> 256 on H x W, input body): planes in du0 region, result -> g[0] (= d body)
-  bf16* dBody = act(ws.g[0]);
   {
     bf16* acc[2] = {act(ws.g[1]), act(ws.g[0])};
     for (int sub = 0; sub < 4; ++sub) {
@@ -252,19 +281,21 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
     }
   }
   // ---- conv_after_body + long skip: body = conv(gout[G-1]) + f0
-  bf16* dCur = act(ws.g[1]);
   {
     const bf16* feat = act(ws.gout0 + (L.G - 1) * ws.act);
     if ((rc = wgrad64(dBody, feat, grads + L.p_after_w, grads + L.p_after_b, B, H, W, 1, 0, st))) return rc;
     if ((rc = conv64(dBody, kb + K.after, zeros, nullptr, nullptr, nullptr, dCur, kEpiBias, B, H, W, st))) return rc;
   }
+  }   // stage 0
   // ---- residual groups, last to first.  dCur = d gout[g]
-  bf16* dX = act(ws.g[2]);
-  bf16* dXn = act(ws.g[3]);
   bf16* dO = act(ws.g[4]);
   bf16* dH = act(ws.g[5]);
   const int hw = H * W;
   for (int g = L.G - 1; g >= 0; --g) {
+    const int stage = L.G - g;
+    if (stage < stage_begin || stage >= stage_end) continue;
+    bf16* dX = act(ws.g[2]);       // (re)written from dCur at the start of every group: the roles need no carry-over
+    bf16* dXn = act(ws.g[3]);
     float* pg = grads + L.p_rcab0 + g * L.p_group_stride;
     const bf16* gin = g ? act(ws.gout0 + (g - 1) * ws.act) : act(ws.f0);
     const bf16* blocks_out = act(ws.xs0 + (g * L.Bk + L.Bk - 1) * ws.act);
@@ -317,6 +348,7 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
     ++g_launches;
   }
   // ---- long skip + conv_first
+  if (stage_begin > L.G + 1 || stage_end <= L.G + 1) return FEN_OK;
   add_bf16_kernel<<<ew_blocks(n8), 256, 0, st>>>(dCur, dBody, dCur, n8);
   FEN_CUDA(cudaGetLastError());
   ++g_launches;

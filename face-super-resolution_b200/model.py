@@ -251,8 +251,10 @@ class FaceEnhanceNet(nn.Module):
                                              ws.data_ptr(), ws.numel(), stream), "fen_forward_train")
         return out, lease
 
-    def _backward(self, x: torch.Tensor, dout: torch.Tensor, lease: "_StepLease") -> torch.Tensor:
-        """fen_backward: flat fp32 gradient in parameter order for the _forward_train that produced `lease`."""
+    def _backward(self, x: torch.Tensor, dout: torch.Tensor, lease: "_StepLease", on_stage=None) -> torch.Tensor:
+        """fen_backward: flat fp32 gradient in parameter order for the _forward_train that produced `lease`.
+        on_stage(grads, begin, count), if given, is called after every stage of the backward with the slice of the flat
+        gradient that stage has just completed (fen_backward_stages; the data-parallel exchange hooks in here)."""
         lib, cfg = _lib.load(), self._c_config()
         ws = lease.ws
         B, _, H, W = x.shape
@@ -262,12 +264,28 @@ class FaceEnhanceNet(nn.Module):
             packed = self._ensure_packed(x.device, stream)
             packed_bwd = self._ensure_packed_bwd(x.device, stream)
             grads = torch.empty(self._flat.numel(), dtype=torch.float32, device=x.device)
-            _lib.check(lib.fen_backward(C.byref(cfg), packed.data_ptr(), packed_bwd.data_ptr(), x.data_ptr(),
-                                        dout.data_ptr(), grads.data_ptr(), B, H, W, ws.data_ptr(), ws.numel(), stream),
-                       "fen_backward")
             emb = self._embedding(x.device)
-            if emb is not None:
-                grads = grads[emb]
+            if on_stage is None or emb is not None:
+                _lib.check(lib.fen_backward(C.byref(cfg), packed.data_ptr(), packed_bwd.data_ptr(), x.data_ptr(),
+                                            dout.data_ptr(), grads.data_ptr(), B, H, W, ws.data_ptr(), ws.numel(),
+                                            stream), "fen_backward")
+                if emb is not None:
+                    grads = grads[emb]
+                if on_stage is not None:
+                    on_stage(grads, 0, grads.numel())
+            else:
+                launches = 0
+                begin, count = C.c_int64(), C.c_int64()
+                for stage in range(lib.fen_backward_num_stages(C.byref(cfg))):
+                    _lib.check(lib.fen_backward_stages(C.byref(cfg), packed.data_ptr(), packed_bwd.data_ptr(),
+                                                       x.data_ptr(), dout.data_ptr(), grads.data_ptr(), B, H, W,
+                                                       ws.data_ptr(), ws.numel(), stage, stage + 1, stream),
+                               "fen_backward_stages")
+                    launches += lib.fen_last_launch_count()
+                    _lib.check(lib.fen_backward_stage_range(C.byref(cfg), stage, C.byref(begin), C.byref(count)),
+                               "fen_backward_stage_range")
+                    on_stage(grads, begin.value, count.value)
+                self._last_backward_launches = launches
         return grads
 
     def _run(self, x: torch.Tensor, want_se: bool, u8: Optional[bool] = None):

@@ -189,6 +189,18 @@ int fen_forward_train(const fen_config* cfg, const void* packed, const float* x,
 int fen_backward(const fen_config* cfg, const void* packed, const void* packed_bwd, const float* x, const float* dout,
                  float* grads, int B, int H, int W, void* step_workspace, int64_t step_workspace_bytes, void* stream);
 
+/* fen_backward cut into stages that each COMPLETE a contiguous slice of the flat gradient, in the order the backward
+ * produces them (the data-parallel trainer all-reduces a slice while the next stage computes; the
+ * reference has no multi-GPU code to cite).  fen_backward_num_stages = num_groups + 2:
+ *   stage 0: conv_last, both upsample stages, conv_after_body; stage 1 + k: residual group G - 1 - k;
+ *   stage G + 1: long skip + conv_first.  fen_backward_stage_range gives the slice [begin, begin + count) of `grads` a
+ * stage completes.  Stages must run in order on one stream; stage 0 zeroes `grads`. */
+int fen_backward_num_stages(const fen_config* cfg);
+int fen_backward_stage_range(const fen_config* cfg, int stage, int64_t* begin, int64_t* count);
+int fen_backward_stages(const fen_config* cfg, const void* packed, const void* packed_bwd, const float* x,
+                        const float* dout, float* grads, int B, int H, int W, void* step_workspace,
+                        int64_t step_workspace_bytes, int stage_begin, int stage_end, void* stream);
+
 /* One 3x3 / pad-1 convolution with 64 input and 64 output channels on NHWC bf16 tensors
  * (the RCAB building block, reference src/models/blocks.py:122-130): out = epilogue(conv(x) + bias).
  *   w_packed [9][64][64] bf16 (tap, cout, cin), as produced by fen_pack_conv3x3

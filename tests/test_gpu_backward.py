@@ -43,7 +43,7 @@ def _compare(named_grads, ref_grads, rel_bar, whole=True, report_to=None):
         rel = (g - r).norm().item() / max(r.norm().item(), 1e-30)
         num += float((g * r).sum()); den_a += float((g * g).sum()); den_b += float((r * r).sum())
         rows.append(f"{k:60s} ref {r.norm().item():.3e} got {g.norm().item():.3e} rel {rel:.3e}")
-        if not rel <= rel_bar:
+        if rel_bar is not None and not rel <= rel_bar:
             bad.append(rows[-1])
     cos = num / max((den_a * den_b) ** 0.5, 1e-300)
     ratio = (den_a / max(den_b, 1e-300)) ** 0.5

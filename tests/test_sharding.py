@@ -41,7 +41,22 @@ def _worker(rank, world, port, q):
         from fsr_b200 import training
         g = torch.full((5,), float(rank + 1)) * torch.arange(1, 6)
         training.allreduce_mean_(g)
-        q.put((rank, b, e, t, n, g.tolist()))
+        # the bucketed exchange: slices of the flat gradient arrive in the order the backward completes them
+        # (descending addresses: tail, groups last to first, head) and are averaged bucket by bucket
+        total = 1000
+        flat = torch.arange(total, dtype=torch.float32) * (rank + 1)
+        ex = training.BucketedAllReduce(total, n_buckets=4)
+        sent = []
+        orig_flush = ex._flush
+        def spy(gr):
+            if ex._lo is not None:
+                sent.append((ex._lo, ex._hi))
+            orig_flush(gr)
+        ex._flush = spy
+        for begin, count in [(900, 100), (750, 150), (600, 150), (450, 150), (300, 150), (150, 150), (10, 140), (0, 10)]:
+            ex.on_stage(flat, begin, count)
+        ex.finish(flat)
+        q.put((rank, b, e, t, n, g.tolist(), flat.tolist() == (torch.arange(total, dtype=torch.float32) * 1.5).tolist(), sent))
     finally:
         dist.destroy_process_group()
 
@@ -63,6 +78,8 @@ def test_two_rank_timing_protocol_gloo():
     assert all(r[3] == 11.0 for r in res)      # max over ranks of the per-rank time
     assert all(r[4] == 65536.0 for r in res)   # every image processed exactly once
     assert all(r[5] == [1.5, 3.0, 4.5, 6.0, 7.5] for r in res)   # mean of the two ranks' gradients, on both
+    assert all(r[6] for r in res)              # bucketed exchange: every element averaged exactly once
+    assert res[0][7] == res[1][7] == [(750, 1000), (450, 750), (150, 450), (0, 150)]   # 4 contiguous buckets, tail first
 
 
 def test_allreduce_mean_is_identity_without_process_group():
