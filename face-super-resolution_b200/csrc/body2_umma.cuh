@@ -41,18 +41,22 @@ namespace fen {
 #define B2TS(P, e) do { if (FEN_B2_TRACE && p.dbg && blockIdx.x == 70 && (P) < 512 && lane == 0) p.dbg[6144 + (P) * 8 + (e)] = clock64(); } while (0)
 #define B2TRACE(P, e) do { if (FEN_B2_TRACE && p.dbg && blockIdx.x == 70 && (P) < 512) p.dbg[(P) * 8 + (e)] = clock64(); } while (0)
 
-constexpr int kB2Threads = 384;
+#ifndef FEN_B2_NI
+#define FEN_B2_NI 2   // MMA issuer warps.  One thread sustains ~81 cycles per tcgen05.mma (tools/umma_probe3.cu), the pipe
+#endif                //   takes one N = 64 MMA every ~48: at least two issuers must be inside their 36-MMA loops at any time
+constexpr int kB2Issuers = FEN_B2_NI;
 constexpr int kB2SeWarp = 0;                       // warp % 4 == 0: may read TMEM lanes 0..31 (the SE result rows)
 constexpr int kB2TmaWarp = 1;
-constexpr int kB2FirstMmaWarp = 2;                 // warps 2, 3
-constexpr int kB2FirstEpiWarp = 4;                 // warps 4..11
+constexpr int kB2FirstMmaWarp = 2;                 // warps 2 .. 2 + kB2Issuers - 1
+constexpr int kB2FirstEpiWarp = kB2FirstMmaWarp + kB2Issuers;   // 8 epilogue warps: lane quarter = warp & 3, column half = (warp - first) >> 2
 constexpr int kB2EpiWarps = 8;
+constexpr int kB2Threads = 32 * (kB2FirstEpiWarp + kB2EpiWarps);
+#ifndef FEN_B2_SMEM_CONST
+#define FEN_B2_SMEM_CONST (FEN_B2_NI > 2)   // 1: the epilogue reads bias / slope / SE scale from shared memory per tile instead of
+#endif                                      //    caching 64 values in registers (more warps per CTA = fewer registers per thread)
 constexpr int kB2AccBufs = 7;                      // 7 x 64 TMEM columns for conv tiles ...
 constexpr uint32_t kB2SeCol = kB2AccBufs * kC;     // ... + 64 columns for the SE mat-vec
 constexpr int kB2SBytes = 9 * 1024;                // SE operand: one 8-row SWIZZLE_128B atom per tap
-#ifndef FEN_B2_TURN
-#define FEN_B2_TURN 0   // 1: the two MMA issuers alternate strictly (tile G is issued only after tile G - 1 has been enqueued)
-#endif
 #ifndef FEN_B2_STAGED_STORE
 #define FEN_B2_STAGED_STORE 0   // 1: outputs go through a shared-memory transpose to coalesced stores (measured slower)
 #endif
@@ -64,8 +68,8 @@ constexpr int kB2DynBytes = kBodyWBytes + kB2SBytes + kB2RingBytes + (FEN_B2_STA
 constexpr int kB2MaxTiles = 64;
 constexpr int kB2MaxBoxes = 96;
 
-struct B2Tile { uint16_t m; uint8_t wait_upto, rel_upto, unit, t; uint16_t pad; };
-struct B2Box { int16_t img; int8_t y0; uint8_t mirror; };
+struct B2Tile { uint16_t m; uint8_t wait_upto, first_box, unit, t; uint16_t pad; };   // views of the tile lie in boxes [first_box, wait_upto)
+struct B2Box { int16_t img; int8_t y0; uint8_t mirror; uint8_t last_tile; uint8_t pad[3]; };   // last_tile: last tile of the pass reading the box
 struct B2Unit { int img, t0, t1, pad; };
 
 // BodyParams::B is the whole batch; total_tiles / tiles_per_cta count the tiles of ONE set.
@@ -167,6 +171,7 @@ __device__ __forceinline__ void st_shared_u32(uint32_t saddr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
 
+// (registers are allocated per group of 4 warps: 12 warps get 168 registers per thread, 13 .. 16 warps 128)
 template <bool kTrain>
 __global__ void __launch_bounds__(kB2Threads, 1)
 body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
@@ -177,12 +182,12 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
   uint8_t* s_buf = smem + kBodyWBytes;                 // [9] atoms of 8 rows x 128 B (rows 2u, 2u+1: hi / lo of unit u)
   uint8_t* ring = s_buf + kB2SBytes;                   // 6 slots + mirror
   uint8_t* stage = ring + kB2RingBytes;                // 8 x 2 KB output staging (one per epilogue warp)
-  __shared__ uint64_t bar_w[9], bar_wfree[9], bar_full[kB2Slots], bar_empty[kB2Slots];
+  __shared__ uint64_t bar_w[9], bar_wfree[9], bar_full[kB2Slots];
+  __shared__ int s_hist[kB2Slots];                     // TMA warp: running index of the last tile that reads the box now in each slot
   __shared__ uint64_t bar_acc_full[kB2AccBufs], bar_acc_empty[kB2AccBufs];
   __shared__ uint64_t bar_done, bar_s_ready, bar_s_free, bar_se_full, bar_se_empty, bar_scale[2];
   __shared__ uint64_t bar_cv[2];                       // per-layer bias / slope vectors staged by the TMA warp (slot L & 1)
   __shared__ __align__(16) float s_cv[2][128];
-  __shared__ volatile uint32_t s_turn;                 // FEN_B2_TURN: number of conv tiles enqueued so far (running index, all passes)
   __shared__ uint32_t tmem_slot;
   // per-pass tables, one set of them per image set (the two sets give a CTA runs of different length)
   __shared__ B2Tile tile_tab2[2][kB2MaxTiles];
@@ -217,7 +222,6 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
       const int g_begin = run_begin(blockIdx.x, s), g_end = run_begin(blockIdx.x + 1, s);
       B2Tile* tile_tab = tile_tab2[s]; B2Box* box_tab = box_tab2[s]; B2Unit* unit_tab = unit_tab2[s];
       // ---- per-pass tables (identical for every layer)
-      int first_box[kB2MaxTiles + 2];
       int b_cum = 0, i = 0, u = 0;
       for (int g = g_begin; g < g_end; ++u) {
         const BUnit bu = body_unit(p, g, g_end);
@@ -226,21 +230,23 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           B2Box e;
           e.img = int16_t(bu.n); e.y0 = int8_t(bu.ra - 1 + j * kBBoxRows);
           e.mirror = uint8_t(j > 0);   // continues the previous box of its unit: mirrored when it lands in slot 0
+          e.last_tile = uint8_t(i); e.pad[0] = e.pad[1] = e.pad[2] = 0;
           box_tab[b_cum + j] = e;
         }
         for (int t = bu.t0; t < bu.t1; ++t, ++i) {
           const int base = kTileM * t - kPitch * bu.ra;
-          first_box[i] = b_cum + base / kBBoxPx;
           B2Tile e;
+          e.pad = 0;
+          e.first_box = uint8_t(b_cum + base / kBBoxPx);
           e.m = uint16_t(b_cum * kBBoxPx + base);   // pixel position of the tile's view, relative to the pass's first box
           e.wait_upto = uint8_t(b_cum + min((base + kTileM + kMaxShift - 1) / kBBoxPx, bu.nboxes - 1) + 1);
-          e.rel_upto = 0; e.unit = uint8_t(u); e.t = uint8_t(t); e.pad = 0;
+          e.unit = uint8_t(u); e.t = uint8_t(t);
           tile_tab[i] = e;
+          for (int b = e.first_box; b < e.wait_upto; ++b) box_tab[b].last_tile = uint8_t(i);
         }
         b_cum += bu.nboxes;
         g += bu.t1 - bu.t0;
       }
-      for (int k = 0; k < i; ++k) tile_tab[k].rel_upto = uint8_t((k + 2 < i) ? first_box[k + 2] : b_cum);
       s_meta[s][0] = i; s_meta[s][1] = b_cum; s_meta[s][2] = u; s_meta[s][3] = 0;
       max_tiles = max(max_tiles, i);
       // peers: CTAs owning tiles of the images this CTA touches in this set (including itself)
@@ -248,17 +254,20 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
       s_peer[s][0] = cta_of(img0 * p.tiles_per_seg, s);
       s_peer[s][1] = cta_of(min(T, (img1 + 1) * p.tiles_per_seg) - 1, s);
     }
-    // ---- barriers.  A CTA with a single tile per pass in every set has no odd tile: issuer warp 3 stays out
-    // of the ring / weight release protocol entirely.
-    const uint32_t n_issuers = (max_tiles >= 2) ? 2u : 1u;
+    // ---- barriers.  Issuer w takes the tiles w, w + n, w + 2n ... of every pass; an issuer that never gets a tile
+    // (fewer tiles per pass than issuer warps, in every set) stays out of the weight release protocol entirely.
+    // Ring slots need no release barriers: a slot may be refilled once every tile that reads its box has COMPLETED,
+    // and tile completion is what bar_acc_full already signals (one tcgen05.commit per tile) - the TMA warp follows
+    // those barriers (s_hist, `frontier`).
+    const uint32_t n_issuers = uint32_t(min(kB2Issuers, max(max_tiles, 1)));
     s_meta[0][3] = int(n_issuers);
+    for (int k = 0; k < kB2Slots; ++k) s_hist[k] = -1;
     for (int k = 0; k < 9; ++k) { mbar_init(&bar_w[k], 1); mbar_init(&bar_wfree[k], n_issuers); }
-    for (int k = 0; k < kB2Slots; ++k) { mbar_init(&bar_full[k], 1); mbar_init(&bar_empty[k], n_issuers); }
+    for (int k = 0; k < kB2Slots; ++k) mbar_init(&bar_full[k], 1);
     for (int k = 0; k < kB2AccBufs; ++k) { mbar_init(&bar_acc_full[k], 1); mbar_init(&bar_acc_empty[k], kB2EpiWarps); }
     mbar_init(&bar_done, kB2EpiWarps);
     mbar_init(&bar_s_ready, 1); mbar_init(&bar_s_free, 1); mbar_init(&bar_se_full, 1); mbar_init(&bar_se_empty, 1);
     mbar_init(&bar_scale[0], 1); mbar_init(&bar_scale[1], 1);
-    s_turn = 0;
     mbar_init(&bar_cv[0], 1); mbar_init(&bar_cv[1], 1);
     fence_mbar_init();
     tma_prefetch_desc(&maps.w);
@@ -275,7 +284,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
     // ============================================================ TMA issuer + peer-flag poller
     // The ring is one running sequence of boxes over all passes (box g -> slot g % kB2Slots, use g / kB2Slots),
     // so the first boxes of a pass are prefetched while the previous pass still owns the other slots.
-    uint32_t P = 0, slot = 0, use = 0;
+    uint32_t P = 0, slot = 0, gbase = 0, frontier = 0;   // frontier: every tile below it (running index) is complete
     constexpr int kPre = 4;                       // boxes of a new layer requested BEFORE its weights
     for (int L = 0; L < p.n_layers; ++L) {
       const B2Layer ly = body2_layer<kTrain>(p, L);
@@ -291,13 +300,19 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           fence_proxy_async_all();
         }
       };
-      auto issue_boxes = [&](int s, int b0, int b1) {     // lane 0 only
+      auto issue_boxes = [&](int s, int b0, int b1, uint32_t gbase_pass) {     // lane 0 only
         const int img_base = s * p.set_B;
         for (int b = b0; b < b1; ++b) {
           const B2Box e = box_tab2[s][b];
           B2T2(P, 9, b);
           B2W(1, 3, L, s, b);
-          mbar_wait(&bar_empty[slot], (use & 1u) ^ 1u);
+          // the box this one replaces must have been read by every tile that uses it: wait for those tiles to complete
+          const int need = s_hist[slot];
+          while (int(frontier) <= need) {
+            mbar_wait(&bar_acc_full[frontier % kB2AccBufs], (frontier / kB2AccBufs) & 1u);
+            ++frontier;
+          }
+          s_hist[slot] = int(gbase_pass) + int(e.last_tile);
           const bool mirror = e.mirror && slot == 0;
           mbar_expect_tx(&bar_full[slot], mirror ? 2 * kBSlotBytes : kBSlotBytes);
           tma_load_5d_hint(&maps.act, &bar_full[slot], smem_u32(ring + slot * kBSlotBytes), 0, -1, e.y0,
@@ -306,14 +321,14 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
             tma_load_5d_hint(&maps.act, &bar_full[slot], smem_u32(ring + kB2Slots * kBSlotBytes), 0, -1, e.y0,
                              img_base + e.img, ly.in, pol);
           B2T2(P, 10, b);
-          if (++slot == kB2Slots) { slot = 0; ++use; }
+          if (++slot == kB2Slots) slot = 0;
         }
       };
       const int pre = min(kPre, s_meta[0][1]);
       wait_flags(0);
       if (lane == 0) {
         B2TRACE(P, 0);
-        issue_boxes(0, 0, pre);
+        issue_boxes(0, 0, pre, gbase);
         // bias (+ slope) of this layer -> s_cv[L & 1].  The slot was last read by the epilogue of layer L - 2, which
         // is complete: wait_flags saw this CTA's own flag reach L, i.e. its epilogue has finished layer L - 1.
         mbar_expect_tx(&bar_cv[L & 1], 512);
@@ -331,12 +346,13 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           wait_flags(s);
           if (lane == 0) B2TRACE(P, 0);
         }
-        if (lane == 0) issue_boxes(s, s == 0 ? pre : 0, s_meta[s][1]);
+        if (lane == 0) issue_boxes(s, s == 0 ? pre : 0, s_meta[s][1], gbase);
+        gbase += uint32_t(s_meta[s][0]);
         __syncwarp();
       }
     }
-  } else if (warp == kB2FirstMmaWarp || warp == kB2FirstMmaWarp + 1) {
-    // ============================================================ MMA issuers: warp 2 even tiles (+ SE batches), warp 3 odd tiles
+  } else if (warp >= kB2FirstMmaWarp && warp < kB2FirstMmaWarp + kB2Issuers) {
+    // ============================================================ MMA issuers: warp 2 + w takes tiles w, w + n, ... (warp 2 also the SE batches)
     constexpr uint32_t idesc = umma_idesc_bf16(kTileM, N);
     constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
     constexpr uint32_t kLbo = 1u << 16;
@@ -346,14 +362,14 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
     const bool leader = elect_one();
     const int wi = warp - kB2FirstMmaWarp;
     uint32_t P = 0, gbase = 0, gbox = 0, se_n = 0;
-    for (int L = 0; L < ((wi == 0 || n_issuers == 2) ? p.n_layers : 0); ++L) {
+    for (int L = 0; L < ((wi < n_issuers) ? p.n_layers : 0); ++L) {
       const bool conv2 = body_layer(p, L).epi == kBEpiSeResidual;   // (the layer kinds do not depend on the variant)
       bool w_seen = false;
       int se_done = 0;
       for (int s = 0; s < p.nset; ++s, ++P) {
         const B2Tile* tile_tab = tile_tab2[s];
         const int n_tiles = s_meta[s][0], n_boxes = s_meta[s][1];
-        const int last_own = ((n_tiles - 1 - wi) >= 0) ? wi + 2 * ((n_tiles - 1 - wi) >> 1) : -1;
+        const int last_own = ((n_tiles - 1 - wi) >= 0) ? wi + n_issuers * ((n_tiles - 1 - wi) / n_issuers) : -1;
         const uint32_t gb0 = gbox;                                  // running index of the pass's first box
         const uint32_t gbase_pass = gbase;
         gbox += uint32_t(n_boxes); gbase += uint32_t(n_tiles);
@@ -367,7 +383,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
         const bool se_layer = conv2 && (wi == 0);
 #endif
         if (s == 0) se_done = 0;
-        uint32_t waited = 0, released = 0;
+        uint32_t waited = 0;
         // one SE batch: D[row, c] = sum_tap S_tap[row, :] . W2_tap[c, :] into the SE accumulator
         auto issue_se = [&]() {
           B2W(2 + wi, 5, L, s, se_n);
@@ -400,24 +416,15 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           __syncwarp();
         };
         if (last_own < 0) {
-          // no tile of this parity in this pass (a one-tile run): see every box of the pass arrive, then hand
-          // it back - and the weights, if this is the layer's last pass (the commit covers this warp's MMAs of
-          // the other set)
-          while (waited < uint32_t(n_boxes)) {
-            const uint32_t g = gb0 + waited;
-            mbar_wait(&bar_full[g % kB2Slots], (g / kB2Slots) & 1u);
-            ++waited;
-          }
+          // no tile for this issuer in this pass (fewer tiles than issuers): only the weights need its hand-back, if
+          // this is the layer's last pass (the commit covers this warp's MMAs of the other set)
           __syncwarp();
-          if (leader) {
-            for (int b = 0; b < n_boxes; ++b) umma_commit(&bar_empty[(gb0 + b) % kB2Slots]);
-            if (last_pass)
-              for (int tap = 0; tap < 9; ++tap) umma_commit(&bar_wfree[tap]);
-          }
+          if (leader && last_pass)
+            for (int tap = 0; tap < 9; ++tap) umma_commit(&bar_wfree[tap]);
           __syncwarp();
           continue;
         }
-        for (int i = wi; i < n_tiles; i += 2) {
+        for (int i = wi; i < n_tiles; i += n_issuers) {
           const B2Tile e = tile_tab[i];
           const uint32_t G = gbase_pass + i, acc = G % kB2AccBufs, aph = (G / kB2AccBufs) & 1;
           B2W(2 + wi, 1, L, s, i);
@@ -445,29 +452,16 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           mbar_wait(&bar_acc_empty[acc], aph ^ 1);
           if (leader) B2T2(P, 5, i);
           B2W(2 + wi, 3, L, s, i);
+          // only the boxes this tile reads (earlier ones may already have been replaced: their readers are complete)
+          if (waited < e.first_box) waited = e.first_box;
           while (waited < e.wait_upto) {
             const uint32_t g = gb0 + waited;
             mbar_wait(&bar_full[g % kB2Slots], (g / kB2Slots) & 1u);
             ++waited;
           }
-          if (leader && i == wi) B2TRACE(P, 1 + wi);
+          if (leader && i == wi && wi < 2) B2TRACE(P, 1 + wi);
           B2W(2 + wi, 4, L, s, i);
           if (leader) B2T2(P, 6, i);
-#if FEN_B2_TURN
-          // Strict alternation.  Left alone the two issuers fall into lock-step (they share the pipe at half rate,
-          // finish together and then do their per-tile barrier work together with the pipe idle); with the turn
-          // token one issuer's bookkeeping always runs under the other one's 36 MMAs.
-          // (A counter, not an mbarrier: a warp may fall several tiles behind, which a one-bit phase cannot express.
-          // Warp 2 keeps serving SE batches while it waits: the other issuer may be blocked on an accumulator that
-          // only frees once the epilogue has the SE scale, i.e. once this warp has issued that batch.)
-          if (n_issuers == 2) {
-            while (s_turn < G) {
-              if (se_layer && se_done < p.nset && w_seen &&
-                  __any_sync(0xffffffffu, mbar_test_wait(&bar_s_ready, se_n & 1)))
-                issue_se();
-            }
-          }
-#endif
           __syncwarp();                            // converge after the spin-waits (see the commits below)
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * N;
@@ -499,30 +493,13 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
             for (int tap = 0; tap < 9; ++tap) FEN_B2_ISSUE_TAP(tap)
           }
           w_seen = true;
-#if FEN_B2_TURN
-          if (leader && n_issuers == 2) s_turn = G + 1;
-#endif
           __syncwarp();
           if (leader) B2T2(P, 7, i);
-          // A box may only be handed back after THIS warp has seen it arrive (the last boxes of a pass are
-          // read by the other issuer alone): an arrival for a use that has not started yet would complete
-          // the slot's previous phase early.
-          while (waited < e.rel_upto) {
-            const uint32_t g = gb0 + waited;
-            mbar_wait(&bar_full[g % kB2Slots], (g / kB2Slots) & 1u);
-            ++waited;
-          }
-          // Lanes leave a spin-wait at different times.  The commits below compile to warp-level UTCBAR
-          // instructions fed by predicated R2UR: executed by a diverged warp, the group WITHOUT the elected
-          // lane would repeat them with stale operands (spurious mbarrier arrivals -> "illegal instruction").
-          __syncwarp();
-          while (released < e.rel_upto) {
-            if (leader) umma_commit(&bar_empty[(gb0 + released) % kB2Slots]);
-            ++released;
-          }
+          // ONE commit per tile: the accumulator is complete.  The epilogue reads it; the TMA warp learns from the same
+          // barrier that the ring boxes this tile read may be replaced.
           if (leader) umma_commit(&bar_acc_full[acc]);
           if (leader) B2T2(P, 8, i);
-          if (leader && i == last_own) B2TRACE(P, 3 + wi);
+          if (leader && i == last_own && wi < 2) B2TRACE(P, 3 + wi);
           __syncwarp();
         }
       }
@@ -717,20 +694,24 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
       const bf16* resp = ly.res >= 0 ? p.act_base + size_t(ly.res) * p.act_elems : nullptr;
       bf16* out2p = (kTrain && ly.out2 >= 0) ? p.act_base + size_t(ly.out2) * p.act_elems : nullptr;
       uint32_t* maskp = (kTrain && ly.epi == kBEpiPreluHsum) ? p.mask0 + size_t(ly.rcab) * p.mask_stride : nullptr;
-      float bias[CW], slope[CW];
       mbar_wait(&bar_cv[L & 1], (L >> 1) & 1);
+      const float* s_bias_l = &s_cv[L & 1][col0];          // this layer's bias / PReLU slope (cv_slope = cv_bias + 64)
+      const float* s_slope_l = &s_cv[L & 1][64 + col0];
+#if !FEN_B2_SMEM_CONST
+      float bias[CW], slope[CW];
 #pragma unroll
       for (int j = 0; j < CW / 4; ++j) {
-        const float4 b4 = *reinterpret_cast<const float4*>(&s_cv[L & 1][col0 + 4 * j]);
+        const float4 b4 = *reinterpret_cast<const float4*>(s_bias_l + 4 * j);
         bias[4 * j] = b4.x; bias[4 * j + 1] = b4.y; bias[4 * j + 2] = b4.z; bias[4 * j + 3] = b4.w;
       }
       if (ly.epi == kBEpiPreluHsum) {
 #pragma unroll
         for (int j = 0; j < CW / 4; ++j) {
-          const float4 s4 = *reinterpret_cast<const float4*>(&s_cv[L & 1][64 + col0 + 4 * j]);   // cv_slope = cv_bias + 64
+          const float4 s4 = *reinterpret_cast<const float4*>(s_slope_l + 4 * j);
           slope[4 * j] = s4.x; slope[4 * j + 1] = s4.y; slope[4 * j + 2] = s4.z; slope[4 * j + 3] = s4.w;
         }
       }
+#endif
       for (int s = 0; s < p.nset; ++s, ++P) {
         const B2Tile* tile_tab = tile_tab2[s];
         const B2Unit* unit_tab = unit_tab2[s];
@@ -775,6 +756,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
             for (int c = 0; c < CW; ++c) csum[c] = 0.f;
             col0sum = 0.f; colLsum = 0.f;
             if (EPI == kBEpiPreluHsum) hs = p.hsum64 + (size_t(ly.rcab) * p.B + img) * (kHsCount * kC);
+#if !FEN_B2_SMEM_CONST
             if (EPI == kBEpiSeResidual) {             // `slope` doubles as the SE scale of this image
 #pragma unroll
               for (int j = 0; j < CW / 4; ++j) {
@@ -782,6 +764,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
                 slope[4 * j] = s4.x; slope[4 * j + 1] = s4.y; slope[4 * j + 2] = s4.z; slope[4 * j + 3] = s4.w;
               }
             }
+#endif
           }
           const uint32_t acc = G % kB2AccBufs, aph = (G / kB2AccBufs) & 1;
           const int lin = kTileM * int(e.t) + row_in_tile;
@@ -816,8 +799,27 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           if (lane == 0) mbar_arrive(&bar_acc_empty[acc]);
           if (ew == 0 && lane == 0) B2T2(P, 2, i);
           float f[CW];
+#if FEN_B2_SMEM_CONST
+          // second operand of the epilogue (PReLU slope of the layer / SE scale of this image), broadcast reads
+          const float* s_mul = (EPI == kBEpiSeResidual) ? &s_scale[s][cur_unit][col0] : s_slope_l;
+#pragma unroll
+          for (int j = 0; j < CW / 4; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias_l + 4 * j);
+            f[4 * j] = __uint_as_float(v[4 * j]) + b4.x; f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4.y;
+            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4.z; f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4.w;
+          }
+#define B2_FOR_MUL(OP)                                                                              \
+  _Pragma("unroll") for (int j = 0; j < CW / 4; ++j) {                                               \
+    const float4 m4 = *reinterpret_cast<const float4*>(s_mul + 4 * j);                               \
+    OP(f[4 * j], m4.x) OP(f[4 * j + 1], m4.y) OP(f[4 * j + 2], m4.z) OP(f[4 * j + 3], m4.w)          \
+  }
+#else
 #pragma unroll
           for (int c = 0; c < CW; ++c) f[c] = __uint_as_float(v[c]) + bias[c];
+#define B2_FOR_MUL(OP) _Pragma("unroll") for (int c = 0; c < CW; ++c) { OP(f[c], slope[c]) }
+#endif
+#define B2_OP_PRELU(x, m) x = fmaxf(x, 0.f) + (m) * fminf(x, 0.f);
+#define B2_OP_SCALE(x, m) x *= (m);
           if (EPI == kBEpiPreluHsum) {
             if (kTrain) {                           // sign bits of the pre-activation, for the PReLU backward
               uint32_t mbits = 0;
@@ -825,8 +827,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
               for (int c = 0; c < CW; ++c) mbits |= (f[c] > 0.f ? 1u : 0u) << c;
               if (valid) maskp[opix * 2 + half] = mbits;
             }
-#pragma unroll
-            for (int c = 0; c < CW; ++c) f[c] = fmaxf(f[c], 0.f) + slope[c] * fminf(f[c], 0.f);
+            B2_FOR_MUL(B2_OP_PRELU)
           } else {
             if (EPI == kBEpiSeResidual) {
               if (kTrain) {                         // o = conv2(h) + b2 is kept: the SE backward needs sum dx' * o
@@ -838,8 +839,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
                   st_global_256(out2p + opix * kC + col0 + 16, *reinterpret_cast<uint32_t(*)[8]>(&o2[8]));
                 }
               }
-#pragma unroll
-              for (int c = 0; c < CW; ++c) f[c] *= slope[c];
+              B2_FOR_MUL(B2_OP_SCALE)
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) {          // + x (RCAB residual) or + skip (group / long skip)
