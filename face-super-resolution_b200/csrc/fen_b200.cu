@@ -148,7 +148,7 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int rows, int n) {
 // ---- per-device state: SM count and the "max dynamic shared memory" function attributes are properties of a
 // device, not of the process (one process may drive several GPUs).
 constexpr int kMaxDevices = 64;
-enum KernelId : int { kKConv64 = 0, kKConv16, kKConv2_64, kKConv2_16, kKBody, kKBody2, kKBody2Train, kKWgMma, kKWgUmma, kKLastDgrad,
+enum KernelId : int { kKConv64 = 0, kKConv16, kKConv2_64, kKConv2_16, kKBody, kKBody2, kKBody2Train, kKWgMma, kKWgUmma, kKWgBatch, kKLastDgrad,
                       kKWgradC3, kKernelIds };
 struct DevState {
   int sms = 0;
@@ -841,15 +841,16 @@ static bool body2_usable(const Layout& L, int B, int H, int W) {
 }
 
 // [nbuf][B][H][W][64] bf16 activation buffers at a constant stride: one 5-D map, box 64 ch x 66 px x 2 rows.
-static int make_act5_map(CUtensorMap* m, const void* base, int64_t buf_stride_bytes, int nbuf, int B, int H, int W) {
-  const MapKey key{base, 2, B, H, W, nbuf, int(buf_stride_bytes >> 8)};
+static int make_act5_map(CUtensorMap* m, const void* base, int64_t buf_stride_bytes, int nbuf, int B, int H, int W,
+                         int box_px, int box_rows) {
+  const MapKey key{base, 2 + 16 * box_rows + 256 * box_px, B, H, W, nbuf, int(buf_stride_bytes >> 8)};
   if (map_lookup(key, m)) return FEN_OK;
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(FEN_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[5] = {cuuint64_t(kC), cuuint64_t(W), cuuint64_t(H), cuuint64_t(B), cuuint64_t(nbuf)};
   cuuint64_t strides[4] = {cuuint64_t(kC) * 2, cuuint64_t(W) * kC * 2, cuuint64_t(H) * W * kC * 2,
                            cuuint64_t(buf_stride_bytes)};
-  cuuint32_t box[5] = {cuuint32_t(kC), cuuint32_t(kPitch), cuuint32_t(kBBoxRows), 1, 1};
+  cuuint32_t box[5] = {cuuint32_t(kC), cuuint32_t(box_px), cuuint32_t(box_rows), 1, 1};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -884,7 +885,7 @@ static int launch_body2(const fen_config* cfg, const Layout& L, const Body2Bufs&
   p.res_scale = cfg->res_scale; p.inv_hw = 1.f / float(H * W);
   p.act_base = reinterpret_cast<bf16*>(bufs.act_base);
   p.act_elems = bufs.act_stride / 2;
-  int rc = make_act5_map(&maps.act, bufs.act_base, bufs.act_stride, bufs.nbuf, B, H, W);
+  int rc = make_act5_map(&maps.act, bufs.act_base, bufs.act_stride, bufs.nbuf, B, H, W, kPitch, kBBoxRows);
   if (rc) return rc;
   if ((rc = make_w_map(&maps.w, k, int(L.k_total / 128), kC))) return rc;
   p.packed = k;

@@ -41,12 +41,19 @@ __global__ void pack_T_all_kernel(const float* __restrict__ params, uint8_t* __r
 }
 
 // ---------------------------------------------------------------- saved activations + gradient buffers
+// All [B][H][W][64] bf16 tensors of the step lie at ONE stride (`act`) from the workspace base, so that a single 5-D
+// tensor map addresses any of them by index (body2_umma_kernel<true>, wgrad_batch_umma_kernel):
+//   0 f0 | 1 body | xs[n] (x' of every RCAB) | h[n] | o[n] | gout[G] |            <- forward, kept for the backward
+//   dO[n] | dH[n] (the output gradients of conv2 / conv1 of every RCAB) | dG[G] (d gout[g]) | dBody | dF | dX0 | dX1
 struct StepWs {
   int64_t act;                      // bytes of one [B][H][W][64] bf16 tensor
-  int64_t f0, body, xs0, h0, o0, gout0, u0, u1, sums;     // forward (xs/h/o: one per RCAB, gout: one per group)
+  int64_t f0, body, xs0, h0, o0, gout0;
+  int64_t dO0, dH0, dG0, dBody, dF, dX0, dX1;
+  int n_act;                        // buffers in the uniformly strided region
+  int64_t u0, u1, sums;
   int64_t m_h0, m_stride, m_u0, m_u1;                     // PReLU sign masks (8 B per pixel): per RCAB conv1, the two stages
   int64_t hsum, flags;                                    // fused forward (body2_umma_kernel<true>)
-  int64_t dy1, du0, dy0, g[6], dsum;                      // backward
+  int64_t dy1, du0, dy0, dsum;                            // backward, upsample resolution
   int64_t total;
 };
 static void make_step_ws(const Layout& L, int B, int H, int W, StepWs* w) {
@@ -59,6 +66,14 @@ static void make_step_ws(const Layout& L, int B, int H, int W, StepWs* w) {
   w->h0 = o; o += act * L.n_rcab;
   w->o0 = o; o += act * L.n_rcab;
   w->gout0 = o; o += act * L.G;
+  w->dO0 = o; o += act * L.n_rcab;
+  w->dH0 = o; o += act * L.n_rcab;
+  w->dG0 = o; o += act * L.G;
+  w->dBody = o; o += act;
+  w->dF = o; o += act;
+  w->dX0 = o; o += act;
+  w->dX1 = o; o += act;
+  w->n_act = int(o / act);
   w->u0 = o; o += 4 * act;
   w->u1 = o; o += 16 * act;
   w->sums = o; o += align256(int64_t(L.n_rcab) * B * 64 * 8);   // fixed-point SE pool sums (hs_add)
@@ -71,7 +86,6 @@ static void make_step_ws(const Layout& L, int B, int H, int W, StepWs* w) {
   w->dy1 = o; o += 16 * act;
   w->du0 = o; o += 4 * act;
   w->dy0 = o; o += 4 * act;
-  for (int i = 0; i < 6; ++i) { w->g[i] = o; o += act; }
   w->dsum = o; o += align256(int64_t(L.n_rcab) * B * 64 * 4);   // sum_px dx' * o per RCAB, image, channel
   w->total = o;
 }
@@ -203,19 +217,73 @@ static int wgrad64(const bf16* dY, const bf16* X, float* dW, float* dB, int B, i
 }
 
 // Backward of step_forward: dout [B,3,4H,4W] fp32 (d loss / d network output) -> grads (flat fp32, the layout of
-// the flat parameter vector, zeroed by stage 0).  The pass is cut into G + 2 STAGES that each complete a contiguous
-// slice of the flat gradient, in the order the backward produces them - so that a data-parallel trainer can start the
-// all-reduce of a slice while the next stage still computes:
-//   stage 0        conv_last, both upsample stages, conv_after_body    -> grads[p_after_w, p_total)
-//   stage 1 + k    residual group G - 1 - k                            -> grads[that group's slice)
-//   stage G + 1    long skip + conv_first                              -> grads[0, p_rcab0)
+// the flat parameter vector, zeroed by stage 0).
+//
+// Weight gradients of the 64 -> 64 body convolutions are DEFERRED: the chain of data-gradient convolutions keeps every
+// layer's output gradient (dO / dH per RCAB, dG per group, dBody), and wgrad_batch_umma_kernel computes all weight
+// gradients of a run of groups in one persistent launch (bwd_is_flush: after the upper half, after group 1, after group 0).
+//
+// The pass is cut into G + 2 STAGES, in the order the backward runs, so that a data-parallel trainer can all-reduce a
+// finished slice of the flat gradient while later stages still compute:
+//   stage 0        conv_last, both upsample stages, data gradient of conv_after_body
+//   stage 1 + k    residual group G - 1 - k   (+ a batched weight-gradient launch where bwd_is_flush)
+//   stage G + 1    long skip + conv_first
+// fen_backward_stage_range gives the slice a stage COMPLETES (empty for a stage that only feeds a later batch).
 // All state between stages lives in the step workspace.  [stage_begin, stage_end) runs a sub-range.
 static int bwd_num_stages(const Layout& L) { return L.G + 2; }
-static void bwd_stage_range(const Layout& L, int stage, int64_t* begin, int64_t* count) {
-  if (stage == 0) { *begin = L.p_after_w; *count = L.p_total - L.p_after_w; }
-  else if (stage <= L.G) { *begin = L.p_rcab0 + int64_t(L.G - stage) * L.p_group_stride; *count = L.p_group_stride; }
-  else { *begin = 0; *count = L.p_rcab0; }
+// batched weight-gradient launches: after group G / 2 (the upper half, with conv_after_body), after group 1 and after
+// group 0 (a small last batch keeps the gradient slice that finishes last - and whose all-reduce is exposed - small)
+static bool bwd_is_flush(const Layout& L, int g) { return g == L.G / 2 || g == 1 || g == 0; }
+static int bwd_prev_flush(const Layout& L, int g) {       // the flush group above g, or -1
+  for (int q = g + 1; q < L.G; ++q)
+    if (bwd_is_flush(L, q)) return q;
+  return -1;
 }
+static void bwd_stage_range(const Layout& L, int stage, int64_t* begin, int64_t* count) {
+  *begin = 0; *count = 0;
+  if (stage == 0) { *begin = L.p_up[0]; *count = L.p_total - L.p_up[0]; }
+  else if (stage <= L.G) {
+    const int g = L.G - stage;
+    if (bwd_is_flush(L, g)) {
+      const int prev = bwd_prev_flush(L, g);
+      const int64_t end = prev < 0 ? L.p_up[0] : L.p_rcab0 + int64_t(prev) * L.p_group_stride;
+      *begin = L.p_rcab0 + int64_t(g) * L.p_group_stride;
+      *count = end - *begin;
+    }
+  } else { *begin = 0; *count = L.p_rcab0; }
+}
+
+// 5-D maps over the workspace's activation-strided region for the batched weight gradient
+static int make_act5_map(CUtensorMap* m, const void* base, int64_t buf_stride_bytes, int nbuf, int B, int H, int W,
+                         int box_px, int box_rows);
+
+static int wgrad_batch(const Layout& L, uint8_t* wsb, const StepWs& ws, float* grads, int B, int H, int W, int job_begin,
+                       int job_end, cudaStream_t st) {
+  if (job_end <= job_begin) return FEN_OK;
+  FEN_CUDA(ensure_smem_attr(kKWgBatch, wgrad_batch_umma_kernel, kWbDynBytes));
+  CUtensorMap tm_y, tm_x;
+  int rc = make_act5_map(&tm_y, wsb, ws.act, ws.n_act, B, H, W, kStripW, 1);
+  if (rc) return rc;
+  if ((rc = make_act5_map(&tm_x, wsb, ws.act, ws.n_act, B, H, W, kPitch, 3))) return rc;
+  WgBatchParams p{};
+  p.B = B; p.H = H; p.W = W; p.G = L.G; p.Bk = L.Bk;
+  p.job_begin = job_begin; p.job_end = job_end;
+  const int bands = B * H * ((W + kStripW - 1) / kStripW);
+  p.chunks = bands >= 16 * 32 ? 16 : (bands >= 64 ? bands / 32 : 1);     // >= 32 bands per work item
+  p.i_xs0 = int(ws.xs0 / ws.act); p.i_h0 = int(ws.h0 / ws.act); p.i_gout0 = int(ws.gout0 / ws.act);
+  p.i_dO0 = int(ws.dO0 / ws.act); p.i_dH0 = int(ws.dH0 / ws.act); p.i_dG0 = int(ws.dG0 / ws.act);
+  p.i_dBody = int(ws.dBody / ws.act);
+  p.p_rcab0 = L.p_rcab0; p.p_rcab_stride = L.p_rcab_stride; p.p_group_stride = L.p_group_stride;
+  p.p_gconv_w_in_group = L.p_gconv_w_in_group; p.p_after_w = L.p_after_w;
+  p.grads = grads;
+  const int items = (job_end - job_begin) * p.chunks;
+  const int grid = items < num_sms() ? items : num_sms();
+  wgrad_batch_umma_kernel<<<grid, kWbThreads, kWbDynBytes, st>>>(tm_y, tm_x, p);
+  FEN_CUDA(cudaGetLastError());
+  ++g_launches;
+  return FEN_OK;
+}
+
 static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* k, const uint8_t* kb,
                          const BwdLayout& K, const float* x, const float* dout, float* grads, int B, int H, int W,
                          uint8_t* wsb, const StepWs& ws, cudaStream_t st, int stage_begin, int stage_end) {
@@ -227,8 +295,9 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
   float* dsum = reinterpret_cast<float*>(wsb + ws.dsum);
   const int Ho = 4 * H, Wo = 4 * W;
   const size_t n8 = size_t(B) * H * W * 8;   // 8-element groups of one body-resolution tensor
-  bf16* dBody = act(ws.g[0]);
-  bf16* dCur = act(ws.g[1]);
+  bf16* dBody = act(ws.dBody);
+  auto dG = [&](int g) { return act(ws.dG0 + g * ws.act); };      // d gout[g]
+  const int per = 1 + 2 * L.Bk;              // deferred weight-gradient jobs per group (wgrad_umma.cuh: wg_job)
   if (stage_begin <= 0 && stage_end > 0) {
   FEN_CUDA(cudaMemsetAsync(grads, 0, size_t(L.p_total) * 4, st));
   FEN_CUDA(cudaMemsetAsync(dsum, 0, size_t(L.n_rcab) * B * 64 * 4, st));
@@ -268,9 +337,9 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
     FEN_CUDA(cudaGetLastError());
     ++g_launches;
   }
-  // ---- upsample stage 0 (conv 64 -> 256 on H x W, input body): planes in du0 region, result -> g[0] (= d body)
+  // ---- upsample stage 0 (conv 64 -> 256 on H x W, input body): planes in du0 region, result -> dBody
   {
-    bf16* acc[2] = {act(ws.g[1]), act(ws.g[0])};
+    bf16* acc[2] = {act(ws.dX0), dBody};
     for (int sub = 0; sub < 4; ++sub) {
       const bf16* dy = act(ws.du0 + sub * ws.act);
       if ((rc = wgrad64(dy, act(ws.body), grads + L.p_up[0], grads + L.p_up[0] + 4 * kConvW, B, H, W, 4, sub, st)))
@@ -280,29 +349,19 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
         return rc;
     }
   }
-  // ---- conv_after_body + long skip: body = conv(gout[G-1]) + f0
-  {
-    const bf16* feat = act(ws.gout0 + (L.G - 1) * ws.act);
-    if ((rc = wgrad64(dBody, feat, grads + L.p_after_w, grads + L.p_after_b, B, H, W, 1, 0, st))) return rc;
-    if ((rc = conv64(dBody, kb + K.after, zeros, nullptr, nullptr, nullptr, dCur, kEpiBias, B, H, W, st))) return rc;
-  }
+  // ---- conv_after_body + long skip: body = conv(gout[G-1]) + f0.  (weight gradient: job 0 of the first batch)
+  if ((rc = conv64(dBody, kb + K.after, zeros, nullptr, nullptr, nullptr, dG(L.G - 1), kEpiBias, B, H, W, st))) return rc;
   }   // stage 0
-  // ---- residual groups, last to first.  dCur = d gout[g]
-  bf16* dO = act(ws.g[4]);
-  bf16* dH = act(ws.g[5]);
+  // ---- residual groups, last to first
   const int hw = H * W;
   for (int g = L.G - 1; g >= 0; --g) {
     const int stage = L.G - g;
     if (stage < stage_begin || stage >= stage_end) continue;
-    bf16* dX = act(ws.g[2]);       // (re)written from dCur at the start of every group: the roles need no carry-over
-    bf16* dXn = act(ws.g[3]);
+    bf16* dCur = dG(g);
+    bf16* dX = act(ws.dX0);        // (re)written from dCur at the start of every group: the roles need no carry-over
+    bf16* dXn = act(ws.dX1);
     float* pg = grads + L.p_rcab0 + g * L.p_group_stride;
-    const bf16* gin = g ? act(ws.gout0 + (g - 1) * ws.act) : act(ws.f0);
-    const bf16* blocks_out = act(ws.xs0 + (g * L.Bk + L.Bk - 1) * ws.act);
-    if ((rc = wgrad64(dCur, blocks_out, pg + L.p_gconv_w_in_group, pg + L.p_gconv_w_in_group + kConvW, B, H, W, 1, 0,
-                      st)))
-      return rc;
-    // d blocks_out, and with it sum_px dx' * o of the group's last RCAB (kEpiDot)
+    // group conv: d blocks_out, and with it sum_px dx' * o of the group's last RCAB (kEpiDot)
     if ((rc = conv64(dCur, kb + K.gconv0 + g * kConvWBytes, zeros, nullptr, nullptr,
                      dsum + size_t(g * L.Bk + L.Bk - 1) * B * 64, dX, kEpiDot, B, H, W, st,
                      act(ws.o0 + (g * L.Bk + L.Bk - 1) * ws.act))))
@@ -311,11 +370,12 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
       const int r = g * L.Bk + b;
       const uint8_t* kr = k + L.k_rcab0 + int64_t(r) * L.k_rcab_stride;
       float* pr = pg + b * L.p_rcab_stride;
-      float* d_c1w = pr; float* d_c1b = d_c1w + kConvW; float* d_sl = d_c1b + 64;
-      float* d_c2w = d_sl + 64; float* d_c2b = d_c2w + kConvW; float* d_fc0 = d_c2b + 64;
+      float* d_sl = pr + kConvW + 64;
+      float* d_fc0 = d_sl + 64 + kConvW + 64;
       float* d_fc2 = d_fc0 + L.R * 64;
-      const bf16* xin = b ? act(ws.xs0 + (r - 1) * ws.act) : gin;
       const bf16* h = act(ws.h0 + r * ws.act);
+      bf16* dO = act(ws.dO0 + r * ws.act);      // kept: the operands of the deferred weight gradients
+      bf16* dH = act(ws.dH0 + r * ws.act);
       // squeeze-and-excitation + scaled residual (the per-image sums of dx' * o came with dX)
       se_bwd_apply_kernel<<<dim3(32, B), 256, 0, st>>>(dX, sums + size_t(r) * B * 64, dsum + size_t(r) * B * 64,
                                                        reinterpret_cast<const float*>(kr + rr.fc0),
@@ -323,14 +383,12 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
                                                        1.f / float(hw), cfg->res_scale, dO, d_fc0, d_fc2, hw);
       FEN_CUDA(cudaGetLastError());
       ++g_launches;
-      // conv2: weight gradient, then data gradient with the PReLU backward in its epilogue (dH holds dA)
-      if ((rc = wgrad64(dO, h, d_c2w, d_c2b, B, H, W, 1, 0, st))) return rc;
+      // conv2: data gradient with the PReLU backward in its epilogue (dH holds dA)
       if ((rc = conv64(dO, kb + K.rcab0 + r * K.rcab_stride + kConvWBytes, zeros,
                        reinterpret_cast<const float*>(kr + rr.slope), h, d_sl, dH, kEpiGate, B, H, W, st, nullptr,
                        reinterpret_cast<uint32_t*>(wsb + ws.m_h0 + r * ws.m_stride))))
         return rc;
       // conv1 + the identity path of the RCAB; the result is dx' of the previous RCAB of the group
-      if ((rc = wgrad64(dH, xin, d_c1w, d_c1b, B, H, W, 1, 0, st))) return rc;
       if (b > 0) {
         if ((rc = conv64(dH, kb + K.rcab0 + r * K.rcab_stride, zeros, nullptr, dX, dsum + size_t(r - 1) * B * 64, dXn,
                          kEpiDot, B, H, W, st, act(ws.o0 + (r - 1) * ws.act))))
@@ -342,20 +400,27 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
       }
       bf16* t = dX; dX = dXn; dXn = t;
     }
-    // group skip: d gin = dX + dCur
-    add_bf16_kernel<<<ew_blocks(n8), 256, 0, st>>>(dX, dCur, dCur, n8);
+    // group skip: d gin = dX + dCur  (-> d gout[g - 1], or the f0-level gradient after group 0)
+    add_bf16_kernel<<<ew_blocks(n8), 256, 0, st>>>(dX, dCur, g ? dG(g - 1) : act(ws.dF), n8);
     FEN_CUDA(cudaGetLastError());
     ++g_launches;
+    // deferred weight gradients: everything since the previous batch (job 0 = conv_after_body rides with the first)
+    if (bwd_is_flush(L, g)) {
+      const int prev = bwd_prev_flush(L, g);
+      const int job_begin = prev < 0 ? 0 : 1 + (L.G - prev) * per;
+      const int job_end = 1 + (L.G - g) * per;
+      if ((rc = wgrad_batch(L, wsb, ws, grads, B, H, W, job_begin, job_end, st))) return rc;
+    }
   }
   // ---- long skip + conv_first
   if (stage_begin > L.G + 1 || stage_end <= L.G + 1) return FEN_OK;
-  add_bf16_kernel<<<ew_blocks(n8), 256, 0, st>>>(dCur, dBody, dCur, n8);
+  add_bf16_kernel<<<ew_blocks(n8), 256, 0, st>>>(act(ws.dF), dBody, act(ws.dF), n8);
   FEN_CUDA(cudaGetLastError());
   ++g_launches;
   {
     const int rows = 2;
     wgrad_c3_kernel<<<dim3((H + rows - 1) / rows, B), 256, 9 * (((W + 31) & ~31) + 4) * sizeof(float), st>>>(
-        dCur, x, grads + L.p_first_w, grads + L.p_first_b, H, W, rows, 0);
+        act(ws.dF), x, grads + L.p_first_w, grads + L.p_first_b, H, W, rows, 0);
     FEN_CUDA(cudaGetLastError());
     ++g_launches;
   }

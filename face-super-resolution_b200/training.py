@@ -102,14 +102,18 @@ class BucketedAllReduce:
 
     def on_stage(self, grads: torch.Tensor, begin: int, count: int) -> None:
         """A slice [begin, begin + count) of the flat gradient is final (slices arrive in descending address order)."""
-        if not self.active():
+        if not self.active() or count == 0:       # (a stage may only feed a later batched weight-gradient launch)
             return
         if self._lo is not None and begin + count != self._lo:      # not adjacent to the pending bucket: send that first
             self._flush(grads)
         self._hi = begin + count if self._lo is None else self._hi
         self._lo = begin
-        if self._hi - self._lo >= self.total // self.n_buckets or begin == 0:
+        if self._hi - self._lo >= self.total // self.n_buckets or begin == 0 or self._small_tail(begin):
             self._flush(grads)
+
+    def _small_tail(self, begin: int) -> bool:
+        # what is still to come is small: send the pending bucket now so that only that small rest is exposed
+        return begin <= self.total // (4 * self.n_buckets)
 
     def finish(self, grads: torch.Tensor) -> None:
         if not self.active():

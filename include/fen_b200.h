@@ -189,12 +189,15 @@ int fen_forward_train(const fen_config* cfg, const void* packed, const float* x,
 int fen_backward(const fen_config* cfg, const void* packed, const void* packed_bwd, const float* x, const float* dout,
                  float* grads, int B, int H, int W, void* step_workspace, int64_t step_workspace_bytes, void* stream);
 
-/* fen_backward cut into stages that each COMPLETE a contiguous slice of the flat gradient, in the order the backward
- * produces them (the data-parallel trainer all-reduces a slice while the next stage computes; the
- * reference has no multi-GPU code to cite).  fen_backward_num_stages = num_groups + 2:
- *   stage 0: conv_last, both upsample stages, conv_after_body; stage 1 + k: residual group G - 1 - k;
- *   stage G + 1: long skip + conv_first.  fen_backward_stage_range gives the slice [begin, begin + count) of `grads` a
- * stage completes.  Stages must run in order on one stream; stage 0 zeroes `grads`. */
+/* fen_backward cut into stages, in the order the backward runs, for a data-parallel trainer that all-reduces finished
+ * slices of the flat gradient while later stages still compute (the reference has no multi-GPU code to
+ * cite).  fen_backward_num_stages = num_groups + 2:
+ *   stage 0: conv_last, both upsample stages, data gradient of conv_after_body; stage 1 + k: residual group G - 1 - k;
+ *   stage G + 1: long skip + conv_first.
+ * fen_backward_stage_range gives the slice [begin, begin + count) of `grads` that is COMPLETE after a stage.  count may
+ * be 0: the weight gradients of the 64 -> 64 convolutions are computed in batched launches after some groups only
+ * (after the upper half, after group 1, after group 0), which then complete the slices of several groups at once.
+ * Stages must run in order on one stream; stage 0 zeroes `grads`. */
 int fen_backward_num_stages(const fen_config* cfg);
 int fen_backward_stage_range(const fen_config* cfg, int stage, int64_t* begin, int64_t* count);
 int fen_backward_stages(const fen_config* cfg, const void* packed, const void* packed_bwd, const float* x,
