@@ -792,11 +792,19 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           if (ew == 0 && lane == 0) B2T2(P, 1, i);
           tc_fence_after();
           uint32_t v[CW];
+#ifdef FEN_EXP_NOEPI      // developer experiment: the accumulator is handed back unread, the tile's epilogue is skipped
+#pragma unroll
+          for (int c = 0; c < CW; ++c) v[c] = 0u;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_acc_empty[acc]);
+          if (v[0] == 0u) continue;
+#else
           tmem_ld_32x32(tmem_base + acc * N + col0 + (uint32_t(q * 32) << 16), v);
           tmem_ld_wait();
           tc_fence_before();                       // accumulator read: hand it back to the MMA issuers
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_acc_empty[acc]);
+#endif
           if (ew == 0 && lane == 0) B2T2(P, 2, i);
           float f[CW];
 #if FEN_B2_SMEM_CONST
