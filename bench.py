@@ -50,14 +50,13 @@ TRAIN_WORKLOAD = ("Stage-1 L1 training step (float LR generation, forward, L1, b
 
 
 def source_hash() -> str:
-    """Hash of the CUDA sources: profile-derived numbers (roofline.traffic) are only valid for the build they were
-    captured on."""
+    """Hash of the body kernel's sources: profile-derived numbers (roofline.traffic) are only valid for the build they
+    were captured on."""
     h = hashlib.sha256()
     d = os.path.join(ROOT, "face-super-resolution_b200", "csrc")
-    for f in sorted(os.listdir(d)):
-        if f.endswith((".cu", ".cuh")):
-            with open(os.path.join(d, f), "rb") as fh:
-                h.update(fh.read())
+    for f in ("body2_umma.cuh", "body_umma.cuh", "conv3x3_umma.cuh", "fen_common.cuh", "ptx_sm100.cuh"):
+        with open(os.path.join(d, f), "rb") as fh:     # what body2_umma_kernel is compiled from
+            h.update(fh.read())
     return h.hexdigest()[:16]
 
 
@@ -438,31 +437,50 @@ def main():
     copy_stream = torch.cuda.Stream(device=dev)
 
     def e2e_leg(u8: bool):
+        """Three-stage pipeline on three streams, as a serving loop would run it: H2D of batch i + 1 (input stream)
+        | forward of batch i (compute stream) | D2H of batch i - 1 (output stream).  Every byte of every step moves
+        inside the timed region; pinned buffers are recycled only after the copy that used them has completed."""
         host_out = [(torch.empty(B, 256, 256, 3, dtype=torch.uint8) if u8 else torch.empty(B, 3, 256, 256)).pin_memory()
                     for _ in range(2)]
-        done = [torch.cuda.Event() for _ in range(2)]
+        dev_in = [torch.empty(B, 3, 64, 64, device=dev) for _ in range(2)]
+        in_stream = torch.cuda.Stream(device=dev)
+        in_ready = [torch.cuda.Event() for _ in range(2)]      # H2D into dev_in[k] complete
+        in_free = [torch.cuda.Event() for _ in range(2)]       # forward that read dev_in[k] complete
+        done = [torch.cuda.Event() for _ in range(2)]          # D2H into host_out[k] complete
+        cur = torch.cuda.current_stream()
 
-        def e2e_step(i):
-            with torch.no_grad():
-                x = host_in[i % 4].to(dev, non_blocking=True)
-                y = model.forward_u8(x) if u8 else model(x)
-                ready = torch.cuda.Event()
-                ready.record()
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(ready)
-                    done[i & 1].synchronize() if i >= 2 else None   # pinned buffer i&1 is free again
-                    host_out[i & 1].copy_(y, non_blocking=True)
-                    y.record_stream(copy_stream)
-                    done[i & 1].record(copy_stream)
+        def upload(i):
+            with torch.cuda.stream(in_stream):
+                if i >= 2:
+                    in_stream.wait_event(in_free[i & 1])
+                dev_in[i & 1].copy_(host_in[i % 4], non_blocking=True)
+                in_ready[i & 1].record(in_stream)
 
-        for i in range(warmup):
-            e2e_step(i)
+        def run(n):
+            upload(0)
+            for i in range(n):
+                if i + 1 < n:
+                    upload(i + 1)
+                with torch.no_grad():
+                    cur.wait_event(in_ready[i & 1])
+                    y = model.forward_u8(dev_in[i & 1]) if u8 else model(dev_in[i & 1])
+                    in_free[i & 1].record(cur)
+                    ready = torch.cuda.Event()
+                    ready.record(cur)
+                    with torch.cuda.stream(copy_stream):
+                        copy_stream.wait_event(ready)
+                        if i >= 2:
+                            done[i & 1].synchronize()           # pinned buffer i & 1 is free again
+                        host_out[i & 1].copy_(y, non_blocking=True)
+                        y.record_stream(copy_stream)
+                        done[i & 1].record(copy_stream)
+            cur.wait_stream(copy_stream)
+
+        run(warmup)
         torch.cuda.synchronize()
         sharding.barrier()
         e0.record()
-        for i in range(args.steps):
-            e2e_step(i)
-        torch.cuda.current_stream().wait_stream(copy_stream)
+        run(args.steps)
         e1.record()
         torch.cuda.synchronize()
         sharding.barrier()
