@@ -527,34 +527,59 @@ __global__ void __launch_bounds__(256)
 se_bwd_apply_kernel(const bf16* __restrict__ dxo, const long long* __restrict__ sums, const float* __restrict__ dsum,
                     const float* __restrict__ fc0, const float* __restrict__ fc2, int R, float inv_hw, float res_scale,
                     bf16* __restrict__ dO, float* __restrict__ dfc0, float* __restrict__ dfc2, int hw) {
+  // The FC chain (4 dependent mat-vecs of 64 x R) runs on all 256 threads - 4 threads per output, both matrices staged
+  // in shared memory by one coalesced pass: as a serial loop per output it was most of this kernel's 15 us.
+  extern __shared__ float s_fc[];                      // fc0 [R][65] | fc2 [64][R + 1] (padded rows)
+  float* s_fc0 = s_fc;
+  float* s_fc2 = s_fc + R * 65;
   __shared__ float s_y[kC], s_z[kC], s_dt[kC], s_dzr[kC], s_mul[kC], s_add[kC];
   const int n = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < R * kC; i += blockDim.x) {
+    s_fc0[(i / kC) * 65 + (i % kC)] = __ldg(fc0 + i);
+    s_fc2[(i / R) * (R + 1) + (i % R)] = __ldg(fc2 + i);
+  }
   if (tid < kC) s_y[tid] = hs_to_float(sums[size_t(n) * kC + tid]) * inv_hw;
+  const float ds_n = (tid < 4 * kC) ? dsum[size_t(n) * kC + (tid >> 2)] : 0.f;
   __syncthreads();
-  if (tid < R) {
+  const int o = tid >> 2, part = tid & 3;              // output index, quarter of the dot product
+  auto quad_sum = [](float a) {
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    return a + __shfl_xor_sync(0xffffffffu, a, 2);
+  };
+  {                                                    // z = relu(fc0 y)
     float a = 0.f;
-    for (int c = 0; c < kC; ++c) a = fmaf(fc0[tid * kC + c], s_y[c], a);
-    s_z[tid] = fmaxf(a, 0.f);
+    if (o < R)
+#pragma unroll
+      for (int k = 0; k < 16; ++k) a = fmaf(s_fc0[o * 65 + part * 16 + k], s_y[part * 16 + k], a);
+    a = quad_sum(a);
+    if (o < R && part == 0) s_z[o] = fmaxf(a, 0.f);
   }
   __syncthreads();
-  if (tid < kC) {
+  {                                                    // s = sigmoid(fc2 z); dt = d loss / d (fc2 z)
     float a = 0.f;
-    for (int j = 0; j < R; ++j) a = fmaf(fc2[tid * R + j], s_z[j], a);
-    const float s = 1.f / (1.f + expf(-a));
-    s_mul[tid] = s * res_scale;
-    s_dt[tid] = res_scale * dsum[size_t(n) * kC + tid] * s * (1.f - s);
+    for (int j = part; j < R; j += 4) a = fmaf(s_fc2[o * (R + 1) + j], s_z[j], a);
+    a = quad_sum(a);
+    if (part == 0) {
+      const float sg = 1.f / (1.f + expf(-a));
+      s_mul[o] = sg * res_scale;
+      s_dt[o] = res_scale * ds_n * sg * (1.f - sg);
+    }
   }
   __syncthreads();
-  if (tid < R) {
+  {                                                    // dz = fc2^T dt, gated by the ReLU
     float a = 0.f;
-    for (int c = 0; c < kC; ++c) a = fmaf(fc2[c * R + tid], s_dt[c], a);
-    s_dzr[tid] = s_z[tid] > 0.f ? a : 0.f;
+    if (o < R)
+#pragma unroll
+      for (int k = 0; k < 16; ++k) a = fmaf(s_fc2[(part * 16 + k) * (R + 1) + o], s_dt[part * 16 + k], a);
+    a = quad_sum(a);
+    if (o < R && part == 0) s_dzr[o] = s_z[o] > 0.f ? a : 0.f;
   }
   __syncthreads();
-  if (tid < kC) {
+  {                                                    // d mean = fc0^T dz; every pixel gets 1 / HW of it
     float a = 0.f;
-    for (int j = 0; j < R; ++j) a = fmaf(fc0[j * kC + tid], s_dzr[j], a);
-    s_add[tid] = a * inv_hw;
+    for (int j = part; j < R; j += 4) a = fmaf(s_fc0[j * 65 + o], s_dzr[j], a);
+    a = quad_sum(a);
+    if (part == 0) s_add[o] = a * inv_hw;
   }
   if (blockIdx.x == 0) {
     for (int i = tid; i < kC * R; i += blockDim.x) {

@@ -377,7 +377,7 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
       bf16* dO = act(ws.dO0 + r * ws.act);      // kept: the operands of the deferred weight gradients
       bf16* dH = act(ws.dH0 + r * ws.act);
       // squeeze-and-excitation + scaled residual (the per-image sums of dx' * o came with dX)
-      se_bwd_apply_kernel<<<dim3(32, B), 256, 0, st>>>(dX, sums + size_t(r) * B * 64, dsum + size_t(r) * B * 64,
+      se_bwd_apply_kernel<<<dim3(32, B), 256, size_t(L.R * 65 + 64 * (L.R + 1)) * sizeof(float), st>>>(dX, sums + size_t(r) * B * 64, dsum + size_t(r) * B * 64,
                                                        reinterpret_cast<const float*>(kr + rr.fc0),
                                                        reinterpret_cast<const float*>(kr + rr.fc2), L.R,
                                                        1.f / float(hw), cfg->res_scale, dO, d_fc0, d_fc2, hw);
