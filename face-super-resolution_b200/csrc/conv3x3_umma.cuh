@@ -141,17 +141,20 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (tid == 0) pdl_launch_dependents();     // the next launch may begin its prologue (it waits before touching data)
 
   if (warp == 0) {
     // ============================================================ TMA producer
     if (lane == 0 && g_begin < g_end) {
-      // Weights arrive tap by tap (one barrier each) so the first MMAs need not wait for all 9;
-      // the first activation box goes out right behind tap 0.
+      // Weights arrive tap by tap (one barrier each) so the first MMAs need not wait for all 9.  They (like the
+      // bias / slope vectors above) were packed long before this launch's predecessor started: all nine taps go
+      // out before the dependency wait, the activation boxes after it.
       auto load_w = [&](int tap) {
         mbar_expect_tx(&bar_w[tap], N * kC * 2);
         tma_load_2d(&tm_w, &bar_w[tap], w_smem + tap * N * 128, 0, (blockIdx.y * 9 + tap) * N);
       };
-      load_w(0);
+      for (int tap = 0; tap < 9; ++tap) load_w(tap);
+      pdl_wait();
       uint32_t gb = 0;  // running box counter of this CTA
       for (int g = g_begin; g < g_end;) {
         const Unit u = make_unit(p, g, g_end);
@@ -166,8 +169,6 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
           if (mirror)
             tma_load_4d(&tm_in, &bar_full[slot], smem_u32(ring + kRingSlots * kSlotBytes), 0, x0,
                         y0 + kBoxRows, u.n);
-          if (gb == 0)
-            for (int tap = 1; tap < 9; ++tap) load_w(tap);
         }
         g += u.t1 - u.t0;
       }
@@ -263,6 +264,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
     const int row_in_tile = q * 32 + lane;
     uint32_t tile_ctr = 0;
     long long dbg_e0 = p.dbg ? clock64() : 0, dbg_ewait = 0, dbg_etail = 0, dbg_eld = 0;
+    pdl_wait();                                // everything below reads / writes what predecessors produced / still read
     for (int g = g_begin; g < g_end;) {
       const Unit u = make_unit(p, g, g_end);
       float csum[CW];
@@ -283,21 +285,21 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
           const bool want_a = p.epi == kEpiGate || p.epi == kEpiResidual || (p.epi == kEpiDot && p.residual != nullptr);
           if (valid && want_a) {
             const bf16* ap = p.residual + ipix * kC + col0;
-            ld_global_nc_256(ap, *reinterpret_cast<uint32_t(*)[8]>(&ra[0]));
-            ld_global_nc_256(ap + 16, *reinterpret_cast<uint32_t(*)[8]>(&ra[8]));
+            ld_global_cg_256(ap, *reinterpret_cast<uint32_t(*)[8]>(&ra[0]));
+            ld_global_cg_256(ap + 16, *reinterpret_cast<uint32_t(*)[8]>(&ra[8]));
           } else {
 #pragma unroll
             for (int e = 0; e < 16; ++e) ra[e] = 0u;
           }
           if (valid && p.epi == kEpiDot) {
             const bf16* xp = p.aux + ipix * kC + col0;
-            ld_global_nc_256(xp, *reinterpret_cast<uint32_t(*)[8]>(&rb[0]));
-            ld_global_nc_256(xp + 16, *reinterpret_cast<uint32_t(*)[8]>(&rb[8]));
+            ld_global_cg_256(xp, *reinterpret_cast<uint32_t(*)[8]>(&rb[0]));
+            ld_global_cg_256(xp + 16, *reinterpret_cast<uint32_t(*)[8]>(&rb[8]));
           } else {
 #pragma unroll
             for (int e = 0; e < 16; ++e) rb[e] = 0u;
           }
-          if (valid && p.epi == kEpiGate) pos_bits = __ldg(p.mask_in + ipix * 2 + half);
+          if (valid && p.epi == kEpiGate) pos_bits = __ldcg(p.mask_in + ipix * 2 + half);
         }
         long long dbg_w0 = p.dbg ? clock64() : 0;
         mbar_wait(&bar_acc_full[acc], (tile_ctr / Cfg::kAccBufs) & 1);

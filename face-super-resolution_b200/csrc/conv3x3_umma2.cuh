@@ -87,6 +87,7 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   const int n_tiles = s_meta[0], n_boxes = s_meta[1];
+  if (tid == 0) pdl_launch_dependents();     // (see conv3x3_umma.cuh: weights before the dependency wait, data after it)
 
   if (warp == 0) {
     // ============================================================ TMA producer
@@ -95,7 +96,8 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         mbar_expect_tx(&bar_w[tap], N * kC * 2);
         tma_load_2d(&tm_w, &bar_w[tap], w_smem + tap * N * 128, 0, (blockIdx.y * 9 + tap) * N);
       };
-      load_w(0);
+      for (int tap = 0; tap < 9; ++tap) load_w(tap);
+      pdl_wait();
       uint32_t slot = 0, use = 0;
       for (int b = 0; b < n_boxes; ++b) {
         const C2Box e = box_tab[b];
@@ -104,8 +106,6 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         mbar_expect_tx(&bar_full[slot], mirror ? 2 * kSlotBytes : kSlotBytes);
         tma_load_4d(&tm_in, &bar_full[slot], smem_u32(ring + slot * kSlotBytes), 0, e.x0, e.y0, e.n);
         if (mirror) tma_load_4d(&tm_in, &bar_full[slot], smem_u32(ring + kRingSlots * kSlotBytes), 0, e.x0, e.y0, e.n);
-        if (b == 0)
-          for (int tap = 1; tap < 9; ++tap) load_w(tap);
         if (++slot == kRingSlots) { slot = 0; ++use; }
       }
     }
@@ -196,6 +196,7 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         }
       }
     };
+    pdl_wait();
     for (int i = 0; i < n_tiles; ++i) {
       const C2Tile e = tile_tab[i];
       const int unit = int(e.unit_lo) | (int(e.unit_hi) << 8);
@@ -294,7 +295,7 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
 #pragma unroll
             for (int j = 0; j < CW / 16; ++j) {
               uint32_t r[8];
-              ld_global_nc_256(rsd + 16 * j, r);
+              ld_global_cg_256(rsd + 16 * j, r);
 #pragma unroll
               for (int ee = 0; ee < 8; ++ee) {
                 f[16 * j + 2 * ee] += bf16lo(r[ee]);

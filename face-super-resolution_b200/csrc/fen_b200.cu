@@ -182,6 +182,24 @@ static cudaError_t ensure_smem_attr(KernelId id, K kernel, int bytes) {
   return e;
 }
 
+// Launch with programmatic stream serialisation (ptx_sm100.cuh: pdl_wait): ONLY for kernels that execute pdl_wait()
+// before touching data of earlier launches.  FEN_PDL=0 launches them the plain way (A/B timing).
+static bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("FEN_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+  return on != 0;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ===================================================================== conv launcher
 struct ConvArgs {
   const void* x;        // NHWC bf16 [B][H][W][64]
@@ -218,9 +236,9 @@ static int launch_conv_n(const ConvArgs& a, cudaStream_t st) {
   const int boxes_bound = p.tiles_per_cta * kTileM / kBoxPx + 3 * ((p.tiles_per_cta + p.tiles_per_seg - 1) / p.tiles_per_seg + 1);
   if ((conv_version == 2 && N == 16 || conv_version == 3) && p.epi < kEpiGate && !p.mask_out && !p.sums64 && p.tiles_per_cta <= kC2MaxTiles && boxes_bound <= kC2MaxBoxes) {
     FEN_CUDA(ensure_smem_attr(N == 64 ? kKConv2_64 : kKConv2_16, conv3x3_umma2_kernel<N>, ConvCfg<N>::kDynBytes));
-    conv3x3_umma2_kernel<N><<<grid, ConvCfg<N>::kThreads, ConvCfg<N>::kDynBytes, st>>>(tm_in, tm_w, p);
+    FEN_CUDA(launch_pdl(conv3x3_umma2_kernel<N>, grid, dim3(ConvCfg<N>::kThreads), ConvCfg<N>::kDynBytes, st, tm_in, tm_w, p));
   } else {
-    conv3x3_umma_kernel<N><<<grid, ConvCfg<N>::kThreads, ConvCfg<N>::kDynBytes, st>>>(tm_in, tm_w, p);
+    FEN_CUDA(launch_pdl(conv3x3_umma_kernel<N>, grid, dim3(ConvCfg<N>::kThreads), ConvCfg<N>::kDynBytes, st, tm_in, tm_w, p));
   }
   FEN_CUDA(cudaGetLastError());
   ++g_launches;

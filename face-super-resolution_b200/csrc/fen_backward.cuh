@@ -539,7 +539,10 @@ se_bwd_apply_kernel(const bf16* __restrict__ dxo, const long long* __restrict__ 
     s_fc2[(i / R) * (R + 1) + (i % R)] = __ldg(fc2 + i);
   }
   if (tid < kC) s_y[tid] = hs_to_float(sums[size_t(n) * kC + tid]) * inv_hw;
-  const float ds_n = (tid < 4 * kC) ? dsum[size_t(n) * kC + (tid >> 2)] : 0.f;
+  // (everything above is forward state; dsum and dxo come from the launch just before this one)
+  if (tid == 0) pdl_launch_dependents();
+  pdl_wait();
+  const float ds_n = (tid < 4 * kC) ? __ldcg(dsum + size_t(n) * kC + (tid >> 2)) : 0.f;
   __syncthreads();
   const int o = tid >> 2, part = tid & 3;              // output index, quarter of the dot product
   auto quad_sum = [](float a) {
@@ -598,7 +601,7 @@ se_bwd_apply_kernel(const bf16* __restrict__ dxo, const long long* __restrict__ 
   uint4* ov = reinterpret_cast<uint4*>(dO) + base;
   for (int i = blockIdx.x * blockDim.x + tid; i < total; i += gridDim.x * blockDim.x) {
     float gf[8], of[8];
-    unpack8(__ldg(gv + i), gf);
+    unpack8(__ldcg(gv + i), gf);
 #pragma unroll
     for (int c = 0; c < 8; ++c) of[c] = fmaf(gf[c], mul[c], add[c]);
     ov[i] = pack8(of);
@@ -611,10 +614,12 @@ add_bf16_kernel(const bf16* a, const bf16* b, bf16* out, size_t n8) {   // out m
   const uint4* av = reinterpret_cast<const uint4*>(a);
   const uint4* bv = reinterpret_cast<const uint4*>(b);
   uint4* ov = reinterpret_cast<uint4*>(out);
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += size_t(gridDim.x) * blockDim.x) {
     float x[8], y[8];
-    unpack8(av[i], x);
-    unpack8(bv[i], y);
+    unpack8(__ldcg(av + i), x);
+    unpack8(__ldcg(bv + i), y);
 #pragma unroll
     for (int c = 0; c < 8; ++c) x[c] += y[c];
     ov[i] = pack8(x);

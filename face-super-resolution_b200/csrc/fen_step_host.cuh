@@ -377,10 +377,10 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
       bf16* dO = act(ws.dO0 + r * ws.act);      // kept: the operands of the deferred weight gradients
       bf16* dH = act(ws.dH0 + r * ws.act);
       // squeeze-and-excitation + scaled residual (the per-image sums of dx' * o came with dX)
-      se_bwd_apply_kernel<<<dim3(32, B), 256, size_t(L.R * 65 + 64 * (L.R + 1)) * sizeof(float), st>>>(dX, sums + size_t(r) * B * 64, dsum + size_t(r) * B * 64,
-                                                       reinterpret_cast<const float*>(kr + rr.fc0),
-                                                       reinterpret_cast<const float*>(kr + rr.fc2), L.R,
-                                                       1.f / float(hw), cfg->res_scale, dO, d_fc0, d_fc2, hw);
+      FEN_CUDA(launch_pdl(se_bwd_apply_kernel, dim3(32, B), dim3(256), size_t(L.R * 65 + 64 * (L.R + 1)) * sizeof(float), st,
+                          dX, sums + size_t(r) * B * 64, dsum + size_t(r) * B * 64,
+                          reinterpret_cast<const float*>(kr + rr.fc0), reinterpret_cast<const float*>(kr + rr.fc2), L.R,
+                          1.f / float(hw), cfg->res_scale, dO, d_fc0, d_fc2, hw));
       FEN_CUDA(cudaGetLastError());
       ++g_launches;
       // conv2: data gradient with the PReLU backward in its epilogue (dH holds dA)
@@ -401,7 +401,7 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
       bf16* t = dX; dX = dXn; dXn = t;
     }
     // group skip: d gin = dX + dCur  (-> d gout[g - 1], or the f0-level gradient after group 0)
-    add_bf16_kernel<<<ew_blocks(n8), 256, 0, st>>>(dX, dCur, g ? dG(g - 1) : act(ws.dF), n8);
+    FEN_CUDA(launch_pdl(add_bf16_kernel, dim3(ew_blocks(n8)), dim3(256), 0, st, dX, dCur, g ? dG(g - 1) : act(ws.dF), n8));
     FEN_CUDA(cudaGetLastError());
     ++g_launches;
     // deferred weight gradients: everything since the previous batch (job 0 = conv_after_body rides with the first)
@@ -414,7 +414,7 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
   }
   // ---- long skip + conv_first
   if (stage_begin > L.G + 1 || stage_end <= L.G + 1) return FEN_OK;
-  add_bf16_kernel<<<ew_blocks(n8), 256, 0, st>>>(act(ws.dF), dBody, act(ws.dF), n8);
+  FEN_CUDA(launch_pdl(add_bf16_kernel, dim3(ew_blocks(n8)), dim3(256), 0, st, act(ws.dF), dBody, act(ws.dF), n8));
   FEN_CUDA(cudaGetLastError());
   ++g_launches;
   {

@@ -253,4 +253,17 @@ __device__ __forceinline__ void griddep_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// Programmatic dependent launch (the per-layer launches of the backward and of the network tail): a kernel launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream still runs - its
+// prologue (barriers, TMEM, weight loads) overlaps the predecessor's tail - and must execute pdl_wait() before it touches
+// anything a predecessor wrote or still reads.  Without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// 256-bit load that is cached in L2 only: data a predecessor grid wrote while this grid was already resident
+__device__ __forceinline__ void ld_global_cg_256(const void* ptr, uint32_t (&v)[8]) {
+  asm volatile("ld.global.cg.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(ptr));
+}
+
 }  // namespace fen
