@@ -386,7 +386,10 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
             } else {
               opix = (size_t(u.n) * p.H + y) * p.W + x;
             }
-            bf16* dst = p.out + opix * kC + col0;
+            size_t spix = opix;
+            if (p.unshuffle)
+              spix = ((size_t(2 * (y & 1) + (x & 1)) * p.B + u.n) * (p.H >> 1) + (y >> 1)) * (p.W >> 1) + (x >> 1);
+            bf16* dst = p.out + spix * kC + col0;
             if ((p.epi == kEpiPrelu || p.epi == kEpiShuffle) && p.mask_out) p.mask_out[opix * 2 + half] = mbits;
             if (p.epi == kEpiGate) {
 #pragma unroll

@@ -110,14 +110,17 @@ static void map_store(const MapKey& k, const CUtensorMap& m) {
 }
 
 // NHWC bf16 activation [B][H][W][64]: box = 64 ch x 66 px x 4 rows, 128B swizzle, OOB -> zeros.
+// chans < 64: a narrow tensor [B][H][W][chans] (chans a multiple of 8: 16-byte pixels at least) seen through the SAME
+// 64-channel box - channels chans .. 63 are out of bounds and arrive as zeros, so the 64-channel kernels run on it
+// unchanged (the 3-channel ends of the network in the backward pass: 16 B per pixel from HBM instead of 128).
 static int make_act_map(CUtensorMap* m, const void* ptr, int B, int H, int W, int box_rows = kBoxRows,
-                        int box_px = kPitch) {
-  const MapKey key{ptr, 0, B, H, W, box_rows, box_px};
+                        int box_px = kPitch, int chans = kC) {
+  const MapKey key{ptr, chans << 8, B, H, W, box_rows, box_px};
   if (map_lookup(key, m)) return FEN_OK;
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(FEN_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
-  cuuint64_t dims[4] = {cuuint64_t(kC), cuuint64_t(W), cuuint64_t(H), cuuint64_t(B)};
-  cuuint64_t strides[3] = {cuuint64_t(kC) * 2, cuuint64_t(W) * kC * 2, cuuint64_t(H) * W * kC * 2};
+  cuuint64_t dims[4] = {cuuint64_t(chans), cuuint64_t(W), cuuint64_t(H), cuuint64_t(B)};
+  cuuint64_t strides[3] = {cuuint64_t(chans) * 2, cuuint64_t(W) * chans * 2, cuuint64_t(H) * W * chans * 2};
   cuuint32_t box[4] = {cuuint32_t(kC), cuuint32_t(box_px), cuuint32_t(box_rows), 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
@@ -207,13 +210,14 @@ struct ConvArgs {
   int n;                // 64 or 16
   int groups;           // gridDim.y (4 for the PixelShuffle convs)
   ConvParams p;
+  int in_chans;         // 0 / 64: x is [B][H][W][64]; 8: a narrow [B][H][W][8] tensor, zero-extended by TMA (make_act_map)
 };
 
 template <int N>
 static int launch_conv_n(const ConvArgs& a, cudaStream_t st) {
   FEN_CUDA(ensure_smem_attr(N == 64 ? kKConv64 : kKConv16, conv3x3_umma_kernel<N>, ConvCfg<N>::kDynBytes));
   CUtensorMap tm_in, tm_w;
-  int rc = make_act_map(&tm_in, a.x, a.p.B, a.p.H, a.p.W);
+  int rc = make_act_map(&tm_in, a.x, a.p.B, a.p.H, a.p.W, kBoxRows, kPitch, a.in_chans ? a.in_chans : kC);
   if (rc) return rc;
   rc = make_w_map(&tm_w, a.w, a.groups * 9 * N, N);
   if (rc) return rc;
@@ -1405,7 +1409,7 @@ int fen_pack_weights_bwd(const fen_config* cfg, const float* params, void* packe
   FEN_CUDA(cudaGetLastError());
   for (int s = 0; s < 2; ++s)
     if ((rc = packT(params + L.p_up[s], 4, K.up[s]))) return rc;
-  pack_last_T_kernel<<<(27 * 64 + 255) / 256, 256, 0, st>>>(params + L.p_last_w, reinterpret_cast<float*>(kb + K.last));
+  pack_last_T_kernel<<<(9 * 64 * 64 + 255) / 256, 256, 0, st>>>(params + L.p_last_w, reinterpret_cast<bf16*>(kb + K.last));
   FEN_CUDA(cudaGetLastError());
   FEN_CUDA(cudaMemsetAsync(kb + K.zeros, 0, 256, st));
   return FEN_OK;

@@ -641,12 +641,28 @@ __global__ void pack_conv_T_kernel(const float* __restrict__ w, bf16* __restrict
     dst[i] = __float2bfloat16(w[(size_t(co) * kC + ci) * 9 + (8 - t)]);
   }
 }
-// conv_last weights OIHW [3][64][3][3] -> wk[co*9 + t][ci] = W[co][ci][8 - t] (fp32) for last_dgrad_kernel
-__global__ void pack_last_T_kernel(const float* __restrict__ w, float* __restrict__ dst) {
+// conv_last weights OIHW [3][64][3][3] as the transposed, tap-flipped 64 -> 64 convolution of its data gradient:
+//   dst[t][c][co] = W[co][c][8 - t] for co < 3, 0 for the padding rows (the input there is the 3-channel d out,
+//   zero-extended to 64 channels by the tensor map)
+__global__ void pack_last_T_kernel(const float* __restrict__ w, bf16* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 27 * kC) return;
-  const int ci = i % kC, k = i / kC, co = k / 9, t = k % 9;
-  dst[i] = w[(size_t(co) * kC + ci) * 9 + (8 - t)];
+  if (i >= 9 * kC * kC) return;
+  const int co = i % kC, c = (i / kC) % kC, t = i / (kC * kC);
+  dst[i] = __float2bfloat16(co < 3 ? w[(size_t(co) * kC + c) * 9 + (8 - t)] : 0.f);
+}
+
+// fp32 NCHW [B][3][H][W] -> bf16 NHWC [B][H][W][8] (channels 3 .. 7 zero): the 3-channel tensors of the backward pass
+// (d out at the network's end, the LR input at its head) in the form the 64-channel tcgen05 kernels read through a
+// narrow tensor map.  One pixel per thread: three coalesced plane reads, one 16-byte store.
+__global__ void __launch_bounds__(256)
+nchw3_to_nhwc8_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int B, size_t hw) {
+  const size_t total = size_t(B) * hw;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+    const size_t b = i / hw, px = i - b * hw;
+    const float* s0 = src + b * 3 * hw + px;
+    const float t8[8] = {__ldg(s0), __ldg(s0 + hw), __ldg(s0 + 2 * hw), 0.f, 0.f, 0.f, 0.f, 0.f};
+    reinterpret_cast<uint4*>(dst)[i] = pack8(t8);
+  }
 }
 
 }  // namespace fen

@@ -66,6 +66,8 @@ struct ConvParams {
   float* out_f32;         // [B][3][H][W] fp32 (kEpiLast), optional when out_u8 is given
   uint8_t* out_u8;        // [B][H][W][3] uint8 = trunc(clip(out * 255, 0, 255)) (kEpiLast), optional
   int bgr;                // out_u8 channel order B, G, R
+  int unshuffle;          // kEpiGate, != 0: `out` is written as the four PixelShuffle sub-pixel planes [4][B][H/2][W/2][64]
+                          //   (plane 2 (y & 1) + (x & 1)): the gradient of the upsample convolution's pre-shuffle output
   long long* dbg;         // optional [gridDim.x][8] cycle counters (developer builds), else nullptr
 };
 

@@ -15,7 +15,7 @@ static void make_bwd_layout(const Layout& L, BwdLayout* K) {
   K->gconv0 = o; o += int64_t(L.G) * kConvWBytes;
   K->after = o; o += kConvWBytes;
   for (int s = 0; s < 2; ++s) { K->up[s] = o; o += 4 * kConvWBytes; }
-  K->last = o; o += align256(27 * 64 * 4);
+  K->last = o; o += kConvWBytes;            // conv_last's data gradient as a 64 -> 64 convolution (pack_last_T_kernel)
   K->zeros = o; o += 256;
   K->total = o;
 }
@@ -54,6 +54,7 @@ struct StepWs {
   int64_t m_h0, m_stride, m_u0, m_u1;                     // PReLU sign masks (8 B per pixel): per RCAB conv1, the two stages
   int64_t hsum, flags;                                    // fused forward (body2_umma_kernel<true>)
   int64_t dy1, du0, dy0, dsum;                            // backward, upsample resolution
+  int64_t d8, x8, wg3;                                    // backward, the 3-channel ends (narrow tensors + scratch)
   int64_t total;
 };
 static void make_step_ws(const Layout& L, int B, int H, int W, StepWs* w) {
@@ -87,13 +88,17 @@ static void make_step_ws(const Layout& L, int B, int H, int W, StepWs* w) {
   w->du0 = o; o += 4 * act;
   w->dy0 = o; o += 4 * act;
   w->dsum = o; o += align256(int64_t(L.n_rcab) * B * 64 * 4);   // sum_px dx' * o per RCAB, image, channel
+  w->d8 = o; o += 2 * act;                                       // d out as bf16 [B][4H][4W][8] (nchw3_to_nhwc8_kernel)
+  w->x8 = o; o += align256(int64_t(B) * H * W * 8 * 2);          // the LR input likewise
+  w->wg3 = o; o += align256((64 * 576 + 64) * 4);        // [64][576] + [64] fp32: weight-gradient scratch of the 3-channel ends
   w->total = o;
 }
 
 static int conv64(const bf16* in, const void* w, const float* bias, const float* slope, const bf16* res, float* sm,
                   bf16* out, int epi, int B, int h, int w_, cudaStream_t st, const bf16* aux = nullptr,
-                  uint32_t* mask = nullptr, long long* sm64 = nullptr) {
+                  uint32_t* mask = nullptr, long long* sm64 = nullptr, int in_chans = 0, int unshuffle = 0) {
   ConvArgs a{};
+  a.in_chans = in_chans; a.p.unshuffle = unshuffle;
   a.x = in; a.w = w; a.n = 64; a.groups = (epi == kEpiShuffle) ? 4 : 1;
   a.p.B = B; a.p.H = h; a.p.W = w_; a.p.epi = epi; a.p.bias = bias; a.p.slope = slope; a.p.residual = res;
   a.p.out = out; a.p.sums = sm; a.p.sums64 = sm64; a.p.aux = aux;
@@ -188,7 +193,7 @@ static int step_forward(const fen_config* cfg, const Layout& L, const uint8_t* k
 }
 
 static int wgrad64(const bf16* dY, const bf16* X, float* dW, float* dB, int B, int H, int W, int co_mul, int co_off,
-                   cudaStream_t st) {
+                   cudaStream_t st, int y_chans = kC, int x_chans = kC) {
   const int bands = B * H * ((W + kStripW - 1) / kStripW);
   const int grid = bands < num_sms() ? bands : num_sms();
   // The product library carries the tcgen05 kernel (wgrad_umma.cuh).  Developer builds (-DFEN_DEV) also hold the
@@ -206,9 +211,9 @@ static int wgrad64(const bf16* dY, const bf16* X, float* dW, float* dB, int B, i
   if (version == 2) {
     FEN_CUDA(ensure_smem_attr(kKWgUmma, wgrad_c64_umma_kernel, kWuDynBytes));
     CUtensorMap tm_y, tm_x;
-    int rc = make_act_map(&tm_y, dY, B, H, W, 1, kStripW);
+    int rc = make_act_map(&tm_y, dY, B, H, W, 1, kStripW, y_chans);
     if (rc) return rc;
-    if ((rc = make_act_map(&tm_x, X, B, H, W, 3, kPitch))) return rc;
+    if ((rc = make_act_map(&tm_x, X, B, H, W, 3, kPitch, x_chans))) return rc;
     wgrad_c64_umma_kernel<<<grid, kWuThreads, kWuDynBytes, st>>>(tm_y, tm_x, dW, dB, B, H, W, co_mul, co_off);
   }
   FEN_CUDA(cudaGetLastError());
@@ -302,19 +307,24 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
   FEN_CUDA(cudaMemsetAsync(grads, 0, size_t(L.p_total) * 4, st));
   FEN_CUDA(cudaMemsetAsync(dsum, 0, size_t(L.n_rcab) * B * 64 * 4, st));
 
-  // ---- conv_last: weight / bias gradient, then data gradient fused with PReLU + PixelShuffle backward of stage 1
+  // ---- conv_last (64 -> 3) on the 64-channel tcgen05 kernels: d out goes to bf16 NHWC with 8 channels, which a narrow
+  // tensor map zero-extends to 64 (make_act_map).  Weight / bias gradient = rows 0..2 of a 64 x 64 weight gradient;
+  // data gradient = a 64 -> 64 convolution with the transposed weights whose epilogue is the backward of stage 1's
+  // PReLU (kEpiGate) and PixelShuffle (unshuffle).  (The CUDA-core kernels these replace took 0.5 + 0.66 ms at batch 32.)
   {
-    const int rows = 8;
-    wgrad_c3_kernel<<<dim3((Ho + rows - 1) / rows, B), 256, 9 * (((Wo + 31) & ~31) + 4) * sizeof(float), st>>>(
-        act(ws.u1), dout, grads + L.p_last_w, grads + L.p_last_b, Ho, Wo, rows, 1);
+    bf16* d8 = act(ws.d8);
+    float* wg = reinterpret_cast<float*>(wsb + ws.wg3);
+    nchw3_to_nhwc8_kernel<<<ew_blocks(size_t(B) * Ho * Wo), 256, 0, st>>>(dout, d8, B, size_t(Ho) * Wo);
     FEN_CUDA(cudaGetLastError());
     ++g_launches;
+    FEN_CUDA(cudaMemsetAsync(wg, 0, (64 * 576 + 64) * 4, st));
+    if ((rc = wgrad64(d8, act(ws.u1), wg, wg + 64 * 576, B, Ho, Wo, 1, 0, st, 8, kC))) return rc;
+    FEN_CUDA(cudaMemcpyAsync(grads + L.p_last_w, wg, 3 * 576 * 4, cudaMemcpyDeviceToDevice, st));
+    FEN_CUDA(cudaMemcpyAsync(grads + L.p_last_b, wg + 64 * 576, 3 * 4, cudaMemcpyDeviceToDevice, st));
     const float* slope1 = reinterpret_cast<const float*>(k + L.k_up[1] + 4 * kConvWBytes + 1024);
-    last_dgrad_kernel<<<dim3(Ho, B), 256, 9 * (Wo + 2) * sizeof(float), st>>>(
-        dout, reinterpret_cast<const float*>(kb + K.last), act(ws.u1), reinterpret_cast<const uint32_t*>(wsb + ws.m_u1),
-        slope1, act(ws.dy1), grads + L.p_up[1] + 4 * kConvW + 256, B, Ho, Wo);
-    FEN_CUDA(cudaGetLastError());
-    ++g_launches;
+    if ((rc = conv64(d8, kb + K.last, zeros, slope1, act(ws.u1), grads + L.p_up[1] + 4 * kConvW + 256, act(ws.dy1), kEpiGate,
+                     B, Ho, Wo, st, nullptr, reinterpret_cast<uint32_t*>(wsb + ws.m_u1), nullptr, 8, 1)))
+      return rc;
   }
   // ---- upsample stage 1 (conv 64 -> 256 on 2H x 2W, input u0): 4 sub-pixel planes
   {
@@ -417,12 +427,17 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
   FEN_CUDA(launch_pdl(add_bf16_kernel, dim3(ew_blocks(n8)), dim3(256), 0, st, act(ws.dF), dBody, act(ws.dF), n8));
   FEN_CUDA(cudaGetLastError());
   ++g_launches;
+  // conv_first (3 -> 64): its weight gradient is columns ci < 3 of a 64 x 64 weight gradient against the LR input,
+  // zero-extended from 8 channels by the tensor map
   {
-    const int rows = 2;
-    wgrad_c3_kernel<<<dim3((H + rows - 1) / rows, B), 256, 9 * (((W + 31) & ~31) + 4) * sizeof(float), st>>>(
-        act(ws.dF), x, grads + L.p_first_w, grads + L.p_first_b, H, W, rows, 0);
+    bf16* x8 = act(ws.x8);
+    float* wg = reinterpret_cast<float*>(wsb + ws.wg3);
+    nchw3_to_nhwc8_kernel<<<ew_blocks(size_t(B) * H * W), 256, 0, st>>>(x, x8, B, size_t(H) * W);
     FEN_CUDA(cudaGetLastError());
     ++g_launches;
+    FEN_CUDA(cudaMemsetAsync(wg, 0, (64 * 576 + 64) * 4, st));
+    if ((rc = wgrad64(act(ws.dF), x8, wg, grads + L.p_first_b, B, H, W, 1, 0, st, kC, 8))) return rc;
+    FEN_CUDA(cudaMemcpy2DAsync(grads + L.p_first_w, 27 * 4, wg, 576 * 4, 27 * 4, 64, cudaMemcpyDeviceToDevice, st));
   }
   return FEN_OK;
 }
