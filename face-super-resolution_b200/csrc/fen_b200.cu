@@ -151,8 +151,7 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int rows, int n) {
 // ---- per-device state: SM count and the "max dynamic shared memory" function attributes are properties of a
 // device, not of the process (one process may drive several GPUs).
 constexpr int kMaxDevices = 64;
-enum KernelId : int { kKConv64 = 0, kKConv16, kKConv2_64, kKConv2_16, kKBody, kKBody2, kKBody2Train, kKWgMma, kKWgUmma, kKWgBatch, kKLastDgrad,
-                      kKWgradC3, kKernelIds };
+enum KernelId : int { kKConv64 = 0, kKConv16, kKConv2_64, kKConv2_16, kKBody, kKBody2, kKBody2Train, kKWgMma, kKWgUmma, kKWgBatch, kKernelIds };
 struct DevState {
   int sms = 0;
   bool attr[kKernelIds] = {};

@@ -280,196 +280,6 @@ wgrad_c64_mma_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, fl
 
 #endif  // FEN_DEV
 // --------------------------------------------------------------------------------------------------------------
-// Weight gradient of the two 3-channel convolutions (conv_first 3 -> 64 and conv_last 64 -> 3): a 64-channel
-// NHWC bf16 tensor F against a 3-channel fp32 NCHW image I, both of size H x W:
-//   a[c3][f][t] = sum_{b,y,x} F[b,y,x,f] * I[b,c3,y+ty-1,x+tx-1]
-// mode 0 (conv_first: F = d f0, I = network input):  dW[f][c3][t] += a, db[f] += sum F
-// mode 1 (conv_last:  F = u1,   I = d out):          dW[c3][f][8-t] += a, db[c3] += sum I
-// grid (ceil(H / rows_per_cta), B), 256 threads = 32 channel PAIRS x 8 column eighths; dynamic smem 9 * (roundup(W, 32) + 4) floats.
-// A thread takes 4 pixels of 2 channels at a time: one 32-bit load per pixel (a warp reads whole 128-byte lines),
-// and the 3 x 6 image window of each image channel comes in as one 128-bit + one 64-bit shared-memory load per row
-// (18 loads for 216 FMAs; one load per FMA made the first version LSU bound).
-__global__ void __launch_bounds__(256)
-wgrad_c3_kernel(const bf16* __restrict__ F, const float* __restrict__ I, float* __restrict__ dW,
-                float* __restrict__ dB, int H, int W, int rows_per_cta, int mode) {
-  extern __shared__ __align__(16) float sI[];   // [c3][r][W + 4], column j = image column j - 1
-  const int tid = threadIdx.x, f2 = tid & 31, xq = tid >> 5;
-  const int b = blockIdx.y;
-  const int Wr = (W + 31) & ~31;          // columns are dealt to the 8 warps in quads: ragged widths are zero-extended
-  const int Wp = Wr + 4;
-  float acc[2][3][9];
-  float bs[2] = {0.f, 0.f}, is[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-  for (int h = 0; h < 2; ++h)
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int t = 0; t < 9; ++t) acc[h][c][t] = 0.f;
-  const int y_begin = blockIdx.x * rows_per_cta;
-  const int y_end = min(H, y_begin + rows_per_cta);
-  for (int y = y_begin; y < y_end; ++y) {
-    __syncthreads();
-    for (int i = tid; i < 9 * Wp; i += 256) {
-      const int col = i % Wp, r = (i / Wp) % 3, c3 = i / (3 * Wp);
-      const int yy = y - 1 + r, xx = col - 1;
-      sI[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(I + ((size_t(b) * 3 + c3) * H + yy) * W + xx) : 0.f;
-    }
-    __syncthreads();
-    const int xw = Wr / 8;
-    const uint32_t* frow = reinterpret_cast<const uint32_t*>(F + ((size_t(b) * H + y) * W) * kC) + f2;
-    for (int x = xq * xw; x < (xq + 1) * xw && x < W; x += 4) {
-      float v[2][4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t pr = (x + j < W) ? __ldg(frow + size_t(x + j) * (kC / 2)) : 0u;
-        v[0][j] = bf16lo(pr); v[1][j] = bf16hi(pr);
-      }
-      bs[0] += (v[0][0] + v[0][1]) + (v[0][2] + v[0][3]);
-      bs[1] += (v[1][0] + v[1][1]) + (v[1][2] + v[1][3]);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const float* p = sI + (c * 3 + r) * Wp + x;
-          const float4 lo = *reinterpret_cast<const float4*>(p);
-          const float2 hi = *reinterpret_cast<const float2*>(p + 4);
-          const float w[6] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y};
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) acc[h][c][r * 3 + kx] = fmaf(v[h][j], w[j + kx], acc[h][c][r * 3 + kx]);
-          if (r == 1 && f2 == 0) is[c] += (w[1] + w[2]) + (w[3] + w[4]);
-        }
-      }
-    }
-  }
-  // the 8 column eighths of a channel meet in shared memory first: one global atomic per output and CTA
-  __shared__ float s_red[3 * 9 * kC + kC];
-  for (int i = tid; i < 3 * 9 * kC + kC; i += 256) s_red[i] = 0.f;
-  __syncthreads();
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int f = 2 * f2 + h;
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int t = 0; t < 9; ++t) atomicAdd(&s_red[(c * 9 + t) * kC + f], acc[h][c][t]);
-    atomicAdd(&s_red[27 * kC + f], bs[h]);
-  }
-  __syncthreads();
-  for (int i = tid; i < 27 * kC; i += 256) {
-    const int f = i % kC, t = (i / kC) % 9, c = i / (9 * kC);
-    if (mode == 0) atomicAdd(dW + (size_t(f) * 3 + c) * 9 + t, s_red[i]);
-    else atomicAdd(dW + (size_t(c) * kC + f) * 9 + (8 - t), s_red[i]);
-  }
-  if (mode == 0 && tid < kC) atomicAdd(dB + tid, s_red[27 * kC + tid]);
-  if (mode != 0 && f2 == 0) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) atomicAdd(dB + c, is[c]);
-  }
-}
-
-// --------------------------------------------------------------------------------------------------------------
-// conv_last data gradient fused with the backward of the last PReLU + PixelShuffle (blocks.py:223-227):
-//   dU[b,y,x,c]  = sum_{co<3,t} dOut[b,co,y+ty-1,x+tx-1] * wk[co*9+t][c]      (wk = tap-flipped conv_last weights)
-//   dPre         = dU * (u > 0 ? 1 : slope[c])          dslope[c] += dU * min(u, 0) / slope[c]
-//   dY[sub][b][y>>1][x>>1][c] = dPre,  sub = 2 (y&1) + (x&1)                  (the conv's sub-pixel planes)
-// u = prelu(pre) is the saved stage output, `mask` the sign bits of pre saved by the forward (ConvParams::mask_out).
-// grid (H, B), 256 threads: 64 columns x 4 channel quarters, like conv_first_kernel; dynamic smem 9 * (W + 2) floats.
-__global__ void __launch_bounds__(256)
-last_dgrad_kernel(const float* __restrict__ dOut, const float* __restrict__ wk, const bf16* __restrict__ u,
-                  const uint32_t* __restrict__ mask, const float* __restrict__ slope, bf16* __restrict__ dY,
-                  float* __restrict__ dslope, int B, int H, int W) {
-  extern __shared__ float s_in[];   // [co 3][row 3][W + 2]: the three dOut rows of this output row, zero padded
-  __shared__ float sw[27 * kC];
-  __shared__ float s_sl[kC], s_ds[kC];
-  const int n = blockIdx.y, y = blockIdx.x;
-  const int Wp = W + 2;
-  for (int i = threadIdx.x; i < 27 * kC; i += blockDim.x) sw[i] = wk[i];
-  if (threadIdx.x < kC) { s_sl[threadIdx.x] = slope[threadIdx.x]; s_ds[threadIdx.x] = 0.f; }
-  for (int i = threadIdx.x; i < 9 * Wp; i += blockDim.x) {
-    const int col = i % Wp, r = (i / Wp) % 3, co = i / (3 * Wp);
-    const int yy = y - 1 + r, xc = col - 1;
-    s_in[i] = (yy >= 0 && yy < H && xc >= 0 && xc < W) ? __ldg(dOut + ((size_t(n) * 3 + co) * H + yy) * W + xc) : 0.f;
-  }
-  __syncthreads();
-  const int q = threadIdx.x >> 6;
-  float ds[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) ds[c] = 0.f;
-  for (int x0 = 0; x0 < W; x0 += 64) {
-    const int xx = x0 + (threadIdx.x & 63);
-    if (xx >= W) continue;                      // ragged width (no barrier inside this loop)
-    float in[27];
-#pragma unroll
-    for (int co = 0; co < 3; ++co)
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) in[co * 9 + ky * 3 + kx] = s_in[(co * 3 + ky) * Wp + xx + kx];
-    float acc[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
-#pragma unroll
-    for (int k = 0; k < 27; ++k) {
-      const float4* wp = reinterpret_cast<const float4*>(sw + k * kC + q * 16);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 w4 = wp[j];
-        acc[4 * j + 0] = fmaf(in[k], w4.x, acc[4 * j + 0]);
-        acc[4 * j + 1] = fmaf(in[k], w4.y, acc[4 * j + 1]);
-        acc[4 * j + 2] = fmaf(in[k], w4.z, acc[4 * j + 2]);
-        acc[4 * j + 3] = fmaf(in[k], w4.w, acc[4 * j + 3]);
-      }
-    }
-    const uint4* up = reinterpret_cast<const uint4*>(u + ((size_t(n) * H + y) * W + xx) * kC + q * 16);
-    float uv[16];
-    {
-      float t8[8];
-      unpack8(__ldg(up), t8);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) uv[c] = t8[c];
-      unpack8(__ldg(up + 1), t8);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) uv[8 + c] = t8[c];
-    }
-    float o[16];
-    const uint32_t pos_bits = __ldg(mask + ((size_t(n) * H + y) * W + xx) * 2 + (q >> 1)) >> ((q & 1) * 16);
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const float sl = s_sl[q * 16 + c];
-      const bool pos = (pos_bits >> c) & 1u;
-      o[c] = pos ? acc[c] : acc[c] * sl;
-      ds[c] += (pos || sl == 0.f) ? 0.f : acc[c] * (uv[c] / sl);
-    }
-    const int sub = 2 * (y & 1) + (xx & 1);
-    uint4* dst = reinterpret_cast<uint4*>(
-        dY + (((size_t(sub) * B + n) * (H >> 1) + (y >> 1)) * (W >> 1) + (xx >> 1)) * kC + q * 16);
-    float t8[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) t8[c] = o[c];
-    dst[0] = pack8(t8);
-#pragma unroll
-    for (int c = 0; c < 8; ++c) t8[c] = o[8 + c];
-    dst[1] = pack8(t8);
-  }
-  // a warp shares its channel quarter: reduce over the 32 pixels of the warp first
-#pragma unroll
-  for (int c = 0; c < 16; ++c) {
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) ds[c] += __shfl_xor_sync(0xffffffffu, ds[c], d);
-  }
-  if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-    for (int c = 0; c < 16; ++c) atomicAdd(&s_ds[q * 16 + c], ds[c]);
-  }
-  __syncthreads();
-  if (threadIdx.x < kC) atomicAdd(dslope + threadIdx.x, s_ds[threadIdx.x]);
-}
-
-// --------------------------------------------------------------------------------------------------------------
 // PReLU backward on NHWC bf16 (RCAB conv1, blocks.py:139-141; upsample stage, blocks.py:227):
 //   out = g * (pre > 0 ? 1 : slope[c])      dslope[c] += g * min(pre, 0),  min(pre, 0) = act / slope[c] on that side
 // act = prelu(pre) is the saved activation, `mask` the sign bits of pre (ConvParams::mask_out of the forward).  unshuffle != 0: g / act are the PixelShuffle'd [B,H,W,64] tensors and
