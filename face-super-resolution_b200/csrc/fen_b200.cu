@@ -13,6 +13,7 @@
 #include "../../include/fen_b200.h"
 #include "conv3x3_umma.cuh"
 #include "conv3x3_umma2.cuh"
+#include "conv_last_umma.cuh"
 #include "body_umma.cuh"
 #include "body2_umma.cuh"
 #include "fen_backward.cuh"
@@ -151,7 +152,7 @@ static int make_w_map(CUtensorMap* m, const void* ptr, int rows, int n) {
 // ---- per-device state: SM count and the "max dynamic shared memory" function attributes are properties of a
 // device, not of the process (one process may drive several GPUs).
 constexpr int kMaxDevices = 64;
-enum KernelId : int { kKConv64 = 0, kKConv16, kKConv2_64, kKConv2_16, kKBody, kKBody2, kKBody2Train, kKWgMma, kKWgUmma, kKWgBatch, kKernelIds };
+enum KernelId : int { kKConv64 = 0, kKConv16, kKConv2_64, kKConv2_16, kKBody, kKBody2, kKBody2Train, kKWgMma, kKWgUmma, kKWgBatch, kKConvLast, kKernelIds };
 struct DevState {
   int sms = 0;
   bool attr[kKernelIds] = {};
@@ -253,6 +254,47 @@ static int launch_conv(const ConvArgs& a, cudaStream_t st) {
   if (a.n == 64) return launch_conv_n<64>(a, st);
   if (a.n == 16) return launch_conv_n<16>(a, st);
   return fail(FEN_EINVAL, "conv: unsupported N");
+}
+
+// packed conv_last record: [w bf16 9*16*64][b 16f][taps-in-N weights bf16 32*64 (conv_last_umma.cuh)]
+static constexpr int64_t kLastBiasOff = 9 * 16 * 64 * 2;
+static constexpr int64_t kLastNOff = kLastBiasOff + 256;
+static constexpr int64_t kLastRec = kLastNOff + kCLWBytes;
+// conv_last + bicubic skip + clamp (conv_last_umma.cuh): `rec` = the packed conv_last record, u1 [B][H][W][64] bf16.
+// FEN_LAST_KERNEL=0 (developer builds) runs the generic N = 16 convolution instead.
+static int launch_conv_last(const uint8_t* rec, const void* u1, const float* lr, float* out_f32, uint8_t* out_u8, int bgr,
+                            int training, int B, int H, int W, cudaStream_t st) {
+#ifdef FEN_DEV
+  { const char* e = getenv("FEN_LAST_KERNEL");
+    if (e && e[0] == '0') {
+      ConvArgs a{};
+      a.x = u1; a.w = rec; a.n = 16; a.groups = 1;
+      a.p.B = B; a.p.H = H; a.p.W = W; a.p.epi = kEpiLast; a.p.training = training;
+      a.p.bias = reinterpret_cast<const float*>(rec + kLastBiasOff);
+      a.p.lr = lr; a.p.out_f32 = out_f32; a.p.out_u8 = out_u8; a.p.bgr = bgr;
+      return launch_conv(a, st);
+    } }
+#endif
+  FEN_CUDA(ensure_smem_attr(kKConvLast, conv_last_umma_kernel, kCLDynBytes));
+  CUtensorMap tm_in, tm_w;
+  int rc = make_act_map(&tm_in, u1, B, H, W, kCLBoxRows, kPitch);
+  if (rc) return rc;
+  if ((rc = make_w_map(&tm_w, rec + kLastNOff, kCLN, kCLN))) return rc;
+  ConvLastParams p{};
+  p.B = B; p.H = H; p.W = W;
+  p.strips = (W + kStripW - 1) / kStripW;
+  p.nblk = (H + kCLRows - 1) / kCLRows;
+  p.items = B * p.strips * p.nblk;
+  int grid = p.items < num_sms() ? p.items : num_sms();
+  p.items_per_cta = (p.items + grid - 1) / grid;
+  grid = (p.items + p.items_per_cta - 1) / p.items_per_cta;
+  p.training = training; p.bgr = bgr;
+  p.bias = reinterpret_cast<const float*>(rec + kLastBiasOff);
+  p.lr = lr; p.out_f32 = out_f32; p.out_u8 = out_u8;
+  FEN_CUDA(launch_pdl(conv_last_umma_kernel, dim3(grid), dim3(kCLThreads), kCLDynBytes, st, tm_in, tm_w, p));
+  FEN_CUDA(cudaGetLastError());
+  ++g_launches;
+  return FEN_OK;
 }
 
 // ===================================================================== small kernels
@@ -652,8 +694,7 @@ static RcabRec rcab_rec(int R) {
 static constexpr int64_t kPlainRec = kConvWBytes + 256;
 // packed upsample record: [w bf16 4 groups][b 256f permuted][slope 64f]
 static constexpr int64_t kUpRec = 4 * kConvWBytes + 1024 + 256;
-// packed conv_last record: [w bf16 9*16*64][b 16f]
-static constexpr int64_t kLastRec = 9 * 16 * 64 * 2 + 256;
+
 
 static int make_layout(const fen_config* cfg, Layout* L) {
   if (!cfg) return fail(FEN_EINVAL, "null config");
@@ -998,7 +1039,9 @@ int fen_pack_weights(const fen_config* cfg, const float* params, void* packed, v
     if ((rc = pack_vec(pu + 4 * kConvW + 256, 64, 64, 1, 0, ku + 4 * kConvWBytes + 1024, st))) return rc;
   }
   if ((rc = pack_conv(params + L.p_last_w, 3, 16, 1, 0, k + L.k_last, st))) return rc;
-  if ((rc = pack_vec(params + L.p_last_b, 3, 16, 1, 0, k + L.k_last + 9 * 16 * 64 * 2, st))) return rc;
+  if ((rc = pack_vec(params + L.p_last_b, 3, 16, 1, 0, k + L.k_last + kLastBiasOff, st))) return rc;
+  pack_last_n_kernel<<<(kCLN * kC + 255) / 256, 256, 0, st>>>(params + L.p_last_w, reinterpret_cast<bf16*>(k + L.k_last + kLastNOff));
+  FEN_CUDA(cudaGetLastError());
   return FEN_OK;
 }
 
@@ -1129,14 +1172,7 @@ static int forward_impl(const fen_config* cfg, const void* packed, const float* 
   }
   if ((rc = stage_check("upsample convs", st))) return rc;
   // conv_last + bicubic skip + clamp
-  {
-    ConvArgs a{};
-    a.x = act(ws.u1); a.w = k + L.k_last; a.n = 16; a.groups = 1;
-    a.p.B = B; a.p.H = 4 * H; a.p.W = 4 * W; a.p.epi = kEpiLast; a.p.training = training;
-    a.p.bias = reinterpret_cast<const float*>(k + L.k_last + 9 * 16 * 64 * 2);
-    a.p.lr = x; a.p.out_f32 = out; a.p.out_u8 = out_u8; a.p.bgr = bgr;
-    if ((rc = launch_conv(a, st))) return rc;
-  }
+  if ((rc = launch_conv_last(k + L.k_last, act(ws.u1), x, out, out_u8, bgr, training, B, 4 * H, 4 * W, st))) return rc;
   if ((rc = stage_check("conv_last", st))) return rc;
   return FEN_OK;
 }

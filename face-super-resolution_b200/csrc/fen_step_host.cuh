@@ -184,12 +184,7 @@ static int step_forward(const fen_config* cfg, const Layout& L, const uint8_t* k
                    reinterpret_cast<const float*>(ku + 4 * kConvWBytes + 1024), nullptr, nullptr, act(ws.u1),
                    kEpiShuffle, B, 2 * H, 2 * W, st, nullptr, reinterpret_cast<uint32_t*>(wsb + ws.m_u1))))
     return rc;
-  ConvArgs a{};
-  a.x = act(ws.u1); a.w = k + L.k_last; a.n = 16; a.groups = 1;
-  a.p.B = B; a.p.H = 4 * H; a.p.W = 4 * W; a.p.epi = kEpiLast; a.p.training = 1;
-  a.p.bias = reinterpret_cast<const float*>(k + L.k_last + 9 * 16 * 64 * 2);
-  a.p.lr = x; a.p.out_f32 = out;
-  return launch_conv(a, st);
+  return launch_conv_last(k + L.k_last, act(ws.u1), x, out, nullptr, 0, 1, B, 4 * H, 4 * W, st);
 }
 
 static int wgrad64(const bf16* dY, const bf16* X, float* dW, float* dB, int B, int H, int W, int co_mul, int co_off,
