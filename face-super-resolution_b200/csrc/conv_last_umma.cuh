@@ -29,8 +29,7 @@ constexpr int kCLBoxBytes = kCLPx * kC * 2;                    // 67 584 = 66 x 
 constexpr int kCLABytes = 2 * kCLBoxBytes;                     // two boxes: item i + 1 streams in while item i is multiplied
 static_assert(kCLBoxBytes % 1024 == 0, "box buffers must keep the 1024-byte swizzle alignment");
 constexpr int kCLWBytes = kCLN * kC * 2;                       // 4 096
-constexpr int kCLDStride = 27;                                 // odd: conflict-free for pixel-per-lane access
-constexpr int kCLDBytes = kCLTiles * kTileM * kCLDStride * 4;  // 69 120
+constexpr int kCLDBytes = 9 * kCLPx * 16;                      // D as [tap][staged pixel][co padded to 4] fp32: one 128-bit access per tap, 76 032
 constexpr int kCLDynBytes = kCLABytes + kCLWBytes + kCLDBytes + 1024;
 constexpr int kCLEpiWarps = 16;                                // 4 per TMEM lane quarter: warp group g takes tiles g, g + 4
 constexpr int kCLEpiThreads = 32 * kCLEpiWarps;
@@ -64,7 +63,7 @@ conv_last_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_smem = smem;                                      // 2 x [528 px][64 ch] bf16, SWIZZLE_128B
   uint8_t* w_smem = smem + kCLABytes;                          // [32][64] bf16, SWIZZLE_128B: row 3 t + co
-  float* d_smem = reinterpret_cast<float*>(smem + kCLABytes + kCLWBytes);   // [640][27] fp32
+  float4* d_smem = reinterpret_cast<float4*>(smem + kCLABytes + kCLWBytes);   // [9][528] x (3 outputs + pad) fp32
   __shared__ uint64_t bar_w, bar_a_full[2], bar_a_free[2], bar_acc_full[2], bar_acc_free[2];
   __shared__ uint32_t tmem_slot;
   __shared__ float s_bias[4];
@@ -99,17 +98,21 @@ conv_last_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
     n = seg / p.strips;
   };
 
+  auto next_item = [&](int& n, int& strip, int& blk) {        // (no divisions in the item loops)
+    if (++blk == p.nblk) { blk = 0; if (++strip == p.strips) { strip = 0; ++n; } }
+  };
+
   if (warp == 0) {
     // ============================================================ TMA producer
     if (lane == 0 && it0 < it1) {
       mbar_expect_tx(&bar_w, kCLWBytes);
       tma_load_2d(&tm_w, &bar_w, w_smem, 0, 0);                // (packed long before the predecessor started)
       pdl_wait();
-      for (int it = it0, k = 0; it < it1; ++it, ++k) {
+      int n, strip, blk;
+      decode(it0, n, strip, blk);
+      for (int it = it0, k = 0; it < it1; ++it, ++k, next_item(n, strip, blk)) {
         const uint32_t slot = uint32_t(k) & 1u;
         if (k >= 2) mbar_wait(&bar_a_free[slot], ((uint32_t(k) >> 1) - 1u) & 1u);   // the MMAs of item k - 2 have read the buffer
-        int n, strip, blk;
-        decode(it, n, strip, blk);
         mbar_expect_tx(&bar_a_full[slot], kCLBoxBytes);
         tma_load_4d(&tm_in, &bar_a_full[slot], smem_u32(a_smem + slot * kCLBoxBytes), 0, strip * kStripW - 1, blk * kCLRows - 1, n);
       }
@@ -150,10 +153,10 @@ conv_last_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
     const int ew = warp - 2, q = warp & 3, grp = ew >> 2;      // TMEM lane quarter, tile group
     const int et = ew * 32 + lane;
     pdl_wait();
-    for (int it = it0, k = 0; it < it1; ++it, ++k) {
+    int n, strip, blk;
+    decode(it0, n, strip, blk);
+    for (int it = it0, k = 0; it < it1; ++it, ++k, next_item(n, strip, blk)) {
       const uint32_t sel = uint32_t(k) & 1u;
-      int n, strip, blk;
-      decode(it, n, strip, blk);
       const int y0 = blk * kCLRows;
       const int rows = min(kCLRows, p.H - y0);
       // ---- bicubic x4 skip, horizontal pass (needs only the network input: done while the MMAs run).  Output row y
@@ -194,13 +197,17 @@ conv_last_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
 #pragma unroll
       for (int tt = 0; tt < 2; ++tt) {
         const int t = grp + 4 * tt;
-        if (t < kCLTiles) {
+        if (t < kCLTiles && t * kTileM + q * 32 < kCLPx) {     // (the last tile holds 16 staged pixels: one warp's worth)
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + sel * kCLSetCols + t * kCLN + (uint32_t(q * 32) << 16), v);
           tmem_ld_wait();
-          float* d = d_smem + (t * kTileM + q * 32 + lane) * kCLDStride;
+          const int s_px = t * kTileM + q * 32 + lane;
+          if (s_px < kCLPx) {
 #pragma unroll
-          for (int c = 0; c < 27; ++c) d[c] = __uint_as_float(v[c]);
+            for (int tap = 0; tap < 9; ++tap)
+              d_smem[tap * kCLPx + s_px] = make_float4(__uint_as_float(v[3 * tap]), __uint_as_float(v[3 * tap + 1]),
+                                                       __uint_as_float(v[3 * tap + 2]), 0.f);
+          }
         }
       }
       tc_fence_before();
@@ -212,12 +219,12 @@ conv_last_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
         const int yl = idx >> 6, xs = idx & 63;
         const int x = strip * kStripW + xs, y = y0 + yl;
         if (x >= p.W) continue;                                // (the last strip of a ragged width is partial)
-        const float* d0 = d_smem + ((yl + 1) * kPitch + xs + 1) * kCLDStride;
+        const float4* d0 = d_smem + (yl + 1) * kPitch + xs + 1;
         float o[3] = {s_bias[0], s_bias[1], s_bias[2]};
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-          const float* d = d0 + ((t / 3 - 1) * kPitch + (t % 3 - 1)) * kCLDStride + 3 * t;
-          o[0] += d[0]; o[1] += d[1]; o[2] += d[2];
+          const float4 d = d0[t * kCLPx + (t / 3 - 1) * kPitch + (t % 3 - 1)];
+          o[0] += d.x; o[1] += d.y; o[2] += d.z;
         }
         const int ry = y & 3;
         const int r0 = (y >> 2) + ((ry < 2) ? -2 : -1) - lo;   // first of the four filtered LR rows, 0 .. 4
