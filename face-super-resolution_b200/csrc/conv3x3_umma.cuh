@@ -445,8 +445,9 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
               csum[i] = keep + __shfl_xor_sync(0xffffffffu, send, d);
             }
           }
-          if (p.epi == kEpiSum && p.sums64) hs_add(p.sums64 + size_t(u.n) * kC + col0 + lane, csum[0]);
-          else atomicAdd(p.sums + (p.epi == kEpiGate ? size_t(0) : size_t(u.n) * kC) + col0 + lane, csum[0]);
+          const size_t si = (p.epi == kEpiGate ? size_t(0) : size_t(u.n) * kC) + col0 + lane;
+          if (p.sums64) { if (p.epi == kEpiSum) hs_add(p.sums64 + si, csum[0]); else gs_add(p.sums64 + si, csum[0]); }
+          else atomicAdd(p.sums + si, csum[0]);
         }
       }
       if (p.dbg) dbg_etail += clock64() - dbg_t2;

@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(256) lr_from_hr_rgb4_kernel(const uint8_t* __r
       uint32_t wds[12];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const uint4 v = __ldg(s128 + k);
+        const uint4 v = __ldcs(s128 + k);      // streamed once: evict-first, the 201 MB batch must not sweep L2
         wds[4 * k] = v.x; wds[4 * k + 1] = v.y; wds[4 * k + 2] = v.z; wds[4 * k + 3] = v.w;
       }
 #pragma unroll

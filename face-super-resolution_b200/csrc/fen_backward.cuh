@@ -286,10 +286,10 @@ wgrad_c64_mma_kernel(const bf16* __restrict__ dY, const bf16* __restrict__ X, fl
 // `out` is written as the four sub-pixel planes [4][B][H/2][W/2][64] of the producing convolution.
 __global__ void __launch_bounds__(256)
 prelu_bwd_kernel(const bf16* g, const bf16* __restrict__ act, const uint32_t* __restrict__ mask,
-                 const float* __restrict__ slope, bf16* out, float* __restrict__ dslope, int B, int H, int W,
-                 int unshuffle) {   // out may alias g (in place)
-  __shared__ float s_ds[kC];
-  if (threadIdx.x < kC) s_ds[threadIdx.x] = 0.f;
+                 const float* __restrict__ slope, bf16* out, long long* __restrict__ dslope, int B, int H, int W,
+                 int unshuffle) {   // out may alias g (in place); dslope: fixed point (gs_add)
+  __shared__ unsigned long long s_ds[kC];     // fixed point as well: the order in which the threads of a block arrive must not matter
+  if (threadIdx.x < kC) s_ds[threadIdx.x] = 0ull;
   __syncthreads();
   const int cg = threadIdx.x & 7;
   float sl[8], ds[8];
@@ -320,9 +320,9 @@ prelu_bwd_kernel(const bf16* g, const bf16* __restrict__ act, const uint32_t* __
     ov[o] = pack8(of);
   }
 #pragma unroll
-  for (int c = 0; c < 8; ++c) atomicAdd(&s_ds[cg * 8 + c], ds[c]);
+  for (int c = 0; c < 8; ++c) atomicAdd(&s_ds[cg * 8 + c], static_cast<unsigned long long>(__float2ll_rn(ds[c] * kGsScale)));
   __syncthreads();
-  if (threadIdx.x < kC) atomicAdd(dslope + threadIdx.x, s_ds[threadIdx.x]);
+  if (threadIdx.x < kC) atomicAdd(reinterpret_cast<unsigned long long*>(dslope) + threadIdx.x, s_ds[threadIdx.x]);
 }
 
 // --------------------------------------------------------------------------------------------------------------
@@ -334,9 +334,9 @@ prelu_bwd_kernel(const bf16* g, const bf16* __restrict__ act, const uint32_t* __
 //   y = sums / HW; z = relu(W0 y); t = W2 z; s = sigmoid(t)
 //   ds = rs * dsum; dt = ds s (1 - s); dW2 += dt z^T; dz = W2^T dt; dzr = dz [z > 0]; dW0 += dzr y^T; dy = W0^T dzr
 __global__ void __launch_bounds__(256)
-se_bwd_apply_kernel(const bf16* __restrict__ dxo, const long long* __restrict__ sums, const float* __restrict__ dsum,
+se_bwd_apply_kernel(const bf16* __restrict__ dxo, const long long* __restrict__ sums, const long long* __restrict__ dsum,
                     const float* __restrict__ fc0, const float* __restrict__ fc2, int R, float inv_hw, float res_scale,
-                    bf16* __restrict__ dO, float* __restrict__ dfc0, float* __restrict__ dfc2, int hw) {
+                    bf16* __restrict__ dO, long long* __restrict__ dfc0, long long* __restrict__ dfc2, int hw) {
   // The FC chain (4 dependent mat-vecs of 64 x R) runs on all 256 threads - 4 threads per output, both matrices staged
   // in shared memory by one coalesced pass: as a serial loop per output it was most of this kernel's 15 us.
   extern __shared__ float s_fc[];                      // fc0 [R][65] | fc2 [64][R + 1] (padded rows)
@@ -352,7 +352,7 @@ se_bwd_apply_kernel(const bf16* __restrict__ dxo, const long long* __restrict__ 
   // (everything above is forward state; dsum and dxo come from the launch just before this one)
   if (tid == 0) pdl_launch_dependents();
   pdl_wait();
-  const float ds_n = (tid < 4 * kC) ? __ldcg(dsum + size_t(n) * kC + (tid >> 2)) : 0.f;
+  const float ds_n = (tid < 4 * kC) ? gs_to_float(__ldcg(dsum + size_t(n) * kC + (tid >> 2))) : 0.f;   // (fixed point: kEpiDot)
   __syncthreads();
   const int o = tid >> 2, part = tid & 3;              // output index, quarter of the dot product
   auto quad_sum = [](float a) {
@@ -396,8 +396,8 @@ se_bwd_apply_kernel(const bf16* __restrict__ dxo, const long long* __restrict__ 
   }
   if (blockIdx.x == 0) {
     for (int i = tid; i < kC * R; i += blockDim.x) {
-      atomicAdd(dfc2 + i, s_dt[i / R] * s_z[i % R]);       // fc2 [64][R]
-      atomicAdd(dfc0 + i, s_dzr[i / kC] * s_y[i % kC]);    // fc0 [R][64]
+      gs_add(dfc2 + i, s_dt[i / R] * s_z[i % R]);       // fc2 [64][R]
+      gs_add(dfc0 + i, s_dzr[i / kC] * s_y[i % kC]);    // fc0 [R][64]
     }
   }
   __syncthreads();
@@ -473,6 +473,52 @@ nchw3_to_nhwc8_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int
     const float t8[8] = {__ldg(s0), __ldg(s0 + hw), __ldg(s0 + 2 * hw), 0.f, 0.f, 0.f, 0.f, 0.f};
     reinterpret_cast<uint4*>(dst)[i] = pack8(t8);
   }
+}
+
+// Fixed-point shadow -> fp32 gradients of the small tensors.  g64 has the layout of the flat gradient vector; this
+// kernel converts, per RCAB of one group (blockIdx.y = block), the PReLU slope [64] and the two SE matrices [2 R 64], or
+// (n_rcab == 0) one plain range.
+__global__ void __launch_bounds__(256)
+grads_from_fixed_kernel(const long long* __restrict__ g64, float* __restrict__ grads, int64_t base, int64_t stride,
+                        int64_t off_a, int cnt_a, int64_t off_b, int cnt_b) {
+  const int64_t r0 = base + int64_t(blockIdx.y) * stride;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt_a + cnt_b; i += gridDim.x * blockDim.x) {
+    const int64_t k = r0 + (i < cnt_a ? off_a + i : off_b + (i - cnt_a));
+    grads[k] = gs_to_float(g64[k]);
+  }
+}
+
+// Sum of the per-CTA partial weight gradients of one convolution, in a FIXED order (wgrad_*_umma_kernel write their
+// [64][576] + [64] partials with plain stores instead of racing fp32 atomics): bit-identical gradients run to run.
+constexpr int kWgPartFloats = kC * kC * 9 + kC;
+__device__ __forceinline__ void wgrad_reduce_one(const float* __restrict__ parts, int n_parts, float* __restrict__ dW,
+                                                 float* __restrict__ dB, int co_mul, int co_off, int first, int step) {
+  constexpr int kRow4 = kC * 9 / 4;                  // float4 per output row
+  for (int e = first; e < kC * kRow4 + kC / 4; e += step) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* src = reinterpret_cast<const float4*>(parts) + e;
+    for (int k0 = 0; k0 < n_parts; k0 += 8) {        // eight loads in flight, added in index order
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        v[j] = (k0 + j < n_parts) ? __ldcg(src + size_t(k0 + j) * (kWgPartFloats / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a.x += v[j].x; a.y += v[j].y; a.z += v[j].z; a.w += v[j].w; }
+    }
+    if (e < kC * kRow4) {
+      const int co = e / kRow4, q = e - co * kRow4;
+      *reinterpret_cast<float4*>(dW + size_t(co * co_mul + co_off) * (kC * 9) + 4 * q) = a;
+    } else {
+      const int c4 = 4 * (e - kC * kRow4);
+      dB[(c4 + 0) * co_mul + co_off] = a.x; dB[(c4 + 1) * co_mul + co_off] = a.y;
+      dB[(c4 + 2) * co_mul + co_off] = a.z; dB[(c4 + 3) * co_mul + co_off] = a.w;
+    }
+  }
+}
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ parts, int n_parts, float* __restrict__ dW, float* __restrict__ dB,
+                    int co_mul, int co_off) {
+  wgrad_reduce_one(parts, n_parts, dW, dB, co_mul, co_off, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 }  // namespace fen

@@ -29,6 +29,14 @@ __device__ __forceinline__ void hs_add(long long* p, float v) {
   atomicAdd(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(__float2ll_rn(v * kHsScale)));
 }
 __device__ __forceinline__ float hs_to_float(long long v) { return __ll2float_rn(v) * (1.f / kHsScale); }
+// The same for the small reductions of the BACKWARD pass (PReLU slope, SE matrix and SE dot-product gradients: sums of many
+// tiny terms from many CTAs).  Scale 2^44: resolution 6e-14, |sum| < 2^19; integer atomics make every parameter gradient
+// independent of the order of arrival (the reference trains with cudnn.deterministic = True, scripts/train.py:52-53).
+constexpr float kGsScale = 17592186044416.f;
+__device__ __forceinline__ void gs_add(long long* p, float v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(p), static_cast<unsigned long long>(__float2ll_rn(v * kGsScale)));
+}
+__device__ __forceinline__ float gs_to_float(long long v) { return float(__ll2double_rn(v) * (1.0 / 17592186044416.0)); }
 
 enum EpilogueKind : int {
   kEpiPrelu = 0,     // out = prelu(acc + bias)                       (RCAB conv1)
@@ -58,7 +66,8 @@ struct ConvParams {
   const bf16* aux;        // NHWC, same shape as out (kEpiDot)
   bf16* out;              // NHWC bf16 output
   float* sums;            // [B][64] fp32, accumulated with atomics (kEpiSum, kEpiDot); [64] for kEpiGate
-  long long* sums64;      // kEpiSum, optional: accumulate there in fixed point (hs_add) instead of `sums`: deterministic
+  long long* sums64;      // optional: accumulate there in fixed point instead of `sums`: deterministic (kEpiSum: hs_add, the
+                          //   forward's scale; kEpiGate / kEpiDot: gs_add, the gradient scale)
   uint32_t* mask_out;     // kEpiPrelu / kEpiShuffle, optional: bit c of word [2 * output pixel + column half] = (pre-activation
                           //   of channel 32 * half + c > 0) - what the PReLU backward needs for slopes of any sign
   const uint32_t* mask_in;  // kEpiGate: those words of the activation being differentiated

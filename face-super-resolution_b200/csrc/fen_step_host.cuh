@@ -40,6 +40,14 @@ __global__ void pack_T_all_kernel(const float* __restrict__ params, uint8_t* __r
   pack_conv64_dev(w, reinterpret_cast<bf16*>(dst), true);
 }
 
+// batched weight-gradient launches: after group G / 2 (the upper half, with conv_after_body), after group 1 and after
+// group 0 (a small last batch keeps the gradient slice that finishes last - and whose all-reduce is exposed - small)
+static bool bwd_is_flush(const Layout& L, int g) { return g == L.G / 2 || g == 1 || g == 0; }
+static int bwd_prev_flush(const Layout& L, int g) {       // the flush group above g, or -1
+  for (int q = g + 1; q < L.G; ++q)
+    if (bwd_is_flush(L, q)) return q;
+  return -1;
+}
 // ---------------------------------------------------------------- saved activations + gradient buffers
 // All [B][H][W][64] bf16 tensors of the step lie at ONE stride (`act`) from the workspace base, so that a single 5-D
 // tensor map addresses any of them by index (body2_umma_kernel<true>, wgrad_batch_umma_kernel):
@@ -55,6 +63,7 @@ struct StepWs {
   int64_t hsum, flags;                                    // fused forward (body2_umma_kernel<true>)
   int64_t dy1, du0, dy0, dsum;                            // backward, upsample resolution
   int64_t d8, x8, wg3;                                    // backward, the 3-channel ends (narrow tensors + scratch)
+  int64_t g64, wg_part;                                   // deterministic reductions: fixed-point shadow, partial weight gradients
   int64_t total;
 };
 static void make_step_ws(const Layout& L, int B, int H, int W, StepWs* w) {
@@ -87,7 +96,21 @@ static void make_step_ws(const Layout& L, int B, int H, int W, StepWs* w) {
   w->dy1 = o; o += 16 * act;
   w->du0 = o; o += 4 * act;
   w->dy0 = o; o += 4 * act;
-  w->dsum = o; o += align256(int64_t(L.n_rcab) * B * 64 * 4);   // sum_px dx' * o per RCAB, image, channel
+  w->dsum = o; o += align256(int64_t(L.n_rcab) * B * 64 * 8);   // sum_px dx' * o per RCAB, image, channel (fixed point, gs_add)
+  w->g64 = o; o += align256(L.p_total * 8);                      // fixed-point shadow of the flat gradient (small tensors only)
+  {
+    // partial weight gradients (wgrad_reduce_kernel): the largest batched launch, or one partial per SM
+    int max_jobs = 1;
+    for (int g = L.G - 1; g >= 0; --g)
+      if (bwd_is_flush(L, g)) {
+        const int prev = bwd_prev_flush(L, g), per = 1 + 2 * L.Bk;
+        const int jb = prev < 0 ? 0 : 1 + (L.G - prev) * per, je = 1 + (L.G - g) * per;
+        if (je - jb > max_jobs) max_jobs = je - jb;
+      }
+    int64_t parts = int64_t(max_jobs) * 16;
+    if (parts < num_sms()) parts = num_sms();
+    w->wg_part = o; o += align256(parts * kWgPartFloats * 4);
+  }
   w->d8 = o; o += 2 * act;                                       // d out as bf16 [B][4H][4W][8] (nchw3_to_nhwc8_kernel)
   w->x8 = o; o += align256(int64_t(B) * H * W * 8 * 2);          // the LR input likewise
   w->wg3 = o; o += align256((64 * 576 + 64) * 4);        // [64][576] + [64] fp32: weight-gradient scratch of the 3-channel ends
@@ -188,7 +211,7 @@ static int step_forward(const fen_config* cfg, const Layout& L, const uint8_t* k
 }
 
 static int wgrad64(const bf16* dY, const bf16* X, float* dW, float* dB, int B, int H, int W, int co_mul, int co_off,
-                   cudaStream_t st, int y_chans = kC, int x_chans = kC) {
+                   cudaStream_t st, float* parts, int y_chans = kC, int x_chans = kC) {
   const int bands = B * H * ((W + kStripW - 1) / kStripW);
   const int grid = bands < num_sms() ? bands : num_sms();
   // The product library carries the tcgen05 kernel (wgrad_umma.cuh).  Developer builds (-DFEN_DEV) also hold the
@@ -209,7 +232,11 @@ static int wgrad64(const bf16* dY, const bf16* X, float* dW, float* dB, int B, i
     int rc = make_act_map(&tm_y, dY, B, H, W, 1, kStripW, y_chans);
     if (rc) return rc;
     if ((rc = make_act_map(&tm_x, X, B, H, W, 3, kPitch, x_chans))) return rc;
-    wgrad_c64_umma_kernel<<<grid, kWuThreads, kWuDynBytes, st>>>(tm_y, tm_x, dW, dB, B, H, W, co_mul, co_off);
+    // every CTA leaves its partial gradient in `parts`; they are added up in CTA order (deterministic)
+    wgrad_c64_umma_kernel<<<grid, kWuThreads, kWuDynBytes, st>>>(tm_y, tm_x, parts, B, H, W);
+    FEN_CUDA(cudaGetLastError());
+    ++g_launches;
+    wgrad_reduce_kernel<<<37, 256, 0, st>>>(parts, grid, dW, dB, co_mul, co_off);
   }
   FEN_CUDA(cudaGetLastError());
   ++g_launches;
@@ -231,14 +258,6 @@ static int wgrad64(const bf16* dY, const bf16* X, float* dW, float* dB, int B, i
 // fen_backward_stage_range gives the slice a stage COMPLETES (empty for a stage that only feeds a later batch).
 // All state between stages lives in the step workspace.  [stage_begin, stage_end) runs a sub-range.
 static int bwd_num_stages(const Layout& L) { return L.G + 2; }
-// batched weight-gradient launches: after group G / 2 (the upper half, with conv_after_body), after group 1 and after
-// group 0 (a small last batch keeps the gradient slice that finishes last - and whose all-reduce is exposed - small)
-static bool bwd_is_flush(const Layout& L, int g) { return g == L.G / 2 || g == 1 || g == 0; }
-static int bwd_prev_flush(const Layout& L, int g) {       // the flush group above g, or -1
-  for (int q = g + 1; q < L.G; ++q)
-    if (bwd_is_flush(L, q)) return q;
-  return -1;
-}
 static void bwd_stage_range(const Layout& L, int stage, int64_t* begin, int64_t* count) {
   *begin = 0; *count = 0;
   if (stage == 0) { *begin = L.p_up[0]; *count = L.p_total - L.p_up[0]; }
@@ -276,9 +295,13 @@ static int wgrad_batch(const Layout& L, uint8_t* wsb, const StepWs& ws, float* g
   p.p_rcab0 = L.p_rcab0; p.p_rcab_stride = L.p_rcab_stride; p.p_group_stride = L.p_group_stride;
   p.p_gconv_w_in_group = L.p_gconv_w_in_group; p.p_after_w = L.p_after_w;
   p.grads = grads;
+  p.parts = reinterpret_cast<float*>(wsb + ws.wg_part);
   const int items = (job_end - job_begin) * p.chunks;
   const int grid = items < num_sms() ? items : num_sms();
   wgrad_batch_umma_kernel<<<grid, kWbThreads, kWbDynBytes, st>>>(tm_y, tm_x, p);
+  FEN_CUDA(cudaGetLastError());
+  ++g_launches;
+  wgrad_reduce_batch_kernel<<<dim3(10, job_end - job_begin), 256, 0, st>>>(p);     // chunk partials -> flat gradient, fixed order
   FEN_CUDA(cudaGetLastError());
   ++g_launches;
   return FEN_OK;
@@ -292,7 +315,9 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
   auto act = [&](int64_t off) { return reinterpret_cast<bf16*>(wsb + off); };
   const float* zeros = reinterpret_cast<const float*>(kb + K.zeros);
   const long long* sums = reinterpret_cast<const long long*>(wsb + ws.sums);
-  float* dsum = reinterpret_cast<float*>(wsb + ws.dsum);
+  long long* dsum = reinterpret_cast<long long*>(wsb + ws.dsum);     // fixed point (gs_add), like every small reduction below
+  long long* g64 = reinterpret_cast<long long*>(wsb + ws.g64);       // shadow of `grads` for the slope / SE-matrix gradients
+  float* parts = reinterpret_cast<float*>(wsb + ws.wg_part);
   const int Ho = 4 * H, Wo = 4 * W;
   const size_t n8 = size_t(B) * H * W * 8;   // 8-element groups of one body-resolution tensor
   bf16* dBody = act(ws.dBody);
@@ -300,7 +325,8 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
   const int per = 1 + 2 * L.Bk;              // deferred weight-gradient jobs per group (wgrad_umma.cuh: wg_job)
   if (stage_begin <= 0 && stage_end > 0) {
   FEN_CUDA(cudaMemsetAsync(grads, 0, size_t(L.p_total) * 4, st));
-  FEN_CUDA(cudaMemsetAsync(dsum, 0, size_t(L.n_rcab) * B * 64 * 4, st));
+  FEN_CUDA(cudaMemsetAsync(dsum, 0, size_t(L.n_rcab) * B * 64 * 8, st));
+  FEN_CUDA(cudaMemsetAsync(g64, 0, size_t(L.p_total) * 8, st));
 
   // ---- conv_last (64 -> 3) on the 64-channel tcgen05 kernels: d out goes to bf16 NHWC with 8 channels, which a narrow
   // tensor map zero-extends to 64 (make_act_map).  Weight / bias gradient = rows 0..2 of a 64 x 64 weight gradient;
@@ -312,13 +338,12 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
     nchw3_to_nhwc8_kernel<<<ew_blocks(size_t(B) * Ho * Wo), 256, 0, st>>>(dout, d8, B, size_t(Ho) * Wo);
     FEN_CUDA(cudaGetLastError());
     ++g_launches;
-    FEN_CUDA(cudaMemsetAsync(wg, 0, (64 * 576 + 64) * 4, st));
-    if ((rc = wgrad64(d8, act(ws.u1), wg, wg + 64 * 576, B, Ho, Wo, 1, 0, st, 8, kC))) return rc;
+    if ((rc = wgrad64(d8, act(ws.u1), wg, wg + 64 * 576, B, Ho, Wo, 1, 0, st, parts, 8, kC))) return rc;
     FEN_CUDA(cudaMemcpyAsync(grads + L.p_last_w, wg, 3 * 576 * 4, cudaMemcpyDeviceToDevice, st));
     FEN_CUDA(cudaMemcpyAsync(grads + L.p_last_b, wg + 64 * 576, 3 * 4, cudaMemcpyDeviceToDevice, st));
     const float* slope1 = reinterpret_cast<const float*>(k + L.k_up[1] + 4 * kConvWBytes + 1024);
-    if ((rc = conv64(d8, kb + K.last, zeros, slope1, act(ws.u1), grads + L.p_up[1] + 4 * kConvW + 256, act(ws.dy1), kEpiGate,
-                     B, Ho, Wo, st, nullptr, reinterpret_cast<uint32_t*>(wsb + ws.m_u1), nullptr, 8, 1)))
+    if ((rc = conv64(d8, kb + K.last, zeros, slope1, act(ws.u1), nullptr, act(ws.dy1), kEpiGate, B, Ho, Wo, st, nullptr,
+                     reinterpret_cast<uint32_t*>(wsb + ws.m_u1), g64 + L.p_up[1] + 4 * kConvW + 256, 8, 1)))
       return rc;
   }
   // ---- upsample stage 1 (conv 64 -> 256 on 2H x 2W, input u0): 4 sub-pixel planes
@@ -328,7 +353,7 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
     bf16* acc[2] = {act(ws.du0), act(ws.dy0)};   // ping-pong; dy0 is free until the unshuffle below
     for (int sub = 0; sub < 4; ++sub) {
       const bf16* dy = act(ws.dy1 + sub * plane);
-      if ((rc = wgrad64(dy, act(ws.u0), grads + L.p_up[1], grads + L.p_up[1] + 4 * kConvW, B, h2, w2, 4, sub, st)))
+      if ((rc = wgrad64(dy, act(ws.u0), grads + L.p_up[1], grads + L.p_up[1] + 4 * kConvW, B, h2, w2, 4, sub, st, parts)))
         return rc;
       if ((rc = conv64(dy, kb + K.up[1] + sub * kConvWBytes, zeros, nullptr, sub ? acc[(sub - 1) & 1] : nullptr,
                        nullptr, acc[sub & 1], sub ? kEpiResidual : kEpiBias, B, h2, w2, st)))
@@ -338,7 +363,7 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
     const float* slope0 = reinterpret_cast<const float*>(k + L.k_up[0] + 4 * kConvWBytes + 1024);
     prelu_bwd_kernel<<<ew_blocks(size_t(B) * h2 * w2 * 8), 256, 0, st>>>(
         acc[1], act(ws.u0), reinterpret_cast<const uint32_t*>(wsb + ws.m_u0), slope0, acc[0],
-        grads + L.p_up[0] + 4 * kConvW + 256, B, h2, w2, 1);
+        g64 + L.p_up[0] + 4 * kConvW + 256, B, h2, w2, 1);
     FEN_CUDA(cudaGetLastError());
     ++g_launches;
   }
@@ -347,7 +372,7 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
     bf16* acc[2] = {act(ws.dX0), dBody};
     for (int sub = 0; sub < 4; ++sub) {
       const bf16* dy = act(ws.du0 + sub * ws.act);
-      if ((rc = wgrad64(dy, act(ws.body), grads + L.p_up[0], grads + L.p_up[0] + 4 * kConvW, B, H, W, 4, sub, st)))
+      if ((rc = wgrad64(dy, act(ws.body), grads + L.p_up[0], grads + L.p_up[0] + 4 * kConvW, B, H, W, 4, sub, st, parts)))
         return rc;
       if ((rc = conv64(dy, kb + K.up[0] + sub * kConvWBytes, zeros, nullptr, sub ? acc[(sub - 1) & 1] : nullptr,
                        nullptr, acc[sub & 1], sub ? kEpiResidual : kEpiBias, B, H, W, st)))
@@ -356,6 +381,11 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
   }
   // ---- conv_after_body + long skip: body = conv(gout[G-1]) + f0.  (weight gradient: job 0 of the first batch)
   if ((rc = conv64(dBody, kb + K.after, zeros, nullptr, nullptr, nullptr, dG(L.G - 1), kEpiBias, B, H, W, st))) return rc;
+  // the two upsample PReLU slope gradients: fixed point -> fp32
+  grads_from_fixed_kernel<<<dim3(1, 1), 128, 0, st>>>(g64, grads, L.p_up[0] + 4 * kConvW + 256, 0, 0, 64,
+                                                       L.p_up[1] - L.p_up[0], 64);
+  FEN_CUDA(cudaGetLastError());
+  ++g_launches;
   }   // stage 0
   // ---- residual groups, last to first
   const int hw = H * W;
@@ -365,19 +395,17 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
     bf16* dCur = dG(g);
     bf16* dX = act(ws.dX0);        // (re)written from dCur at the start of every group: the roles need no carry-over
     bf16* dXn = act(ws.dX1);
-    float* pg = grads + L.p_rcab0 + g * L.p_group_stride;
     // group conv: d blocks_out, and with it sum_px dx' * o of the group's last RCAB (kEpiDot)
-    if ((rc = conv64(dCur, kb + K.gconv0 + g * kConvWBytes, zeros, nullptr, nullptr,
-                     dsum + size_t(g * L.Bk + L.Bk - 1) * B * 64, dX, kEpiDot, B, H, W, st,
-                     act(ws.o0 + (g * L.Bk + L.Bk - 1) * ws.act))))
+    if ((rc = conv64(dCur, kb + K.gconv0 + g * kConvWBytes, zeros, nullptr, nullptr, nullptr, dX, kEpiDot, B, H, W, st,
+                     act(ws.o0 + (g * L.Bk + L.Bk - 1) * ws.act), nullptr, dsum + size_t(g * L.Bk + L.Bk - 1) * B * 64)))
       return rc;
     for (int b = L.Bk - 1; b >= 0; --b) {
       const int r = g * L.Bk + b;
       const uint8_t* kr = k + L.k_rcab0 + int64_t(r) * L.k_rcab_stride;
-      float* pr = pg + b * L.p_rcab_stride;
-      float* d_sl = pr + kConvW + 64;
-      float* d_fc0 = d_sl + 64 + kConvW + 64;
-      float* d_fc2 = d_fc0 + L.R * 64;
+      long long* pr = g64 + L.p_rcab0 + g * L.p_group_stride + b * L.p_rcab_stride;   // (fixed-point shadow: gs_add)
+      long long* d_sl = pr + kConvW + 64;
+      long long* d_fc0 = d_sl + 64 + kConvW + 64;
+      long long* d_fc2 = d_fc0 + L.R * 64;
       const bf16* h = act(ws.h0 + r * ws.act);
       bf16* dO = act(ws.dO0 + r * ws.act);      // kept: the operands of the deferred weight gradients
       bf16* dH = act(ws.dH0 + r * ws.act);
@@ -390,13 +418,13 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
       ++g_launches;
       // conv2: data gradient with the PReLU backward in its epilogue (dH holds dA)
       if ((rc = conv64(dO, kb + K.rcab0 + r * K.rcab_stride + kConvWBytes, zeros,
-                       reinterpret_cast<const float*>(kr + rr.slope), h, d_sl, dH, kEpiGate, B, H, W, st, nullptr,
-                       reinterpret_cast<uint32_t*>(wsb + ws.m_h0 + r * ws.m_stride))))
+                       reinterpret_cast<const float*>(kr + rr.slope), h, nullptr, dH, kEpiGate, B, H, W, st, nullptr,
+                       reinterpret_cast<uint32_t*>(wsb + ws.m_h0 + r * ws.m_stride), d_sl)))
         return rc;
       // conv1 + the identity path of the RCAB; the result is dx' of the previous RCAB of the group
       if (b > 0) {
-        if ((rc = conv64(dH, kb + K.rcab0 + r * K.rcab_stride, zeros, nullptr, dX, dsum + size_t(r - 1) * B * 64, dXn,
-                         kEpiDot, B, H, W, st, act(ws.o0 + (r - 1) * ws.act))))
+        if ((rc = conv64(dH, kb + K.rcab0 + r * K.rcab_stride, zeros, nullptr, dX, nullptr, dXn, kEpiDot, B, H, W, st,
+                         act(ws.o0 + (r - 1) * ws.act), nullptr, dsum + size_t(r - 1) * B * 64)))
           return rc;
       } else {
         if ((rc = conv64(dH, kb + K.rcab0 + r * K.rcab_stride, zeros, nullptr, dX, nullptr, dXn, kEpiResidual, B, H,
@@ -407,6 +435,11 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
     }
     // group skip: d gin = dX + dCur  (-> d gout[g - 1], or the f0-level gradient after group 0)
     FEN_CUDA(launch_pdl(add_bf16_kernel, dim3(ew_blocks(n8)), dim3(256), 0, st, dX, dCur, g ? dG(g - 1) : act(ws.dF), n8));
+    FEN_CUDA(cudaGetLastError());
+    ++g_launches;
+    // slope and SE-matrix gradients of the group's RCABs: fixed point -> fp32
+    grads_from_fixed_kernel<<<dim3(2, L.Bk), 256, 0, st>>>(g64, grads, L.p_rcab0 + g * L.p_group_stride, L.p_rcab_stride,
+                                                            kConvW + 64, 64, 2 * (kConvW + 64) + 64, 2 * L.R * 64);
     FEN_CUDA(cudaGetLastError());
     ++g_launches;
     // deferred weight gradients: everything since the previous batch (job 0 = conv_after_body rides with the first)
@@ -430,8 +463,7 @@ static int step_backward(const fen_config* cfg, const Layout& L, const uint8_t* 
     nchw3_to_nhwc8_kernel<<<ew_blocks(size_t(B) * H * W), 256, 0, st>>>(x, x8, B, size_t(H) * W);
     FEN_CUDA(cudaGetLastError());
     ++g_launches;
-    FEN_CUDA(cudaMemsetAsync(wg, 0, (64 * 576 + 64) * 4, st));
-    if ((rc = wgrad64(act(ws.dF), x8, wg, grads + L.p_first_b, B, H, W, 1, 0, st, kC, 8))) return rc;
+    if ((rc = wgrad64(act(ws.dF), x8, wg, grads + L.p_first_b, B, H, W, 1, 0, st, parts, kC, 8))) return rc;
     FEN_CUDA(cudaMemcpy2DAsync(grads + L.p_first_w, 27 * 4, wg, 576 * 4, 27 * 4, 64, cudaMemcpyDeviceToDevice, st));
   }
   return FEN_OK;

@@ -31,7 +31,10 @@ static_assert(16 * kWgOutPitch * 4 <= kWuStages * kWuStageBytes, "output staging
 
 __global__ void __launch_bounds__(kWuThreads, 1)
 wgrad_c64_umma_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_x,
-                      float* __restrict__ dW, float* __restrict__ dB, int B, int H, int W, int co_mul, int co_off) {
+                      float* __restrict__ parts, int B, int H, int W) {
+  // parts: [gridDim.x][64 x 576 + 64] fp32 - every CTA leaves its partial weight / bias gradient there with plain
+  // stores; wgrad_reduce_kernel adds them up in CTA order (deterministic; the racing fp32 atomics this replaces gave
+  // run-to-run differences in the last bits).
   extern __shared__ uint8_t wu_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(wu_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ones = smem + kWuStages * kWuStageBytes;
@@ -115,6 +118,7 @@ wgrad_c64_umma_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_con
   // TMEM lane = 64 * (second tap of the pair) + ci, column = 64 * pair + co.
   __syncthreads();   // every MMA has completed (the epilogue warps waited for bar_done): the stages are free
   float* stage = reinterpret_cast<float*>(smem);
+  float* part = parts + size_t(blockIdx.x) * kWgPartFloats;
   const int q = warp & 3;                       // TMEM lane quarter this warp may read
   const int tsel = q >> 1, ci = (32 * q + lane) & 63;
   for (int pass = 0; pass < 4; ++pass) {
@@ -130,7 +134,7 @@ wgrad_c64_umma_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_con
           for (int j = 0; j < 16; ++j) stage[j * kWgOutPitch + ci * 9 + tap] = __uint_as_float(v[j]);
         } else if (ci == 0) {   // lanes 64..127 of the fifth accumulator: the bias gradient (64 identical copies)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(dB + (16 * pass + j) * co_mul + co_off, __uint_as_float(v[j]));
+          for (int j = 0; j < 16; ++j) part[kC * kC * 9 + 16 * pass + j] = __uint_as_float(v[j]);
         }
       }
     }
@@ -138,8 +142,7 @@ wgrad_c64_umma_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_con
     for (int i = tid; i < 16 * (kC * 9 / 4); i += kWuThreads) {
       const int row = i / (kC * 9 / 4), qq = i % (kC * 9 / 4);
       const float4 v4 = *reinterpret_cast<const float4*>(stage + row * kWgOutPitch + 4 * qq);
-      const int co = (16 * pass + row) * co_mul + co_off;
-      red_add_v4(dW + size_t(co) * (kC * 9) + 4 * qq, v4);
+      *reinterpret_cast<float4*>(part + size_t(16 * pass + row) * (kC * 9) + 4 * qq) = v4;
     }
     __syncthreads();
   }
@@ -171,6 +174,7 @@ struct WgBatchParams {
   // flat-gradient offsets (floats)
   int64_t p_rcab0, p_rcab_stride, p_group_stride, p_gconv_w_in_group, p_after_w;
   float* grads;
+  float* parts;                     // [n_items][64 x 576 + 64] fp32 partial gradients, item = (job - job_begin) * chunks + chunk
 };
 struct WgJob { int y_buf, x_buf; float* dW; float* dB; };
 __device__ __forceinline__ WgJob wg_job(const WgBatchParams& p, int j) {
@@ -248,6 +252,9 @@ wgrad_batch_umma_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_c
     const int chunk = item % p.chunks;
     const int band0 = chunk * per_chunk, band1 = min(bands, band0 + per_chunk);
     const int nb = max(0, band1 - band0);
+    float* part = p.parts + size_t(item) * kWgPartFloats;      // this item's partial (plain stores: see wgrad_reduce_kernel)
+    if (nb == 0)                                               // (an empty band range still owes its - zero - partial)
+      for (int i = tid; i < kWgPartFloats; i += kWbThreads) part[i] = 0.f;
     if (warp == 0) {
       // ============================================================ TMA producer
       for (int k = 0; k < nb; ++k) {
@@ -319,7 +326,7 @@ wgrad_batch_umma_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_c
             for (int j = 0; j < 16; ++j) stage[j * kWgOutPitch + ci * 9 + tap] = __uint_as_float(v[j]);
           } else if (ci == 0) {   // lanes 64..127 of the fifth accumulator: the bias gradient (64 identical copies)
 #pragma unroll
-            for (int j = 0; j < 16; ++j) atomicAdd(job.dB + 16 * pass + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 16; ++j) part[kC * kC * 9 + 16 * pass + j] = __uint_as_float(v[j]);
           }
         }
       }
@@ -329,7 +336,7 @@ wgrad_batch_umma_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_c
         for (int i = tid; i < 16 * (kC * 9 / 4); i += kWbThreads) {
           const int row = i / (kC * 9 / 4), qq = i % (kC * 9 / 4);
           const float4 v4 = *reinterpret_cast<const float4*>(stage + row * kWgOutPitch + 4 * qq);
-          red_add_v4(job.dW + size_t(16 * pass + row) * (kC * 9) + 4 * qq, v4);
+          *reinterpret_cast<float4*>(part + size_t(16 * pass + row) * (kC * 9) + 4 * qq) = v4;
         }
       }
       __syncthreads();
@@ -339,6 +346,14 @@ wgrad_batch_umma_kernel(const __grid_constant__ CUtensorMap tm_y, const __grid_c
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kWuTmemCols);
+}
+
+// The partials of a batched launch -> the flat gradient: blockIdx.y = job, the chunks summed in order.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_batch_kernel(const WgBatchParams p) {
+  const WgJob job = wg_job(p, p.job_begin + blockIdx.y);
+  wgrad_reduce_one(p.parts + size_t(blockIdx.y) * p.chunks * kWgPartFloats, p.chunks, job.dW, job.dB, 1, 0,
+                   blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 }  // namespace fen

@@ -265,3 +265,29 @@ def test_backward_rejects_bad_arguments(dev, built_lib):
     assert built_lib.fen_backward(C.byref(cfg), p, None, p, p, p, 1, 64, 64, p, 1 << 40, None) == _lib.FEN_EINVAL
     assert built_lib.fen_step_workspace_bytes(C.byref(cfg), 2, 64, 64) > built_lib.fen_forward_workspace_bytes(
         C.byref(cfg), 2, 64, 64)
+
+
+@pytest.mark.parametrize("cfg,batch", [(dict(num_groups=2, blocks_per_group=2), 5), (dict(num_groups=6, blocks_per_group=10), 8)])
+def test_backward_is_bit_deterministic(cfg, batch, dev):
+    """scripts/train.py:52-53 trains with cudnn.deterministic = True.  Every cross-CTA reduction of the backward is
+    order-independent here (weight gradients: per-CTA partials summed in CTA order; slope / SE-matrix / SE dot-product
+    sums: 64-bit fixed-point integer atomics): repeated forward + backward passes give bit-identical gradients."""
+    sd = weights.make_state_dict(3, "T1", **cfg)
+    m = _model(cfg, sd, dev)
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(batch, 3, 64, 64, generator=g).to(dev)
+    dout = ((torch.rand(batch, 3, 256, 256, generator=g) - 0.5) * 1e-4).to(dev)
+    ref = None
+    for it in range(4):
+        m.zero_grad(set_to_none=True)
+        m(x).backward(dout)
+        flat = torch.cat([p.grad.reshape(-1) for p in m.parameters()])
+        assert torch.isfinite(flat).all()
+        if ref is None:
+            ref = flat.clone()
+            ref_named = {k: p.grad.clone() for k, p in m.named_parameters()}
+            assert float(ref.abs().max()) > 0.0
+        else:
+            if not torch.equal(flat, ref):
+                names = [k for k, p in m.named_parameters() if not torch.equal(p.grad, ref_named[k])]
+                raise AssertionError(f"run {it}: {int((flat != ref).sum())} of {flat.numel()} gradient elements differ, in {names[:12]}")
