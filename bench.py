@@ -234,14 +234,42 @@ def train_record(args, rank: int, local_rank: int, world: int, dev, steps: int, 
     ms_total, loss = timed(steps, True)
     ms_nocomm = timed(steps, False)[0] if world > 1 else ms_total
     stepper.exchange = True
-    # e2e: pinned host HR batch -> H2D -> step -> loss read back on the host, every step
+    # e2e: pinned host HR batch -> H2D -> step -> loss read back on the host, every step, the way a training loop with a
+    # pinned-memory loader runs it: the upload of batch i + 1 (copy stream, second device buffer) overlaps step i, and
+    # the host reads the loss of step i - 1 while step i runs (every loss is read; none is skipped)
     host = [torch.rand(B, 3, 256, 256).pin_memory() for _ in range(2)]
-    for i in range(2):
-        stepper.step(host[i & 1].to(dev, non_blocking=True))[0].item()
+    dbuf = [torch.empty(B, 3, 256, 256, device=dev) for _ in range(2)]
+    loss_pin = torch.zeros(2, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    up = [torch.cuda.Event() for _ in range(2)]          # upload of buffer k complete
+    done = [torch.cuda.Event() for _ in range(2)]        # the step that read buffer k (and wrote loss_pin[k]) complete
+
+    def e2e_loop(n):
+        last = None
+        with torch.cuda.stream(copy_stream):
+            dbuf[0].copy_(host[0], non_blocking=True); up[0].record(copy_stream)
+        for i in range(n):
+            k = i & 1
+            if i + 1 < n:
+                with torch.cuda.stream(copy_stream):
+                    if i >= 1:
+                        copy_stream.wait_event(done[k ^ 1])       # step i - 1 has finished with that buffer
+                    dbuf[k ^ 1].copy_(host[k ^ 1], non_blocking=True); up[k ^ 1].record(copy_stream)
+            main.wait_event(up[k])
+            loss_dev = stepper.step(dbuf[k])[0]
+            if i >= 1:
+                done[k ^ 1].synchronize()                         # (already recorded) the loss of step i - 1 is on the host
+                last = float(loss_pin[k ^ 1])
+            loss_pin[k:k + 1].copy_(loss_dev.reshape(1), non_blocking=True)
+            done[k].record(main)
+        done[(n - 1) & 1].synchronize()
+        return float(loss_pin[(n - 1) & 1])
+
+    e2e_loop(2)
     torch.cuda.synchronize(); sharding.barrier()
     e0.record()
-    for i in range(steps):
-        loss_host = stepper.step(host[i & 1].to(dev, non_blocking=True))[0].item()
+    loss_host = e2e_loop(steps)
     e1.record(); torch.cuda.synchronize(); sharding.barrier()
     ms_e2e = sharding.max_over_ranks(e0.elapsed_time(e1), dev)
     del stepper, model, pool

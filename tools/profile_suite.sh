@@ -1,6 +1,5 @@
 #!/bin/bash
-# The ncu evidence under profiles/ (one gpurun call): launch list of the forward, full captures of the body kernel and of
-# the batched weight gradient.  Every command runs once without ncu first (B200_PROFILING.md).
+# The ncu evidence under profiles/ (one gpurun call).  Every command runs once WITHOUT ncu first (B200_PROFILING.md).
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 CMD="python bench.py --steps 2 --warmup 3 --no-train --no-eager --no-cpu-baseline"
@@ -9,5 +8,12 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 python tools/launch_summary.py gpurun_out/r02_launches.csv > gpurun_out/r02_launches_summary.txt 2>&1
 python tools/fwd_time.py 64 > gpurun_out/plain_fwd.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:body2_umma -s 4 -c 1 -o gpurun_out/r02_body2_kernel_full python tools/fwd_time.py 64 > gpurun_out/ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:conv_last_umma -s 4 -c 1 -o gpurun_out/r02_conv_last_kernel_full python tools/fwd_time.py 64 > gpurun_out/ncu2b.log 2>&1
 python tools/step_once.py 32 2 > gpurun_out/plain_step.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r02_step_launches.csv python tools/step_once.py 32 2 > gpurun_out/ncu3a.log 2>&1
+python tools/launch_summary.py gpurun_out/r02_step_launches.csv > gpurun_out/r02_step_launches_summary.txt 2>&1
 ncu --set full --clock-control none --import-source on -k regex:wgrad_batch -s 3 -c 1 -o gpurun_out/r02_wgrad_batch_kernel_full python tools/step_once.py 32 2 > gpurun_out/ncu3.log 2>&1
+FEN_BODY_MS=1 python tools/step_once.py 32 3 > gpurun_out/r02_train_body.txt 2>&1
+python tools/train_bench.py > gpurun_out/r02_train_step.txt 2>&1; cat gpurun_out/r02_train_body.txt >> gpurun_out/r02_train_step.txt
+python tools/lr_bandwidth.py 1024 4096 > gpurun_out/r02_lr_kernel_bandwidth.json 2>&1
+tail -3 gpurun_out/r02_train_step.txt
