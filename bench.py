@@ -49,6 +49,37 @@ TRAIN_WORKLOAD = ("Stage-1 L1 training step (float LR generation, forward, L1, b
                   "clip 0.5 + AdamW), FaceEnhanceNet 6x10x64, batch 32/GPU, random-init T1 weights (BASELINE config 5)")
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1 when
+    NCCL_DEBUG is set in the environment): everything but the final line goes to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
+
+POOL_N = 48                        # input batches the timed forwards rotate through (48 x 3.1 MB = 151 MB > the 126 MB L2)
+
+
+def bench_config(world: int, B: int) -> dict:
+    """The `config` object of the JSON line - the SAME for both arms (the reference arm times the workload of this
+    config on the host cores; what differs about it is said in its `cpu_baseline`)."""
+    return {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"batch-sharded x{world}, no collective",
+            "l2": f"inputs rotate through a {POOL_N * B * 3 * 64 * 64 * 4 / 1e6:.0f} MB pool (> 126 MB L2); "
+                  "per-step activation working set ~1 GB"}
+
+
 def source_hash() -> str:
     """Hash of the body kernel's sources: profile-derived numbers (roofline.traffic) are only valid for the build they
     were captured on."""
@@ -188,17 +219,18 @@ def run_reference(args, rank: int):
             fwd(x)
         dt = time.perf_counter() - t0
     value = B * args.steps / dt
-    sample = f"{args.steps} fp32 forwards of batch {B} on {threads} host threads, torch {torch.__version__}; {desc}"
+    sample = (f"{args.steps} fp32 forwards of batch {B} on {threads} host threads (rank 0 only, no GPU), "
+              f"torch {torch.__version__}; {desc}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": B, "parallelism": "host CPU (rank 0 only)"},
+        "config": bench_config(max(1, args.gpus), B),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ===================================================================== BASELINE config 5: the Stage-1 step
@@ -339,7 +371,7 @@ def run_train(args, rank: int, local_rank: int, world: int):
                      "peak_source": peaks["source"] + " bf16_tflops_sustained"},
         "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ===================================================================== the reference module, eager, on the GPU
@@ -383,6 +415,7 @@ def gpu_eager_baseline(dev, B: int):
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -430,7 +463,7 @@ def main():
     model = model.to(dev).eval()
 
     # input pool larger than L2 (126 MB): 48 x 3.1 MB batches, a different one every step
-    pool_n = 48
+    pool_n = POOL_N
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     pool = [torch.rand(B, 3, 64, 64, device=dev, generator=gen) for _ in range(pool_n)]
 
@@ -577,9 +610,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"batch-sharded x{world}, no collective",
-                   "l2": f"inputs rotate through a {pool_n * B * 3 * 64 * 64 * 4 / 1e6:.0f} MB pool (> 126 MB L2); "
-                         "per-step activation working set ~1 GB"},
+        "config": bench_config(world, B),
         "e2e": e2e, "e2e_fp32": e2e_fp32,
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "tensor", "kernel": k_name,
@@ -599,7 +630,7 @@ def main():
         line["cpu_baseline"] = cpu
     if eager is not None:
         line["gpu_eager_baseline"] = eager
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 if __name__ == "__main__":
