@@ -60,7 +60,7 @@ constexpr int kB2SBytes = 9 * 1024;                // SE operand: one 8-row SWIZ
 #ifndef FEN_B2_STAGED_STORE
 #define FEN_B2_STAGED_STORE 0   // 1: outputs go through a shared-memory transpose to coalesced stores (measured slower)
 #endif
-constexpr int kB2Slots = FEN_B2_STAGED_STORE ? 6 : 7;   // activation ring: two-row boxes, + 1 mirror slot
+constexpr int kB2Slots = FEN_B2_STAGED_STORE ? 6 : 7;   // activation ring: two-row boxes, + 1 mirror slot (6: same time, 5: + 2 %)
 constexpr int kB2RingPx = kB2Slots * kBBoxPx;      // 792 pixels, + the 132-pixel mirror slot
 constexpr int kB2RingBytes = (kB2Slots + 1) * kBSlotBytes;
 constexpr int kB2StageBytes = 2048;                // per epilogue warp: 32 pixels x 32 channels bf16, SWIZZLE_64B
@@ -972,8 +972,14 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
         if (ly.epi == kBEpiPreluHsum) run_tiles(std::integral_constant<int, kBEpiPreluHsum>{});
         else if (ly.epi == kBEpiSeResidual) run_tiles(std::integral_constant<int, kBEpiSeResidual>{});
         else run_tiles(std::integral_constant<int, kBEpiResidual>{});
-        // ---- pass done for this warp: make its global writes visible, then publish the CTA's flag
-        __threadfence();
+        // ---- pass done for this warp: publish the CTA's flag once every epilogue warp has arrived.
+        // No per-thread __threadfence() here.  The chain [other lanes' stores] -> __syncwarp -> mbarrier.arrive
+        // (release.cta) -> mbarrier wait of the flag writer (acquire.cta) -> st.release.gpu of the flag is cumulative
+        // in the PTX memory model: the ONE gpu-scope release covers every store that happened before it through the
+        // CTA-scope synchronisation - the idiom of cooperative-groups grid.sync (bar.sync, then thread 0 fences).
+        // 256 concurrent gpu-scope fences per pass cost 2 % of the kernel (3.085 -> 3.020 ms at batch 64; ERRBAR /
+        // MEMBAR samples of the epilogue warps in the round-2 ncu capture).  Measured and rejected: flags published by
+        // the TMA warp from a shared counter (the epilogue warps never wait): 3.10 ms - that warp is not idle enough.
         __syncwarp();
         // arrivals of pass P may only start once pass P-1 is complete (a warp running ahead over short
         // passes could otherwise complete a phase with two of its own arrivals)
