@@ -41,6 +41,11 @@ namespace fen {
 #define B2TS(P, e) do { if (FEN_B2_TRACE && p.dbg && blockIdx.x == 70 && (P) < 512 && lane == 0) p.dbg[6144 + (P) * 8 + (e)] = clock64(); } while (0)
 #define B2TRACE(P, e) do { if (FEN_B2_TRACE && p.dbg && blockIdx.x == 70 && (P) < 512) p.dbg[(P) * 8 + (e)] = clock64(); } while (0)
 
+#ifndef FEN_B2_WFREE1
+#define FEN_B2_WFREE1 1   // 1: the weights of a layer are handed back with ONE tcgen05.commit per issuer (after its last tile's
+#endif                    //    last tap) instead of one per tap.  Same time (3.14 ms both), and the last tile of a layer no
+                          //    longer carries 10 commits: every tile tools/soak2.py ever caught wrong was such a tile
+
 #ifndef FEN_B2_NI
 #define FEN_B2_NI 2   // MMA issuer warps.  One thread sustains ~81 cycles per tcgen05.mma (tools/umma_probe3.cu), the pipe
 #endif                //   takes one N = 64 MMA every ~48: at least two issuers must be inside their 36-MMA loops at any time
@@ -54,7 +59,10 @@ constexpr int kB2Threads = 32 * (kB2FirstEpiWarp + kB2EpiWarps);
 #ifndef FEN_B2_SMEM_CONST
 #define FEN_B2_SMEM_CONST (FEN_B2_NI > 2)   // 1: the epilogue reads bias / slope / SE scale from shared memory per tile instead of
 #endif                                      //    caching 64 values in registers (more warps per CTA = fewer registers per thread)
-constexpr int kB2AccBufs = 7;                      // 7 x 64 TMEM columns for conv tiles ...
+#ifndef FEN_B2_ACCBUFS
+#define FEN_B2_ACCBUFS 7
+#endif
+constexpr int kB2AccBufs = FEN_B2_ACCBUFS;         // 7 x 64 TMEM columns for conv tiles ...
 constexpr uint32_t kB2SeCol = kB2AccBufs * kC;     // ... + 64 columns for the SE mat-vec
 constexpr int kB2SBytes = 9 * 1024;                // SE operand: one 8-row SWIZZLE_128B atom per tap
 #ifndef FEN_B2_STAGED_STORE
@@ -300,11 +308,14 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           fence_proxy_async_all();
         }
       };
-      auto issue_boxes = [&](int s, int b0, int b1, uint32_t gbase_pass) {     // lane 0 only
+      // Every wait below is executed by the WHOLE (converged) warp; lane 0 only issues, in straight-line blocks (rule 1
+      // of DESIGN.md 4.2 - TMA issue is a uniform-datapath instruction like tcgen05: it must not sit in an elected-lane
+      // block that also spins).
+      auto issue_boxes = [&](int s, int b0, int b1, uint32_t gbase_pass) {
         const int img_base = s * p.set_B;
         for (int b = b0; b < b1; ++b) {
           const B2Box e = box_tab2[s][b];
-          B2T2(P, 9, b);
+          if (lane == 0) B2T2(P, 9, b);
           B2W(1, 3, L, s, b);
           // the box this one replaces must have been read by every tile that uses it: wait for those tiles to complete
           const int need = s_hist[slot];
@@ -312,41 +323,49 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
             mbar_wait(&bar_acc_full[frontier % kB2AccBufs], (frontier / kB2AccBufs) & 1u);
             ++frontier;
           }
-          s_hist[slot] = int(gbase_pass) + int(e.last_tile);
+          __syncwarp();                              // (every lane has read s_hist[slot] before lane 0 replaces it)
           const bool mirror = e.mirror && slot == 0;
-          mbar_expect_tx(&bar_full[slot], mirror ? 2 * kBSlotBytes : kBSlotBytes);
-          tma_load_5d_hint(&maps.act, &bar_full[slot], smem_u32(ring + slot * kBSlotBytes), 0, -1, e.y0,
-                           img_base + e.img, ly.in, pol);
-          if (mirror)
-            tma_load_5d_hint(&maps.act, &bar_full[slot], smem_u32(ring + kB2Slots * kBSlotBytes), 0, -1, e.y0,
+          if (lane == 0) {
+            s_hist[slot] = int(gbase_pass) + int(e.last_tile);
+            mbar_expect_tx(&bar_full[slot], mirror ? 2 * kBSlotBytes : kBSlotBytes);
+            tma_load_5d_hint(&maps.act, &bar_full[slot], smem_u32(ring + slot * kBSlotBytes), 0, -1, e.y0,
                              img_base + e.img, ly.in, pol);
-          B2T2(P, 10, b);
+            if (mirror)
+              tma_load_5d_hint(&maps.act, &bar_full[slot], smem_u32(ring + kB2Slots * kBSlotBytes), 0, -1, e.y0,
+                               img_base + e.img, ly.in, pol);
+            B2T2(P, 10, b);
+          }
+          __syncwarp();
           if (++slot == kB2Slots) slot = 0;
         }
       };
       const int pre = min(kPre, s_meta[0][1]);
       wait_flags(0);
+      if (lane == 0) B2TRACE(P, 0);
+      issue_boxes(0, 0, pre, gbase);
+      // bias (+ slope) of this layer -> s_cv[L & 1].  The slot was last read by the epilogue of layer L - 2, which
+      // is complete: wait_flags saw this CTA's own flag reach L, i.e. its epilogue has finished layer L - 1.
       if (lane == 0) {
-        B2TRACE(P, 0);
-        issue_boxes(0, 0, pre, gbase);
-        // bias (+ slope) of this layer -> s_cv[L & 1].  The slot was last read by the epilogue of layer L - 2, which
-        // is complete: wait_flags saw this CTA's own flag reach L, i.e. its epilogue has finished layer L - 1.
         mbar_expect_tx(&bar_cv[L & 1], 512);
         bulk_load_1d(smem_u32(&s_cv[L & 1][0]), p.cvec + ly.cv_bias, 512, &bar_cv[L & 1]);
-        for (int tap = 0; tap < 9; ++tap) {     // weights, tap by tap, as soon as the previous layer released the tap
-          B2W(1, 1, L, 0, tap);
-          if (L > 0) mbar_wait(&bar_wfree[tap], (L - 1) & 1);
+      }
+      __syncwarp();
+      for (int tap = 0; tap < 9; ++tap) {     // weights, tap by tap, as soon as the previous layer released the tap
+        B2W(1, 1, L, 0, tap);
+        if (L > 0 && (!FEN_B2_WFREE1 || tap == 0)) mbar_wait(&bar_wfree[tap], (L - 1) & 1);
+        __syncwarp();
+        if (lane == 0) {
           mbar_expect_tx(&bar_w[tap], N * kC * 2);
           tma_load_2d(&maps.w, &bar_w[tap], w_smem + tap * N * 128, 0, ly.w_row + tap * N);
         }
+        __syncwarp();
       }
-      __syncwarp();
       for (int s = 0; s < p.nset; ++s, ++P) {
         if (s > 0) {
           wait_flags(s);
           if (lane == 0) B2TRACE(P, 0);
         }
-        if (lane == 0) issue_boxes(s, s == 0 ? pre : 0, s_meta[s][1], gbase);
+        issue_boxes(s, s == 0 ? pre : 0, s_meta[s][1], gbase);
         gbase += uint32_t(s_meta[s][0]);
         __syncwarp();
       }
@@ -420,7 +439,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           // this is the layer's last pass (the commit covers this warp's MMAs of the other set)
           __syncwarp();
           if (leader && last_pass)
-            for (int tap = 0; tap < 9; ++tap) umma_commit(&bar_wfree[tap]);
+            for (int tap = 0; tap < (FEN_B2_WFREE1 ? 1 : 9); ++tap) umma_commit(&bar_wfree[tap]);
           __syncwarp();
           continue;
         }
@@ -478,7 +497,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
     const uint32_t b_lo = w_lo + (tap) * (N * 128 >> 4);                                                   \
     _Pragma("unroll") for (int k = 0; k < 4; ++k)                                                          \
         umma_bf16_ss_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, kDescHi, idesc, ((tap) | k) != 0);           \
-    if (w_rel) umma_commit(&bar_wfree[tap]); /* the next layer's tap may overwrite once these MMAs finish */ \
+    if (w_rel && (!FEN_B2_WFREE1 || (tap) == 8)) umma_commit(&bar_wfree[FEN_B2_WFREE1 ? 0 : (tap)]); /* the next layer's tap may overwrite once these MMAs finish */ \
   }
           if (!w_seen) {
 #pragma unroll
@@ -639,7 +658,13 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
               ps[lane] = __float2ll_rn(kHsScale * fmaf(__ldg(p.cvec + ly.cv_bias + lane), hw, s_raw[2 * u][lane] + s_raw[2 * u + 1][lane]));
               ps[lane + 32] = __float2ll_rn(kHsScale * fmaf(__ldg(p.cvec + ly.cv_bias + lane + 32), hw, s_raw[2 * u][lane + 32] + s_raw[2 * u + 1][lane + 32]));
             }
+#ifdef FEN_SE_DUMP3   /* developer: EVERY CTA sharing the image records the channel-0 pool total it read, slot = CTA % 64 */
+            if (p.se_out && lane == 0)
+              p.se_out[(size_t(img_base + unit_tab[u].img) * (p.G * p.Bk) + ly.rcab) * kC + (blockIdx.x & 63)] = qv[u][kHsTotal].x;
+            if (false) {
+#else
             if (p.se_out && unit_tab[u].t0 == 0) {   // the CTA owning tile 0 of the image publishes the attention vector
+#endif
               float* so = p.se_out + (size_t(img_base + unit_tab[u].img) * (p.G * p.Bk) + ly.rcab) * kC;
               so[lane] = sv0;
               so[lane + 32] = sv1;
@@ -972,14 +997,17 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
         if (ly.epi == kBEpiPreluHsum) run_tiles(std::integral_constant<int, kBEpiPreluHsum>{});
         else if (ly.epi == kBEpiSeResidual) run_tiles(std::integral_constant<int, kBEpiSeResidual>{});
         else run_tiles(std::integral_constant<int, kBEpiResidual>{});
-        // ---- pass done for this warp: publish the CTA's flag once every epilogue warp has arrived.
-        // No per-thread __threadfence() here.  The chain [other lanes' stores] -> __syncwarp -> mbarrier.arrive
-        // (release.cta) -> mbarrier wait of the flag writer (acquire.cta) -> st.release.gpu of the flag is cumulative
-        // in the PTX memory model: the ONE gpu-scope release covers every store that happened before it through the
-        // CTA-scope synchronisation - the idiom of cooperative-groups grid.sync (bar.sync, then thread 0 fences).
-        // 256 concurrent gpu-scope fences per pass cost 2 % of the kernel (3.085 -> 3.020 ms at batch 64; ERRBAR /
-        // MEMBAR samples of the epilogue warps in the round-2 ncu capture).  Measured and rejected: flags published by
-        // the TMA warp from a shared counter (the epilogue warps never wait): 3.10 ms - that warp is not idle enough.
+        // ---- pass done for this warp: make its global writes visible, then publish the CTA's flag.
+        // (Measured without the per-thread fence - one cumulative st.release.gpu by the flag writer behind the mbarrier,
+        // valid in the PTX memory model: 3.085 -> 3.020 ms at batch 64, but tools/soak2.py then caught a quarter tile of
+        // stale input, 8 times in 12 000 forwards, on one box.  The fence stays.)
+#ifndef FEN_B2_NO_WRITER_PROXY_FENCE
+        // the stores above went through the generic proxy; the readers are TMA loads (async proxy) of this and other CTAs
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+#endif
+#ifndef FEN_B2_NO_PASS_FENCE
+        __threadfence();
+#endif
         __syncwarp();
         // arrivals of pass P may only start once pass P-1 is complete (a warp running ahead over short
         // passes could otherwise complete a phase with two of its own arrivals)

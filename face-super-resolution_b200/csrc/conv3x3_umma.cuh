@@ -145,15 +145,20 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
 
   if (warp == 0) {
     // ============================================================ TMA producer
-    if (lane == 0 && g_begin < g_end) {
+    // (every wait is executed by the whole, converged warp; lane 0 only issues, in straight-line blocks: TMA issue is a
+    // uniform-datapath instruction and must not share an elected-lane block with a spin loop - DESIGN.md 4.2, rule 1)
+    if (g_begin < g_end) {
       // Weights arrive tap by tap (one barrier each) so the first MMAs need not wait for all 9.  They (like the
       // bias / slope vectors above) were packed long before this launch's predecessor started: all nine taps go
       // out before the dependency wait, the activation boxes after it.
-      auto load_w = [&](int tap) {
-        mbar_expect_tx(&bar_w[tap], N * kC * 2);
-        tma_load_2d(&tm_w, &bar_w[tap], w_smem + tap * N * 128, 0, (blockIdx.y * 9 + tap) * N);
-      };
-      for (int tap = 0; tap < 9; ++tap) load_w(tap);
+      if (lane == 0) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_expect_tx(&bar_w[tap], N * kC * 2);
+          tma_load_2d(&tm_w, &bar_w[tap], w_smem + tap * N * 128, 0, (blockIdx.y * 9 + tap) * N);
+        }
+      }
+      __syncwarp();
       pdl_wait();
       uint32_t gb = 0;  // running box counter of this CTA
       for (int g = g_begin; g < g_end;) {
@@ -162,13 +167,17 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
         for (int j = 0; j < u.nboxes; ++j, ++gb) {
           const uint32_t slot = gb % kRingSlots, ph = (gb / kRingSlots) & 1;
           mbar_wait(&bar_empty[slot], ph ^ 1);
-          const bool mirror = (slot == kRingSlots - 1) && (j + 1 < u.nboxes);
-          mbar_expect_tx(&bar_full[slot], mirror ? 2 * kSlotBytes : kSlotBytes);
-          const int y0 = u.ra - 1 + j * kBoxRows;
-          tma_load_4d(&tm_in, &bar_full[slot], smem_u32(ring + slot * kSlotBytes), 0, x0, y0, u.n);
-          if (mirror)
-            tma_load_4d(&tm_in, &bar_full[slot], smem_u32(ring + kRingSlots * kSlotBytes), 0, x0,
-                        y0 + kBoxRows, u.n);
+          __syncwarp();
+          if (lane == 0) {
+            const bool mirror = (slot == kRingSlots - 1) && (j + 1 < u.nboxes);
+            mbar_expect_tx(&bar_full[slot], mirror ? 2 * kSlotBytes : kSlotBytes);
+            const int y0 = u.ra - 1 + j * kBoxRows;
+            tma_load_4d(&tm_in, &bar_full[slot], smem_u32(ring + slot * kSlotBytes), 0, x0, y0, u.n);
+            if (mirror)
+              tma_load_4d(&tm_in, &bar_full[slot], smem_u32(ring + kRingSlots * kSlotBytes), 0, x0,
+                          y0 + kBoxRows, u.n);
+          }
+          __syncwarp();
         }
         g += u.t1 - u.t0;
       }

@@ -91,21 +91,29 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
 
   if (warp == 0) {
     // ============================================================ TMA producer
-    if (lane == 0 && n_tiles > 0) {
-      auto load_w = [&](int tap) {
-        mbar_expect_tx(&bar_w[tap], N * kC * 2);
-        tma_load_2d(&tm_w, &bar_w[tap], w_smem + tap * N * 128, 0, (blockIdx.y * 9 + tap) * N);
-      };
-      for (int tap = 0; tap < 9; ++tap) load_w(tap);
+    // (whole-warp waits, lane 0 issues in straight-line blocks: see conv3x3_umma.cuh)
+    if (n_tiles > 0) {
+      if (lane == 0) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_expect_tx(&bar_w[tap], N * kC * 2);
+          tma_load_2d(&tm_w, &bar_w[tap], w_smem + tap * N * 128, 0, (blockIdx.y * 9 + tap) * N);
+        }
+      }
+      __syncwarp();
       pdl_wait();
       uint32_t slot = 0, use = 0;
       for (int b = 0; b < n_boxes; ++b) {
         const C2Box e = box_tab[b];
         mbar_wait(&bar_empty[slot], (use & 1u) ^ 1u);
-        const bool mirror = e.cont && slot == 0;
-        mbar_expect_tx(&bar_full[slot], mirror ? 2 * kSlotBytes : kSlotBytes);
-        tma_load_4d(&tm_in, &bar_full[slot], smem_u32(ring + slot * kSlotBytes), 0, e.x0, e.y0, e.n);
-        if (mirror) tma_load_4d(&tm_in, &bar_full[slot], smem_u32(ring + kRingSlots * kSlotBytes), 0, e.x0, e.y0, e.n);
+        __syncwarp();
+        if (lane == 0) {
+          const bool mirror = e.cont && slot == 0;
+          mbar_expect_tx(&bar_full[slot], mirror ? 2 * kSlotBytes : kSlotBytes);
+          tma_load_4d(&tm_in, &bar_full[slot], smem_u32(ring + slot * kSlotBytes), 0, e.x0, e.y0, e.n);
+          if (mirror) tma_load_4d(&tm_in, &bar_full[slot], smem_u32(ring + kRingSlots * kSlotBytes), 0, e.x0, e.y0, e.n);
+        }
+        __syncwarp();
         if (++slot == kRingSlots) { slot = 0; ++use; }
       }
     }

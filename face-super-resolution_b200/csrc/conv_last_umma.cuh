@@ -104,17 +104,25 @@ conv_last_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_co
 
   if (warp == 0) {
     // ============================================================ TMA producer
-    if (lane == 0 && it0 < it1) {
-      mbar_expect_tx(&bar_w, kCLWBytes);
-      tma_load_2d(&tm_w, &bar_w, w_smem, 0, 0);                // (packed long before the predecessor started)
+    // (whole-warp waits, lane 0 issues in straight-line blocks: see conv3x3_umma.cuh)
+    if (it0 < it1) {
+      if (lane == 0) {
+        mbar_expect_tx(&bar_w, kCLWBytes);
+        tma_load_2d(&tm_w, &bar_w, w_smem, 0, 0);                // (packed long before the predecessor started)
+      }
+      __syncwarp();
       pdl_wait();
       int n, strip, blk;
       decode(it0, n, strip, blk);
       for (int it = it0, k = 0; it < it1; ++it, ++k, next_item(n, strip, blk)) {
         const uint32_t slot = uint32_t(k) & 1u;
         if (k >= 2) mbar_wait(&bar_a_free[slot], ((uint32_t(k) >> 1) - 1u) & 1u);   // the MMAs of item k - 2 have read the buffer
-        mbar_expect_tx(&bar_a_full[slot], kCLBoxBytes);
-        tma_load_4d(&tm_in, &bar_a_full[slot], smem_u32(a_smem + slot * kCLBoxBytes), 0, strip * kStripW - 1, blk * kCLRows - 1, n);
+        __syncwarp();
+        if (lane == 0) {
+          mbar_expect_tx(&bar_a_full[slot], kCLBoxBytes);
+          tma_load_4d(&tm_in, &bar_a_full[slot], smem_u32(a_smem + slot * kCLBoxBytes), 0, strip * kStripW - 1, blk * kCLRows - 1, n);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
