@@ -175,6 +175,14 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src,
                : "r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void st_release_cta_shared(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cta_shared(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_shared_u32(uint32_t saddr, uint32_t v) {
   asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
@@ -190,7 +198,20 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
   uint8_t* s_buf = smem + kBodyWBytes;                 // [9] atoms of 8 rows x 128 B (rows 2u, 2u+1: hi / lo of unit u)
   uint8_t* ring = s_buf + kB2SBytes;                   // 6 slots + mirror
   uint8_t* stage = ring + kB2RingBytes;                // 8 x 2 KB output staging (one per epilogue warp)
-  __shared__ uint64_t bar_w[9], bar_wfree[9], bar_full[kB2Slots];
+  // TWO mbarriers per ring slot, used alternately (box g -> slot g % kB2Slots, barrier g % (2 kB2Slots), parity of
+  // g / (2 kB2Slots)).  An issuer only waits for the boxes its own tiles read (issuer B never sees the first box of a
+  // pass arrive).  With one barrier per slot, B asking for box g while box g - 7 - same slot, a box only A's tile reads -
+  // was still in flight found the barrier one phase behind its own count, and a parity wait cannot tell "phase n not
+  // complete" from "phase n - 1 not complete": it passed, and B's tile read a slot whose box had not been requested
+  // yet.  That was the rare single wrong tile of tools/soak2.py (always B's last tile of a pass, from its last lane
+  // quarter on; tools/body2_protocol_sim.py reproduces it from the protocol alone).  With two barriers the previous
+  // phase of box g's barrier belongs to box g - 14, which has landed before box g - 7 could be REQUESTED, and box g - 7
+  // has been requested before any box B's previous tile read (boxes are requested in order) as long as two consecutive
+  // tiles of an issuer lie less than 7 boxes apart.  s_issued makes it unconditional: the TMA warp publishes the running
+  // count of boxes it has requested, and an issuer only trusts the parity wait for box g once s_issued > g - box g is
+  // only requested after every reader of box g - 7 has completed, so all earlier phases of its barrier are complete.
+  __shared__ uint64_t bar_w[9], bar_wfree[9], bar_full[2 * kB2Slots];
+  __shared__ uint32_t s_issued;
   __shared__ int s_hist[kB2Slots];                     // TMA warp: running index of the last tile that reads the box now in each slot
   __shared__ uint64_t bar_acc_full[kB2AccBufs], bar_acc_empty[kB2AccBufs];
   __shared__ uint64_t bar_done, bar_s_ready, bar_s_free, bar_se_full, bar_se_empty, bar_scale[2];
@@ -270,8 +291,9 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
     const uint32_t n_issuers = uint32_t(min(kB2Issuers, max(max_tiles, 1)));
     s_meta[0][3] = int(n_issuers);
     for (int k = 0; k < kB2Slots; ++k) s_hist[k] = -1;
+    s_issued = 0;
     for (int k = 0; k < 9; ++k) { mbar_init(&bar_w[k], 1); mbar_init(&bar_wfree[k], n_issuers); }
-    for (int k = 0; k < kB2Slots; ++k) mbar_init(&bar_full[k], 1);
+    for (int k = 0; k < 2 * kB2Slots; ++k) mbar_init(&bar_full[k], 1);
     for (int k = 0; k < kB2AccBufs; ++k) { mbar_init(&bar_acc_full[k], 1); mbar_init(&bar_acc_empty[k], kB2EpiWarps); }
     mbar_init(&bar_done, kB2EpiWarps);
     mbar_init(&bar_s_ready, 1); mbar_init(&bar_s_free, 1); mbar_init(&bar_se_full, 1); mbar_init(&bar_se_empty, 1);
@@ -292,7 +314,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
     // ============================================================ TMA issuer + peer-flag poller
     // The ring is one running sequence of boxes over all passes (box g -> slot g % kB2Slots, use g / kB2Slots),
     // so the first boxes of a pass are prefetched while the previous pass still owns the other slots.
-    uint32_t P = 0, slot = 0, gbase = 0, frontier = 0;   // frontier: every tile below it (running index) is complete
+    uint32_t P = 0, slot = 0, fb = 0, n_req = 0, gbase = 0, frontier = 0;   // fb: barrier of the next box (running box index n_req mod 2 kB2Slots); frontier: every tile below it (running index) is complete
     constexpr int kPre = 4;                       // boxes of a new layer requested BEFORE its weights
     for (int L = 0; L < p.n_layers; ++L) {
       const B2Layer ly = body2_layer<kTrain>(p, L);
@@ -327,16 +349,19 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           const bool mirror = e.mirror && slot == 0;
           if (lane == 0) {
             s_hist[slot] = int(gbase_pass) + int(e.last_tile);
-            mbar_expect_tx(&bar_full[slot], mirror ? 2 * kBSlotBytes : kBSlotBytes);
-            tma_load_5d_hint(&maps.act, &bar_full[slot], smem_u32(ring + slot * kBSlotBytes), 0, -1, e.y0,
+            mbar_expect_tx(&bar_full[fb], mirror ? 2 * kBSlotBytes : kBSlotBytes);
+            tma_load_5d_hint(&maps.act, &bar_full[fb], smem_u32(ring + slot * kBSlotBytes), 0, -1, e.y0,
                              img_base + e.img, ly.in, pol);
             if (mirror)
-              tma_load_5d_hint(&maps.act, &bar_full[slot], smem_u32(ring + kB2Slots * kBSlotBytes), 0, -1, e.y0,
+              tma_load_5d_hint(&maps.act, &bar_full[fb], smem_u32(ring + kB2Slots * kBSlotBytes), 0, -1, e.y0,
                                img_base + e.img, ly.in, pol);
+            st_release_cta_shared(&s_issued, n_req + 1);
             B2T2(P, 10, b);
           }
           __syncwarp();
           if (++slot == kB2Slots) slot = 0;
+          if (++fb == 2 * kB2Slots) fb = 0;
+          ++n_req;
         }
       };
       const int pre = min(kPre, s_meta[0][1]);
@@ -475,7 +500,10 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           if (waited < e.first_box) waited = e.first_box;
           while (waited < e.wait_upto) {
             const uint32_t g = gb0 + waited;
-            mbar_wait(&bar_full[g % kB2Slots], (g / kB2Slots) & 1u);
+            uint64_t* bf = &bar_full[g % (2 * kB2Slots)];
+            const uint32_t bph = (g / (2 * kB2Slots)) & 1u;
+            while (ld_acquire_cta_shared(&s_issued) <= g) mbar_try_wait(bf, bph);   // (not requested yet: try_wait only as a pause)
+            mbar_wait(bf, bph);
             ++waited;
           }
           if (leader && i == wi && wi < 2) B2TRACE(P, 1 + wi);
