@@ -377,23 +377,30 @@ class Sim:
                 m_cnt += 1
 
 
-def main():
+def sweep(ctas, seeds, layers, mode, regimes=(1, 4, 16)):
+    """Runs the model for every (CTA, seed, timing regime); returns the violation messages."""
     global FIX
-    seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-    if len(sys.argv) > 3: FIX = sys.argv[3]
-    layers = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-    bad = 0
-    ctas = [0, 1, 19, 20, 21, 70, 127, 128, 129, 147] + list(range(2, 148, 9))
+    FIX = mode
+    out = []
     for cta in ctas:
         for seed in range(seeds):
-            for slow in (1, 4, 16):
+            for slow in regimes:
                 try:
                     Sim(cta, layers, seed * 7919 + cta, slow).run()
                 except Violation as v:
-                    bad += 1
-                    if bad <= 12:
-                        print(f"CTA {cta} seed {seed} slow {slow}: {v}")
-    print(f"{len(ctas)} CTAs x {seeds} seeds x 3 timing regimes x {layers} layers: {bad} violations")
+                    out.append(f"CTA {cta} seed {seed} slow {slow}: {v}")
+    return out
+
+
+def main():
+    seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+    layers = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+    mode = sys.argv[3] if len(sys.argv) > 3 else FIX
+    ctas = [0, 1, 19, 20, 21, 70, 127, 128, 129, 147] + list(range(2, 148, 9))
+    bad = sweep(ctas, seeds, layers, mode)
+    for line in bad[:12]:
+        print(line)
+    print(f"{mode}: {len(ctas)} CTAs x {seeds} seeds x 3 timing regimes x {layers} layers: {len(bad)} violations")
 
 
 if __name__ == "__main__":
