@@ -32,20 +32,35 @@ namespace fen {
 #ifndef FEN_B2_TRACE
 #define FEN_B2_TRACE 0   // 1: pass-level timeline of CTA 70 into Body2Params::dbg (developer builds)
 #endif
+#ifndef FEN_B2_TRACE_CTA
+#define FEN_B2_TRACE_CTA 70
+#endif
 #ifndef FEN_B2_WATCH
 #define FEN_B2_WATCH 0   // 1: every role logs (stage, L, s, i) into Body2Params::dbg (host-mapped memory) - hang post-mortems
 #endif
 #define B2W(role, stage, L, s, i) do { if (FEN_B2_WATCH && p.dbg && lane == 0) { *(volatile long long*)(p.dbg + blockIdx.x * 8 + (role)) = (long long)(stage) | ((long long)(L) << 8) | ((long long)(s) << 20) | ((long long)(i) << 24); } } while (0)
 // per-tile trace (FEN_B2_TRACE=1): passes 80..83 of CTA 70 -> dbg[4096 + (P-80)*512 + e*32 + i]
-#define B2T2(P, e, i) do { if (FEN_B2_TRACE && p.dbg && blockIdx.x == 70 && (P) >= 80 && (P) < 84 && (i) < 32) p.dbg[4096 + ((P) - 80) * 512 + (e) * 32 + (i)] = clock64(); } while (0)
-#define B2TS(P, e) do { if (FEN_B2_TRACE && p.dbg && blockIdx.x == 70 && (P) < 512 && lane == 0) p.dbg[6144 + (P) * 8 + (e)] = clock64(); } while (0)
-#define B2TRACE(P, e) do { if (FEN_B2_TRACE && p.dbg && blockIdx.x == 70 && (P) < 512) p.dbg[(P) * 8 + (e)] = clock64(); } while (0)
+#define B2T2(P, e, i) do { if (FEN_B2_TRACE && p.dbg && blockIdx.x == FEN_B2_TRACE_CTA && (P) >= 80 && (P) < 84 && (i) < 32) p.dbg[4096 + ((P) - 80) * 512 + (e) * 32 + (i)] = clock64(); } while (0)
+#define B2TS(P, e) do { if (FEN_B2_TRACE && p.dbg && blockIdx.x == FEN_B2_TRACE_CTA && (P) < 512 && lane == 0) p.dbg[6144 + (P) * 8 + (e)] = clock64(); } while (0)
+#define B2TRACE(P, e) do { if (FEN_B2_TRACE && p.dbg && blockIdx.x == FEN_B2_TRACE_CTA && (P) < 512) p.dbg[(P) * 8 + (e)] = clock64(); } while (0)
 
 #ifndef FEN_B2_WFREE1
 #define FEN_B2_WFREE1 1   // 1: the weights of a layer are handed back with ONE tcgen05.commit per issuer (after its last tile's
 #endif                    //    last tap) instead of one per tap.  Same time (3.14 ms both), and the last tile of a layer no
                           //    longer carries 10 commits: every tile tools/soak2.py ever caught wrong was such a tile
 
+#ifndef FEN_B2_ISSUE
+#define FEN_B2_ISSUE 2    // shape of the 36-MMA issue block of a tile: 0 fully unrolled, 1 a loop over the 3 tap rows (12 MMAs
+#endif                    //   per iteration), 2 a loop over the 9 taps (4 MMAs per iteration)
+#ifndef FEN_B2_ROTATE
+#define FEN_B2_ROTATE 0   // 1: the issuers' tile shares rotate per pass (balances tiles + SE batches between the two issuers; measured
+#endif                    //    SLOWER: 3.17 - 3.20 ms against 3.09 at batch 64)
+#ifndef FEN_B2_TURN
+#define FEN_B2_TURN 1      // 1: the issuers take turns, one whole tile each (see the tile loop)
+#endif
+#ifndef FEN_B2_NEAR_FLAGS
+#define FEN_B2_NEAR_FLAGS 0   // 1: the TMA warp only waits for the CTAs whose rows its boxes read (c - 1, c, c + 1) instead of every CTA of the image
+#endif
 #ifndef FEN_B2_NI
 #define FEN_B2_NI 2   // MMA issuer warps.  One thread sustains ~81 cycles per tcgen05.mma (tools/umma_probe3.cu), the pipe
 #endif                //   takes one N = 64 MMA every ~48: at least two issuers must be inside their 36-MMA loops at any time
@@ -215,6 +230,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
   __shared__ int s_hist[kB2Slots];                     // TMA warp: running index of the last tile that reads the box now in each slot
   __shared__ uint64_t bar_acc_full[kB2AccBufs], bar_acc_empty[kB2AccBufs];
   __shared__ uint64_t bar_done, bar_s_ready, bar_s_free, bar_se_full, bar_se_empty, bar_scale[2];
+  __shared__ uint64_t bar_turn[4];                     // FEN_B2_TURN: tile G's issuer arrives on [G % 4] once its MMAs are issued
   __shared__ uint64_t bar_cv[2];                       // per-layer bias / slope vectors staged by the TMA warp (slot L & 1)
   __shared__ __align__(16) float s_cv[2][128];
   __shared__ uint32_t tmem_slot;
@@ -299,6 +315,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
     mbar_init(&bar_s_ready, 1); mbar_init(&bar_s_free, 1); mbar_init(&bar_se_full, 1); mbar_init(&bar_se_empty, 1);
     mbar_init(&bar_scale[0], 1); mbar_init(&bar_scale[1], 1);
     mbar_init(&bar_cv[0], 1); mbar_init(&bar_cv[1], 1);
+    for (int k = 0; k < 4; ++k) mbar_init(&bar_turn[k], 1);
     fence_mbar_init();
     tma_prefetch_desc(&maps.w);
   }
@@ -324,7 +341,14 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
         B2W(1, 2, L, s, 0);
         if (L > 0) {
           const int* fl = p.flags + s * int(gridDim.x);
-          for (int k = s_peer[s][0] + lane; k <= s_peer[s][1]; k += 32)
+#if FEN_B2_NEAR_FLAGS
+          // halo rows come from the neighbouring runs only (a run is at least one tile = 128 pixels, a halo row 66); the
+          // buffers this CTA overwrites in layer L were read by the same neighbours in layer L - 1
+          const int k0 = max(s_peer[s][0], int(blockIdx.x) - 1), k1 = min(s_peer[s][1], int(blockIdx.x) + 1);
+#else
+          const int k0 = s_peer[s][0], k1 = s_peer[s][1];
+#endif
+          for (int k = k0 + lane; k <= k1; k += 32)
             while (ld_acquire_gpu(fl + k) < L) { __nanosleep(20); }
           __syncwarp();
           fence_proxy_async_all();
@@ -413,7 +437,17 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
       for (int s = 0; s < p.nset; ++s, ++P) {
         const B2Tile* tile_tab = tile_tab2[s];
         const int n_tiles = s_meta[s][0], n_boxes = s_meta[s][1];
-        const int last_own = ((n_tiles - 1 - wi) >= 0) ? wi + n_issuers * ((n_tiles - 1 - wi) / n_issuers) : -1;
+        // Which tiles of the pass this issuer takes: w0, w0 + n, ...  With a fixed w0 = wi issuer A gets 4 of 7 tiles in
+        // every pass AND the SE batches (5 blocks of 36 MMAs against B's 3 in a conv2 pass), and whenever one issuer idles
+        // the other feeds the pipe at the single-thread rate.  The start index therefore rotates: in conv2 passes the SE
+        // issuer (A) takes the odd tiles - the smaller share -, in the other layers the extra tile alternates with the set.
+#if FEN_B2_ROTATE
+        const int rot = (n_issuers == 2 && n_tiles >= 2) ? (conv2 ? 1 : (s & 1)) : 0;
+#else
+        const int rot = 0;
+#endif
+        const int w0 = (wi + rot) % n_issuers;
+        const int last_own = ((n_tiles - 1 - w0) >= 0) ? w0 + n_issuers * ((n_tiles - 1 - w0) / n_issuers) : -1;
         const uint32_t gb0 = gbox;                                  // running index of the pass's first box
         const uint32_t gbase_pass = gbase;
         gbox += uint32_t(n_boxes); gbase += uint32_t(n_tiles);
@@ -442,6 +476,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           }
           __syncwarp();                            // converge after the spin-waits before any tcgen05 issue
           if (leader) {
+#if FEN_B2_ISSUE == 0
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               const uint32_t a_lo = s_lo + tap * (1024 >> 4);
@@ -451,6 +486,17 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
                 umma_bf16_ss_lohi(tmem_base + kB2SeCol, a_lo + 2 * k, b_lo + 2 * k, kDescHi, idesc, (tap | k) != 0);
               }
             }
+#else
+            uint32_t a_lo = s_lo, b_lo = w_lo;      // (a real loop: see the tile loop below)
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_ss_lohi_p(tmem_base + kB2SeCol, a_lo + 2 * k, b_lo + 2 * k, kDescHi, idesc, k ? 1u : uint32_t(tap));
+              a_lo += 1024 >> 4;
+              b_lo += N * 128 >> 4;
+            }
+#endif
             umma_commit(&bar_se_full);
             umma_commit(&bar_s_free);
           }
@@ -468,7 +514,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
           __syncwarp();
           continue;
         }
-        for (int i = wi; i < n_tiles; i += n_issuers) {
+        for (int i = w0; i < n_tiles; i += n_issuers) {
           const B2Tile e = tile_tab[i];
           const uint32_t G = gbase_pass + i, acc = G % kB2AccBufs, aph = (G / kB2AccBufs) & 1;
           B2W(2 + wi, 1, L, s, i);
@@ -506,7 +552,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
             mbar_wait(bf, bph);
             ++waited;
           }
-          if (leader && i == wi && wi < 2) B2TRACE(P, 1 + wi);
+          if (leader && i == w0 && wi < 2) B2TRACE(P, 1 + wi);
           B2W(2 + wi, 4, L, s, i);
           if (leader) B2T2(P, 6, i);
           __syncwarp();                            // converge after the spin-waits (see the commits below)
@@ -527,6 +573,15 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
         umma_bf16_ss_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, kDescHi, idesc, ((tap) | k) != 0);           \
     if (w_rel && (!FEN_B2_WFREE1 || (tap) == 8)) umma_commit(&bar_wfree[FEN_B2_WFREE1 ? 0 : (tap)]); /* the next layer's tap may overwrite once these MMAs finish */ \
   }
+#if FEN_B2_TURN
+          // The issuers take turns, a whole tile each, in tile order: while one feeds the pipe its 36 MMAs the other does
+          // the bookkeeping of its next tile (the waits above, ~ 1 300 cycles).  Issuing concurrently they fall into
+          // lock-step - both blocked by the same full pipe, both finishing together - and their gaps coincide.
+          // Tile G - 1's issuer arrives on bar_turn[(G - 1) % 4]; tiles are issued strictly in order, so exactly
+          // (G - 1) / 4 phases of that barrier are complete before the arrival: the parity wait is unambiguous.
+          if (G > 0) mbar_wait(&bar_turn[(G - 1) & 3u], ((G - 1) >> 2) & 1u);
+          __syncwarp();
+#endif
           if (!w_seen) {
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
@@ -536,11 +591,57 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
               __syncwarp();
             }
           } else if (leader) {
+#if FEN_B2_ISSUE == 0 || !FEN_B2_WFREE1
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) FEN_B2_ISSUE_TAP(tap)
+#else
+            // The fully unrolled form above lets ptxas hoist all 72 descriptor moves (R2UR) ahead of the first MMA; they do
+            // not fit the uniform register file, and the block becomes a chain of uniform-register spills and fills: ~ 9
+            // instructions and ~ 81 cycles per MMA from one thread, although one thread can issue an N = 64 MMA every
+            // ~ 52 cycles (tools/umma_probe.cu T5).  A real loop bounds what can be hoisted.
+            uint32_t b_lo = w_lo, row = m;
+#if FEN_B2_ISSUE == 1
+#pragma unroll 1
+            for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                uint32_t pos = row + dx;
+                if (pos >= uint32_t(kB2RingPx)) pos -= kB2RingPx;
+                const uint32_t a_lo = ring_lo + pos * 8;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_ss_lohi_p(d_tmem, a_lo + 2 * k, b_lo + 2 * k, kDescHi, idesc, (dx | k) ? 1u : uint32_t(dy));
+                b_lo += N * 128 >> 4;
+              }
+              row += kPitch;
+              if (row >= uint32_t(kB2RingPx)) row -= kB2RingPx;
+            }
+#else
+            uint32_t dx = 0;
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+              uint32_t pos = row + dx;
+              if (pos >= uint32_t(kB2RingPx)) pos -= kB2RingPx;
+              const uint32_t a_lo = ring_lo + pos * 8;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_ss_lohi_p(d_tmem, a_lo + 2 * k, b_lo + 2 * k, kDescHi, idesc, k ? 1u : uint32_t(tap));
+              b_lo += N * 128 >> 4;
+              if (++dx == 3) {
+                dx = 0;
+                row += kPitch;
+                if (row >= uint32_t(kB2RingPx)) row -= kB2RingPx;
+              }
+            }
+#endif
+            if (w_rel) umma_commit(&bar_wfree[0]);   // the next layer's weights may overwrite once these MMAs finish
+#endif
           }
           w_seen = true;
           __syncwarp();
+#if FEN_B2_TURN
+          if (leader) mbar_arrive(&bar_turn[G & 3u]);
+#endif
           if (leader) B2T2(P, 7, i);
           // ONE commit per tile: the accumulator is complete.  The epilogue reads it; the TMA warp learns from the same
           // barrier that the ring boxes this tile read may be replaced.

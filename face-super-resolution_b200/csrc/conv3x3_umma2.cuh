@@ -11,6 +11,10 @@
 #pragma once
 #include "conv3x3_umma.cuh"
 
+#ifndef FEN_C2_ISSUE
+#define FEN_C2_ISSUE 1   // shape of a tile's 36-MMA issue block: 0 unrolled, 1 loop over tap rows, 2 loop over taps (body2_umma.cuh)
+#endif
+
 namespace fen {
 
 constexpr int kC2MaxTiles = 256;
@@ -159,8 +163,47 @@ conv3x3_umma2_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
           __syncwarp();
         }
       } else if (leader) {
+#if FEN_C2_ISSUE == 0
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) FEN_C2_ISSUE_TAP(tap)
+#else
+        // a real loop instead of 36 unrolled MMAs: see body2_umma.cuh (the unrolled block spills uniform registers)
+        uint32_t b_lo = w_lo, row = m;
+#if FEN_C2_ISSUE == 1
+#pragma unroll 1
+        for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            uint32_t pos = row + dx;
+            if (pos >= uint32_t(kC2RingPx)) pos -= kC2RingPx;
+            const uint32_t a_lo = ring_lo + pos * 8;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_ss_lohi_p(d_tmem, a_lo + 2 * k, b_lo + 2 * k, kDescHi, idesc, (dx | k) ? 1u : uint32_t(dy));
+            b_lo += N * 128 >> 4;
+          }
+          row += kPitch;
+          if (row >= uint32_t(kC2RingPx)) row -= kC2RingPx;
+        }
+#else
+        uint32_t dx = 0;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          uint32_t pos = row + dx;
+          if (pos >= uint32_t(kC2RingPx)) pos -= kC2RingPx;
+          const uint32_t a_lo = ring_lo + pos * 8;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss_lohi_p(d_tmem, a_lo + 2 * k, b_lo + 2 * k, kDescHi, idesc, k ? 1u : uint32_t(tap));
+          b_lo += N * 128 >> 4;
+          if (++dx == 3) {
+            dx = 0;
+            row += kPitch;
+            if (row >= uint32_t(kC2RingPx)) row -= kC2RingPx;
+          }
+        }
+#endif
+#endif
       }
       w_seen = true;
       __syncwarp();

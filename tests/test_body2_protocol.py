@@ -11,11 +11,17 @@ CTAS = [1, 19, 20, 70, 128, 147]
 
 
 def test_shipped_protocol_has_no_violation():
-    for mode in ("two", "count"):
+    for mode in ("both", "two", "count"):
         assert sim.sweep(CTAS, 1, 4, mode, regimes=(4, 16)) == []
 
 
+def test_build_options_are_deadlock_free():
+    # FEN_B2_TURN = 0 (issuers run concurrently) and FEN_B2_ROTATE = 1 (tile shares rotate per pass)
+    assert sim.sweep(CTAS[:3], 1, 4, "both", regimes=(4,), turn=False) == []
+    assert sim.sweep(CTAS[:3], 1, 4, "both", regimes=(4,), rotate=True) == []
+
+
 def test_model_catches_the_protocol_before_the_fix():
-    bad = sim.sweep(CTAS, 1, 4, "nofix", regimes=(4, 16))
+    bad = sim.sweep(CTAS, 1, 4, "nofix", regimes=(4, 16), turn=False)
     assert bad, "the model no longer reproduces the phase aliasing of the single-barrier ring"
     assert all("issuer 1" in b and "inflight=True" in b for b in bad), bad[:3]

@@ -12,11 +12,14 @@ import heapq, random, sys
 
 kTileM, kPitch, kMaxShift, kBoxRows, kBoxPx = 128, 66, 134, 2, 132
 kSlots, kAcc, kPre = 7, 7, 4
-FIX = "two"   # "two": two alternating mbarriers per ring slot (what the kernel does now); "count": a shared issue counter; "nofix": the protocol as it was (reproduces the aliasing)
+TURN = True     # the issuers take turns, one whole tile each (FEN_B2_TURN)
+ROTATE = False   # the issuers' tile shares rotate per pass (FEN_B2_ROTATE)
+FIX = "both"   # "both": two alternating mbarriers per ring slot + a shared count of requested boxes (the kernel); "two" / "count": either alone; "nofix": the protocol as it was (reproduces the aliasing)
 H, TPS = 64, 33
 import os
 C, SET_B = 148, int(os.environ.get("SET_B", "32"))   # images per set (batch 64 = 2 x 32)
 T = SET_B * TPS
+C = min(C, T)                 # (the host launches one CTA per tile when there are fewer tiles than SMs)
 RQ, RR = T // C, T % C
 
 
@@ -87,15 +90,18 @@ class Sim:
         self.cta, self.NL, self.slow = cta, n_layers, slow
         self.tab = [tables(cta, 0), tables(cta, 1)]
         self.bar_w = [Bar(1) for _ in range(9)]
-        self.bar_wfree = Bar(2)
+        self.n_issuers = min(2, max(len(self.tab[0][0]), len(self.tab[1][0]), 1))
+        self.bar_wfree = Bar(self.n_issuers)
         self.bar_full = [Bar(1) for _ in range(2 * kSlots)]
-        self.nb = 2 * kSlots if FIX == "two" else kSlots   # barriers in use
+        self.nb = 2 * kSlots if FIX in ("two", "both") else kSlots   # barriers in use
         self.bar_acc_full = [Bar(1) for _ in range(kAcc)]
         self.bar_acc_empty = [Bar(8) for _ in range(kAcc)]
         self.bar_done = Bar(8)
         self.bar_s_ready, self.bar_s_free, self.bar_se_full, self.bar_se_empty = Bar(1), Bar(1), Bar(1), Bar(1)
         self.bar_scale = [Bar(1), Bar(1)]
+        self.bar_turn = [Bar(1) for _ in range(4)]
         self.s_hist = [-1] * kSlots
+        self.turn_next = 0
         self.issued = 0                          # boxes issued so far (the fix: s_issued in shared memory)
         # ground truth
         self.slot_box = [None] * kSlots          # global box id whose data is in the slot
@@ -143,7 +149,8 @@ class Sim:
     def run(self):
         self.spawn(self.tma())
         self.spawn(self.issuer(0))
-        self.spawn(self.issuer(1))
+        if self.n_issuers == 2:
+            self.spawn(self.issuer(1))
         self.spawn(self.se_warp())
         for w in range(8):
             self.spawn(self.epilogue(w))
@@ -229,7 +236,10 @@ class Sim:
             for s in range(2):
                 tiles, boxes = self.tab[s]
                 n_tiles, n_boxes = len(tiles), len(boxes)
-                last_own = wi + 2 * ((n_tiles - 1 - wi) // 2) if n_tiles - 1 - wi >= 0 else -1
+                rot = (1 if conv2 else s & 1) if (ROTATE and self.n_issuers == 2 and n_tiles >= 2) else 0      # FEN_B2_ROTATE
+                w0 = (wi + rot) % self.n_issuers
+                ni = self.n_issuers
+                last_own = w0 + ni * ((n_tiles - 1 - w0) // ni) if n_tiles - 1 - w0 >= 0 else -1
                 gb0, gbase_pass = gbox, gbase
                 gbox += n_boxes; gbase += n_tiles
                 last_pass = s == 1
@@ -260,8 +270,11 @@ class Sim:
                     w_seen = True
                     se_n += 1; se_done += 1
 
-                assert last_own >= 0
-                for i in range(wi, n_tiles, 2):
+                if last_own < 0:          # no tile for this issuer in this pass: only the weight hand-back, in the last pass
+                    if last_pass:
+                        self.at(max(self.now, self.last_done[wi]), self.bar_wfree.arrive)
+                    continue
+                for i in range(w0, n_tiles, ni):
                     e = tiles[i]
                     G = gbase_pass + i; acc = G % kAcc; aph = (G // kAcc) & 1
                     if se_layer and se_done <= s:
@@ -282,10 +295,12 @@ class Sim:
                     waited = max(waited, e["first_box"])
                     while waited < e["wait_upto"]:
                         g = gb0 + waited
-                        if FIX == "count":
+                        if FIX in ("count", "both"):
                             yield ("wait", lambda g=g: self.issued > g)
                         yield ("wait", lambda g=g: self.bar_full[g % self.nb].test((g // self.nb) & 1))
                         waited += 1
+                    if TURN and G > 0:
+                        yield ("wait", lambda G=G: self.bar_turn[(G - 1) & 3].test(((G - 1) >> 2) & 1))
                     if not w_seen:
                         for tap in range(9):
                             yield ("wait", lambda tap=tap: self.bar_w[tap].test(L & 1))
@@ -305,6 +320,11 @@ class Sim:
                         self.readers[(gb0 + b) % kSlots].add(tag)
                     self.w_readers.add(tag)
                     yield ("delay", 36 * (50 + self.jit(40)))
+                    if TURN:
+                        if self.turn_next != G:
+                            raise Violation(f"L{L} set {s} tile {i}: issued out of turn (expected global tile {self.turn_next}, got {G})")
+                        self.turn_next = G + 1
+                        self.bar_turn[G & 3].arrive()
                     done = max(self.now + self.tail(300, p=0.05, mult=20), self.last_done[wi] + 50)
                     self.last_done[wi] = done
                     w_rel = last_pass and i == last_own
@@ -377,10 +397,10 @@ class Sim:
                 m_cnt += 1
 
 
-def sweep(ctas, seeds, layers, mode, regimes=(1, 4, 16)):
+def sweep(ctas, seeds, layers, mode, regimes=(1, 4, 16), turn=True, rotate=False):
     """Runs the model for every (CTA, seed, timing regime); returns the violation messages."""
-    global FIX
-    FIX = mode
+    global FIX, TURN, ROTATE
+    FIX, TURN, ROTATE = mode, turn, rotate
     out = []
     for cta in ctas:
         for seed in range(seeds):
@@ -396,7 +416,7 @@ def main():
     seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     layers = int(sys.argv[2]) if len(sys.argv) > 2 else 8
     mode = sys.argv[3] if len(sys.argv) > 3 else FIX
-    ctas = [0, 1, 19, 20, 21, 70, 127, 128, 129, 147] + list(range(2, 148, 9))
+    ctas = [c for c in [0, 1, 19, 20, 21, 70, 127, 128, 129, 147] + list(range(2, 148, 9)) if c < C]
     bad = sweep(ctas, seeds, layers, mode)
     for line in bad[:12]:
         print(line)
