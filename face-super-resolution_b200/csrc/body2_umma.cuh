@@ -58,6 +58,9 @@ namespace fen {
 #ifndef FEN_B2_TURN
 #define FEN_B2_TURN 1      // 1: the issuers take turns, one whole tile each (see the tile loop)
 #endif
+#ifndef FEN_B2_SE_SELF
+#define FEN_B2_SE_SELF 1   // 1: the SE warp issues the 36 MMAs of its mat-vec itself (no hand-over to issuer A)
+#endif
 #ifndef FEN_B2_NEAR_FLAGS
 #define FEN_B2_NEAR_FLAGS 0   // 1: the TMA warp only waits for the CTAs whose rows its boxes read (c - 1, c, c + 1) instead of every CTA of the image
 #endif
@@ -308,7 +311,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
     s_meta[0][3] = int(n_issuers);
     for (int k = 0; k < kB2Slots; ++k) s_hist[k] = -1;
     s_issued = 0;
-    for (int k = 0; k < 9; ++k) { mbar_init(&bar_w[k], 1); mbar_init(&bar_wfree[k], n_issuers); }
+    for (int k = 0; k < 9; ++k) { mbar_init(&bar_w[k], 1); mbar_init(&bar_wfree[k], n_issuers + (FEN_B2_SE_SELF ? 1u : 0u)); }
     for (int k = 0; k < 2 * kB2Slots; ++k) mbar_init(&bar_full[k], 1);
     for (int k = 0; k < kB2AccBufs; ++k) { mbar_init(&bar_acc_full[k], 1); mbar_init(&bar_acc_empty[k], kB2EpiWarps); }
     mbar_init(&bar_done, kB2EpiWarps);
@@ -455,7 +458,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
         const bool last_pass = (s == p.nset - 1);
         // SE batches of this layer still owed: the one of set s must run before this pass's epilogue can start,
         // those of later sets may run as soon as their operand is ready (W2 is in shared memory all layer long)
-#ifdef FEN_B2_X2
+#if defined(FEN_B2_X2) || FEN_B2_SE_SELF
         const bool se_layer = false;
 #else
         const bool se_layer = conv2 && (wi == 0);
@@ -656,13 +659,31 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
     // ============================================================ SE warp
     uint32_t se_n = 0, m_cnt = 0;
     const uint32_t s_base = smem_u32(s_buf);
+#if FEN_B2_SE_SELF
+    constexpr uint32_t se_idesc = umma_idesc_bf16(kTileM, kC);
+    constexpr uint32_t kSeDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t se_s_lo = (smem_u32(s_buf) >> 4) | (1u << 16), se_w_lo = (smem_u32(w_smem) >> 4) | (1u << 16);
+    const bool se_leader = elect_one();
+#endif
 #ifdef FEN_B2_X2
     for (int L = 0; L < 0; ++L) {
 #else
     for (int L = 0; L < p.n_layers; ++L) {
 #endif
       const B2Layer ly = body2_layer<kTrain>(p, L);
+#if FEN_B2_SE_SELF
+      // This warp reads the layer's weights too (its MMAs run against W2 in shared memory): it is a party of the weight
+      // hand-back.  In a layer without SE it arrives at once - but never a phase ahead of the issuers.
+      if (ly.epi != kBEpiSeResidual) {
+        if (L > 0) mbar_wait(&bar_wfree[0], (L - 1) & 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_wfree[0]);
+        __syncwarp();
+        continue;
+      }
+#else
       if (ly.epi != kBEpiSeResidual) continue;
+#endif
       const uint8_t* rec = p.packed + p.k_rcab0 + int64_t(ly.rcab) * p.k_rcab_stride;
       const float* fc0 = reinterpret_cast<const float*>(rec + p.k_rcab_fc0);
       const float* fc2 = reinterpret_cast<const float*>(rec + p.k_rcab_fc2);
@@ -694,7 +715,9 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
         }
         B2W(0, 2, L, s, se_n);
         B2TS(L * p.nset + s, 1);
+#if !FEN_B2_SE_SELF
         if (se_n >= 1) mbar_wait(&bar_s_free, (se_n - 1) & 1);   // the previous batch has consumed the operand
+#endif                                                           // (SE_SELF: this warp has seen the previous batch complete)
 #pragma unroll
         for (int u = 0; u < kBodyMaxUnits; ++u) {
           if (u < n_units) {
@@ -722,7 +745,31 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
         }
         fence_proxy_async_smem();
         __syncwarp();
+#if FEN_B2_SE_SELF
+        {
+          // D[row, c] = sum_tap S_tap[row, :] . W2_tap[c, :] into the SE accumulator, once all nine taps of THIS layer's
+          // weights have landed (no MMA of the previous layer is in flight any more then)
+          for (int tap = 0; tap < 9; ++tap) mbar_wait(&bar_w[tap], L & 1);
+          __syncwarp();
+          tc_fence_after();
+          if (se_leader) {
+            uint32_t a_lo = se_s_lo, b_lo = se_w_lo;
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_ss_lohi_p(tmem_base + kB2SeCol, a_lo + 2 * k, b_lo + 2 * k, kSeDescHi, se_idesc, k ? 1u : uint32_t(tap));
+              a_lo += 1024 >> 4;
+              b_lo += kC * 128 >> 4;
+            }
+            umma_commit(&bar_se_full);
+            if (s == p.nset - 1) umma_commit(&bar_wfree[0]);   // the layer's last batch: the weights may go once it has run
+          }
+          __syncwarp();
+        }
+#else
         if (lane == 0) mbar_arrive(&bar_s_ready);
+#endif
         B2TS(L * p.nset + s, 2);
         const bool fast_fc = (p.R == 16);   // lane l: hidden unit l & 15 of units (l >> 4), (l >> 4) + 2; channels l, l + 32
         // ---- result rows 0..7 of the SE accumulator (lane r = row r = hi / lo part of unit r / 2) -> smem

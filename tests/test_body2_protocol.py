@@ -19,9 +19,10 @@ def test_build_options_are_deadlock_free():
     # FEN_B2_TURN = 0 (issuers run concurrently) and FEN_B2_ROTATE = 1 (tile shares rotate per pass)
     assert sim.sweep(CTAS[:3], 1, 4, "both", regimes=(4,), turn=False) == []
     assert sim.sweep(CTAS[:3], 1, 4, "both", regimes=(4,), rotate=True) == []
+    assert sim.sweep(CTAS[:3], 1, 5, "both", regimes=(4,), se_self=False) == []     # FEN_B2_SE_SELF = 0: SE batches issued by issuer A
 
 
 def test_model_catches_the_protocol_before_the_fix():
-    bad = sim.sweep(CTAS, 1, 4, "nofix", regimes=(4, 16), turn=False)
+    bad = sim.sweep(CTAS, 1, 4, "nofix", regimes=(4, 16), turn=False, se_self=False)
     assert bad, "the model no longer reproduces the phase aliasing of the single-barrier ring"
     assert all("issuer 1" in b and "inflight=True" in b for b in bad), bad[:3]

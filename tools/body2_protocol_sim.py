@@ -12,6 +12,7 @@ import heapq, random, sys
 
 kTileM, kPitch, kMaxShift, kBoxRows, kBoxPx = 128, 66, 134, 2, 132
 kSlots, kAcc, kPre = 7, 7, 4
+SE_SELF = True   # the SE warp issues its own MMAs and is a party of the weight hand-back (FEN_B2_SE_SELF)
 TURN = True     # the issuers take turns, one whole tile each (FEN_B2_TURN)
 ROTATE = False   # the issuers' tile shares rotate per pass (FEN_B2_ROTATE)
 FIX = "both"   # "both": two alternating mbarriers per ring slot + a shared count of requested boxes (the kernel); "two" / "count": either alone; "nofix": the protocol as it was (reproduces the aliasing)
@@ -91,7 +92,7 @@ class Sim:
         self.tab = [tables(cta, 0), tables(cta, 1)]
         self.bar_w = [Bar(1) for _ in range(9)]
         self.n_issuers = min(2, max(len(self.tab[0][0]), len(self.tab[1][0]), 1))
-        self.bar_wfree = Bar(self.n_issuers)
+        self.bar_wfree = Bar(self.n_issuers + (1 if SE_SELF else 0))
         self.bar_full = [Bar(1) for _ in range(2 * kSlots)]
         self.nb = 2 * kSlots if FIX in ("two", "both") else kSlots   # barriers in use
         self.bar_acc_full = [Bar(1) for _ in range(kAcc)]
@@ -243,7 +244,7 @@ class Sim:
                 gb0, gbase_pass = gbox, gbase
                 gbox += n_boxes; gbase += n_tiles
                 last_pass = s == 1
-                se_layer = conv2 and wi == 0
+                se_layer = conv2 and wi == 0 and not SE_SELF
                 if s == 0:
                     se_done = 0
                 waited = 0
@@ -344,15 +345,34 @@ class Sim:
         se_n = 0
         for L in range(self.NL):
             if not self.conv2(L):
+                if SE_SELF:
+                    if L > 0:
+                        yield ("wait", lambda: self.bar_wfree.test((L - 1) & 1))
+                    self.bar_wfree.arrive()
                 continue
             for s in range(2):
                 yield from self.wait_flags(L, s)
                 yield ("delay", self.tail(600, p=0.3, mult=30))
-                if se_n >= 1:
+                if se_n >= 1 and not SE_SELF:
                     n0 = se_n
                     yield ("wait", lambda: self.bar_s_free.test((n0 - 1) & 1))
                 yield ("delay", 300)
-                self.bar_s_ready.arrive()
+                if SE_SELF:
+                    for tap in range(9):
+                        yield ("wait", lambda tap=tap: self.bar_w[tap].test(L & 1))
+                    if any(self.w_layer[t] != L or self.w_inflight[t] for t in range(9)):
+                        raise Violation(f"L{L}: SE batch reads weights {self.w_layer}")
+                    yield ("delay", 36 * 55)
+                    tag = ("se", L, s)
+                    self.w_readers.add(tag)
+                    def fin(tag=tag, last=(s == 1)):
+                        self.w_readers.discard(tag)
+                        self.bar_se_full.arrive()
+                        if last:
+                            self.bar_wfree.arrive()
+                    self.at(self.now + 400 + self.tail(300, p=0.1, mult=20), fin)
+                else:
+                    self.bar_s_ready.arrive()
                 n0 = se_n
                 yield ("wait", lambda: self.bar_se_full.test(n0 & 1))
                 yield ("delay", 200)
@@ -397,10 +417,10 @@ class Sim:
                 m_cnt += 1
 
 
-def sweep(ctas, seeds, layers, mode, regimes=(1, 4, 16), turn=True, rotate=False):
+def sweep(ctas, seeds, layers, mode, regimes=(1, 4, 16), turn=True, rotate=False, se_self=True):
     """Runs the model for every (CTA, seed, timing regime); returns the violation messages."""
-    global FIX, TURN, ROTATE
-    FIX, TURN, ROTATE = mode, turn, rotate
+    global FIX, TURN, ROTATE, SE_SELF
+    FIX, TURN, ROTATE, SE_SELF = mode, turn, rotate, se_self
     out = []
     for cta in ctas:
         for seed in range(seeds):
@@ -417,7 +437,7 @@ def main():
     layers = int(sys.argv[2]) if len(sys.argv) > 2 else 8
     mode = sys.argv[3] if len(sys.argv) > 3 else FIX
     ctas = [c for c in [0, 1, 19, 20, 21, 70, 127, 128, 129, 147] + list(range(2, 148, 9)) if c < C]
-    bad = sweep(ctas, seeds, layers, mode)
+    bad = sweep(ctas, seeds, layers, mode, se_self=bool(int(os.environ.get("SE_SELF", "1"))))
     for line in bad[:12]:
         print(line)
     print(f"{mode}: {len(ctas)} CTAs x {seeds} seeds x 3 timing regimes x {layers} layers: {len(bad)} violations")
