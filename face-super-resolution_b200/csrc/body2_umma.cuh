@@ -21,8 +21,14 @@
 //  * One running activation ring over all passes, the first boxes of a layer requested before its weights;
 //    tile runs of q or q + 1 tiles with the extra tile on opposite ends for the two sets (all 148 SMs busy).
 //  * Rules every role follows (found with cuda-gdb): every mbarrier wait is executed by the
-//    whole warp and followed by __syncwarp() before any tcgen05 / TMA issue; elected-lane blocks contain
-//    straight-line code only; a ring slot is released only by a warp that has seen it arrive.
+//    whole warp and followed by __syncwarp() before any tcgen05 / TMA issue; elected-lane blocks never
+//    wait; a parity wait is only trusted by a waiter that has seen every earlier phase of the barrier or
+//    has been told by a counter that its phase has begun (the ring: two barriers per slot + s_issued).
+//  * The two issuers take turns, a whole tile each (FEN_B2_TURN): one feeds the pipe its 36 MMAs - a real
+//    loop over the taps, which one thread issues at the pipe's rate - while the other does the waits of
+//    its next tile.  The SE warp issues the MMAs of its mat-vec itself (FEN_B2_SE_SELF) and is the third
+//    party of the weight hand-back.  tools/body2_protocol_sim.py is a discrete-event model of all of
+//    this (tests/test_body2_protocol.py).
 #pragma once
 #include <type_traits>
 #include "body_umma.cuh"
@@ -423,7 +429,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
       }
     }
   } else if (warp >= kB2FirstMmaWarp && warp < kB2FirstMmaWarp + kB2Issuers) {
-    // ============================================================ MMA issuers: warp 2 + w takes tiles w, w + n, ... (warp 2 also the SE batches)
+    // ============================================================ MMA issuers: warp 2 + w takes tiles w, w + n, ... (FEN_B2_SE_SELF = 0: warp 2 also the SE batches)
     constexpr uint32_t idesc = umma_idesc_bf16(kTileM, N);
     constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
     constexpr uint32_t kLbo = 1u << 16;
@@ -1177,6 +1183,7 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
         // (Measured without the per-thread fence - one cumulative st.release.gpu by the flag writer behind the mbarrier,
         // valid in the PTX memory model: 3.085 -> 3.020 ms at batch 64, but tools/soak2.py then caught a quarter tile of
         // stale input, 8 times in 12 000 forwards, on one box.  The fence stays.)
+        if (ew == 0) B2TS(P, 5);                  // (trace: this warp's tiles of the pass are stored)
 #ifndef FEN_B2_NO_WRITER_PROXY_FENCE
         // the stores above went through the generic proxy; the readers are TMA loads (async proxy) of this and other CTAs
         asm volatile("fence.proxy.async.global;" ::: "memory");
@@ -1188,10 +1195,12 @@ body2_umma_kernel(const __grid_constant__ Body2Maps maps, const Body2Params p) {
         // arrivals of pass P may only start once pass P-1 is complete (a warp running ahead over short
         // passes could otherwise complete a phase with two of its own arrivals)
         if (P > 0) mbar_wait(&bar_done, (P - 1) & 1);
+        if (ew == 7) B2TS(P, 7);                  // (trace: the last epilogue warp arrives, fences done)
         if (lane == 0) mbar_arrive(&bar_done);
         if (flag_writer) {
           B2W(4, 3, L, s, 0);
           mbar_wait(&bar_done, P & 1);
+          B2TS(P, 6);                             // (trace: all eight warps have arrived)
           if (lane == 0) {
             st_release_gpu(p.flags + s * int(gridDim.x) + blockIdx.x, L + 1);
             B2TRACE(P, 7);

@@ -27,6 +27,10 @@ for P in range(80, 104):
     if ts[P, 0].item() == 0: continue
     base = t[P, 0].item()
     print(f"{P:4d}  " + "  ".join(f"{ts[P, e].item() - base:9d}" for e in range(5)))
+print("pass end (relative to the pass's tma start): warp 0 tiles stored | warp 7 fenced + arrived | all 8 arrived | flag out")
+for P in range(80, 104):
+    base = t[P, 0].item()
+    print(f"{P:4d}  " + "  ".join(f"{ts[P, e].item() - base:9d}" for e in (5, 7, 6)) + f"  {t[P, 7].item() - base:9d}")
 tot = t[253, 7].item() - t[0, 0].item()
 print("total cycles pass 0 -> flag of pass 253:", tot)
 
