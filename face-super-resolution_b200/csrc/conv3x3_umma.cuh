@@ -27,6 +27,10 @@
 #include "fen_common.cuh"
 #include "ptx_sm100.cuh"
 
+#ifndef FEN_C1_TURN
+#define FEN_C1_TURN 0   // 1: the two MMA issuers of conv3x3_umma_kernel take turns, one whole tile each (measured: 3.63 vs 3.60 ms per batch-64 forward - its CTAs run 228-tile passes without the body kernel's per-pass waits; off)
+#endif
+
 namespace fen {
 
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar, uint32_t dst_smem,
@@ -110,6 +114,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
   uint8_t* w_smem = smem;                                   // [9][N][64] bf16, SWIZZLE_128B
   uint8_t* ring = smem + Cfg::kWBytes;                      // (kRingSlots + 1) x kSlotBytes
   __shared__ uint64_t bar_w[9], bar_full[kRingSlots], bar_empty[kRingSlots], bar_acc_full[Cfg::kAccBufs], bar_acc_empty[Cfg::kAccBufs];
+  __shared__ uint64_t bar_turn[4];                          // FEN_C1_TURN: tile T's issuer arrives on [T % 4] once its MMAs are issued
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_bias[N];
   __shared__ __align__(16) float s_slope[kC];
@@ -127,6 +132,7 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
     for (int i = 0; i < 9; ++i) mbar_init(&bar_w[i], 1);
     for (int i = 0; i < kRingSlots; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], Cfg::kMmaWarps); }
     for (int i = 0; i < Cfg::kAccBufs; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], Cfg::kEpiWarps); }
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_turn[i], 1);
     fence_mbar_init();
     tma_prefetch_desc(&tm_in);
     tma_prefetch_desc(&tm_w);
@@ -227,17 +233,42 @@ conv3x3_umma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_cons
           const uint32_t a0 = ring_lo + slot0 * (kSlotBytes >> 4) + r0 * 8;
           const uint32_t a1 = ring_lo + slot1 * (kSlotBytes >> 4) + (r0 - kBoxPx) * 8;
           const long long dbg_i0 = p.dbg ? clock64() : 0;
+#if FEN_C1_TURN
+          // the two issuers take turns, a whole tile each, in tile order (body2_umma.cuh: issuing concurrently they fall
+          // into lock-step and do their per-tile bookkeeping at the same time, with the pipe idle)
+          if (mine && tile_ctr > 0) mbar_wait(&bar_turn[(tile_ctr - 1) & 3u], ((tile_ctr - 1) >> 2) & 1u);
+          __syncwarp();
+#endif
           if (leader && mine) {
+            if (first) {
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              if (first) mbar_wait(&bar_w[tap], 0);
-              const int off = (tap / 3) * kPitch + (tap % 3);
-              const uint32_t a_lo = ((r0 + off < kBoxPx) ? a0 : a1) + off * 8;
-              const uint32_t b_lo = w_lo + tap * (N * 128 >> 4);
+              for (int tap = 0; tap < 9; ++tap) {
+                mbar_wait(&bar_w[tap], 0);
+                const int off = (tap / 3) * kPitch + (tap % 3);
+                const uint32_t a_lo = ((r0 + off < kBoxPx) ? a0 : a1) + off * 8;
+                const uint32_t b_lo = w_lo + tap * (N * 128 >> 4);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16_ss_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, kDescHi, idesc, (tap | k) != 0);
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_ss_lohi(d_tmem, a_lo + 2 * k, b_lo + 2 * k, kDescHi, idesc, (tap | k) != 0);
+              }
+            } else {
+              // a real loop over the taps: 36 unrolled MMAs with 72 distinct descriptors spill the uniform registers
+              uint32_t b_lo = w_lo;
+              int off_row = 0, dx = 0;
+#pragma unroll 1
+              for (int tap = 0; tap < 9; ++tap) {
+                const int off = off_row + dx;
+                const uint32_t a_lo = ((r0 + off < kBoxPx) ? a0 : a1) + off * 8;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16_ss_lohi_p(d_tmem, a_lo + 2 * k, b_lo + 2 * k, kDescHi, idesc, k ? 1u : uint32_t(tap));
+                b_lo += N * 128 >> 4;
+                if (++dx == 3) { dx = 0; off_row += kPitch; }
+              }
             }
+#if FEN_C1_TURN
+            mbar_arrive(&bar_turn[tile_ctr & 3u]);
+#endif
           }
           __syncwarp();
           if (p.dbg) dbg_issue += clock64() - dbg_i0;
