@@ -544,3 +544,19 @@ def test_forward_is_deterministic(dev):
             ref = m(x).clone()
             for _ in range(10):
                 assert torch.equal(m(x), ref)
+
+
+def test_forward_batch64_is_bit_repeatable(dev):
+    """BASELINE config 2 itself (6 x 10 x 64, batch 64: 7 or 8 tiles per pass and CTA in the persistent body kernel, the
+    geometry in which an issuer could run one mbarrier phase ahead of a ring slot - DESIGN.md 4.2): 400 forwards of one
+    batch agree bit for bit with the first.  (tools/soak2.py is the long version: 12 000 forwards, every stage compared.)"""
+    cfg = dict(num_groups=6, blocks_per_group=10)
+    sd = weights.make_state_dict(3, "T1", **cfg)
+    g = torch.Generator().manual_seed(11)
+    sd["conv_last.weight"] = torch.randn(sd["conv_last.weight"].shape, generator=g) * 1e-2   # expose the body
+    m = _model(cfg, sd, dev)
+    x = torch.rand(64, 3, 64, 64, device=dev)
+    with torch.no_grad():
+        ref = m(x).clone()
+        bad = sum(int(not torch.equal(m(x), ref)) for _ in range(400))
+    assert bad == 0, f"{bad} of 400 batch-64 forwards differ from the first"
